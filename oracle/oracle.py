@@ -1,0 +1,328 @@
+"""ctypes front-end of the CPU ORACLE (oracle/libedoracle.so).
+
+TEST INFRASTRUCTURE ONLY -- parity unpinned (see oracle/ed_oracle.h).  Import this module only
+from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int)
+c_i32p = C.POINTER(C.c_int32)
+c_i64p = C.POINTER(C.c_int64)
+
+
+def build(force=False):
+    """Compile oracle/libedoracle.so with the committed Makefile (gcc only)."""
+    so = os.path.join(_HERE, "libedoracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("ed_oracle.c", "ed_oracle.h", "Makefile")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "libedoracle.so"])
+    return so
+
+
+class _Csr(C.Structure):
+    _fields_ = [("nrow", C.c_int64), ("ncol", C.c_int64), ("rowptr", c_i64p),
+                ("cols", c_i64p), ("vals", c_dp)]
+
+
+class _Sector(C.Structure):
+    _fields_ = [("ctx", C.c_void_p), ("nup", C.c_int), ("ndw", C.c_int),
+                ("dimup", C.c_int64), ("dimdw", C.c_int64), ("dim", C.c_int64),
+                ("map_up", c_i32p), ("map_dw", c_i32p),
+                ("rank", C.c_int), ("nranks", C.c_int),
+                ("qdw", C.c_int64), ("rdw", C.c_int64), ("q", C.c_int64), ("r", C.c_int64),
+                ("istart", C.c_int64), ("iend", C.c_int64), ("ishift", C.c_int64),
+                ("sparse_h", C.c_int), ("h0d", c_dp),
+                ("hup", _Csr), ("hdw", _Csr), ("hnd", _Csr)]
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "libedoracle.so")
+        if not os.path.exists(so):
+            build()
+        L = C.CDLL(so)
+        L.orc_ctx_create.restype = C.c_void_p
+        L.orc_ctx_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, c_dp, C.c_double, C.c_double,
+                                     C.c_double, C.c_double, C.c_double, c_dp, c_dp, c_dp]
+        L.orc_ctx_destroy.argtypes = [C.c_void_p]
+        L.orc_init_dmft_bath.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, c_dp, c_dp]
+        L.orc_binomial.restype = C.c_int
+        L.orc_build_sector_map.restype = C.c_int64
+        L.orc_build_sector_map.argtypes = [C.c_int, C.c_int, c_i32p]
+        L.orc_c.argtypes = [C.c_int, C.c_int32, c_i32p, c_dp]
+        L.orc_cdg.argtypes = [C.c_int, C.c_int32, c_i32p, c_dp]
+        L.orc_binary_search.restype = C.c_int64
+        L.orc_binary_search.argtypes = [c_i32p, C.c_int64, C.c_int32]
+        L.orc_build_hv_sector.restype = C.POINTER(_Sector)
+        L.orc_build_hv_sector.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.orc_delete_hv_sector.argtypes = [C.POINTER(_Sector)]
+        L.orc_vecdim_hv_sector.restype = C.c_int64
+        L.orc_vecdim_hv_sector.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.orc_build_hmat.argtypes = [C.POINTER(_Sector), c_dp]
+        L.orc_spmatvec_main.argtypes = [C.POINTER(_Sector), C.c_int64, c_dp, c_dp]
+        L.orc_directmatvec_main.argtypes = [C.POINTER(_Sector), C.c_int64, c_dp, c_dp]
+        L.orc_spmatvec_mpi_main_all.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_dp, c_dp]
+        L.orc_directmatvec_mpi_main_all.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_dp, c_dp]
+        L.orc_spmatvec_mpi_main_prebuilt.argtypes = [C.POINTER(C.POINTER(_Sector)), C.c_int, C.c_int, c_dp, c_dp]
+        L.orc_vector_transpose_all.argtypes = [C.c_int, C.c_int64, C.c_int64, C.POINTER(c_dp), C.POINTER(c_dp)]
+        L.orc_tql2.argtypes = [C.c_int, c_dp, c_dp, c_dp]
+        L.orc_lanc_eigh_sector.argtypes = [C.POINTER(_Sector), C.c_int, c_dp, c_dp, C.c_int, C.c_double,
+                                           C.c_int, c_ip, c_dp, c_dp]
+        L.orc_lanc_tridiag_sector.argtypes = [C.POINTER(_Sector), C.c_int, c_dp, c_dp, c_dp, C.c_int, C.c_double]
+        L.orc_gf_start_vector.restype = C.c_int64
+        L.orc_gf_start_vector.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dp, C.c_int, C.c_int, C.c_int,
+                                          c_dp, c_dp, c_ip, c_ip]
+        L.orc_add_to_lanczos_gf.argtypes = [C.c_double, C.c_double, C.c_double, c_dp, c_dp, C.c_int, C.c_int,
+                                            c_dp, C.c_int, c_dp, c_dp, C.c_int, C.c_double, c_dp]
+        L.orc_lanc_build_gf_normal_main.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dp, C.c_double, C.c_double,
+                                                    C.c_int, C.c_int, C.c_int, C.c_int, c_dp, C.c_int, c_dp,
+                                                    c_dp, C.c_int, C.c_double, c_dp, c_dp, c_ip]
+        L.orc_sigma_normal.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dp, C.c_int, c_dp, c_dp, c_dp]
+        L.orc_allocate_grids.argtypes = [C.c_double, C.c_int, C.c_double, C.c_double, C.c_int, c_dp, c_dp]
+        _LIB = L
+    return _LIB
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_dp)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def init_dmft_bath(norb, nbath, nspin=1, hwband=2.0):
+    """Returns (e, v) shaped (nspin, norb, nbath) [ED_BATH/dmft_aux.f90:102-133]."""
+    e = np.zeros(nspin * norb * nbath)
+    v = np.zeros(nspin * norb * nbath)
+    lib().orc_init_dmft_bath(norb, nbath, nspin, hwband, _dp(e), _dp(v))
+    shp = (nspin, norb, nbath)
+    return e.reshape(shp, order="F"), v.reshape(shp, order="F")
+
+
+def build_sector_map(ns, n):
+    dim = lib().orc_build_sector_map(ns, n, None)
+    m = np.zeros(dim, dtype=np.int32)
+    lib().orc_build_sector_map(ns, n, m.ctypes.data_as(c_i32p))
+    return m
+
+
+def _csr_np(cs):
+    n = cs.nrow
+    rowptr = np.ctypeslib.as_array(cs.rowptr, shape=(n + 1,)).copy() if n else np.zeros(1, np.int64)
+    nnz = int(rowptr[-1])
+    cols = np.ctypeslib.as_array(cs.cols, shape=(nnz,)).copy() if nnz else np.zeros(0, np.int64)
+    vals = np.ctypeslib.as_array(cs.vals, shape=(nnz,)).copy() if nnz else np.zeros(0)
+    return rowptr, cols, vals
+
+
+class Sector:
+    """build_Hv_sector ... delete_Hv_sector lifetime (ED_HAMILTONIAN.f90:43-222)."""
+
+    def __init__(self, ora, nup, ndw, rank=0, nranks=1, sparse_h=True):
+        self.ora = ora
+        self.p = lib().orc_build_hv_sector(ora.h, nup, ndw, rank, nranks, int(bool(sparse_h)))
+        s = self.p.contents
+        self.nup, self.ndw = nup, ndw
+        self.dimup, self.dimdw, self.dim = s.dimup, s.dimdw, s.dim
+        self.qdw, self.ishift, self.istart, self.iend = s.qdw, s.ishift, s.istart, s.iend
+        self.nloc = s.dimup * s.qdw
+        self.sparse_h = bool(sparse_h)
+
+    def close(self):
+        if self.p is not None:
+            lib().orc_delete_hv_sector(self.p)
+            self.p = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # introspection
+    def map_up(self):
+        return np.ctypeslib.as_array(self.p.contents.map_up, shape=(self.dimup,)).copy()
+
+    def map_dw(self):
+        return np.ctypeslib.as_array(self.p.contents.map_dw, shape=(self.dimdw,)).copy()
+
+    def h0d(self):
+        return np.ctypeslib.as_array(self.p.contents.h0d, shape=(self.nloc,)).copy()
+
+    def hup(self):
+        return _csr_np(self.p.contents.hup)
+
+    def hdw(self):
+        return _csr_np(self.p.contents.hdw)
+
+    def hnd(self):
+        return _csr_np(self.p.contents.hnd)
+
+    def hmat(self):
+        h = np.zeros(self.dim * self.dim)
+        lib().orc_build_hmat(self.p, _dp(h))
+        return h.reshape((self.dim, self.dim), order="F")
+
+    # operators
+    def spmatvec(self, v):
+        v = _f64(v)
+        hv = np.empty_like(v)
+        lib().orc_spmatvec_main(self.p, v.size, _dp(v), _dp(hv))
+        return hv
+
+    def directmatvec(self, v):
+        v = _f64(v)
+        hv = np.empty_like(v)
+        lib().orc_directmatvec_main(self.p, v.size, _dp(v), _dp(hv))
+        return hv
+
+    def lanc_eigh(self, v0=None, nitermax=512, threshold=1e-18, ncheck=10, mode=0):
+        """sp_lanc_eigh as called at ED_DIAG.f90:177-185.  Returns (egs, vect, alanc, blanc)."""
+        nit = int(min(self.dim, nitermax))
+        vect = np.zeros(self.dim) if v0 is None else _f64(v0).copy()
+        egs = C.c_double(0.0)
+        nl = C.c_int(0)
+        a = np.zeros(nit + 2)
+        b = np.zeros(nit + 2)
+        lib().orc_lanc_eigh_sector(self.p, mode, C.byref(egs), _dp(vect), nit, threshold, ncheck,
+                                   C.byref(nl), _dp(a), _dp(b))
+        return egs.value, vect, a[:nl.value].copy(), b[:nl.value].copy()
+
+    def lanc_tridiag(self, vin, nlanc, threshold=1e-12, mode=0):
+        """sp_lanc_tridiag as called at ED_GF_NORMAL.f90:232-237.  Returns (alanc, blanc)."""
+        v = _f64(vin).copy()
+        a = np.zeros(nlanc)
+        b = np.zeros(nlanc)
+        lib().orc_lanc_tridiag_sector(self.p, mode, _dp(v), _dp(a), _dp(b), nlanc, threshold)
+        return a, b
+
+
+class Oracle:
+    """Holds the module-global inputs of the reference (orc_ctx)."""
+
+    def __init__(self, norb, nbath, nspin=1, uloc=(2.0,), ust=0.0, jh=0.0, jx=0.0, jp=0.0, xmu=0.0,
+                 hfmode=True, imphloc=None, bath_e=None, bath_v=None, hwband=2.0):
+        self.norb, self.nbath, self.nspin = norb, nbath, nspin
+        self.ns = (nbath + 1) * norb
+        ul = np.zeros(5)
+        ul[:len(uloc)] = uloc
+        if bath_e is None or bath_v is None:
+            bath_e, bath_v = init_dmft_bath(norb, nbath, nspin, hwband)
+        self.bath_e = np.asfortranarray(bath_e, dtype=np.float64).reshape((nspin, norb, nbath), order="F")
+        self.bath_v = np.asfortranarray(bath_v, dtype=np.float64).reshape((nspin, norb, nbath), order="F")
+        if imphloc is None:
+            imphloc = np.zeros((nspin, nspin, norb, norb))
+        self.imphloc = np.asfortranarray(imphloc, dtype=np.float64)
+        self.uloc, self.ust, self.jh, self.jx, self.jp, self.xmu, self.hfmode = ul, ust, jh, jx, jp, xmu, hfmode
+        fe = np.ravel(self.bath_e, order="F").copy()
+        fv = np.ravel(self.bath_v, order="F").copy()
+        fh = np.ravel(self.imphloc, order="F").copy()
+        self.h = lib().orc_ctx_create(norb, nbath, nspin, int(hfmode), _dp(ul), ust, jh, jx, jp, xmu,
+                                      _dp(fh), _dp(fe), _dp(fv))
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().orc_ctx_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def sector(self, nup, ndw, rank=0, nranks=1, sparse_h=True):
+        return Sector(self, nup, ndw, rank, nranks, sparse_h)
+
+    def vecdim(self, nup, ndw, rank, nranks):
+        return lib().orc_vecdim_hv_sector(self.h, nup, ndw, rank, nranks)
+
+    def spmatvec_mpi(self, nup, ndw, nranks, v, nthreads=1):
+        v = _f64(v)
+        hv = np.empty_like(v)
+        lib().orc_spmatvec_mpi_main_all(self.h, nup, ndw, nranks, nthreads, _dp(v), _dp(hv))
+        return hv
+
+    def directmatvec_mpi(self, nup, ndw, nranks, v, nthreads=1):
+        v = _f64(v)
+        hv = np.empty_like(v)
+        lib().orc_directmatvec_mpi_main_all(self.h, nup, ndw, nranks, nthreads, _dp(v), _dp(hv))
+        return hv
+
+    def gf_start_vector(self, nup, ndw, gs, iorb, ispin, add):
+        gs = _f64(gs)
+        jn, jd = C.c_int(0), C.c_int(0)
+        n2 = C.c_double(0.0)
+        jdim = lib().orc_gf_start_vector(self.h, nup, ndw, _dp(gs), iorb, ispin, int(add), None,
+                                         C.byref(n2), C.byref(jn), C.byref(jd))
+        if jdim == 0:
+            return None, 0.0, (jn.value, jd.value)
+        vv = np.zeros(jdim)
+        lib().orc_gf_start_vector(self.h, nup, ndw, _dp(gs), iorb, ispin, int(add), _dp(vv),
+                                  C.byref(n2), C.byref(jn), C.byref(jd))
+        return vv, n2.value, (jn.value, jd.value)
+
+    def build_gf_normal(self, nup, ndw, gs, e0, iorb, ispin=1, ngfiter=200, mode=0, zeta=1.0,
+                        beta=1000.0, lmats=5000, wini=-5.0, wfin=5.0, lreal=5000, eps=0.01):
+        """lanc_build_gf_normal_main for one (iorb, ispin).  Returns dict with G, chains, grids."""
+        wm, wr = allocate_grids(beta, lmats, wini, wfin, lreal)
+        gm = np.zeros(lmats, dtype=np.complex128)
+        gr = np.zeros(lreal, dtype=np.complex128)
+        chain = np.zeros((2, 1 + 2 * ngfiter))
+        nl = (C.c_int * 2)(0, 0)
+        gs = _f64(gs)
+        lib().orc_lanc_build_gf_normal_main(self.h, nup, ndw, _dp(gs), e0, zeta, iorb, ispin, ngfiter, mode,
+                                            _dp(wm), lmats, gm.ctypes.data_as(c_dp),
+                                            _dp(wr), lreal, eps, gr.ctypes.data_as(c_dp),
+                                            _dp(chain), nl)
+        out = {"wm": wm, "wr": wr, "gmats": gm, "greal": gr, "chains": []}
+        for p in range(2):
+            n = nl[p]
+            out["chains"].append({"norm2": chain[p, 0], "alanc": chain[p, 1:1 + n].copy(),
+                                  "blanc": chain[p, 1 + ngfiter:1 + ngfiter + n].copy(), "nlanc": n})
+        return out
+
+    def sigma_normal(self, iorb, ispin, z, g):
+        z = np.ascontiguousarray(z, dtype=np.complex128)
+        g = np.ascontiguousarray(g, dtype=np.complex128)
+        s = np.zeros_like(z)
+        i0 = np.zeros_like(z)
+        lib().orc_sigma_normal(self.h, iorb, ispin, z.ctypes.data_as(c_dp), z.size, g.ctypes.data_as(c_dp),
+                               s.ctypes.data_as(c_dp), i0.ctypes.data_as(c_dp))
+        return s, i0
+
+
+def allocate_grids(beta, lmats, wini, wfin, lreal):
+    wm = np.zeros(lmats)
+    wr = np.zeros(lreal)
+    lib().orc_allocate_grids(beta, lmats, wini, wfin, lreal, _dp(wm), _dp(wr))
+    return wm, wr
+
+
+def add_to_lanczos_gf(norm2, ei, alanc, blanc, isign, wm, wr, eps, zeta=1.0):
+    a, b = _f64(alanc), _f64(blanc)
+    gm = np.zeros(len(wm), dtype=np.complex128)
+    gr = np.zeros(len(wr), dtype=np.complex128)
+    wm, wr = _f64(wm), _f64(wr)
+    lib().orc_add_to_lanczos_gf(norm2, zeta, ei, _dp(a), _dp(b), a.size, isign, _dp(wm), wm.size,
+                                gm.ctypes.data_as(c_dp), _dp(wr), wr.size, eps, gr.ctypes.data_as(c_dp))
+    return gm, gr
+
+
+def tql2(d, e):
+    """Eigen-decomposition of the symmetric tridiagonal (d, e[1:]); returns (w, Z)."""
+    n = len(d)
+    dd = _f64(d).copy()
+    ee = np.zeros(n + 1)
+    ee[1:n] = np.asarray(e)[1:n]
+    z = np.eye(n).ravel(order="F").copy()
+    rc = lib().orc_tql2(n, _dp(dd), _dp(ee), _dp(z))
+    assert rc == 0
+    return dd, z.reshape((n, n), order="F")
