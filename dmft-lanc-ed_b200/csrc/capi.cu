@@ -1,0 +1,549 @@
+// capi.cu -- context, sector lifecycle (build_Hv_sector / delete_Hv_sector), basis and stored
+// factor construction on device, introspection.  See include/edgpu.h for the reference
+// interfaces each entry point replaces.
+#include <cub/device/device_scan.cuh>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "engine.h"
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+static edgpu_ctx *g_current = nullptr;   // context of the last build_hv_sector (spHtimesV_p analogue)
+
+int edgpu_set_err(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+extern "C" const char *edgpu_last_error(void) { return g_err; }
+
+extern "C" int edgpu_device_count(int *n) {
+  int k = 0;
+  cudaError_t e = cudaGetDeviceCount(&k);
+  if (e != cudaSuccess) { *n = 0; return edgpu_set_err(EDGPU_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e)); }
+  *n = k;
+  return EDGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// parameters
+// ------------------------------------------------------------------------------------------
+static int load_params(edgpu_ctx *c, const edgpu_params *p) {
+  if (!p) return edgpu_set_err(EDGPU_ERR_INVALID, "params == NULL");
+  if (p->norb < 1 || p->norb > EDGPU_MAX_ORB) return edgpu_set_err(EDGPU_ERR_INVALID, "NORB out of range");
+  if (p->nspin < 1 || p->nspin > 2) return edgpu_set_err(EDGPU_ERR_INVALID, "NSPIN out of range");
+  if (p->nph != 0) return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "DimPh > 1 (NPH /= 0) is outside the hot path");
+  if (!p->ed_total_ud) return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "ed_total_ud = F (_orbs variants) is outside the hot path");
+  int ns = (p->nbath + 1) * p->norb;                        // ED_SETUP.f90:113-116, bath_type normal
+  if (p->nbath < 1 || ns > EDGPU_MAX_SITES - 1) return edgpu_set_err(EDGPU_ERR_INVALID, "Ns = %d out of range", ns);
+  if (!p->bath_e || !p->bath_v) return edgpu_set_err(EDGPU_ERR_INVALID, "bath arrays == NULL");
+  c->hp = *p;
+  c->ns = ns;
+  size_t nh = (size_t)p->nspin * p->nspin * p->norb * p->norb, nb = (size_t)p->nspin * p->norb * p->nbath;
+  c->h_hloc.assign(nh, 0.0);
+  if (p->imphloc) memcpy(c->h_hloc.data(), p->imphloc, nh * sizeof(double));
+  c->h_be.assign(p->bath_e, p->bath_e + nb);
+  c->h_bv.assign(p->bath_v, p->bath_v + nb);
+  c->hp.imphloc = c->h_hloc.data();
+  c->hp.bath_e = c->h_be.data();
+  c->hp.bath_v = c->h_bv.data();
+  DevParams &d = c->dp;
+  memset(&d, 0, sizeof(d));
+  d.norb = p->norb; d.nbath = p->nbath; d.ns = ns; d.hfmode = p->hfmode; d.nspin = p->nspin;
+  d.jhflag = (p->norb > 1 && (p->jx != 0.0 || p->jp != 0.0));   // ED_SETUP.f90:147-148
+  for (int i = 0; i < EDGPU_MAX_ORB; i++) d.uloc[i] = (i < p->norb) ? p->uloc[i] : 0.0;
+  d.ust = p->ust; d.jh = p->jh; d.jx = p->jx; d.jp = p->jp; d.xmu = p->xmu;
+  const int nsn = p->nspin, sl = p->nspin - 1;
+  for (int io = 0; io < p->norb; io++)
+    for (int jo = 0; jo < p->norb; jo++) {
+      d.hloc_up[io * EDGPU_MAX_ORB + jo] = c->h_hloc[0 + nsn * (0 + nsn * (io + p->norb * jo))];
+      d.hloc_dw[io * EDGPU_MAX_ORB + jo] = c->h_hloc[sl + nsn * (sl + nsn * (io + p->norb * jo))];
+    }
+  for (int io = 0; io < p->norb; io++)
+    for (int kp = 0; kp < p->nbath; kp++) {
+      d.be_up[io * p->nbath + kp] = c->h_be[0 + nsn * (io + p->norb * kp)];
+      d.be_dw[io * p->nbath + kp] = c->h_be[sl + nsn * (io + p->norb * kp)];
+      d.bv_up[io * p->nbath + kp] = c->h_bv[0 + nsn * (io + p->norb * kp)];
+      d.bv_dw[io * p->nbath + kp] = c->h_bv[sl + nsn * (io + p->norb * kp)];
+    }
+  return EDGPU_OK;
+}
+
+extern "C" int edgpu_create(const edgpu_params *p, int device, edgpu_ctx **out) {
+  if (!out) return edgpu_set_err(EDGPU_ERR_INVALID, "out == NULL");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return edgpu_set_err(EDGPU_ERR_NO_DEVICE, "no CUDA device: this engine has no CPU fallback");
+  edgpu_ctx *c = new edgpu_ctx();
+  int rc = load_params(c, p);
+  if (rc) { delete c; return rc; }
+  if (device < 0) cudaGetDevice(&device);
+  c->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) { delete c; return edgpu_set_err(EDGPU_ERR_NO_DEVICE, "cudaSetDevice(%d) failed", device); }
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) { delete c; return edgpu_set_err(EDGPU_ERR_NO_DEVICE, "device %s is sm_%d%d; this engine is built for sm_100a only", prop.name, prop.major, prop.minor); }
+  c->sm_count = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&c->ev0));
+  CK(cudaEventCreate(&c->ev1));
+  // exact binomials by Pascal's rule (== binomial(), ED_SETUP.f90:1017-1035, for these sizes)
+  memset(c->h_binom, 0, sizeof(c->h_binom));
+  for (int n = 0; n < EDGPU_BINOM_LD; n++) {
+    c->h_binom[n * EDGPU_BINOM_LD + 0] = 1;
+    for (int k = 1; k <= n; k++) {
+      uint64_t v = (uint64_t)c->h_binom[(n - 1) * EDGPU_BINOM_LD + k - 1] +
+                   (uint64_t)(k <= n - 1 ? c->h_binom[(n - 1) * EDGPU_BINOM_LD + k] : 0);
+      c->h_binom[n * EDGPU_BINOM_LD + k] = (v > 0xffffffffull) ? 0xffffffffu : (uint32_t)v;
+    }
+  }
+  CK(cudaMalloc(&c->d_binom, sizeof(c->h_binom)));
+  CK(cudaMemcpy(c->d_binom, c->h_binom, sizeof(c->h_binom), cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&c->d_partials, 4096 * sizeof(double)));
+  CK(cudaMalloc(&c->d_st, sizeof(LancState)));
+  CK(cudaMemset(c->d_st, 0, sizeof(LancState)));
+  CK(cudaMallocHost(&c->h_pinned, 4096 * sizeof(double)));
+  *out = c;
+  return EDGPU_OK;
+}
+
+extern "C" int edgpu_set_params(edgpu_ctx *c, const edgpu_params *p) {
+  if (!c) return edgpu_set_err(EDGPU_ERR_INVALID, "ctx == NULL");
+  if (c->hstatus) return edgpu_set_err(EDGPU_ERR_INVALID, "set_params while a sector is live");
+  return load_params(c, p);
+}
+
+extern "C" int edgpu_set_option(edgpu_ctx *c, const char *key, int64_t value) {
+  if (!c || !key) return edgpu_set_err(EDGPU_ERR_INVALID, "bad option call");
+  if (!strcmp(key, "hxv_algo")) { c->algo = (int)value; return EDGPU_OK; }
+  if (!strcmp(key, "tile_rows")) { c->opt_tile_rows = value; return EDGPU_OK; }
+  if (!strcmp(key, "tile_h")) { c->opt_tile_h = value; return EDGPU_OK; }
+  if (!strcmp(key, "col_h")) { c->opt_col_h = value; return EDGPU_OK; }
+  return edgpu_set_err(EDGPU_ERR_INVALID, "unknown option %s", key);
+}
+
+// ------------------------------------------------------------------------------------------
+// sector numbering and shard geometry (host arithmetic)
+// ------------------------------------------------------------------------------------------
+extern "C" int edgpu_get_sector(const edgpu_ctx *c, int nup, int ndw, int *isector) {
+  if (!c || nup < 0 || ndw < 0 || nup > c->ns || ndw > c->ns) return edgpu_set_err(EDGPU_ERR_INVALID, "bad (nup,ndw)");
+  *isector = 1 + ndw + nup * (c->ns + 1);                   // get_Sector, ED_SETUP.f90:446-457
+  return EDGPU_OK;
+}
+extern "C" int edgpu_get_nup_ndw(const edgpu_ctx *c, int isector, int *nup, int *ndw) {
+  int nsec = (c->ns + 1) * (c->ns + 1);                     // Nsectors, ED_SETUP.f90:134
+  if (!c || isector < 1 || isector > nsec) return edgpu_set_err(EDGPU_ERR_INVALID, "isector out of range");
+  int count = isector - 1;                                  // get_Nup/get_Ndw, ED_SETUP.f90:477-500
+  *ndw = count % (c->ns + 1);
+  *nup = count / (c->ns + 1);
+  return EDGPU_OK;
+}
+extern "C" void edgpu_split(int64_t n, int nranks, int rank, int64_t *q, int64_t *off) {
+  int64_t qq = n / nranks, m = n % nranks;                  // ED_HAMILTONIAN.f90:96-110
+  if (q) *q = qq + (rank < m ? 1 : 0);
+  if (off) *off = (rank < m) ? rank * (qq + 1) : m * (qq + 1) + (rank - m) * qq;
+}
+static int64_t binom64(const edgpu_ctx *c, int n, int k) {
+  if (k < 0 || k > n) return 0;
+  return c->h_binom[n * EDGPU_BINOM_LD + k];
+}
+extern "C" int edgpu_vecdim_hv_sector(const edgpu_ctx *c, int isector, int64_t *vecdim) {
+  int nup, ndw;
+  TRY(edgpu_get_nup_ndw(c, isector, &nup, &ndw));
+  int64_t q;
+  edgpu_split(binom64(c, c->ns, ndw), c->nranks, c->rank, &q, nullptr);
+  *vecdim = binom64(c, c->ns, nup) * q;                     // DimUp*mpiQdw*DimPh
+  return EDGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// basis / factor construction kernels (integer work, bit-exact against the reference)
+// ------------------------------------------------------------------------------------------
+// build_sector, ED_SETUP.f90:764-777: the ascending popcount-filtered scan, done as a parallel
+// filter whose output slot is the closed-form rank of the word.
+__global__ void k_build_map(int ns, int n, const uint32_t *__restrict__ binom, int32_t *__restrict__ map) {
+  const uint64_t top = 1ull << ns;
+  for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < top; s += (uint64_t)gridDim.x * blockDim.x)
+    if (__popc((uint32_t)s) == n) map[hd_rank((uint32_t)s, binom)] = (int32_t)s;
+}
+
+__global__ void k_factor_count(DevParams P, int spin, const int32_t *__restrict__ map, int64_t n,
+                               int32_t *__restrict__ counts) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int32_t cols[EDGPU_MAX_ROW_NNZ]; double vals[EDGPU_MAX_ROW_NNZ];
+  counts[i] = hd_factor_row(P, spin, map, n, (uint32_t)map[i], cols, vals);
+}
+__global__ void k_factor_fill(DevParams P, int spin, const int32_t *__restrict__ map, int64_t n,
+                              const int32_t *__restrict__ rowptr, int32_t *__restrict__ ocols,
+                              double *__restrict__ ovals) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int32_t cols[EDGPU_MAX_ROW_NNZ]; double vals[EDGPU_MAX_ROW_NNZ];
+  int m = hd_factor_row(P, spin, map, n, (uint32_t)map[i], cols, vals);
+  int32_t p = rowptr[i];
+  for (int k = 0; k < m; k++) { ocols[p + k] = cols[k]; ovals[p + k] = vals[k]; }
+}
+__global__ void k_dfac(DevParams P, int spin, const int32_t *__restrict__ map, int64_t n, double *__restrict__ out) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = hd_diag_factor(P, spin, (uint32_t)map[i]);
+}
+// spH0d, stored/H_local.f90:1-80: one value per local row, exact reference summation order
+__global__ void k_diag_stored(DevParams P, const int32_t *__restrict__ map_up, const int32_t *__restrict__ map_dw,
+                              int64_t dimup, int64_t coloff, int64_t qdw, double *__restrict__ diag) {
+  for (int64_t jl = blockIdx.y; jl < qdw; jl += gridDim.y) {
+    uint32_t mdw = (uint32_t)map_dw[coloff + jl];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < dimup; i += (int64_t)gridDim.x * blockDim.x)
+      diag[i + jl * dimup] = hd_diag_element(P, (uint32_t)map_up[i], mdw);
+  }
+}
+// spH0nd rows (stored/H_non_local.f90:4-85); columns are global electron indices
+__global__ void k_nd_count(DevParams P, const int32_t *__restrict__ map_up, const int32_t *__restrict__ map_dw,
+                           int64_t dimup, int64_t coloff, int64_t nloc, int64_t *__restrict__ counts) {
+  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= nloc) return;
+  uint32_t cu[2 * EDGPU_MAX_ORB * EDGPU_MAX_ORB], cd[2 * EDGPU_MAX_ORB * EDGPU_MAX_ORB];
+  double v[2 * EDGPU_MAX_ORB * EDGPU_MAX_ORB];
+  counts[r] = hd_nonlocal_row(P, (uint32_t)map_up[r % dimup], (uint32_t)map_dw[coloff + r / dimup], cu, cd, v);
+}
+__global__ void k_nd_fill(DevParams P, const int32_t *__restrict__ map_up, const int32_t *__restrict__ map_dw,
+                          int64_t dimup, int64_t dimdw, int64_t coloff, int64_t nloc,
+                          const int64_t *__restrict__ rowptr, int64_t *__restrict__ ocols, double *__restrict__ ovals) {
+  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= nloc) return;
+  uint32_t cu[2 * EDGPU_MAX_ORB * EDGPU_MAX_ORB], cd[2 * EDGPU_MAX_ORB * EDGPU_MAX_ORB];
+  double v[2 * EDGPU_MAX_ORB * EDGPU_MAX_ORB];
+  int m = hd_nonlocal_row(P, (uint32_t)map_up[r % dimup], (uint32_t)map_dw[coloff + r / dimup], cu, cd, v);
+  int64_t p = rowptr[r];
+  for (int k = 0; k < m; k++) {
+    int64_t ju = hd_binary_search(map_up, dimup, (int32_t)cu[k]) - 1;
+    int64_t jd = hd_binary_search(map_dw, dimdw, (int32_t)cd[k]) - 1;
+    // spin-exchange / pair-hopping targets of one row are pairwise distinct, so no entry of
+    // spH0nd ever accumulates (sp_insert_element's append branch only)
+    ocols[p + k] = ju + jd * dimup;
+    ovals[p + k] = v[k];
+  }
+}
+
+static int build_factor(edgpu_ctx *c, Factor &f, int spin, int npart, bool stored) {
+  f.n = binom64(c, c->ns, npart);
+  CK(cudaMalloc(&f.d_map, (size_t)f.n * sizeof(int32_t)));
+  {
+    uint64_t top = 1ull << c->ns;
+    int blocks = (int)((top + 255) / 256);
+    if (blocks > 65535 * 4) blocks = 65535 * 4;
+    k_build_map<<<blocks, 256, 0, c->stream>>>(c->ns, npart, c->d_binom, f.d_map);
+    CKL(c);
+  }
+  int blocks = (int)((f.n + 127) / 128);
+  // the CSR factors are built in both modes: in "direct" mode they stand in for the per-call
+  // c/cdg/binary_search regeneration (they are O(DimUp*Ns/2), not O(dim))
+  int32_t *d_counts = nullptr;
+  CK(cudaMalloc(&d_counts, (size_t)(f.n + 1) * sizeof(int32_t)));
+  CK(cudaMemsetAsync(d_counts, 0, (size_t)(f.n + 1) * sizeof(int32_t), c->stream));
+  k_factor_count<<<blocks, 128, 0, c->stream>>>(c->dp, spin, f.d_map, f.n, d_counts);
+  CKL(c);
+  CK(cudaMalloc(&f.d_rowptr, (size_t)(f.n + 1) * sizeof(int32_t)));
+  size_t tmp_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_counts, f.d_rowptr, (int)(f.n + 1), c->stream);
+  void *d_tmp = nullptr;
+  CK(cudaMalloc(&d_tmp, tmp_bytes));
+  cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_counts, f.d_rowptr, (int)(f.n + 1), c->stream);
+  c->launches++;
+  int32_t nnz = 0;
+  CK(cudaMemcpyAsync(&nnz, f.d_rowptr + f.n, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  f.nnz = nnz;
+  // max row length (for kernels that want an ELL bound)
+  {
+    std::vector<int32_t> hc((size_t)f.n);
+    CK(cudaMemcpy(hc.data(), d_counts, (size_t)f.n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    f.maxrow = 0;
+    for (int64_t i = 0; i < f.n; i++) if (hc[i] > f.maxrow) f.maxrow = hc[i];
+  }
+  CK(cudaMalloc(&f.d_cols, (size_t)(nnz > 0 ? nnz : 1) * sizeof(int32_t)));
+  CK(cudaMalloc(&f.d_vals, (size_t)(nnz > 0 ? nnz : 1) * sizeof(double)));
+  k_factor_fill<<<blocks, 128, 0, c->stream>>>(c->dp, spin, f.d_map, f.n, f.d_rowptr, f.d_cols, f.d_vals);
+  CKL(c);
+  if (!stored) {
+    CK(cudaMalloc(&f.d_dfac, (size_t)f.n * sizeof(double)));
+    k_dfac<<<blocks, 128, 0, c->stream>>>(c->dp, spin, f.d_map, f.n, f.d_dfac);
+    CKL(c);
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  cudaFree(d_counts);
+  cudaFree(d_tmp);
+  return EDGPU_OK;
+}
+
+static void free_factor(Factor &f) {
+  cudaFree(f.d_map); cudaFree(f.d_rowptr); cudaFree(f.d_cols); cudaFree(f.d_vals); cudaFree(f.d_dfac);
+  f = Factor();
+}
+
+extern "C" int edgpu_build_hv_sector(edgpu_ctx *c, int isector) {
+  if (!c) return edgpu_set_err(EDGPU_ERR_INVALID, "ctx == NULL");
+  if (c->hstatus) return edgpu_set_err(EDGPU_ERR_INVALID, "build_Hv_sector: a sector is already live (Hstatus=T)");
+  CK(cudaSetDevice(c->device));
+  int nup, ndw;
+  TRY(edgpu_get_nup_ndw(c, isector, &nup, &ndw));
+  c->isector = isector; c->nup = nup; c->ndw = ndw;
+  c->dimup = binom64(c, c->ns, nup);
+  c->dimdw = binom64(c, c->ns, ndw);
+  if (c->dimdw < c->nranks)                                 // the reference shrinks the communicator here
+    return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "DimDw=%lld < nranks=%d (communicator shrinking, ED_HAMILTONIAN.f90:66-94, is out of scope)",
+                         (long long)c->dimdw, c->nranks);
+  edgpu_split(c->dimdw, c->nranks, c->rank, &c->qdw, &c->coloff);
+  edgpu_split(c->dimup, c->nranks, c->rank, &c->qup, &c->rowoff);
+  c->nloc = c->dimup * c->qdw;
+  const bool stored = c->hp.ed_sparse_h != 0;
+  c->hstatus = true;
+  int rc = build_factor(c, c->up, 0, nup, stored);
+  if (!rc) rc = build_factor(c, c->dw, 1, ndw, stored);
+  if (rc) { edgpu_delete_hv_sector(c); return rc; }
+  if (stored) {
+    CK(cudaMalloc(&c->d_diag, (size_t)c->nloc * sizeof(double)));
+    dim3 grid((unsigned)((c->dimup + 255) / 256), (unsigned)(c->qdw < 32768 ? c->qdw : 32768));
+    k_diag_stored<<<grid, 256, 0, c->stream>>>(c->dp, c->up.d_map, c->dw.d_map, c->dimup, c->coloff, c->qdw, c->d_diag);
+    CKL(c);
+  }
+  if (c->dp.jhflag) {
+    int64_t *d_counts = nullptr;
+    CK(cudaMalloc(&d_counts, (size_t)(c->nloc + 1) * sizeof(int64_t)));
+    CK(cudaMemsetAsync(d_counts, 0, (size_t)(c->nloc + 1) * sizeof(int64_t), c->stream));
+    int blocks = (int)((c->nloc + 127) / 128);
+    k_nd_count<<<blocks, 128, 0, c->stream>>>(c->dp, c->up.d_map, c->dw.d_map, c->dimup, c->coloff, c->nloc, d_counts);
+    CKL(c);
+    CK(cudaMalloc(&c->d_nd_rowptr, (size_t)(c->nloc + 1) * sizeof(int64_t)));
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_counts, c->d_nd_rowptr, (int)(c->nloc + 1), c->stream);
+    void *d_tmp = nullptr;
+    CK(cudaMalloc(&d_tmp, tmp_bytes));
+    cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_counts, c->d_nd_rowptr, (int)(c->nloc + 1), c->stream);
+    c->launches++;
+    CK(cudaMemcpyAsync(&c->nd_nnz, c->d_nd_rowptr + c->nloc, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMalloc(&c->d_nd_cols, (size_t)(c->nd_nnz > 0 ? c->nd_nnz : 1) * sizeof(int64_t)));
+    CK(cudaMalloc(&c->d_nd_vals, (size_t)(c->nd_nnz > 0 ? c->nd_nnz : 1) * sizeof(double)));
+    k_nd_fill<<<blocks, 128, 0, c->stream>>>(c->dp, c->up.d_map, c->dw.d_map, c->dimup, c->dimdw, c->coloff, c->nloc,
+                                             c->d_nd_rowptr, c->d_nd_cols, c->d_nd_vals);
+    CKL(c);
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(d_counts);
+    cudaFree(d_tmp);
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  g_current = c;
+  return EDGPU_OK;
+}
+
+extern "C" int edgpu_delete_hv_sector(edgpu_ctx *c) {
+  if (!c) return edgpu_set_err(EDGPU_ERR_INVALID, "ctx == NULL");
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  tiled_plan_free(c);
+  free_factor(c->up);
+  free_factor(c->dw);
+  cudaFree(c->d_diag); c->d_diag = nullptr;
+  cudaFree(c->d_nd_rowptr); cudaFree(c->d_nd_cols); cudaFree(c->d_nd_vals);
+  c->d_nd_rowptr = c->d_nd_cols = nullptr; c->d_nd_vals = nullptr; c->nd_nnz = 0;
+  double **bufs[] = { &c->d_in, &c->d_out, &c->d_vt, &c->d_hvt, &c->d_send, &c->d_recv, &c->d_full,
+                      &c->d_lx, &c->d_lp, &c->d_lt, &c->d_l0, &c->d_lv };
+  for (auto b : bufs) { cudaFree(*b); *b = nullptr; }
+  c->hstatus = false;
+  c->isector = 0;
+  if (g_current == c) g_current = nullptr;
+  return EDGPU_OK;
+}
+
+extern "C" int edgpu_destroy(edgpu_ctx *c) {
+  if (!c) return EDGPU_OK;
+  cudaSetDevice(c->device);
+  if (c->hstatus) edgpu_delete_hv_sector(c);
+  edgpu_comm_finalize(c);
+  cudaFree(c->d_gs);
+  cudaFree(c->d_binom); cudaFree(c->d_partials); cudaFree(c->d_st);
+  cudaFree(c->d_alanc); cudaFree(c->d_blanc);
+  cudaFreeHost(c->h_pinned);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return EDGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// the operator through host pointers (spHtimesV_p)
+// ------------------------------------------------------------------------------------------
+static int ensure_buf(double **p, int64_t n) {
+  if (*p) return EDGPU_OK;
+  CK(cudaMalloc(p, (size_t)n * sizeof(double)));
+  return EDGPU_OK;
+}
+
+extern "C" int edgpu_hxv_device(edgpu_ctx *c, int64_t nloc, const double *d_v, double *d_hv) {
+  if (!c || !c->hstatus) return edgpu_set_err(EDGPU_ERR_INVALID, "HxV: Hsector NOT set");
+  if (nloc != c->nloc) return edgpu_set_err(EDGPU_ERR_INVALID, "HxV: Nloc=%lld != vecDim=%lld", (long long)nloc, (long long)c->nloc);
+  CK(cudaSetDevice(c->device));
+  return hxv_apply(c, d_v, d_hv);
+}
+
+extern "C" int edgpu_hxv(edgpu_ctx *c, int64_t nloc, const double *v, double *hv) {
+  if (!c || !c->hstatus) return edgpu_set_err(EDGPU_ERR_INVALID, "HxV: Hsector NOT set");
+  if (nloc != c->nloc) return edgpu_set_err(EDGPU_ERR_INVALID, "HxV: Nloc=%lld != vecDim=%lld", (long long)nloc, (long long)c->nloc);
+  CK(cudaSetDevice(c->device));
+  TRY(ensure_buf(&c->d_in, c->nloc));
+  TRY(ensure_buf(&c->d_out, c->nloc));
+  CK(cudaMemcpyAsync(c->d_in, v, (size_t)nloc * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  TRY(hxv_apply(c, c->d_in, c->d_out));
+  CK(cudaMemcpyAsync(hv, c->d_out, (size_t)nloc * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return EDGPU_OK;
+}
+
+extern "C" void edgpu_sphtimesv(const int32_t *nloc, const double *v, double *hv) {
+  if (!g_current) { fprintf(stderr, "edgpu_sphtimesv ERROR: Hsector NOT set\n"); abort(); }
+  int rc = edgpu_hxv(g_current, (int64_t)*nloc, v, hv);
+  if (rc) { fprintf(stderr, "edgpu_sphtimesv ERROR: %s\n", edgpu_last_error()); abort(); }
+}
+
+// ------------------------------------------------------------------------------------------
+// introspection
+// ------------------------------------------------------------------------------------------
+extern "C" int edgpu_get_dims(const edgpu_ctx *c, int64_t *dimup, int64_t *dimdw, int64_t *qdw,
+                              int64_t *ishift, int64_t *nloc) {
+  if (!c || !c->hstatus) return edgpu_set_err(EDGPU_ERR_INVALID, "no live sector");
+  if (dimup) *dimup = c->dimup;
+  if (dimdw) *dimdw = c->dimdw;
+  if (qdw) *qdw = c->qdw;
+  if (ishift) *ishift = c->coloff * c->dimup;               // mpiIshift, ED_HAMILTONIAN.f90:110
+  if (nloc) *nloc = c->nloc;
+  return EDGPU_OK;
+}
+extern "C" int edgpu_get_sector_map(const edgpu_ctx *c, int which, int32_t *out) {
+  if (!c || !c->hstatus) return edgpu_set_err(EDGPU_ERR_INVALID, "no live sector");
+  const Factor &f = which ? c->dw : c->up;
+  CK(cudaMemcpy(out, f.d_map, (size_t)f.n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  return EDGPU_OK;
+}
+extern "C" int edgpu_get_csr(const edgpu_ctx *c, int which, int64_t *nrow, int64_t *nnz,
+                             int64_t *rowptr, int64_t *cols, double *vals) {
+  if (!c || !c->hstatus) return edgpu_set_err(EDGPU_ERR_INVALID, "no live sector");
+  if (which == 2) {
+    if (nrow) *nrow = c->dp.jhflag ? c->nloc : 0;
+    if (nnz) *nnz = c->nd_nnz;
+    if (!rowptr || !c->dp.jhflag) return EDGPU_OK;
+    CK(cudaMemcpy(rowptr, c->d_nd_rowptr, (size_t)(c->nloc + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(cols, c->d_nd_cols, (size_t)c->nd_nnz * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(vals, c->d_nd_vals, (size_t)c->nd_nnz * sizeof(double), cudaMemcpyDeviceToHost));
+    return EDGPU_OK;
+  }
+  const Factor &f = which ? c->dw : c->up;
+  if (nrow) *nrow = f.n;
+  if (nnz) *nnz = f.nnz;
+  if (!rowptr) return EDGPU_OK;
+  std::vector<int32_t> rp((size_t)f.n + 1), cc((size_t)f.nnz);
+  CK(cudaMemcpy(rp.data(), f.d_rowptr, rp.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(cc.data(), f.d_cols, cc.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < rp.size(); i++) rowptr[i] = rp[i];
+  for (size_t i = 0; i < cc.size(); i++) cols[i] = cc[i];
+  CK(cudaMemcpy(vals, f.d_vals, (size_t)f.nnz * sizeof(double), cudaMemcpyDeviceToHost));
+  return EDGPU_OK;
+}
+
+__global__ void k_diag_direct(DevParams P, const int32_t *__restrict__ map_up, const int32_t *__restrict__ map_dw,
+                              const double *__restrict__ fu, const double *__restrict__ fd,
+                              int64_t dimup, int64_t coloff, int64_t qdw, double *__restrict__ out) {
+  for (int64_t jl = blockIdx.y; jl < qdw; jl += gridDim.y) {
+    uint32_t mdw = (uint32_t)map_dw[coloff + jl];
+    double dj = fd[coloff + jl];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < dimup; i += (int64_t)gridDim.x * blockDim.x)
+      out[i + jl * dimup] = fu[i] + dj + hd_diag_cross(P, (uint32_t)map_up[i], mdw);
+  }
+}
+extern "C" int edgpu_get_diag(const edgpu_ctx *cc, double *out, int64_t nloc) {
+  edgpu_ctx *c = const_cast<edgpu_ctx *>(cc);
+  if (!c || !c->hstatus) return edgpu_set_err(EDGPU_ERR_INVALID, "no live sector");
+  if (nloc != c->nloc) return edgpu_set_err(EDGPU_ERR_INVALID, "nloc mismatch");
+  if (c->d_diag) {
+    CK(cudaMemcpy(out, c->d_diag, (size_t)nloc * sizeof(double), cudaMemcpyDeviceToHost));
+    return EDGPU_OK;
+  }
+  double *d_tmp = nullptr;
+  CK(cudaMalloc(&d_tmp, (size_t)nloc * sizeof(double)));
+  dim3 grid((unsigned)((c->dimup + 255) / 256), (unsigned)(c->qdw < 32768 ? c->qdw : 32768));
+  k_diag_direct<<<grid, 256, 0, c->stream>>>(c->dp, c->up.d_map, c->dw.d_map, c->up.d_dfac, c->dw.d_dfac,
+                                             c->dimup, c->coloff, c->qdw, d_tmp);
+  CKL(c);
+  CK(cudaMemcpyAsync(out, d_tmp, (size_t)nloc * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  cudaFree(d_tmp);
+  return EDGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------
+extern "C" int edgpu_dev_alloc(edgpu_ctx *c, int64_t nbytes, void **dptr) {
+  CK(cudaSetDevice(c->device));
+  CK(cudaMalloc(dptr, (size_t)nbytes));
+  return EDGPU_OK;
+}
+extern "C" int edgpu_dev_free(edgpu_ctx *c, void *dptr) {
+  CK(cudaSetDevice(c->device));
+  CK(cudaFree(dptr));
+  return EDGPU_OK;
+}
+extern "C" int edgpu_dev_upload(edgpu_ctx *c, void *dptr, const void *host, int64_t nbytes) {
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemcpyAsync(dptr, host, (size_t)nbytes, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return EDGPU_OK;
+}
+extern "C" int edgpu_dev_download(edgpu_ctx *c, void *host, const void *dptr, int64_t nbytes) {
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemcpyAsync(host, dptr, (size_t)nbytes, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return EDGPU_OK;
+}
+__global__ void k_fill_bench(double *__restrict__ v, int64_t n, int64_t off) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    v[i] = sin(0.37 * (double)(off + i + 1)) + 0.1;         // v_i = sin(0.37 i) + 0.1
+}
+extern "C" int edgpu_dev_fill_bench_vector(edgpu_ctx *c, double *d_v, int64_t nloc, int64_t global_offset) {
+  CK(cudaSetDevice(c->device));
+  k_fill_bench<<<c->sm_count * 8, 256, 0, c->stream>>>(d_v, nloc, global_offset);
+  CKL(c);
+  return EDGPU_OK;
+}
+extern "C" int edgpu_sync(edgpu_ctx *c) {
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  return EDGPU_OK;
+}
+extern "C" int edgpu_launch_count(const edgpu_ctx *c, int64_t *n) {
+  *n = c->launches;
+  return EDGPU_OK;
+}
+extern "C" int edgpu_time_hxv_device(edgpu_ctx *c, int64_t nloc, const double *d_v, double *d_hv,
+                                     int reps, double *ms_total) {
+  if (!c || !c->hstatus) return edgpu_set_err(EDGPU_ERR_INVALID, "HxV: Hsector NOT set");
+  if (nloc != c->nloc) return edgpu_set_err(EDGPU_ERR_INVALID, "nloc mismatch");
+  CK(cudaSetDevice(c->device));
+  CK(cudaEventRecord(c->ev0, c->stream));
+  for (int r = 0; r < reps; r++) TRY(hxv_apply(c, d_v, d_hv));
+  CK(cudaEventRecord(c->ev1, c->stream));
+  CK(cudaEventSynchronize(c->ev1));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  *ms_total = ms;
+  return EDGPU_OK;
+}

@@ -1,0 +1,234 @@
+// comm.cu -- multi-GPU plumbing: one process per GPU, NCCL over NVLink.
+//
+// Replaces vector_transpose_MPI (ED_HAMILTONIAN_COMMON.f90:53-118: ceil(DimDw/P) MPI_AllToAllV
+// calls of one column each + local_transpose) with ONE grouped all-to-all of dense sub-blocks per
+// transpose, the per-dot MPI_Allreduce of SciFortran's MPI Lanczos with a device-resident
+// ncclAllReduce, and allgather_vector_MPI (ED_SETUP.f90:687-733) with a grouped exchange.
+//
+// NCCL is resolved at run time with dlopen so that the library shares the copy already loaded by
+// the host process (torch's bundled libnccl in the tests/bench, the system one under a Fortran/MPI
+// host) instead of linking a second one.
+#include <dlfcn.h>
+#include <nccl.h>
+#include <string.h>
+
+#include "engine.h"
+
+namespace {
+struct NcclApi {
+  void *h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+} g_nccl;
+
+int nccl_load() {
+  if (g_nccl.h) return EDGPU_OK;
+  const char *env = getenv("EDGPU_NCCL_LIB");
+  void *h = nullptr;
+  if (env) h = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);   // copy already in the process
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return edgpu_set_err(EDGPU_ERR_NCCL, "cannot load libnccl.so.2: %s", dlerror());
+#define SYM(field, name)                                                          \
+  *(void **)(&g_nccl.field) = dlsym(h, name);                                     \
+  if (!g_nccl.field) return edgpu_set_err(EDGPU_ERR_NCCL, "libnccl lacks %s", name)
+  SYM(GetUniqueId, "ncclGetUniqueId");
+  SYM(CommInitRank, "ncclCommInitRank");
+  SYM(CommDestroy, "ncclCommDestroy");
+  SYM(AllReduce, "ncclAllReduce");
+  SYM(Send, "ncclSend");
+  SYM(Recv, "ncclRecv");
+  SYM(GroupStart, "ncclGroupStart");
+  SYM(GroupEnd, "ncclGroupEnd");
+  SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+  g_nccl.h = h;
+  return EDGPU_OK;
+}
+}  // namespace
+
+#define NK(call)                                                                              \
+  do {                                                                                        \
+    ncclResult_t r_ = (call);                                                                 \
+    if (r_ != ncclSuccess)                                                                    \
+      return edgpu_set_err(EDGPU_ERR_NCCL, "%s:%d %s: %s", __FILE__, __LINE__, #call,         \
+                           g_nccl.GetErrorString(r_));                                        \
+  } while (0)
+
+extern "C" int edgpu_comm_unique_id(char id[128]) {
+  TRY(nccl_load());
+  ncclUniqueId u;
+  NK(g_nccl.GetUniqueId(&u));
+  memcpy(id, u.internal, 128);
+  return EDGPU_OK;
+}
+
+extern "C" int edgpu_comm_init(edgpu_ctx *c, int rank, int nranks, const char id[128]) {
+  if (!c) return edgpu_set_err(EDGPU_ERR_INVALID, "ctx == NULL");
+  if (c->hstatus) return edgpu_set_err(EDGPU_ERR_INVALID, "comm_init while a sector is live");
+  if (nranks < 1 || nranks > 64 || rank < 0 || rank >= nranks) return edgpu_set_err(EDGPU_ERR_INVALID, "bad rank/nranks");
+  if (c->comm) TRY(edgpu_comm_finalize(c));
+  c->rank = rank; c->nranks = nranks;
+  if (nranks == 1) return EDGPU_OK;
+  TRY(nccl_load());
+  CK(cudaSetDevice(c->device));
+  ncclUniqueId u;
+  memcpy(u.internal, id, 128);
+  ncclComm_t comm;
+  NK(g_nccl.CommInitRank(&comm, nranks, u, rank));
+  c->comm = (void *)comm;
+  return EDGPU_OK;
+}
+
+extern "C" int edgpu_comm_finalize(edgpu_ctx *c) {
+  if (c && c->comm) {
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    g_nccl.CommDestroy((ncclComm_t)c->comm);
+    c->comm = nullptr;
+  }
+  if (c) { c->rank = 0; c->nranks = 1; }
+  return EDGPU_OK;
+}
+
+int comm_allreduce_scalar(edgpu_ctx *c, double *d_scalar) {
+  if (c->nranks == 1) return EDGPU_OK;
+  NK(g_nccl.AllReduce(d_scalar, d_scalar, 1, ncclDouble, ncclSum, (ncclComm_t)c->comm, c->stream));
+  return EDGPU_OK;
+}
+
+// out[b + nb*a] = A[(a0 + a) + lda*b],  a < na, b < nb   (32x32 tiles through shared memory)
+__global__ void k_pack_transpose(const double *__restrict__ A, int64_t lda, int64_t a0, int64_t na, int64_t nb,
+                                 double *__restrict__ out) {
+  __shared__ double tile[32][33];
+  const int64_t tiles_a = (na + 31) / 32, tiles_b = (nb + 31) / 32;
+  for (int64_t t = blockIdx.x; t < tiles_a * tiles_b; t += gridDim.x) {
+    const int64_t ta = t % tiles_a, tb = t / tiles_a;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8 threads
+    for (int k = ty; k < 32; k += 8) {
+      int64_t a = ta * 32 + tx, b = tb * 32 + k;
+      if (a < na && b < nb) tile[k][tx] = A[(a0 + a) + lda * b];
+    }
+    __syncthreads();
+    for (int k = ty; k < 32; k += 8) {
+      int64_t b = tb * 32 + tx, a = ta * 32 + k;
+      if (a < na && b < nb) out[b + nb * a] = tile[tx][k];
+    }
+    __syncthreads();
+  }
+}
+// B[(x0 + x) + ldb*y] (+)= in[x + nx*y]
+template <bool ACC>
+__global__ void k_unpack(const double *__restrict__ in, int64_t nx, int64_t ny, double *__restrict__ B, int64_t ldb,
+                         int64_t x0) {
+  for (int64_t y = blockIdx.y; y < ny; y += gridDim.y)
+    for (int64_t x = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; x < nx; x += (int64_t)gridDim.x * blockDim.x) {
+      if (ACC) B[(x0 + x) + ldb * y] += in[x + nx * y];
+      else B[(x0 + x) + ldb * y] = in[x + nx * y];
+    }
+}
+
+static int ensure(double **p, int64_t n) {
+  if (*p) return EDGPU_OK;
+  CK(cudaMalloc(p, (size_t)(n > 0 ? n : 1) * sizeof(double)));
+  return EDGPU_OK;
+}
+
+static int exchange(edgpu_ctx *c, const double *send, const int64_t *soff, const int64_t *scnt, double *recv,
+                    const int64_t *roff, const int64_t *rcnt) {
+  const int P = c->nranks, me = c->rank;
+  NK(g_nccl.GroupStart());
+  for (int p = 0; p < P; p++) {
+    if (p == me) continue;
+    if (scnt[p]) NK(g_nccl.Send(send + soff[p], (size_t)scnt[p], ncclDouble, p, (ncclComm_t)c->comm, c->stream));
+    if (rcnt[p]) NK(g_nccl.Recv(recv + roff[p], (size_t)rcnt[p], ncclDouble, p, (ncclComm_t)c->comm, c->stream));
+  }
+  NK(g_nccl.GroupEnd());
+  if (scnt[me])
+    CK(cudaMemcpyAsync(recv + roff[me], send + soff[me], (size_t)scnt[me] * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  return EDGPU_OK;
+}
+
+// V(DimUp, qdw) -> Vt(DimDw, qup): block (me -> d) = V[rows(d), :] transposed
+int comm_transpose_fwd(edgpu_ctx *c, const double *d_x, double *d_vt) {
+  const int P = c->nranks;
+  TRY(ensure(&c->d_send, c->nloc > c->dimdw * c->qup ? c->nloc : c->dimdw * c->qup));
+  TRY(ensure(&c->d_recv, c->nloc > c->dimdw * c->qup ? c->nloc : c->dimdw * c->qup));
+  int64_t soff[64] = {0}, scnt[64] = {0}, roff[64] = {0}, rcnt[64] = {0};
+  for (int p = 0; p < P; p++) {
+    int64_t qr, ro, qc, co;
+    edgpu_split(c->dimup, P, p, &qr, &ro);
+    edgpu_split(c->dimdw, P, p, &qc, &co);
+    soff[p] = ro * c->qdw; scnt[p] = qr * c->qdw;              // rows(p) x my columns
+    roff[p] = co * c->qup; rcnt[p] = qc * c->qup;              // columns(p) x my rows
+    if (scnt[p]) {
+      int64_t tiles = ((qr + 31) / 32) * ((c->qdw + 31) / 32);
+      int grid = (int)(tiles < (int64_t)c->sm_count * 8 ? tiles : (int64_t)c->sm_count * 8);
+      k_pack_transpose<<<grid, 256, 0, c->stream>>>(d_x, c->dimup, ro, qr, c->qdw, c->d_send + soff[p]);
+      CKL(c);
+    }
+  }
+  TRY(exchange(c, c->d_send, soff, scnt, c->d_recv, roff, rcnt));
+  for (int p = 0; p < P; p++) {
+    int64_t qc, co;
+    edgpu_split(c->dimdw, P, p, &qc, &co);
+    if (!rcnt[p]) continue;
+    dim3 grid((unsigned)((qc + 255) / 256), (unsigned)(c->qup < 4096 ? c->qup : 4096));
+    k_unpack<false><<<grid, 256, 0, c->stream>>>(c->d_recv + roff[p], qc, c->qup, d_vt, c->dimdw, co);
+    CKL(c);
+  }
+  return EDGPU_OK;
+}
+
+// Hv(DimUp, qdw) += (Hvt(DimDw, qup))^T : block (me -> s) = Hvt[cols(s), :] transposed
+int comm_transpose_bwd_add(edgpu_ctx *c, const double *d_hvt, double *d_y) {
+  const int P = c->nranks;
+  int64_t soff[64] = {0}, scnt[64] = {0}, roff[64] = {0}, rcnt[64] = {0};
+  for (int p = 0; p < P; p++) {
+    int64_t qr, ro, qc, co;
+    edgpu_split(c->dimup, P, p, &qr, &ro);
+    edgpu_split(c->dimdw, P, p, &qc, &co);
+    soff[p] = co * c->qup; scnt[p] = qc * c->qup;              // dw-rows(p) x my up-rows
+    roff[p] = ro * c->qdw; rcnt[p] = qr * c->qdw;              // up-rows(p) x my columns
+    if (scnt[p]) {
+      int64_t tiles = ((qc + 31) / 32) * ((c->qup + 31) / 32);
+      int grid = (int)(tiles < (int64_t)c->sm_count * 8 ? tiles : (int64_t)c->sm_count * 8);
+      k_pack_transpose<<<grid, 256, 0, c->stream>>>(d_hvt, c->dimdw, co, qc, c->qup, c->d_send + soff[p]);
+      CKL(c);
+    }
+  }
+  TRY(exchange(c, c->d_send, soff, scnt, c->d_recv, roff, rcnt));
+  for (int p = 0; p < P; p++) {
+    int64_t qr, ro;
+    edgpu_split(c->dimup, P, p, &qr, &ro);
+    if (!rcnt[p]) continue;
+    dim3 grid((unsigned)((qr + 255) / 256), (unsigned)(c->qdw < 4096 ? c->qdw : 4096));
+    k_unpack<true><<<grid, 256, 0, c->stream>>>(c->d_recv + roff[p], qr, c->qdw, d_y, c->dimup, ro);
+    CKL(c);
+  }
+  return EDGPU_OK;
+}
+
+// allgather_vector_MPI (ED_SETUP.f90:687-733): shards are contiguous slices of the full vector
+int comm_allgather(edgpu_ctx *c, const double *d_x, double *d_full) {
+  const int P = c->nranks, me = c->rank;
+  NK(g_nccl.GroupStart());
+  for (int p = 0; p < P; p++) {
+    int64_t qc, co;
+    edgpu_split(c->dimdw, P, p, &qc, &co);
+    if (p == me) continue;
+    NK(g_nccl.Send(d_x, (size_t)c->nloc, ncclDouble, p, (ncclComm_t)c->comm, c->stream));
+    NK(g_nccl.Recv(d_full + co * c->dimup, (size_t)(qc * c->dimup), ncclDouble, p, (ncclComm_t)c->comm, c->stream));
+  }
+  NK(g_nccl.GroupEnd());
+  CK(cudaMemcpyAsync(d_full + c->coloff * c->dimup, d_x, (size_t)c->nloc * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  return EDGPU_OK;
+}

@@ -1,0 +1,118 @@
+// engine.h -- internal state of the B200 engine (not part of the C-ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/edgpu.h"
+#include "hd_funcs.h"
+
+struct Factor {                 // spH0ups(1) / spH0dws(1) on device, CSR in insertion order
+  int64_t n = 0, nnz = 0;
+  int maxrow = 0;
+  int32_t *d_map = nullptr;     // Hs(.)%map
+  int32_t *d_rowptr = nullptr;  // n+1
+  int32_t *d_cols = nullptr;
+  double *d_vals = nullptr;
+  double *d_dfac = nullptr;     // factorised diagonal table (direct mode)
+};
+
+struct LancState {              // device-resident Lanczos scalars (no host sync inside a step)
+  double red;                   // last reduction result (all-reduced in place with NCCL)
+  double alpha, beta;
+  double sx;                    // v_k     = sx * X
+  double cprev;                 // beta_{k-1} * (scale of Xp)
+  double norm2;
+};
+
+struct TiledPlan;               // hxv_tiled.cu
+
+struct edgpu_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int sm_count = 148;
+  // inputs
+  edgpu_params hp{};
+  std::vector<double> h_hloc, h_be, h_bv;
+  DevParams dp{};
+  int ns = 0;
+  uint32_t h_binom[EDGPU_BINOM_LD * EDGPU_BINOM_LD];
+  uint32_t *d_binom = nullptr;
+  // communicator
+  int rank = 0, nranks = 1;
+  void *comm = nullptr;         // ncclComm_t
+  // live sector (Hstatus / Hsector, ED_HAMILTONIAN_COMMON.f90:17-18)
+  bool hstatus = false;
+  int isector = 0, nup = 0, ndw = 0;
+  int64_t dimup = 0, dimdw = 0;
+  int64_t qdw = 0, coloff = 0, nloc = 0;      // dw split (columns owned)
+  int64_t qup = 0, rowoff = 0;                // up split used by the transposed layout
+  Factor up, dw;
+  double *d_diag = nullptr;                   // spH0d (stored mode), nloc values
+  int64_t *d_nd_rowptr = nullptr, *d_nd_cols = nullptr;
+  double *d_nd_vals = nullptr;
+  int64_t nd_nnz = 0;
+  // work buffers (grown on demand, freed by delete_hv_sector)
+  double *d_in = nullptr, *d_out = nullptr;   // staging for the host-pointer operator
+  double *d_vt = nullptr, *d_hvt = nullptr;   // transposed shard DimDw x qup
+  double *d_send = nullptr, *d_recv = nullptr;
+  double *d_full = nullptr;                   // all-gathered vector for spH0nd when nranks>1
+  double *d_lx = nullptr, *d_lp = nullptr, *d_lt = nullptr, *d_l0 = nullptr, *d_lv = nullptr;
+  double *d_partials = nullptr;
+  LancState *d_st = nullptr;
+  double *d_alanc = nullptr, *d_blanc = nullptr;
+  int lanc_cap = 0;
+  double *h_pinned = nullptr;                 // small pinned scratch for scalar read-back
+  // GF state
+  double *d_gs = nullptr;
+  int gs_nup = -1, gs_ndw = -1;
+  int64_t gs_nloc = 0;
+  double gs_e0 = 0.0;
+  // options
+  int algo = EDGPU_ALGO_AUTO;
+  int64_t opt_tile_rows = 0, opt_tile_h = -1, opt_col_h = -1;
+  TiledPlan *plan = nullptr;
+  int64_t launches = 0;
+};
+
+// ---- error plumbing -------------------------------------------------------------------------
+int edgpu_set_err(int code, const char *fmt, ...);
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return edgpu_set_err(EDGPU_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call,         \
+                           cudaGetErrorString(e_));                                           \
+  } while (0)
+#define CKL(c)                                                                                \
+  do {                                                                                        \
+    (c)->launches++;                                                                          \
+    cudaError_t e_ = cudaGetLastError();                                                      \
+    if (e_ != cudaSuccess)                                                                    \
+      return edgpu_set_err(EDGPU_ERR_CUDA, "%s:%d kernel launch: %s", __FILE__, __LINE__,     \
+                           cudaGetErrorString(e_));                                           \
+  } while (0)
+#define TRY(expr)                                                                             \
+  do {                                                                                        \
+    int rc_ = (expr);                                                                         \
+    if (rc_) return rc_;                                                                      \
+  } while (0)
+
+// ---- cross-file entry points ------------------------------------------------------------------
+// hxv.cu: y = H x on the local shard (device pointers), all terms, any nranks
+int hxv_apply(edgpu_ctx *c, const double *d_x, double *d_y);
+// Lanczos-fused form: w = sx*(H x) - cprev*xp (written over xp), partial sums of (sx*x).w go to
+// c->d_partials; scalars are read from c->d_st on device.
+int hxv_release_plan(edgpu_ctx *c);
+// hxv_tiled.cu
+int tiled_plan_build(edgpu_ctx *c);
+int tiled_plan_free(edgpu_ctx *c);
+bool tiled_supported(const edgpu_ctx *c);
+int tiled_apply_local(edgpu_ctx *c, const double *d_x, double *d_y);   // nranks==1: full operator
+// comm.cu
+int comm_allreduce_scalar(edgpu_ctx *c, double *d_scalar);
+int comm_transpose_fwd(edgpu_ctx *c, const double *d_x, double *d_vt);          // V(DimUp,qdw) -> Vt(DimDw,qup)
+int comm_transpose_bwd_add(edgpu_ctx *c, const double *d_hvt, double *d_y);     // Hv += (Hvt)^T
+int comm_allgather(edgpu_ctx *c, const double *d_x, double *d_full);

@@ -1,0 +1,83 @@
+// selftest.cu -- HOST evaluation of the __host__ __device__ integer/bit logic in hd_funcs.h, so
+// that the CPU-only test-suite can check the exact code the kernels run (rank formula, factor rows,
+// diagonal order) against the oracle without a GPU.  These hooks are test instrumentation
+// (include/edgpu_selftest.h); no product entry point calls them and they are not a compute path.
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/edgpu_selftest.h"
+#include "engine.h"
+
+static void host_binom(uint32_t *b) {
+  memset(b, 0, sizeof(uint32_t) * EDGPU_BINOM_LD * EDGPU_BINOM_LD);
+  for (int n = 0; n < EDGPU_BINOM_LD; n++) {
+    b[n * EDGPU_BINOM_LD] = 1;
+    for (int k = 1; k <= n; k++)
+      b[n * EDGPU_BINOM_LD + k] = b[(n - 1) * EDGPU_BINOM_LD + k - 1] + (k <= n - 1 ? b[(n - 1) * EDGPU_BINOM_LD + k] : 0);
+  }
+}
+static DevParams make_dp(const edgpu_params *p) {
+  DevParams d;
+  memset(&d, 0, sizeof(d));
+  d.norb = p->norb; d.nbath = p->nbath; d.ns = (p->nbath + 1) * p->norb; d.hfmode = p->hfmode; d.nspin = p->nspin;
+  d.jhflag = (p->norb > 1 && (p->jx != 0.0 || p->jp != 0.0));
+  for (int i = 0; i < EDGPU_MAX_ORB; i++) d.uloc[i] = (i < p->norb) ? p->uloc[i] : 0.0;
+  d.ust = p->ust; d.jh = p->jh; d.jx = p->jx; d.jp = p->jp; d.xmu = p->xmu;
+  const int nsn = p->nspin, sl = p->nspin - 1;
+  for (int io = 0; io < p->norb; io++)
+    for (int jo = 0; jo < p->norb; jo++) {
+      d.hloc_up[io * EDGPU_MAX_ORB + jo] = p->imphloc ? p->imphloc[0 + nsn * (0 + nsn * (io + p->norb * jo))] : 0.0;
+      d.hloc_dw[io * EDGPU_MAX_ORB + jo] = p->imphloc ? p->imphloc[sl + nsn * (sl + nsn * (io + p->norb * jo))] : 0.0;
+    }
+  for (int io = 0; io < p->norb; io++)
+    for (int kp = 0; kp < p->nbath; kp++) {
+      d.be_up[io * p->nbath + kp] = p->bath_e[0 + nsn * (io + p->norb * kp)];
+      d.be_dw[io * p->nbath + kp] = p->bath_e[sl + nsn * (io + p->norb * kp)];
+      d.bv_up[io * p->nbath + kp] = p->bath_v[0 + nsn * (io + p->norb * kp)];
+      d.bv_dw[io * p->nbath + kp] = p->bath_v[sl + nsn * (io + p->norb * kp)];
+    }
+  return d;
+}
+
+extern "C" int64_t edgpu_selftest_map(int ns, int n, int32_t *map) {
+  uint32_t b[EDGPU_BINOM_LD * EDGPU_BINOM_LD];
+  host_binom(b);
+  int64_t dim = b[ns * EDGPU_BINOM_LD + n];
+  if (!map) return dim;
+  for (uint64_t s = 0; s < (1ull << ns); s++)
+    if (hd_popc((uint32_t)s) == n) map[hd_rank((uint32_t)s, b)] = (int32_t)s;
+  return dim;
+}
+
+extern "C" int64_t edgpu_selftest_factor(const edgpu_params *p, int spin, int npart, int64_t *rowptr,
+                                         int64_t *cols, double *vals) {
+  DevParams d = make_dp(p);
+  int64_t n = edgpu_selftest_map(d.ns, npart, nullptr);
+  std::vector<int32_t> map((size_t)n);
+  edgpu_selftest_map(d.ns, npart, map.data());
+  int64_t nnz = 0;
+  int32_t c[EDGPU_MAX_ROW_NNZ]; double v[EDGPU_MAX_ROW_NNZ];
+  for (int64_t i = 0; i < n; i++) {
+    int m = hd_factor_row(d, spin, map.data(), n, (uint32_t)map[i], c, v);
+    if (rowptr) {
+      rowptr[i] = nnz;
+      for (int k = 0; k < m; k++) { cols[nnz + k] = c[k]; vals[nnz + k] = v[k]; }
+    }
+    nnz += m;
+  }
+  if (rowptr) rowptr[n] = nnz;
+  return nnz;
+}
+
+extern "C" double edgpu_selftest_diag(const edgpu_params *p, uint32_t mup, uint32_t mdw, int factorised) {
+  DevParams d = make_dp(p);
+  if (!factorised) return hd_diag_element(d, mup, mdw);
+  return hd_diag_factor(d, 0, mup) + hd_diag_factor(d, 1, mdw) + hd_diag_cross(d, mup, mdw);
+}
+
+extern "C" int edgpu_selftest_nonlocal_row(const edgpu_params *p, uint32_t mup, uint32_t mdw, uint32_t *cup,
+                                           uint32_t *cdw, double *val) {
+  DevParams d = make_dp(p);
+  return hd_nonlocal_row(d, mup, mdw, cup, cdw, val);
+}

@@ -1,0 +1,29 @@
+/*
+ * edgpu_selftest.h -- test instrumentation exported by libedgpu.so: HOST evaluation of the
+ * __host__ __device__ bit logic shared with the kernels (dmft-lanc-ed_b200/csrc/hd_funcs.h).
+ * Not part of the drop-in boundary; no product entry point calls these and they do not compute
+ * H*v.  They let the CPU-only test-suite compare the kernels' index/sign/diagonal code with the
+ * oracle (ED_SETUP.f90:745-831,1042-1059; ED_HAMILTONIAN/stored/H_local.f90, H_up.f90,
+ * H_non_local.f90) before any GPU time is spent.
+ */
+#ifndef EDGPU_SELFTEST_H
+#define EDGPU_SELFTEST_H
+#include <stdint.h>
+#include "edgpu.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+/* sector map by the closed-form rank (build_sector); map==NULL returns the dimension */
+int64_t edgpu_selftest_map(int ns, int n, int32_t *map);
+/* CSR of spH0ups(1) (spin=0) / spH0dws(1) (spin=1); rowptr==NULL returns nnz */
+int64_t edgpu_selftest_factor(const edgpu_params *p, int spin, int npart, int64_t *rowptr, int64_t *cols,
+                              double *vals);
+/* diagonal element: factorised=0 reference summation order, 1 the factorised form of direct mode */
+double edgpu_selftest_diag(const edgpu_params *p, uint32_t mup, uint32_t mdw, int factorised);
+/* one row of spH0nd: returns the entry count, outputs column words and values */
+int edgpu_selftest_nonlocal_row(const edgpu_params *p, uint32_t mup, uint32_t mdw, uint32_t *cup, uint32_t *cdw,
+                                double *val);
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -498,6 +498,47 @@ void orc_spmatvec_main(const orc_sector *s, int64_t nloc, const double *v, doubl
         hv[i] = hv[i] + s->hnd.vals[jj] * v[s->hnd.cols[jj]];
 }
 
+/* spMatVec_main restricted to the i_dw column block owned by sector view s (rank r of P):
+ * the same loop nests and term order as orc_spmatvec_main, rows istart..iend only, reading the
+ * full vector.  Used by bench.py to time a BOUNDED sample of the CPU path (one block per thread
+ * = the work one MPI rank of the reference would do, communication excluded). */
+void orc_spmatvec_block(const orc_sector *s, const double *v_full, double *hv_block) {
+  const int64_t du = s->dimup, c0 = s->istart / du, c1 = s->iend / du;
+  const int64_t nloc = s->iend - s->istart, sh = s->ishift;
+  for (int64_t i = 0; i < nloc; i++) hv_block[i] = 0.0;
+  for (int64_t i = 0; i < nloc; i++) hv_block[i] = hv_block[i] + s->h0d[i] * v_full[i + sh];
+  for (int64_t iup = 0; iup < du; iup++)
+    for (int64_t idw = c0; idw < c1; idw++) {
+      int64_t i = iup + idw * du - sh;
+      for (int64_t jj = s->hdw.rowptr[idw]; jj < s->hdw.rowptr[idw + 1]; jj++)
+        hv_block[i] = hv_block[i] + s->hdw.vals[jj] * v_full[iup + s->hdw.cols[jj] * du];
+    }
+  for (int64_t idw = c0; idw < c1; idw++)
+    for (int64_t iup = 0; iup < du; iup++) {
+      int64_t i = iup + idw * du - sh;
+      for (int64_t jj = s->hup.rowptr[iup]; jj < s->hup.rowptr[iup + 1]; jj++)
+        hv_block[i] = hv_block[i] + s->hup.vals[jj] * v_full[s->hup.cols[jj] + idw * du];
+    }
+  if (s->ctx->jhflag)
+    for (int64_t i = 0; i < nloc; i++)
+      for (int64_t jj = s->hnd.rowptr[i]; jj < s->hnd.rowptr[i + 1]; jj++)
+        hv_block[i] = hv_block[i] + s->hnd.vals[jj] * v_full[s->hnd.cols[jj]];
+}
+typedef struct { orc_sector **secs; const double *v; double **out; } blk_job;
+static void blk_rank(int r, void *arg) {
+  blk_job *b = (blk_job *)arg;
+  orc_spmatvec_block(b->secs[r], b->v, b->out[r]);
+}
+/* nblk blocks on nthreads threads; returns the number of vector elements processed */
+int64_t orc_spmatvec_blocks_mt(orc_sector **secs, int nblk, int nthreads, const double *v_full,
+                               double **hv_blocks) {
+  blk_job b = { secs, v_full, hv_blocks };
+  par_for(nthreads, nblk, blk_rank, &b);
+  int64_t n = 0;
+  for (int r = 0; r < nblk; r++) n += secs[r]->iend - secs[r]->istart;
+  return n;
+}
+
 /* ===================================================================================== */
 /* directMatVec_main, ED_HAMILTONIAN_DIRECT_HxV.f90:21-95 + direct/HxV_*.f90 (scatter)   */
 /* ===================================================================================== */

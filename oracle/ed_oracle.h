@@ -85,6 +85,10 @@ void    orc_build_hmat(const orc_sector *s, double *hmat);   /* dense, column-ma
 
 void orc_spmatvec_main(const orc_sector *s, int64_t nloc, const double *v, double *hv);
 void orc_directmatvec_main(const orc_sector *s, int64_t nloc, const double *v, double *hv);
+/* spMatVec_main loops restricted to the column block of sector view s (rank r of P), full v in */
+void orc_spmatvec_block(const orc_sector *s, const double *v_full, double *hv_block);
+int64_t orc_spmatvec_blocks_mt(orc_sector **secs, int nblk, int nthreads, const double *v_full,
+                               double **hv_blocks);
 /* Emulation of nranks MPI ranks in one process; v/hv are the concatenated shards (= the
  * serial vector, because the split is by contiguous i_dw column blocks). */
 void orc_spmatvec_mpi_main_all(const orc_ctx *c, int nup, int ndw, int nranks, int nthreads,

@@ -70,6 +70,9 @@ def lib():
         L.orc_build_hmat.argtypes = [C.POINTER(_Sector), c_dp]
         L.orc_spmatvec_main.argtypes = [C.POINTER(_Sector), C.c_int64, c_dp, c_dp]
         L.orc_directmatvec_main.argtypes = [C.POINTER(_Sector), C.c_int64, c_dp, c_dp]
+        L.orc_spmatvec_block.argtypes = [C.POINTER(_Sector), c_dp, c_dp]
+        L.orc_spmatvec_blocks_mt.restype = C.c_int64
+        L.orc_spmatvec_blocks_mt.argtypes = [C.POINTER(C.POINTER(_Sector)), C.c_int, C.c_int, c_dp, C.POINTER(c_dp)]
         L.orc_spmatvec_mpi_main_all.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_dp, c_dp]
         L.orc_directmatvec_mpi_main_all.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_dp, c_dp]
         L.orc_spmatvec_mpi_main_prebuilt.argtypes = [C.POINTER(C.POINTER(_Sector)), C.c_int, C.c_int, c_dp, c_dp]
@@ -178,6 +181,13 @@ class Sector:
         v = _f64(v)
         hv = np.empty_like(v)
         lib().orc_spmatvec_main(self.p, v.size, _dp(v), _dp(hv))
+        return hv
+
+    def spmatvec_block(self, v_full):
+        """spMatVec_main loops for this sector view's column block only (full vector in)."""
+        v = _f64(v_full)
+        hv = np.empty(self.nloc)
+        lib().orc_spmatvec_block(self.p, _dp(v), _dp(hv))
         return hv
 
     def directmatvec(self, v):
@@ -326,3 +336,12 @@ def tql2(d, e):
     rc = lib().orc_tql2(n, _dp(dd), _dp(ee), _dp(z))
     assert rc == 0
     return dd, z.reshape((n, n), order="F")
+
+
+def spmatvec_blocks_mt(sectors, v_full, outs, nthreads):
+    """Time-able multi-threaded sample: one column block (sector view) per thread."""
+    n = len(sectors)
+    arr = (C.POINTER(_Sector) * n)(*[s.p for s in sectors])
+    po = (c_dp * n)(*[_dp(o) for o in outs])
+    v = _f64(v_full)
+    return lib().orc_spmatvec_blocks_mt(arr, n, nthreads, _dp(v), po)

@@ -1,0 +1,248 @@
+"""Known-answer tests that pin the CPU oracle (the reference ships no golden
+vectors, so these stand in for them).  No GPU needed."""
+import numpy as np
+import pytest
+
+import oracle as O
+from edgpu import configs
+from conftest import make_oracle
+
+
+def test_init_dmft_bath_matches_reference_formula():
+    # ED_BATH/dmft_aux.f90:102-133 with HWBAND=2: Nbath=7 -> -2,-4/3,-2/3,0,2/3,4/3,2 ; V = 1/sqrt(7)
+    e, v = O.init_dmft_bath(1, 7)
+    assert np.allclose(e.ravel(), [-2, -4 / 3, -2 / 3, 0, 2 / 3, 4 / 3, 2], atol=1e-15)
+    assert np.allclose(v, 1 / np.sqrt(7))
+    e, v = O.init_dmft_bath(2, 4)
+    assert np.allclose(e[0, 0], [-2, -0.1, 0.1, 2]) and np.allclose(v, 0.5)
+    e2, v2 = configs.init_dmft_bath(2, 4)          # the product's host-side restatement agrees
+    assert (e2 == e).all() and (v2 == v).all()
+    for nb in (3, 5, 6, 8, 13, 15, 17):
+        a, b = O.init_dmft_bath(1, nb)
+        c, d = configs.init_dmft_bath(1, nb)
+        assert (a == c).all() and (b == d).all()
+
+
+def test_sector_map_binary_search_binomial():
+    L = O.lib()
+    for ns, n in [(8, 4), (10, 3), (12, 6), (14, 7)]:
+        m = O.build_sector_map(ns, n)
+        assert len(m) == L.orc_binomial(ns, n)
+        assert (np.diff(m) > 0).all()
+        assert all(bin(int(x)).count("1") == n for x in m[:: max(1, len(m) // 200)])
+        p = m.ctypes.data_as(O.c_i32p)
+        for k in (0, 1, len(m) // 2, len(m) - 1):
+            assert L.orc_binary_search(p, len(m), int(m[k])) == k + 1        # 1-based
+        assert L.orc_binary_search(p, len(m), int(m[-1]) + 1) == 0           # absent
+
+
+def test_c_cdg_signs():
+    L = O.lib()
+    import ctypes as C
+    out, sg = C.c_int32(0), C.c_double(0)
+    # |0b1011>: destroy site 4 (bit 3): two occupied below -> sign +1 ... site 2 (bit1): one below -> -1
+    assert L.orc_c(4, 0b1011, C.byref(out), C.byref(sg)) == 0 and out.value == 0b0011 and sg.value == 1.0
+    assert L.orc_c(2, 0b1011, C.byref(out), C.byref(sg)) == 0 and out.value == 0b1001 and sg.value == -1.0
+    assert L.orc_c(3, 0b1011, C.byref(out), C.byref(sg)) == 1                 # empty site: error
+    assert L.orc_cdg(3, 0b1011, C.byref(out), C.byref(sg)) == 0 and out.value == 0b1111 and sg.value == 1.0
+    assert L.orc_cdg(1, 0b1011, C.byref(out), C.byref(sg)) == 1               # occupied: error
+
+
+@pytest.mark.parametrize("nbath,nup,ndw", [(3, 2, 2), (5, 3, 3), (7, 4, 4), (5, 2, 4)])
+def test_u0_free_fermions(nbath, nup, ndw):
+    """U=0: E0(sector) = sum of the lowest Nup + lowest Ndw levels of the one-body matrix."""
+    cfg = configs.config("NS%d" % (nbath + 1))
+    cfg.update(uloc=(0.0,), hfmode=False)
+    o = O.Oracle(**configs.solver_kwargs(cfg))
+    ns = nbath + 1
+    h1 = np.zeros((ns, ns))
+    e, v = cfg["bath_e"].ravel(), cfg["bath_v"].ravel()
+    h1[1:, 1:] = np.diag(e)
+    h1[0, 1:] = v
+    h1[1:, 0] = v
+    w1 = np.linalg.eigvalsh(h1)
+    with o.sector(nup, ndw) as s:
+        w = np.linalg.eigvalsh(s.hmat())
+    assert abs(w[0] - (w1[:nup].sum() + w1[:ndw].sum())) < 1e-12
+
+
+def test_atomic_limit_is_diagonal():
+    cfg = configs.config("C4")
+    cfg["bath_v"] = np.zeros_like(cfg["bath_v"])
+    cfg.update(jx=0.0, jp=0.0)
+    o = O.Oracle(**configs.solver_kwargs(cfg))
+    with o.sector(5, 5) as s:
+        rp, cols, vals = s.hup()
+        assert rp[-1] == 0
+        v = configs.bench_vector(s.dim)
+        assert np.array_equal(s.spmatvec(v), 0.0 + s.h0d() * v)
+
+
+@pytest.mark.parametrize("name,sec", [("C1", (4, 4)), ("C1", (5, 3)), ("NS6", (3, 2)), ("C4", None)])
+def test_stored_direct_sharded_dense_agree(name, sec):
+    cfg, o = make_oracle(name)
+    if name == "C4":
+        h = np.zeros((1, 1, 2, 2))
+        h[0, 0, 0, 1] = h[0, 0, 1, 0] = 0.3
+        h[0, 0, 0, 0], h[0, 0, 1, 1] = 0.1, -0.2
+        cfg, o = make_oracle(name, imphloc=h)
+        sec = (4, 3)                                  # dim 210*120 = 25200: dense is too big, skip dense
+    nup, ndw = sec
+    with o.sector(nup, ndw) as s, o.sector(nup, ndw, sparse_h=False) as sd:
+        v = configs.bench_vector(s.dim)
+        v /= np.linalg.norm(v)
+        hv = s.spmatvec(v)
+        scale = np.abs(hv).max()
+        assert np.abs(sd.directmatvec(v) - hv).max() < 1e-13 * scale
+        if s.dim <= 5000:
+            H = s.hmat()
+            assert np.abs(H - H.T).max() == 0.0
+            assert np.abs(H @ v - hv).max() < 1e-13 * scale
+        for P in (1, 2, 3, 5, 8):
+            if P > s.dimdw:
+                continue
+            assert np.abs(o.spmatvec_mpi(nup, ndw, P, v, nthreads=2) - hv).max() < 1e-13 * scale
+            assert np.abs(o.directmatvec_mpi(nup, ndw, P, v) - hv).max() < 1e-13 * scale
+        # <x,Hy> = <Hx,y>
+        y = np.cos(0.11 * np.arange(s.dim))
+        assert abs(v @ s.spmatvec(y) - hv @ y) < 1e-11 * scale
+
+
+def test_shard_geometry_matches_reference_rule():
+    cfg, o = make_oracle("C1")
+    tot = 0
+    for r in range(8):
+        with o.sector(4, 4, r, 8) as s:                # DimDw=70 = 8*8+6
+            assert s.qdw == (9 if r < 6 else 8)
+            assert s.ishift == tot and s.nloc == o.vecdim(4, 4, r, 8)
+            tot += s.nloc
+    assert tot == 4900
+
+
+def test_vector_transpose_layout():
+    """Appendix B of SURVEY.md: after vector_transpose_MPI rank d holds vt(g, r) = V(rowstart_d + r, g)."""
+    import ctypes as C
+    nrow, ncol, P = 13, 11, 4
+    V = np.arange(nrow * ncol, dtype=np.float64).reshape((nrow, ncol), order="F")
+    qc = [ncol // P + (1 if r < ncol % P else 0) for r in range(P)]
+    qr = [nrow // P + (1 if r < nrow % P else 0) for r in range(P)]
+    co = np.cumsum([0] + qc)
+    ro = np.cumsum([0] + qr)
+    a = [np.asfortranarray(V[:, co[r]:co[r + 1]]).ravel(order="F").copy() for r in range(P)]
+    b = [np.zeros(ncol * qr[r]) for r in range(P)]
+    pa = (O.c_dp * P)(*[x.ctypes.data_as(O.c_dp) for x in a])
+    pb = (O.c_dp * P)(*[x.ctypes.data_as(O.c_dp) for x in b])
+    O.lib().orc_vector_transpose_all(P, nrow, ncol, pa, pb)
+    for d in range(P):
+        vt = b[d].reshape((ncol, qr[d]), order="F")
+        assert np.array_equal(vt, V[ro[d]:ro[d + 1], :].T)
+
+
+def test_tql2_vs_lapack():
+    rng = np.random.default_rng(1)
+    for n in (1, 2, 7, 50, 200):
+        d = rng.normal(size=n)
+        e = np.zeros(n)
+        e[1:] = rng.normal(size=n - 1)
+        w, z = O.tql2(d, e)
+        T = np.diag(d) + np.diag(e[1:], 1) + np.diag(e[1:], -1)
+        assert np.allclose(w, np.linalg.eigvalsh(T), atol=1e-12)
+        assert np.allclose(T @ z, z * w, atol=1e-11)
+
+
+def test_lanczos_e0_vs_dense_c1():
+    """Cross-check value of BASELINE.md section 6: E0 = -9.361735245469, E1 = -8.950104113137."""
+    cfg, o = make_oracle("C1")
+    with o.sector(4, 4) as s:
+        w = np.linalg.eigvalsh(s.hmat())
+        assert abs(w[0] - (-9.361735245469)) < 1e-11 and abs(w[1] - (-8.950104113137)) < 1e-11
+        e0, vec, a, b = s.lanc_eigh(v0=np.ones(s.dim) / np.sqrt(s.dim))
+        assert abs(e0 - w[0]) < 1e-12 * abs(w[0])
+        assert abs(np.linalg.norm(vec) - 1) < 1e-12
+        assert np.linalg.norm(s.spmatvec(vec) - e0 * vec) < 1e-6
+        e0d, _, _, _ = s.lanc_eigh(v0=np.ones(s.dim) / np.sqrt(s.dim), mode=1)
+        assert abs(e0d - e0) < 1e-12
+        e0r, _, _, _ = s.lanc_eigh()                  # zero start vector -> pseudo-random
+        assert abs(e0r - w[0]) < 1e-12 * abs(w[0])
+
+
+def test_lanczos_tridiag_matches_dense_krylov():
+    cfg, o = make_oracle("NS6")
+    with o.sector(3, 3) as s:
+        H = s.hmat()
+        v = configs.bench_vector(s.dim)
+        a, b = s.lanc_tridiag(v, 30)
+        # explicit Gram-Schmidt Krylov reference
+        q = v / np.linalg.norm(v)
+        qp = np.zeros_like(q)
+        beta = 0.0
+        for k in range(12):
+            w = H @ q - beta * qp
+            alpha = q @ w
+            w -= alpha * q
+            assert abs(alpha - a[k]) < 1e-10
+            beta = np.linalg.norm(w)
+            assert abs(beta - b[k + 1]) < 1e-10
+            qp, q = q, w / beta
+
+
+def test_gf_sum_rules_and_half_filling_symmetry():
+    cfg, o = make_oracle("C1")
+    with o.sector(4, 4) as s:
+        e0, gs, _, _ = s.lanc_eigh(v0=np.ones(s.dim) / np.sqrt(s.dim))
+    r = o.build_gf_normal(4, 4, gs, e0, 1, lmats=256, lreal=64)
+    n_add, n_rem = r["chains"][0]["norm2"], r["chains"][1]["norm2"]
+    assert abs(n_add + n_rem - 1.0) < 1e-12            # {c, c^+} = 1
+    assert abs(n_rem - 0.5) < 1e-6                     # <n_up> = 1/2 at half filling
+    assert np.abs(r["gmats"].real).max() < 1e-6        # particle-hole symmetry
+    # high-frequency tail G(iw) -> 1/(iw)
+    wm = r["wm"]
+    g_big = O.add_to_lanczos_gf(n_add, e0, r["chains"][0]["alanc"], r["chains"][0]["blanc"], 1,
+                                np.array([1e6]), np.array([0.0]), 0.01)[0]
+    g_big2 = O.add_to_lanczos_gf(n_rem, e0, r["chains"][1]["alanc"], r["chains"][1]["blanc"], -1,
+                                 np.array([1e6]), np.array([0.0]), 0.01)[0]
+    assert abs((g_big + g_big2)[0] * 1j * 1e6 - 1.0) < 1e-6
+    sig, invg0 = o.sigma_normal(1, 1, 1j * wm, r["gmats"])
+    assert np.abs(sig.real).max() < 1e-4               # HFMODE: Hartree shift absorbed (GS known to ~1e-8)
+    assert (sig.imag < 1e-12).all()
+
+
+def test_gf_lanczos_vs_full_spectral_sum():
+    """ed_diag_type=full analogue (ED_GF_NORMAL.f90:672-790): G(iw) from all eigenpairs of the N+1 / N-1 sectors."""
+    cfg, o = make_oracle("NS6")
+    nup = ndw = 3
+    with o.sector(nup, ndw) as s:
+        w, U = np.linalg.eigh(s.hmat())
+    e0, gs = w[0], U[:, 0]
+    r = o.build_gf_normal(nup, ndw, gs, e0, 1, lmats=64, lreal=16, ngfiter=200)
+    wm = r["wm"]
+    g = np.zeros(len(wm), dtype=complex)
+    for add, isign in ((True, 1), (False, -1)):
+        vv, n2, (jn, jd) = o.gf_start_vector(nup, ndw, gs, 1, 1, add)
+        with o.sector(jn, jd) as sj:
+            wj, Uj = np.linalg.eigh(sj.hmat())
+        amp = (Uj.T @ vv) ** 2 * n2
+        for k in range(len(wj)):
+            g += amp[k] / (1j * wm - isign * (wj[k] - e0))
+    assert np.abs(g - r["gmats"]).max() < 1e-9
+
+
+def test_golden_fixture_c1():
+    """tests/golden/c1_golden.npz is produced by tests/golden/make_golden.py from this oracle;
+    it freezes the oracle's outputs so that later edits cannot drift silently."""
+    import os
+    path = os.path.join(os.path.dirname(__file__), "golden", "c1_golden.npz")
+    gold = np.load(path)
+    cfg, o = make_oracle("C1")
+    with o.sector(4, 4) as s:
+        assert np.array_equal(s.map_up(), gold["map_up"])
+        rp, cols, vals = s.hup()
+        assert np.array_equal(rp, gold["hup_rowptr"]) and np.array_equal(cols, gold["hup_cols"])
+        assert np.array_equal(vals, gold["hup_vals"])
+        assert np.array_equal(s.h0d(), gold["h0d"])
+        v = configs.bench_vector(s.dim)
+        v /= np.linalg.norm(v)
+        assert np.abs(s.spmatvec(v) - gold["hv"]).max() < 1e-15
+        e0, gs, a, b = s.lanc_eigh(v0=np.ones(s.dim) / np.sqrt(s.dim))
+        assert abs(e0 - gold["e0"]) < 1e-13
+        assert np.abs(a - gold["alanc"]).max() < 1e-9
