@@ -157,18 +157,41 @@ static int exchange(edgpu_ctx *c, const double *send, const int64_t *soff, const
   return EDGPU_OK;
 }
 
+// Block geometry of the two all-to-all transposes (pure host arithmetic, exported so that the
+// world_size-2 gloo tests can drive the exact offsets the CUDA path uses).
+//   dir = 0: V(DimUp, qdw) -> Vt(DimDw, qup).  Block (me -> p) = V[rows(p), my columns] stored
+//            transposed, [c + qdw_me * r];      received block (p -> me) = [c + qdw_p * r], r < qup_me.
+//   dir = 1: Hvt(DimDw, qup) -> Hv(DimUp, qdw). Block (me -> p) = Hvt[columns(p), my rows] stored
+//            transposed, [r + qup_me * c];      received block (p -> me) = [r + qup_p * c], c < qdw_me.
+extern "C" void edgpu_transpose_plan(int64_t dimup, int64_t dimdw, int nranks, int rank, int dir,
+                                     int64_t *soff, int64_t *scnt, int64_t *roff, int64_t *rcnt) {
+  int64_t qdw, qup;
+  edgpu_split(dimdw, nranks, rank, &qdw, nullptr);
+  edgpu_split(dimup, nranks, rank, &qup, nullptr);
+  for (int p = 0; p < nranks; p++) {
+    int64_t qr, ro, qc, co;
+    edgpu_split(dimup, nranks, p, &qr, &ro);
+    edgpu_split(dimdw, nranks, p, &qc, &co);
+    if (dir == 0) {
+      soff[p] = ro * qdw; scnt[p] = qr * qdw;      // rows(p) x my columns
+      roff[p] = co * qup; rcnt[p] = qc * qup;      // columns(p) x my rows
+    } else {
+      soff[p] = co * qup; scnt[p] = qc * qup;      // dw-rows(p) x my up-rows
+      roff[p] = ro * qdw; rcnt[p] = qr * qdw;      // up-rows(p) x my columns
+    }
+  }
+}
+
 // V(DimUp, qdw) -> Vt(DimDw, qup): block (me -> d) = V[rows(d), :] transposed
 int comm_transpose_fwd(edgpu_ctx *c, const double *d_x, double *d_vt) {
   const int P = c->nranks;
   TRY(ensure(&c->d_send, c->nloc > c->dimdw * c->qup ? c->nloc : c->dimdw * c->qup));
   TRY(ensure(&c->d_recv, c->nloc > c->dimdw * c->qup ? c->nloc : c->dimdw * c->qup));
   int64_t soff[64] = {0}, scnt[64] = {0}, roff[64] = {0}, rcnt[64] = {0};
+  edgpu_transpose_plan(c->dimup, c->dimdw, P, c->rank, 0, soff, scnt, roff, rcnt);
   for (int p = 0; p < P; p++) {
-    int64_t qr, ro, qc, co;
+    int64_t qr, ro;
     edgpu_split(c->dimup, P, p, &qr, &ro);
-    edgpu_split(c->dimdw, P, p, &qc, &co);
-    soff[p] = ro * c->qdw; scnt[p] = qr * c->qdw;              // rows(p) x my columns
-    roff[p] = co * c->qup; rcnt[p] = qc * c->qup;              // columns(p) x my rows
     if (scnt[p]) {
       int64_t tiles = ((qr + 31) / 32) * ((c->qdw + 31) / 32);
       int grid = (int)(tiles < (int64_t)c->sm_count * 8 ? tiles : (int64_t)c->sm_count * 8);
@@ -192,12 +215,10 @@ int comm_transpose_fwd(edgpu_ctx *c, const double *d_x, double *d_vt) {
 int comm_transpose_bwd_add(edgpu_ctx *c, const double *d_hvt, double *d_y) {
   const int P = c->nranks;
   int64_t soff[64] = {0}, scnt[64] = {0}, roff[64] = {0}, rcnt[64] = {0};
+  edgpu_transpose_plan(c->dimup, c->dimdw, P, c->rank, 1, soff, scnt, roff, rcnt);
   for (int p = 0; p < P; p++) {
-    int64_t qr, ro, qc, co;
-    edgpu_split(c->dimup, P, p, &qr, &ro);
+    int64_t qc, co;
     edgpu_split(c->dimdw, P, p, &qc, &co);
-    soff[p] = co * c->qup; scnt[p] = qc * c->qup;              // dw-rows(p) x my up-rows
-    roff[p] = ro * c->qdw; rcnt[p] = qr * c->qdw;              // up-rows(p) x my columns
     if (scnt[p]) {
       int64_t tiles = ((qc + 31) / 32) * ((c->qup + 31) / 32);
       int grid = (int)(tiles < (int64_t)c->sm_count * 8 ? tiles : (int64_t)c->sm_count * 8);

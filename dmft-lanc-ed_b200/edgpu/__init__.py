@@ -28,7 +28,7 @@ ALGO_AUTO, ALGO_GATHER, ALGO_TILED = 0, 1, 2
 ABI_SYMBOLS = [
     "edgpu_create", "edgpu_destroy", "edgpu_set_params", "edgpu_last_error", "edgpu_set_option",
     "edgpu_device_count", "edgpu_comm_unique_id", "edgpu_comm_init", "edgpu_comm_finalize",
-    "edgpu_get_sector", "edgpu_get_nup_ndw", "edgpu_split", "edgpu_build_hv_sector",
+    "edgpu_get_sector", "edgpu_get_nup_ndw", "edgpu_split", "edgpu_transpose_plan", "edgpu_build_hv_sector",
     "edgpu_delete_hv_sector", "edgpu_vecdim_hv_sector", "edgpu_hxv", "edgpu_sphtimesv",
     "edgpu_hxv_device", "edgpu_sp_lanc_eigh", "edgpu_sp_lanc_tridiag", "edgpu_gf_set_state",
     "edgpu_gf_chains", "edgpu_add_to_lanczos_gf", "edgpu_get_dims", "edgpu_get_sector_map",
@@ -73,6 +73,8 @@ def lib():
         L.edgpu_get_nup_ndw.argtypes = [C.c_void_p, C.c_int, c_ip, c_ip]
         L.edgpu_split.argtypes = [C.c_int64, C.c_int, C.c_int, c_i64p, c_i64p]
         L.edgpu_split.restype = None
+        L.edgpu_transpose_plan.argtypes = [C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, c_i64p, c_i64p, c_i64p, c_i64p]
+        L.edgpu_transpose_plan.restype = None
         L.edgpu_build_hv_sector.argtypes = [C.c_void_p, C.c_int]
         L.edgpu_delete_hv_sector.argtypes = [C.c_void_p]
         L.edgpu_vecdim_hv_sector.argtypes = [C.c_void_p, C.c_int, c_i64p]
@@ -127,6 +129,13 @@ def split(n, nranks, rank):
     q, off = C.c_int64(0), C.c_int64(0)
     lib().edgpu_split(n, nranks, rank, C.byref(q), C.byref(off))
     return q.value, off.value
+
+
+def transpose_plan(dimup, dimdw, nranks, rank, direction):
+    """(soff, scnt, roff, rcnt) of the grouped all-to-all transpose, as comm.cu uses them."""
+    arrs = [np.zeros(nranks, dtype=np.int64) for _ in range(4)]
+    lib().edgpu_transpose_plan(dimup, dimdw, nranks, rank, direction, *[a.ctypes.data_as(c_i64p) for a in arrs])
+    return arrs
 
 
 def comm_unique_id():

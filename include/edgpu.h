@@ -86,6 +86,11 @@ int  edgpu_get_nup_ndw(const edgpu_ctx *c, int isector, int *nup, int *ndw);   /
 /* Shard geometry, pure host arithmetic (ED_HAMILTONIAN.f90:96-110, ED_HAMILTONIAN_COMMON.f90:62-79):
  * q = n/P (+1 if r < mod(n,P)), off = first index owned by r. */
 void edgpu_split(int64_t n, int nranks, int rank, int64_t *q, int64_t *off);
+/* Send/receive offsets and counts (in doubles, arrays of nranks) of the grouped all-to-all that
+ * replaces vector_transpose_MPI (ED_HAMILTONIAN_COMMON.f90:53-118); dir 0: V(DimUp,qdw) ->
+ * Vt(DimDw,qup), dir 1: the way back.  Pure host arithmetic (block layouts: see comm.cu). */
+void edgpu_transpose_plan(int64_t dimup, int64_t dimdw, int nranks, int rank, int dir,
+                          int64_t *soff, int64_t *scnt, int64_t *roff, int64_t *rcnt);
 
 /* ---- operator lifecycle ------------------------------------------------------------------ */
 /* build_Hv_sector(isector), ED_HAMILTONIAN.f90:43-168: builds the basis maps on device

@@ -1,0 +1,99 @@
+"""Launched under torchrun (one process per GPU) by tests/test_gpu_multi.py or by hand:
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multigpu_worker.py
+Checks the sharded operator, Lanczos and GF chains against the oracle (rank 0 holds the reference)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (os.path.join(ROOT, "dmft-lanc-ed_b200"), os.path.join(ROOT, "oracle")):
+    sys.path.insert(0, p)
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import edgpu  # noqa: E402
+import oracle as O  # noqa: E402
+from edgpu import configs  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(edgpu.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    uid = bytes(idt.cpu().numpy().tobytes())
+    fails = []
+
+    def check(name, ok, detail=""):
+        if not ok:
+            fails.append("%s rank %d %s" % (name, rank, detail))
+
+    cases = [("C1", (4, 4), True), ("C1", (4, 4), False), ("C1", (5, 3), True), ("NS10", (5, 5), False),
+             ("NS10", (6, 4), True), ("C4", (5, 5), True), ("C4", (5, 5), False), ("C4", (6, 5), True)]
+    for name, sec, sparse in cases:
+        cfg = configs.config(name)
+        kw = configs.solver_kwargs(cfg)
+        o = O.Oracle(**kw)
+        s = edgpu.Solver(ed_sparse_h=sparse, device=local, **kw)
+        s.set_comm(rank, world, uid)
+        with o.sector(*sec) as full, o.sector(sec[0], sec[1], rank, world) as mine:
+            v = configs.bench_vector(full.dim)
+            v /= np.linalg.norm(v)
+            ref = full.spmatvec(v)
+            isec = s.get_sector(*sec)
+            check("vecdim", s.vecDim_Hv_sector(isec) == mine.nloc)
+            s.build_Hv_sector(isec)
+            check("ishift", s.ishift == mine.ishift and s.nloc == mine.nloc)
+            sl = slice(mine.ishift, mine.ishift + mine.nloc)
+            if sparse:
+                check("diag", np.array_equal(s.diag(), mine.h0d()))
+                rp, cols, vals = s.csr(2)
+                orp, ocols, ovals = mine.hnd()
+                if cfg["norb"] > 1:
+                    check("hnd", np.array_equal(rp, orp) and np.array_equal(cols, ocols) and np.array_equal(vals, ovals))
+            hv = s.spHtimesV(v[sl])
+            err = np.abs(hv - ref[sl]).max() / np.abs(ref).max()
+            check("hxv %s %s sparse=%s" % (name, sec, sparse), err < 1e-13, "err %.3e" % err)
+            # Lanczos ground state on shards
+            v0 = np.ones(full.dim) / np.sqrt(full.dim)
+            e_ref, vec_ref, a_ref, b_ref = full.lanc_eigh(v0=v0)
+            e0, vec, a, b = s.sp_lanc_eigh(v0[sl])
+            check("E0", abs(e0 - e_ref) < 1e-12 * abs(e_ref), "%.15g vs %.15g" % (e0, e_ref))
+            n = min(50, len(a), len(a_ref))
+            check("alanc", np.abs(a[:n] - a_ref[:n]).max() < 1e-8 and np.abs(b[:n] - b_ref[:n]).max() < 1e-8)
+            sgn = np.sign(vec[0] * vec_ref[sl][0]) if vec[0] != 0 else 1.0
+            check("vec", np.abs(sgn * vec - vec_ref[sl]).max() < 1e-6)
+            s.delete_Hv_sector()
+            # GF chains from the sharded ground state
+            s.gf_set_state(isec, vec_ref[sl], e_ref)
+            chans = [(io, 1, sg) for io in range(1, cfg["norb"] + 1) for sg in (1, -1)]
+            res = s.gf_chains(chans, nlanc_max=60)
+            k = 0
+            for io in range(1, cfg["norb"] + 1):
+                rr = o.build_gf_normal(sec[0], sec[1], vec_ref, e_ref, io, ngfiter=60, lmats=8, lreal=8)
+                for p in range(2):
+                    r, rc = res[k], rr["chains"][p]
+                    k += 1
+                    check("gf nlanc", r["nlanc"] == rc["nlanc"])
+                    if rc["nlanc"]:
+                        m = min(50, rc["nlanc"])
+                        check("gf norm2", abs(r["norm2"] - rc["norm2"]) < 1e-12)
+                        check("gf a", np.abs(r["alanc"][:m] - rc["alanc"][:m]).max() < 1e-8)
+                        check("gf b", np.abs(r["blanc"][:m] - rc["blanc"][:m]).max() < 1e-8)
+        s.close()
+    t = torch.tensor([len(fails)], device="cuda")
+    dist.all_reduce(t)
+    for f in fails:
+        print("FAIL:", f, flush=True)
+    if rank == 0:
+        print("MULTIGPU %s: %d ranks, %d failures" % ("OK" if t.item() == 0 else "FAILED", world, int(t.item())), flush=True)
+    dist.destroy_process_group()
+    sys.exit(1 if t.item() else 0)
+
+
+if __name__ == "__main__":
+    main()

@@ -122,8 +122,12 @@ def test_lanczos_ground_state(name, sec, sparse):
             ov = abs(vec @ vec_ref)
             assert abs(ov - 1) < 1e-10                          # same eigenvector up to sign
             assert np.linalg.norm(os_.spmatvec(vec) - e0 * vec) < 1e-6
-            e0r, _, _, _ = s.sp_lanc_eigh()                     # zero start -> pseudo-random start
-            assert abs(e0r - e_ref) < 1e-12 * abs(e_ref)
+            # zero start vector -> pseudo-random start (no symmetry constraint: may land BELOW the energy
+            # reached from the uniform vector, which stays in the totally symmetric subspace)
+            e0r, _, _, _ = s.sp_lanc_eigh()
+            e_rand, _, _, _ = os_.lanc_eigh()
+            assert abs(e0r - e_rand) < 1e-10 * abs(e_rand)
+            assert e0r <= e_ref + 1e-10
             s.delete_Hv_sector()
     finally:
         s.close()
