@@ -111,6 +111,8 @@ int tiled_plan_build(edgpu_ctx *c);
 int tiled_plan_free(edgpu_ctx *c);
 bool tiled_supported(const edgpu_ctx *c);
 int tiled_apply_local(edgpu_ctx *c, const double *d_x, double *d_y);   // nranks==1: full operator
+// y = [Hd o x +] F_k x, contiguous dimension = index of factor k (0 up, 1 dw), ncols local columns
+int tiled_apply_col(edgpu_ctx *c, int k, bool with_diag, const double *d_x, double *d_y, int64_t ncols, int64_t coloff);
 // comm.cu
 int comm_allreduce_scalar(edgpu_ctx *c, double *d_scalar);
 int comm_transpose_fwd(edgpu_ctx *c, const double *d_x, double *d_vt);          // V(DimUp,qdw) -> Vt(DimDw,qup)

@@ -166,11 +166,17 @@ int hxv_apply(edgpu_ctx *c, const double *d_x, double *d_y) {
     TRY(comm_allgather(c, d_x, c->d_full));
     d_full = c->d_full;
   }
-  TRY(gather_local(c, d_x, d_y, false, d_full));
+  int algo = c->algo;
+  if (algo == EDGPU_ALGO_AUTO) algo = tiled_supported(c) ? EDGPU_ALGO_TILED : EDGPU_ALGO_GATHER;
+  if (algo == EDGPU_ALGO_TILED && !tiled_supported(c))
+    return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "tiled H*v does not cover this sector/model");
+  if (algo == EDGPU_ALGO_TILED) TRY(tiled_apply_col(c, 0, true, d_x, d_y, c->qdw, c->coloff));
+  else TRY(gather_local(c, d_x, d_y, false, d_full));
   TRY(ensure(&c->d_vt, c->dimdw * c->qup));
   TRY(ensure(&c->d_hvt, c->dimdw * c->qup));
   TRY(comm_transpose_fwd(c, d_x, c->d_vt));
-  TRY(gather_transposed_dw(c, c->d_vt, c->d_hvt));
+  if (algo == EDGPU_ALGO_TILED) TRY(tiled_apply_col(c, 1, false, c->d_vt, c->d_hvt, c->qup, c->rowoff));
+  else TRY(gather_transposed_dw(c, c->d_vt, c->d_hvt));
   TRY(comm_transpose_bwd_add(c, c->d_hvt, d_y));
   return EDGPU_OK;
 }

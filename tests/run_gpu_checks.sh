@@ -1,9 +1,8 @@
 #!/bin/bash
-# One GPU-box call: parity tests, smoke, short bench.  Logs land in gpurun_out/.
-set -x
+# One GPU-box call: parity tests, smoke, short benches.  Logs land in gpurun_out/.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
 nproc > gpurun_out/nproc.txt; free -g >> gpurun_out/nproc.txt
-python -m pytest tests -m gpu -x -q 2>&1 | tail -40 > gpurun_out/pytest_gpu.log
+timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -40 > gpurun_out/pytest_gpu.log
 cat gpurun_out/pytest_gpu.log
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; cat gpurun_out/smoke.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; cat gpurun_out/smoke.log

@@ -293,3 +293,57 @@ def test_full_size_properties(name):
     with o.sector(nup, ndw, 0, 256) as blk:
         ref = blk.spmatvec_block(x)
         assert np.abs(outs[True][:blk.nloc] - ref).max() < 1e-13 * scale
+
+
+TILED_CASES = [("C1", (4, 4), {}), ("C1", (5, 3), {}), ("C1", (3, 6), {"col_h": 2, "tile_h": 3}),
+               ("NS10", (5, 5), {"col_h": 3, "tile_h": 2}), ("NS12", (6, 6), {"col_h": 4, "tile_h": 5}),
+               ("NS12", (7, 4), {"col_h": 2, "tile_h": 7, "tile_rows": 8}), ("NS12", (6, 6), {"tile_rows": 8}),
+               ("NS6", (3, 3), {"col_h": 5, "tile_h": 6})]
+
+
+@pytest.mark.parametrize("name,sec,opts", TILED_CASES)
+@pytest.mark.parametrize("sparse", [True, False])
+def test_tiled_hxv_matches_oracle(name, sec, opts, sparse):
+    """Shared-memory staged two-pass kernels, including chunkings that force cross-chunk hops."""
+    cfg, o = make_oracle(name)
+    s = _solver(cfg, sparse, edgpu.ALGO_TILED)
+    for k, v in opts.items():
+        s.set_option(k, v)
+    try:
+        with o.sector(*sec) as os_:
+            v = configs.bench_vector(os_.dim)
+            v /= np.linalg.norm(v)
+            ref = os_.spmatvec(v)
+            s.build_Hv_sector(s.get_sector(*sec))
+            hv = s.spHtimesV(v)
+            assert np.abs(hv - ref).max() < 1e-13 * np.abs(ref).max()
+            e_ref, _, a_ref, b_ref = os_.lanc_eigh(v0=np.ones(os_.dim) / np.sqrt(os_.dim))
+            e0, _, a, b = s.sp_lanc_eigh(np.ones(os_.dim) / np.sqrt(os_.dim))
+            assert abs(e0 - e_ref) < 1e-12 * abs(e_ref)
+            s.delete_Hv_sector()
+    finally:
+        s.close()
+
+
+@pytest.mark.parametrize("name", ["C2", "C3"])
+def test_tiled_equals_gather_full_size(name):
+    cfg = configs.config(name)
+    out = {}
+    for algo in (edgpu.ALGO_GATHER, edgpu.ALGO_TILED):
+        s = _solver(cfg, False, algo)
+        try:
+            s.build_Hv_sector(s.get_sector(cfg["nup"], cfg["ndw"]))
+            n = s.nloc
+            dx, dy = s.dev_alloc(8 * n), s.dev_alloc(8 * n)
+            s.dev_fill_bench_vector(dx, n, 0)
+            s.hxv_device(dx, dy)
+            s.sync()
+            out[algo] = np.empty(n)
+            s.dev_download(dy, out[algo])
+            s.dev_free(dx)
+            s.dev_free(dy)
+            s.delete_Hv_sector()
+        finally:
+            s.close()
+    scale = np.abs(out[edgpu.ALGO_GATHER]).max()
+    assert np.abs(out[edgpu.ALGO_GATHER] - out[edgpu.ALGO_TILED]).max() < 1e-12 * scale
