@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--stored", action="store_true", help="ED_SPARSE_H=T: stream spH0d (24 B/element) instead of recomputing the diagonal (16 B/element)")
     ap.add_argument("--algo", default="auto", choices=["auto", "gather", "tiled"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--hxv-only", action="store_true", help="only the device-resident H*v loop (used under ncu)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
 
@@ -219,6 +220,13 @@ def run_b200(args):
         ms = float(t.item())
     ms_step = ms / args.steps
     value = 1000.0 / ms_step
+    if args.hxv_only:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": ms_step, "hxv_only": True,
+                              "gpu_launches": int(launches)}))
+        s.delete_Hv_sector()
+        s.close()
+        return
 
     # ---- Lanczos iterations per second (device-resident recurrence, no host sync inside) ------------
     s.time_lanczos_device(d_v, 3)

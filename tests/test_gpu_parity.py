@@ -17,6 +17,20 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def stable_steps(a1, b1, a2, b2, nmax=50, tol=1e-10):
+    """Number of leading Lanczos steps for which the coefficient comparison is well posed.
+
+    The three-term recurrence amplifies rounding differences exponentially once extremal Ritz values
+    have converged, so two CORRECT evaluations that differ only in summation order (the reference's
+    own stored and direct variants) drift apart after some step.  a1/b1 and a2/b2 are
+    the oracle's coefficients from spMatVec_main and directMatVec_main; beyond the first step where
+    they disagree by more than `tol` a 1e-8 comparison says nothing about correctness."""
+    n = min(nmax, len(a1), len(a2))
+    d = np.maximum(np.abs(a1[:n] - a2[:n]), np.abs(b1[:n] - b2[:n]))
+    bad = np.nonzero(d > tol)[0]
+    return int(bad[0]) if len(bad) else n
+
+
 def _solver(cfg, sparse=True, algo=None):
     s = edgpu.Solver(ed_sparse_h=sparse, device=0, **configs.solver_kwargs(cfg))
     if algo is not None:
@@ -196,15 +210,20 @@ def test_gf_chains_g_and_sigma(name):
         res = s.gf_chains(chans, nlanc_max=200)
         for iorb in range(1, cfg["norb"] + 1):
             ref = o.build_gf_normal(nup, ndw, gs, e0, iorb, lmats=lmats, lreal=32)
+            ref_direct = o.build_gf_normal(nup, ndw, gs, e0, iorb, lmats=lmats, lreal=32, mode=1)
+            assert np.abs(ref_direct["gmats"] - ref["gmats"]).max() < 1e-9      # the observable is stable
             z = 1j * ref["wm"]
             g = np.zeros(lmats, dtype=complex)
             for k, isign in ((0, 1), (1, -1)):
                 r = res[2 * (iorb - 1) + k]
                 rc = ref["chains"][k]
+                rc2 = ref_direct["chains"][k]
                 assert r["nlanc"] == rc["nlanc"]
                 assert abs(r["norm2"] - rc["norm2"]) < 1e-12
-                assert np.abs(r["alanc"][:50] - rc["alanc"][:50]).max() < 1e-8
-                assert np.abs(r["blanc"][:50] - rc["blanc"][:50]).max() < 1e-8
+                ns_ = stable_steps(rc["alanc"], rc["blanc"], rc2["alanc"], rc2["blanc"])
+                assert ns_ >= 25, ns_
+                assert np.abs(r["alanc"][:ns_] - rc["alanc"][:ns_]).max() < 1e-8
+                assert np.abs(r["blanc"][:ns_] - rc["blanc"][:ns_]).max() < 1e-8
                 g += edgpu.add_to_lanczos_gf(r["norm2"], e0, r["alanc"], r["blanc"], isign, z)
             assert np.abs(g - ref["gmats"]).max() < 1e-8
             sig, _ = edgpu.sigma_normal(z, g, cfg["xmu"], 0.0, cfg["bath_e"][0, iorb - 1], cfg["bath_v"][0, iorb - 1])
