@@ -41,10 +41,11 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("EDGPU_BENCH_WORKLOAD", "C3"))
     ap.add_argument("--stored", action="store_true", help="ED_SPARSE_H=T: stream spH0d (24 B/element) instead of recomputing the diagonal (16 B/element)")
-    ap.add_argument("--algo", default="auto", choices=["auto", "gather", "tiled"])
+    ap.add_argument("--algo", default="auto", choices=["auto", "gather", "tiled", "fast"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--hxv-only", action="store_true", help="only the device-resident H*v loop (used under ncu)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--opt", action="append", default=[], help="engine option key=value (edgpu_set_option), repeatable")
     return ap.parse_args()
 
 
@@ -188,7 +189,10 @@ def run_b200(args):
     cfg = configs.config(args.workload)
     nup, ndw = cfg["nup"], cfg["ndw"]
     s = edgpu.Solver(ed_sparse_h=args.stored, device=local, **configs.solver_kwargs(cfg))
-    s.set_option("hxv_algo", {"auto": edgpu.ALGO_AUTO, "gather": edgpu.ALGO_GATHER, "tiled": edgpu.ALGO_TILED}[args.algo])
+    s.set_option("hxv_algo", {"auto": edgpu.ALGO_AUTO, "gather": edgpu.ALGO_GATHER, "tiled": edgpu.ALGO_TILED, "fast": edgpu.ALGO_FAST}[args.algo])
+    for kv in args.opt:
+        k, v = kv.split("=")
+        s.set_option(k, int(v))
     if world > 1:
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:

@@ -127,6 +127,10 @@ extern "C" int edgpu_set_option(edgpu_ctx *c, const char *key, int64_t value) {
   if (!strcmp(key, "tile_rows")) { c->opt_tile_rows = value; return EDGPU_OK; }
   if (!strcmp(key, "tile_h")) { c->opt_tile_h = value; return EDGPU_OK; }
   if (!strcmp(key, "col_h")) { c->opt_col_h = value; return EDGPU_OK; }
+  if (!strcmp(key, "srow_lr")) { c->opt_srow_lr = value; return EDGPU_OK; }
+  if (!strcmp(key, "srow_cmax")) { c->opt_srow_cmax = value; return EDGPU_OK; }
+  if (!strcmp(key, "dbg")) { c->opt_dbg = value; return EDGPU_OK; }
+  if (!strcmp(key, "no_uniform")) { c->opt_no_uniform = value; return EDGPU_OK; }
   return edgpu_set_err(EDGPU_ERR_INVALID, "unknown option %s", key);
 }
 
@@ -274,7 +278,8 @@ static int build_factor(edgpu_ctx *c, Factor &f, int spin, int npart, bool store
   k_factor_fill<<<blocks, 128, 0, c->stream>>>(c->dp, spin, f.d_map, f.n, f.d_rowptr, f.d_cols, f.d_vals);
   CKL(c);
   if (!stored) {
-    CK(cudaMalloc(&f.d_dfac, (size_t)f.n * sizeof(double)));
+    CK(cudaMalloc(&f.d_dfac, (size_t)(f.n + 2) * sizeof(double)));   // +2: 16-byte bulk copies may read one past the end
+    CK(cudaMemsetAsync(f.d_dfac, 0, (size_t)(f.n + 2) * sizeof(double), c->stream));
     k_dfac<<<blocks, 128, 0, c->stream>>>(c->dp, spin, f.d_map, f.n, f.d_dfac);
     CKL(c);
   }
@@ -350,6 +355,7 @@ extern "C" int edgpu_delete_hv_sector(edgpu_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   tiled_plan_free(c);
+  fast_plan_free(c);
   free_factor(c->up);
   free_factor(c->dw);
   cudaFree(c->d_diag); c->d_diag = nullptr;

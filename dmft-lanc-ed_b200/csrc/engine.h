@@ -27,6 +27,7 @@ struct LancState {              // device-resident Lanczos scalars (no host sync
 };
 
 struct TiledPlan;               // hxv_tiled.cu
+struct FastPlan;                // hxv_fast.cu
 
 struct edgpu_ctx {
   int device = 0;
@@ -74,6 +75,8 @@ struct edgpu_ctx {
   int algo = EDGPU_ALGO_AUTO;
   int64_t opt_tile_rows = 0, opt_tile_h = -1, opt_col_h = -1;
   TiledPlan *plan = nullptr;
+  FastPlan *fplan = nullptr;
+  int64_t opt_srow_lr = 0, opt_srow_cmax = 0, opt_no_uniform = 0, opt_dbg = 0;
   int64_t launches = 0;
 };
 
@@ -113,6 +116,14 @@ bool tiled_supported(const edgpu_ctx *c);
 int tiled_apply_local(edgpu_ctx *c, const double *d_x, double *d_y);   // nranks==1: full operator
 // y = [Hd o x +] F_k x, contiguous dimension = index of factor k (0 up, 1 dw), ncols local columns
 int tiled_apply_col(edgpu_ctx *c, int k, bool with_diag, const double *d_x, double *d_y, int64_t ncols, int64_t coloff);
+// hxv_fast.cu: TMA-staged whole-column kernel + structured single-band row kernel
+int fast_plan_build(edgpu_ctx *c);
+int fast_plan_free(edgpu_ctx *c);
+bool fast_supported_local(edgpu_ctx *c);          // nranks==1 full operator
+bool fast_supported_col(edgpu_ctx *c, int k);     // whole-column kernel for factor k
+int fast_apply_local(edgpu_ctx *c, const double *d_x, double *d_y);
+int fast_apply_col(edgpu_ctx *c, int k, bool with_diag, bool acc, const double *d_x, double *d_y, int64_t ncols, int64_t coloff);
+int fast_apply_row(edgpu_ctx *c, bool with_diag, bool acc, const double *d_x, double *d_y);
 // comm.cu
 int comm_allreduce_scalar(edgpu_ctx *c, double *d_scalar);
 int comm_transpose_fwd(edgpu_ctx *c, const double *d_x, double *d_vt);          // V(DimUp,qdw) -> Vt(DimDw,qup)

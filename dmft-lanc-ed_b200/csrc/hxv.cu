@@ -148,10 +148,26 @@ static int ensure(double **p, int64_t n) {
   return EDGPU_OK;
 }
 
+// algorithm actually used for the local full operator / for one whole-column factor application
+static int pick_local(edgpu_ctx *c) {
+  int algo = c->algo;
+  if (algo == EDGPU_ALGO_AUTO) algo = fast_supported_local(c) ? EDGPU_ALGO_FAST : (tiled_supported(c) ? EDGPU_ALGO_TILED : EDGPU_ALGO_GATHER);
+  return algo;
+}
+static int pick_col(edgpu_ctx *c) {
+  int algo = c->algo;
+  if (algo == EDGPU_ALGO_AUTO)
+    algo = (fast_supported_col(c, 0) && fast_supported_col(c, 1)) ? EDGPU_ALGO_FAST : (tiled_supported(c) ? EDGPU_ALGO_TILED : EDGPU_ALGO_GATHER);
+  return algo;
+}
+
 int hxv_apply(edgpu_ctx *c, const double *d_x, double *d_y) {
   if (c->nranks == 1) {
-    int algo = c->algo;
-    if (algo == EDGPU_ALGO_AUTO) algo = tiled_supported(c) ? EDGPU_ALGO_TILED : EDGPU_ALGO_GATHER;
+    const int algo = pick_local(c);
+    if (algo == EDGPU_ALGO_FAST) {
+      if (!fast_supported_local(c)) return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "fast H*v does not cover this sector/model");
+      return fast_apply_local(c, d_x, d_y);
+    }
     if (algo == EDGPU_ALGO_TILED) {
       if (!tiled_supported(c)) return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "tiled H*v does not cover this sector/model");
       return tiled_apply_local(c, d_x, d_y);
@@ -166,16 +182,19 @@ int hxv_apply(edgpu_ctx *c, const double *d_x, double *d_y) {
     TRY(comm_allgather(c, d_x, c->d_full));
     d_full = c->d_full;
   }
-  int algo = c->algo;
-  if (algo == EDGPU_ALGO_AUTO) algo = tiled_supported(c) ? EDGPU_ALGO_TILED : EDGPU_ALGO_GATHER;
+  const int algo = pick_col(c);
+  if (algo == EDGPU_ALGO_FAST && !(fast_supported_col(c, 0) && fast_supported_col(c, 1)))
+    return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "fast H*v does not cover this sector/model");
   if (algo == EDGPU_ALGO_TILED && !tiled_supported(c))
     return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "tiled H*v does not cover this sector/model");
-  if (algo == EDGPU_ALGO_TILED) TRY(tiled_apply_col(c, 0, true, d_x, d_y, c->qdw, c->coloff));
+  if (algo == EDGPU_ALGO_FAST) TRY(fast_apply_col(c, 0, true, false, d_x, d_y, c->qdw, c->coloff));
+  else if (algo == EDGPU_ALGO_TILED) TRY(tiled_apply_col(c, 0, true, d_x, d_y, c->qdw, c->coloff));
   else TRY(gather_local(c, d_x, d_y, false, d_full));
   TRY(ensure(&c->d_vt, c->dimdw * c->qup));
   TRY(ensure(&c->d_hvt, c->dimdw * c->qup));
   TRY(comm_transpose_fwd(c, d_x, c->d_vt));
-  if (algo == EDGPU_ALGO_TILED) TRY(tiled_apply_col(c, 1, false, c->d_vt, c->d_hvt, c->qup, c->rowoff));
+  if (algo == EDGPU_ALGO_FAST) TRY(fast_apply_col(c, 1, false, false, c->d_vt, c->d_hvt, c->qup, c->rowoff));
+  else if (algo == EDGPU_ALGO_TILED) TRY(tiled_apply_col(c, 1, false, c->d_vt, c->d_hvt, c->qup, c->rowoff));
   else TRY(gather_transposed_dw(c, c->d_vt, c->d_hvt));
   TRY(comm_transpose_bwd_add(c, c->d_hvt, d_y));
   return EDGPU_OK;

@@ -1,0 +1,845 @@
+// hxv_fast.cu -- the engine's fast H*v path: two HBM passes, each staged through shared memory by
+// TMA bulk copies (cp.async.bulk + mbarrier, double buffered, persistent CTAs, one CTA per SM).
+//
+//   y = Hd o x + Hup x + x Hdw^T       x(i_up, i_dw) column-major, i_up contiguous
+//
+//   pass 1  k_fcol : one WHOLE column x(:, j) per stage in shared memory (a contiguous 8*DimUp byte
+//                    bulk copy), y(:, j) = [Hd o x +] F x(:, j).  F is any one-spin factor
+//                    (spH0ups / spH0dws, ED_HAMILTONIAN/stored/H_up.f90, H_dw.f90) in a packed
+//                    4-byte ELL form streamed from L2; every gather hits shared memory.
+//   pass 2  k_srow : tile = 32 consecutive i_up rows x one chunk of i_dw columns; lanes run along
+//                    i_up so every shared-memory access is unit stride, and the dw hops are
+//                    generated from the bit structure of the star geometry (Norb = 1: every hop
+//                    is impurity bit 0 <-> bath bit k): the columns of one "low group" (same high
+//                    bits, LR low bits) live in registers, hops among the low bits are register
+//                    to register, a hop on a high bit moves the whole group to ONE other group
+//                    whose base column comes from a Lin table.  No per-element index data at all.
+//                    y += Hd o x + x Hdw^T.
+//
+// The factor values are exactly the reference's V_k * sg1 * sg2 (stored/H_up.f90:55-81); only the
+// order of the floating-point sums differs.
+#include <cuda.h>
+
+#include <algorithm>
+#include <map>
+#include <utility>
+#include <vector>
+
+#include "engine.h"
+
+#define F_COL_BITS 20
+#define F_COL_MASK 0xFFFFFu
+#define F_VID_MASK 0x7FFu
+#define F_MAXVALS 256
+#define FCOL_THREADS 1024
+// consumer threads per CTA (+1 producer warp): LR=5 -> 512 threads x 128 registers, LR=4 -> 768 x 85
+__host__ __device__ constexpr int srow_consumers(int LR) { return LR >= 5 ? 480 : 736; }
+#define SROW_R 32
+#define SROW_BC 32                // columns per TMA box (32 rows x 32 columns x 8 B = 8 KB per copy)
+#define SMEM_LIMIT 232448        // 227 KB per CTA on sm_100
+
+struct FastFactor {
+  int W = 0, WT = 0, nvals = 0;
+  int64_t n = 0;
+  uint32_t *d_ell = nullptr;     // [WT][n] slot-major, padding entries point at column n (zero slot)
+  double *d_vtab = nullptr;      // [nvals] magnitudes, vtab[0] = 0
+  uint16_t *d_ell16 = nullptr;   // [WT][n] uniform factors with n < 32768: column | sign << 15 (halves the L2 index traffic)
+  bool uniform = false;          // every stored magnitude identical -> y = v * sum(+-x)
+  double vuni = 0.0;
+};
+
+struct SRowPlan {
+  bool ok = false;
+  int LR = 0, nhigh = 0, ngroups = 0, nchunks = 0, cmax = 0;
+  int32_t *d_jhi = nullptr;      // [2^nhigh] first column of group h, -1 if the group is empty
+  uint16_t *d_grp = nullptr;     // [ngroups] high words of the non-empty groups, ascending
+  int4 *d_chunks = nullptr;      // [nchunks] (group begin, group end, column begin, column end)
+  double *d_dr0 = nullptr, *d_dr1 = nullptr;   // direct mode: dfac_up[row] (+ Uloc when the up impurity is occupied)
+  double vk[EDGPU_MAX_SITES];    // V_k of the dw spin, k = bath bit (1-based site k+1)
+  size_t smem = 0;
+};
+
+struct FastPlan {
+  FastFactor ff[2];
+  bool col_ok[2] = {false, false};
+  size_t col_smem[2] = {0, 0};
+  SRowPlan sr;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1-D bulk copy (TMA engine; SASS: UBLKCP / SYNCS)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tm, int c0, int c1, uint64_t *bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ double flip_sign(double v, uint32_t signbit31) {
+  return __hiloint2double(__double2hiint(v) ^ (int)signbit31, __double2loint(v));
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass 1: whole-column kernel
+// ---------------------------------------------------------------------------------------------
+struct FColArgs {
+  const double *x;
+  double *y;
+  int n;                         // factor dimension (even)
+  int64_t ncols, coloff;
+  const uint32_t *ell;
+  const uint16_t *ell16;
+  const double *vtab;
+  int nvals;
+  double vuni;
+  const double *diag;            // DIAG == 1
+  const double *dfac_c, *dfac_s; // DIAG == 2
+  const int32_t *map_c, *map_s;
+  int norb;
+  double uloc[EDGPU_MAX_ORB];
+  double ust;
+};
+
+// UNI: 0 = general (value table), 1 = uniform magnitude with 4-byte entries, 2 = uniform with 2-byte entries
+template <int WT, int DIAG, int UNI, bool ACC>
+__global__ void __launch_bounds__(FCOL_THREADS, 1) k_fcol(FColArgs a) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int n = a.n, ld = n + 2;
+  double *buf0 = reinterpret_cast<double *>(smraw);
+  double *buf1 = buf0 + ld;
+  double *vtab = buf1 + ld;
+  uint64_t *bar = reinterpret_cast<uint64_t *>(vtab + F_MAXVALS);
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    fence_barrier_init();
+    buf0[n] = 0.0; buf0[n + 1] = 0.0;      // zero slot for the ELL padding entries
+    buf1[n] = 0.0; buf1[n + 1] = 0.0;
+  }
+  if (UNI == 0)
+    for (int i = tid; i < a.nvals; i += FCOL_THREADS) vtab[i] = a.vtab[i];
+  __syncthreads();
+  const uint32_t colbytes = (uint32_t)n * 8u;
+  const int64_t G = gridDim.x;
+  if (tid == 0) {
+    fence_proxy_async();
+    for (int b = 0; b < 2; b++) {
+      const int64_t j = blockIdx.x + b * G;
+      if (j < a.ncols) {
+        mbar_expect_tx(&bar[b], colbytes);
+        const char *src = reinterpret_cast<const char *>(a.x + j * (int64_t)n);
+        char *dst = reinterpret_cast<char *>(b ? buf1 : buf0);
+        for (uint32_t off = 0; off < colbytes; off += 32768u)
+          bulk_g2s(dst + off, src + off, min(32768u, colbytes - off), &bar[b]);
+      }
+    }
+  }
+  for (int64_t it = 0;; it++) {
+    const int64_t j = blockIdx.x + it * G;
+    if (j >= a.ncols) break;
+    const int b = (int)(it & 1);
+    const double *xs = b ? buf1 : buf0;
+    mbar_wait(&bar[b], (uint32_t)((it >> 1) & 1));
+    double dcol = 0.0;
+    uint32_t ms = 0;
+    if (DIAG == 2) { dcol = a.dfac_s[a.coloff + j]; ms = (uint32_t)a.map_s[a.coloff + j]; }
+    double *yc = a.y + j * (int64_t)n;
+    uint32_t en[WT];
+    if (tid < n) {
+#pragma unroll
+      for (int s = 0; s < WT; s++) en[s] = (UNI == 2) ? (uint32_t)__ldg(a.ell16 + (size_t)s * n + tid) : __ldg(a.ell + (size_t)s * n + tid);
+    }
+    for (int r = tid; r < n; r += FCOL_THREADS) {
+      uint32_t e[WT];
+#pragma unroll
+      for (int s = 0; s < WT; s++) e[s] = en[s];
+      double yold = 0.0;
+      if (ACC) yold = __ldcs(yc + r);
+      if (r + FCOL_THREADS < n) {                // software prefetch of the next row's ELL entries
+#pragma unroll
+        for (int s = 0; s < WT; s++)
+          en[s] = (UNI == 2) ? (uint32_t)__ldg(a.ell16 + (size_t)s * n + r + FCOL_THREADS) : __ldg(a.ell + (size_t)s * n + r + FCOL_THREADS);
+      }
+      double acc0 = 0.0;
+      if (DIAG == 1) acc0 = __ldcs(a.diag + j * (int64_t)n + r) * xs[r];
+      if (DIAG == 2) {
+        double d = __ldg(a.dfac_c + r) + dcol;
+        const uint32_t mc = (uint32_t)__ldg(a.map_c + r);
+        for (int o = 0; o < a.norb; o++)
+          if ((mc >> o) & 1u)
+            for (int q = 0; q < a.norb; q++)
+              if ((ms >> q) & 1u) d += (o == q) ? a.uloc[o] : a.ust;
+        acc0 = d * xs[r];
+      }
+      double acc = 0.0;
+#pragma unroll
+      for (int s = 0; s < WT; s++) {
+        if (UNI == 2) { acc += flip_sign(xs[e[s] & 0x7FFFu], (e[s] & 0x8000u) << 16); continue; }
+        const double xv = xs[e[s] & F_COL_MASK];
+        if (UNI) acc += flip_sign(xv, e[s] & 0x80000000u);
+        else acc = fma(flip_sign(vtab[(e[s] >> F_COL_BITS) & F_VID_MASK], e[s] & 0x80000000u), xv, acc);
+      }
+      if (UNI) acc0 = fma(a.vuni, acc, acc0); else acc0 += acc;
+      if (ACC) acc0 += yold;
+      __stcs(yc + r, acc0);
+    }
+    __syncthreads();                           // every thread is done reading this buffer
+    const int64_t j2 = j + 2 * G;
+    if (tid == 0 && j2 < a.ncols) {
+      fence_proxy_async();
+      mbar_expect_tx(&bar[b], colbytes);
+      const char *src = reinterpret_cast<const char *>(a.x + j2 * (int64_t)n);
+      char *dst = reinterpret_cast<char *>(b ? buf1 : buf0);
+      for (uint32_t off = 0; off < colbytes; off += 32768u)
+        bulk_g2s(dst + off, src + off, min(32768u, colbytes - off), &bar[b]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass 2: structured row-tile kernel for the single-band star geometry
+// ---------------------------------------------------------------------------------------------
+namespace lowtab {
+__host__ __device__ constexpr int popc(int v) { int c = 0; for (; v; v &= v - 1) c++; return c; }
+__host__ __device__ constexpr int binom(int n, int k) {
+  if (k < 0 || k > n) return 0;
+  long long r = 1;
+  for (int i = 1; i <= k; i++) r = r * (n - k + i) / i;
+  return (int)r;
+}
+// position of lo among the ascending LR-bit patterns with the same popcount
+__host__ __device__ constexpr int rank(int lo) {
+  int r = 0;
+  const int p = popc(lo);
+  for (int q = 0; q < lo; q++) if (popc(q) == p) r++;
+  return r;
+}
+// i-th ascending LR-bit pattern with N set bits
+__host__ __device__ constexpr int pat(int LR, int N, int i) {
+  int r = 0;
+  for (int q = 0; q < (1 << LR); q++)
+    if (popc(q) == N) { if (r == i) return q; r++; }
+  return -1;
+}
+// among the class-N patterns, the position (0-based) of pattern index i within those whose bit 0 == B
+__host__ __device__ constexpr int half_index(int LR, int N, int i, int B) {
+  int r = 0;
+  for (int q = 0; q < i; q++) if ((pat(LR, N, q) & 1) == B) r++;
+  return r;
+}
+__host__ __device__ constexpr int imax(int a, int b) { return a > b ? a : b; }
+}  // namespace lowtab
+
+template <typename F, int... I>
+__device__ __forceinline__ void static_for_impl(F &&f, std::integer_sequence<int, I...>) {
+  (f(std::integral_constant<int, I>{}), ...);
+}
+template <int N, typename F>
+__device__ __forceinline__ void static_for(F &&f) {
+  static_for_impl(f, std::make_integer_sequence<int, N>{});
+}
+
+struct SRowArgs {
+  const double *x;
+  double *y;
+  int n;                         // DimUp (contiguous, even)
+  int nf;                        // DimDw (all columns local)
+  int ndw, nhigh, ngroups, nchunks, cmax;
+  const int32_t *jhi;
+  const uint16_t *grp;
+  const int4 *chunks;
+  double vk[EDGPU_MAX_SITES];    // vk[k], k = 1 .. Ns-1
+  const double *diag;            // DIAG == 1: spH0d, one value per element
+  const double *dr0, *dr1;       // DIAG == 2: per-row tables, dw impurity empty / occupied
+  const double *dfac_s;          // DIAG == 2: per-column table (padded by 2 doubles)
+  int dbg;                       // timing experiments only (wrong results): 1 = skip far hops, 2 = skip in-chunk hops, 4 = skip y read
+};
+
+struct SRowTile {
+  const double *tl;              // shared-memory tile of this item + lane: column c at tl[(c - cb) * 32]
+  const double *dsc;             // shared: dfac_s[cb ..], DIAG == 2
+  const double *xg;              // x + i0 + (row of this lane, clamped into the matrix)
+  double *yg;                    // y + i0 + row
+  const double *dgg;             // diag + i0 + row (DIAG == 1)
+  const int32_t *jhi;            // shared
+  const double *vhigh;           // shared, vhigh[kk] = V_{LR+kk}
+  size_t n;                      // column stride in elements
+  int cb, csz, nhigh, dbg;
+  bool active;                   // this lane's row exists (stores only)
+  double drow0, drow1;
+};
+
+// One high-bit hop applied to the register block.  BK = the hopped bath bit is occupied in the target
+// group: targets are the columns with the impurity empty, sources lo|1 in class N+1; otherwise targets
+// have the impurity occupied and sources are lo&~1 in class N-1.  NB hops are fused so that all their
+// loads are in flight before the first use (far sources come from L2 with ~1 us latency).
+template <int LR, int N, int CNT, bool BK, bool FAR, int NB>
+__device__ __forceinline__ void srow_hops(const double (&sv)[NB], const double *const (&src)[NB], size_t ss, double (&acc)[CNT]) {
+  constexpr int HB = lowtab::imax(1, BK ? lowtab::binom(LR - 1, N) : lowtab::binom(LR - 1, N - 1));
+  double v[NB][HB];
+  static_for<NB>([&](auto bc) {
+    constexpr int q = decltype(bc)::value;
+    static_for<CNT>([&](auto ic) {
+      constexpr int i = decltype(ic)::value;
+      constexpr int lo = lowtab::pat(LR, N, i);
+      if constexpr (((lo & 1) == 0) == BK) {
+        constexpr int j = lowtab::rank(BK ? (lo | 1) : (lo & ~1));
+        constexpr int hi = lowtab::half_index(LR, N, i, BK ? 0 : 1);
+        v[q][hi] = FAR ? __ldg(src[q] + j * ss) : src[q][j * SROW_R];
+      }
+    });
+  });
+  static_for<NB>([&](auto bc) {
+    constexpr int q = decltype(bc)::value;
+    static_for<CNT>([&](auto ic) {
+      constexpr int i = decltype(ic)::value;
+      constexpr int lo = lowtab::pat(LR, N, i);
+      if constexpr (((lo & 1) == 0) == BK) {
+        constexpr int par = lowtab::popc(lo >> 1) & 1;
+        constexpr int hi = lowtab::half_index(LR, N, i, BK ? 0 : 1);
+        if constexpr (par) acc[i] = fma(-sv[q], v[q][hi], acc[i]);
+        else acc[i] = fma(sv[q], v[q][hi], acc[i]);
+      }
+    });
+  });
+}
+
+// all hops of one kind (BK, FAR) of a group: the set bits of `m`, NB at a time
+template <int LR, int N, int CNT, bool BK, bool FAR, int NB>
+__device__ __forceinline__ void srow_hop_set(const SRowTile &k, uint32_t h, uint32_t par, uint32_t m, double (&acc)[CNT]) {
+  if constexpr ((BK && N == LR) || (!BK && N == 0)) return;        // no such targets in this class
+  while (m) {
+    double sv[NB];
+    const double *src[NB];
+#pragma unroll
+    for (int q = 0; q < NB; q++) {
+      const bool ok = m != 0;                                     // q == 0 is always a real hop
+      const int kk = ok ? __ffs((int)m) - 1 : 0;
+      m &= m - 1;
+      const long long vb = __double_as_longlong(k.vhigh[kk]) ^ ((long long)((par >> kk) & 1u) << 63);
+      sv[q] = ok ? __longlong_as_double(vb) : 0.0;                  // padding slot: re-reads slot 0's source, weight 0
+      const int c2 = k.jhi[h ^ (1u << kk)];
+      const double *p = FAR ? k.xg + (size_t)c2 * k.n : k.tl + (c2 - k.cb) * SROW_R;
+      src[q] = (ok || q == 0) ? p : src[0];
+    }
+    srow_hops<LR, N, CNT, BK, FAR, NB>(sv, src, k.n, acc);
+  }
+}
+
+template <int LR, int N, int DIAG, bool ACC>
+__device__ __forceinline__ void srow_group(const SRowTile &k, const uint32_t h, const int base, const double (&vlow)[LR]) {
+  constexpr int CNT = lowtab::binom(LR, N);
+  double xv[CNT], acc[CNT];
+  const int lb = base - k.cb;
+  const double *tl = k.tl + lb * SROW_R;
+  static_for<CNT>([&](auto ic) { constexpr int i = decltype(ic)::value; xv[i] = tl[i * SROW_R]; });
+  // diagonal (direct mode: factorised tables staged in shared memory); streamed inputs are read at the end
+  static_for<CNT>([&](auto ic) {
+    constexpr int i = decltype(ic)::value;
+    constexpr int lo = lowtab::pat(LR, N, i);
+    if (DIAG == 2) acc[i] = (((lo & 1) ? k.drow1 : k.drow0) + k.dsc[lb + i]) * xv[i];
+    else acc[i] = 0.0;
+  });
+  // hops among the low bits: register to register
+  static_for<CNT>([&](auto ic) {
+    constexpr int i = decltype(ic)::value;
+    constexpr int lo = lowtab::pat(LR, N, i);
+    static_for<LR - 1>([&](auto kc) {
+      constexpr int kb = decltype(kc)::value + 1;
+      if constexpr (((lo >> kb) & 1) != (lo & 1)) {
+        constexpr int lo2 = lo ^ (1 | (1 << kb));
+        constexpr int j = lowtab::rank(lo2);
+        constexpr int par = lowtab::popc(lo & ((1 << kb) - 2)) & 1;
+        if constexpr (par) acc[i] = fma(-vlow[kb], xv[j], acc[i]);
+        else acc[i] = fma(vlow[kb], xv[j], acc[i]);
+      }
+    });
+  });
+  // hops on the high bits: the whole group maps onto ONE other group (Lin table jhi).  Sources inside
+  // the chunk come from the shared-memory tile, the others straight from L2.
+  uint32_t par = h ^ (h << 1);                                     // bit kk of par = parity of h below bit kk
+  par ^= par << 2; par ^= par << 4; par ^= par << 8;
+  par = (par << 1);
+  uint32_t inmask = 0;                                             // high bits whose partner group is in the tile
+#pragma unroll 1
+  for (int kk = 0; kk < k.nhigh; kk++)
+    if ((unsigned)(k.jhi[h ^ (1u << kk)] - k.cb) < (unsigned)k.csz) inmask |= 1u << kk;
+  const uint32_t all = (1u << k.nhigh) - 1u;
+  const uint32_t farmask = all & ~inmask;
+  if (!(k.dbg & 1)) {                                              // far sources first: longest latency
+    srow_hop_set<LR, N, CNT, true, true, 3>(k, h, par, farmask & h, acc);
+    srow_hop_set<LR, N, CNT, false, true, 3>(k, h, par, farmask & ~h, acc);
+  }
+  if (!(k.dbg & 2)) {
+    srow_hop_set<LR, N, CNT, true, false, 2>(k, h, par, inmask & h, acc);
+    srow_hop_set<LR, N, CNT, false, false, 2>(k, h, par, inmask & ~h, acc);
+  }
+  double *yp = k.yg + (size_t)base * k.n;
+  if (DIAG == 1) {
+    const double *dp = k.dgg + (size_t)base * k.n;
+    double dg[CNT];
+    static_for<CNT>([&](auto ic) { constexpr int i = decltype(ic)::value; dg[i] = __ldcs(dp + i * k.n); });
+    static_for<CNT>([&](auto ic) { constexpr int i = decltype(ic)::value; acc[i] = fma(dg[i], xv[i], acc[i]); });
+  }
+  if (ACC && !(k.dbg & 4)) {
+    double yold[CNT];
+    static_for<CNT>([&](auto ic) { constexpr int i = decltype(ic)::value; yold[i] = __ldcs(yp + i * k.n); });
+    static_for<CNT>([&](auto ic) { constexpr int i = decltype(ic)::value; acc[i] += yold[i]; });
+  }
+  if (k.active) static_for<CNT>([&](auto ic) { constexpr int i = decltype(ic)::value; __stcs(yp + i * k.n, acc[i]); });
+}
+
+template <int LR, int DIAG, bool ACC, int... NS>
+__device__ __forceinline__ void srow_dispatch(const SRowTile &k, uint32_t h, int base, int nlow, const double (&vlow)[LR],
+                                              std::integer_sequence<int, NS...>) {
+  ((nlow == NS ? (srow_group<LR, NS, DIAG, ACC>(k, h, base, vlow), 0) : 0), ...);
+}
+
+// 16 consumer warps + 1 producer warp.  full[b]: the TMA copies of buffer b have landed; empty[b]: every
+// consumer warp is done with buffer b.  Consumer warps take the low groups of the tile from a shared
+// counter and run ahead into the next buffer without a CTA-wide barrier.
+template <int LR, int DIAG, bool ACC>
+__global__ void __launch_bounds__(srow_consumers(LR) + 32, 1) k_srow(const __grid_constant__ CUtensorMap tmx, SRowArgs a) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int cpad = ((a.cmax + SROW_BC - 1) / SROW_BC) * SROW_BC;
+  const int tsz = cpad * SROW_R;                                  // doubles per tile buffer
+  double *tile0 = reinterpret_cast<double *>(smraw);
+  double *dsc0 = tile0 + 2 * tsz;                                 // [2][cpad + 2]
+  double *drw0 = dsc0 + 2 * (cpad + 2);                           // [2][2][32]
+  double *vhigh = drw0 + 4 * SROW_R;                              // [32]
+  uint64_t *bar = reinterpret_cast<uint64_t *>(vhigh + 32);       // full[2], empty[2]
+  int *gctr = reinterpret_cast<int *>(bar + 4);                   // [2] (+2 pad)
+  int32_t *jhi = reinterpret_cast<int32_t *>(gctr + 4);           // [2^nhigh]
+  uint16_t *grp = reinterpret_cast<uint16_t *>(jhi + (1 << a.nhigh));   // [ngroups]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    mbar_init(&bar[2], srow_consumers(LR) / 32);
+    mbar_init(&bar[3], srow_consumers(LR) / 32);
+    fence_barrier_init();
+    gctr[0] = 0; gctr[1] = 0;
+  }
+  for (int i = tid; i < (1 << a.nhigh); i += blockDim.x) jhi[i] = a.jhi[i];
+  for (int i = tid; i < a.ngroups; i += blockDim.x) grp[i] = a.grp[i];
+  if (tid < 32) vhigh[tid] = (tid < a.nhigh) ? a.vk[LR + tid] : 0.0;
+  __syncthreads();
+
+  const int64_t nrb = (a.n + SROW_R - 1) / SROW_R;
+  const int64_t nitems = nrb * a.nchunks;
+  const int64_t G = gridDim.x;
+  if (warp == srow_consumers(LR) / 32) {
+    // ---- producer warp ----
+    for (int64_t it = 0;; it++) {
+      const int64_t t = blockIdx.x + it * G;
+      if (t >= nitems) break;
+      const int b = (int)(it & 1);
+      if (it >= 2) mbar_wait(&bar[2 + b], (uint32_t)(((it >> 1) - 1) & 1));
+      const int64_t rb = t / a.nchunks;
+      const int4 ch = __ldg(a.chunks + (int)(t % a.nchunks));
+      const int nc = ch.w - ch.z;
+      const int nops = (nc + SROW_BC - 1) / SROW_BC;
+      const int64_t i0 = rb * SROW_R;
+      const int nr = (int)min((int64_t)SROW_R, (int64_t)a.n - i0);
+      const int lead = ch.z & 1;
+      const uint32_t dsc_bytes = (uint32_t)((lead + nc + 1) & ~1) * 8u;
+      if (lane == 0) {
+        gctr[b] = 0;
+        fence_proxy_async();
+        uint32_t bytes = (uint32_t)nops * (uint32_t)(SROW_BC * SROW_R * 8);
+        if (DIAG == 2) bytes += dsc_bytes + 2u * (uint32_t)nr * 8u;
+        mbar_expect_tx(&bar[b], bytes);
+      }
+      __syncwarp();
+      if (lane < nops)
+        tma_load_2d(tile0 + (size_t)b * tsz + (size_t)lane * SROW_BC * SROW_R, &tmx, (int)i0, ch.z + lane * SROW_BC, &bar[b]);
+      if (DIAG == 2) {
+        if (lane == 29) bulk_g2s(dsc0 + (size_t)b * (cpad + 2), a.dfac_s + (ch.z - lead), dsc_bytes, &bar[b]);
+        if (lane == 30) bulk_g2s(drw0 + (size_t)b * 2 * SROW_R, a.dr0 + i0, (uint32_t)nr * 8u, &bar[b]);
+        if (lane == 31) bulk_g2s(drw0 + (size_t)b * 2 * SROW_R + SROW_R, a.dr1 + i0, (uint32_t)nr * 8u, &bar[b]);
+      }
+    }
+    return;
+  }
+  // ---- consumer warps ----
+  double vlow[LR];
+#pragma unroll
+  for (int q = 0; q < LR; q++) vlow[q] = a.vk[q];                 // vlow[0] unused
+  for (int64_t it = 0;; it++) {
+    const int64_t t = blockIdx.x + it * G;
+    if (t >= nitems) break;
+    const int b = (int)(it & 1);
+    const int64_t rb = t / a.nchunks;
+    const int4 ch = __ldg(a.chunks + (int)(t % a.nchunks));
+    SRowTile k;
+    const int64_t i0 = rb * SROW_R;
+    const int64_t row = min(i0 + lane, (int64_t)a.n - 1);            // clamp: loads of a ragged last block stay in range
+    k.tl = tile0 + (size_t)b * tsz + lane;
+    k.dsc = dsc0 + (size_t)b * (cpad + 2) + (ch.z & 1);
+    k.xg = a.x + row; k.yg = a.y + row; k.dgg = a.diag + row;
+    k.jhi = jhi; k.vhigh = vhigh;
+    k.n = (size_t)a.n; k.cb = ch.z; k.csz = ch.w - ch.z; k.nhigh = a.nhigh; k.dbg = a.dbg;
+    k.active = (i0 + lane) < a.n;
+    mbar_wait(&bar[b], (uint32_t)((it >> 1) & 1));
+    k.drow0 = 0.0; k.drow1 = 0.0;
+    if (DIAG == 2) {
+      k.drow0 = drw0[b * 2 * SROW_R + lane];
+      k.drow1 = drw0[b * 2 * SROW_R + SROW_R + lane];
+    }
+    for (;;) {
+      int g = 0;
+      if (lane == 0) g = atomicAdd(&gctr[b], 1);
+      g = __shfl_sync(0xffffffffu, g, 0) + ch.x;
+      if (g >= ch.y) break;
+      const uint32_t h = grp[g];
+      const int base = jhi[h];
+      const int nlow = a.ndw - __popc(h);
+      srow_dispatch<LR, DIAG, ACC>(k, h, base, nlow, vlow, std::make_integer_sequence<int, LR + 1>{});
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bar[2 + b]);                       // this warp is done with buffer b
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------------------------
+static int pack_fast(edgpu_ctx *c, const Factor &f, FastFactor &ff) {
+  std::vector<int32_t> rp((size_t)f.n + 1), cols((size_t)std::max<int64_t>(f.nnz, 1));
+  std::vector<double> vals((size_t)std::max<int64_t>(f.nnz, 1));
+  CK(cudaMemcpy(rp.data(), f.d_rowptr, rp.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  if (f.nnz) {
+    CK(cudaMemcpy(cols.data(), f.d_cols, (size_t)f.nnz * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(vals.data(), f.d_vals, (size_t)f.nnz * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  ff.n = f.n;
+  ff.W = std::max(f.maxrow, 1);
+  ff.WT = ff.W <= 8 ? 8 : (ff.W <= 12 ? 12 : 16);
+  if (ff.W > 16) return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "factor row too long for the fast column kernel");
+  std::map<double, int> ids;
+  std::vector<double> vtab(1, 0.0);
+  std::vector<uint32_t> ell((size_t)ff.WT * f.n, (uint32_t)f.n);       // padding: zero slot, value id 0
+  for (int64_t i = 0; i < f.n; i++) {
+    int k = 0;
+    for (int32_t p = rp[i]; p < rp[i + 1]; p++, k++) {
+      const double av = vals[p] < 0 ? -vals[p] : vals[p];
+      auto it = ids.find(av);
+      int id;
+      if (it == ids.end()) { id = (int)vtab.size(); ids[av] = id; vtab.push_back(av); }
+      else id = it->second;
+      if (id >= F_MAXVALS) return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "too many distinct matrix elements for the fast column kernel");
+      ell[(size_t)k * f.n + i] = (uint32_t)cols[p] | ((uint32_t)id << F_COL_BITS) | (vals[p] < 0 ? 0x80000000u : 0u);
+    }
+  }
+  ff.nvals = (int)vtab.size();
+  ff.uniform = (ff.nvals == 2);
+  ff.vuni = ff.uniform ? vtab[1] : 0.0;
+  CK(cudaMalloc(&ff.d_ell, ell.size() * sizeof(uint32_t)));
+  CK(cudaMalloc(&ff.d_vtab, vtab.size() * sizeof(double)));
+  CK(cudaMemcpy(ff.d_ell, ell.data(), ell.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ff.d_vtab, vtab.data(), vtab.size() * sizeof(double), cudaMemcpyHostToDevice));
+  if (ff.uniform && f.n < 32768) {
+    std::vector<uint16_t> e16(ell.size());
+    for (size_t i = 0; i < ell.size(); i++) e16[i] = (uint16_t)((ell[i] & 0x7FFFu) | ((ell[i] >> 31) << 15));
+    CK(cudaMalloc(&ff.d_ell16, e16.size() * sizeof(uint16_t)));
+    CK(cudaMemcpy(ff.d_ell16, e16.data(), e16.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  }
+  return EDGPU_OK;
+}
+
+static size_t fcol_smem(int64_t n) { return (size_t)2 * (n + 2) * 8 + F_MAXVALS * 8 + 16; }
+static size_t srow_smem(int cmax, int nhigh, int ngroups) {
+  const size_t cpad = (size_t)((cmax + SROW_BC - 1) / SROW_BC) * SROW_BC;
+  size_t b = (size_t)2 * cpad * SROW_R * 8 + (size_t)2 * (cpad + 2) * 8 + 4 * SROW_R * 8 + 32 * 8 + 32 + 16 + ((size_t)4 << nhigh) + (size_t)2 * ngroups;
+  return (b + 15) & ~(size_t)15;
+}
+
+static int build_srow(edgpu_ctx *c, SRowPlan &sr, int LR) {
+  // single band, star geometry, no inter-orbital terms: every dw hop is bit 0 <-> bit k
+  sr.ok = false;
+  if (c->dp.norb != 1 || c->dp.jhflag) return EDGPU_OK;
+  if (c->ns <= LR || c->ns - LR > 15 || (c->dimup & 1)) return EDGPU_OK;
+  if (c->opt_srow_lr == 4 || c->opt_srow_lr == 5) LR = (int)c->opt_srow_lr;
+  sr.LR = LR;
+  sr.nhigh = c->ns - LR;
+  const int nh = 1 << sr.nhigh;
+  std::vector<int32_t> jhi((size_t)nh, -1);
+  std::vector<uint16_t> grp;
+  std::vector<int> gsize;
+  int64_t col = 0;
+  for (int h = 0; h < nh; h++) {
+    const int nlow = c->ndw - __builtin_popcount((unsigned)h);
+    if (nlow < 0 || nlow > LR) continue;
+    jhi[(size_t)h] = (int32_t)col;
+    grp.push_back((uint16_t)h);
+    const int sz = lowtab::binom(LR, nlow);
+    gsize.push_back(sz);
+    col += sz;
+  }
+  if (col != c->dimdw) return edgpu_set_err(EDGPU_ERR_INVALID, "internal: Lin table does not cover the dw basis");
+  sr.ngroups = (int)grp.size();
+  // chunk size from the shared-memory budget (or the option), chunks = runs of whole groups
+  int cmax = (int)((SMEM_LIMIT - 4096 - ((size_t)4 << sr.nhigh) - 2 * (size_t)sr.ngroups) / (2 * (SROW_R + 1) * 8));
+  cmax = cmax / SROW_BC * SROW_BC;
+  if (cmax > 32 * SROW_BC) cmax = 32 * SROW_BC;             // one tensor copy per lane of the producer warp
+  // measured on B200 (C3): tiles of ~288 columns beat the largest that fits; the L1 that is left over
+  // (228 KB - shared memory) serves the out-of-tile sources
+  if (c->opt_srow_cmax <= 0 && cmax > 288) cmax = 288;
+  if (c->opt_srow_cmax > 0 && c->opt_srow_cmax < cmax) cmax = (int)c->opt_srow_cmax;
+  if (cmax < lowtab::binom(LR, LR / 2)) return EDGPU_OK;
+  // balance: all chunks about the same size
+  const int nch0 = (int)((c->dimdw + cmax - 1) / cmax);
+  const int target = (int)((c->dimdw + nch0 - 1) / nch0);
+  std::vector<int4> chunks;
+  int gb = 0, cb = 0, cur = 0;
+  for (int g = 0; g < sr.ngroups; g++) {
+    if (cur > 0 && (cur + gsize[g] > cmax || cur >= target)) {
+      chunks.push_back(make_int4(gb, g, cb, cb + cur));
+      gb = g; cb += cur; cur = 0;
+    }
+    cur += gsize[g];
+  }
+  if (cur > 0) chunks.push_back(make_int4(gb, sr.ngroups, cb, cb + cur));
+  sr.nchunks = (int)chunks.size();
+  sr.cmax = 0;
+  for (auto &ch : chunks) sr.cmax = std::max(sr.cmax, ch.w - ch.z);
+  sr.smem = srow_smem(sr.cmax, sr.nhigh, sr.ngroups);
+  if (sr.smem > SMEM_LIMIT) return EDGPU_OK;
+  for (int k = 0; k < EDGPU_MAX_SITES; k++) sr.vk[k] = 0.0;
+  for (int k = 1; k < c->ns; k++) sr.vk[k] = c->dp.bv_dw[k - 1];
+  CK(cudaMalloc(&sr.d_jhi, jhi.size() * sizeof(int32_t)));
+  CK(cudaMalloc(&sr.d_grp, grp.size() * sizeof(uint16_t)));
+  CK(cudaMalloc(&sr.d_chunks, chunks.size() * sizeof(int4)));
+  CK(cudaMemcpy(sr.d_jhi, jhi.data(), jhi.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(sr.d_grp, grp.data(), grp.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(sr.d_chunks, chunks.data(), chunks.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  if (c->up.d_dfac) {                                              // direct mode: per-row diagonal tables
+    std::vector<double> d0((size_t)c->dimup + 32, 0.0), d1((size_t)c->dimup + 32, 0.0);
+    std::vector<int32_t> mu((size_t)c->dimup);
+    CK(cudaMemcpy(d0.data(), c->up.d_dfac, (size_t)c->dimup * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(mu.data(), c->up.d_map, (size_t)c->dimup * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < c->dimup; i++) d1[(size_t)i] = d0[(size_t)i] + ((mu[(size_t)i] & 1) ? c->dp.uloc[0] : 0.0);
+    CK(cudaMalloc(&sr.d_dr0, d0.size() * sizeof(double)));
+    CK(cudaMalloc(&sr.d_dr1, d1.size() * sizeof(double)));
+    CK(cudaMemcpy(sr.d_dr0, d0.data(), d0.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(sr.d_dr1, d1.data(), d1.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  sr.ok = true;
+  return EDGPU_OK;
+}
+
+int fast_plan_free(edgpu_ctx *c) {
+  if (!c->fplan) return EDGPU_OK;
+  for (int k = 0; k < 2; k++) { cudaFree(c->fplan->ff[k].d_ell); cudaFree(c->fplan->ff[k].d_ell16); cudaFree(c->fplan->ff[k].d_vtab); }
+  cudaFree(c->fplan->sr.d_jhi); cudaFree(c->fplan->sr.d_grp); cudaFree(c->fplan->sr.d_chunks);
+  cudaFree(c->fplan->sr.d_dr0); cudaFree(c->fplan->sr.d_dr1);
+  delete c->fplan;
+  c->fplan = nullptr;
+  return EDGPU_OK;
+}
+
+template <int WT, int DIAG>
+static cudaError_t set_fcol_attr() {
+  cudaError_t e = cudaSuccess;
+#define SETF(U, A) if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fcol<WT, DIAG, U, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT)
+  SETF(0, false); SETF(1, false); SETF(2, false); SETF(0, true); SETF(1, true); SETF(2, true);
+#undef SETF
+  return e;
+}
+template <int LR, int DIAG>
+static cudaError_t set_srow_attr() {
+  cudaError_t e = cudaFuncSetAttribute(k_srow<LR, DIAG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_srow<LR, DIAG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+}
+
+int fast_plan_build(edgpu_ctx *c) {
+  if (c->fplan) return EDGPU_OK;
+  static bool attr_done = false;
+  if (!attr_done) {
+    CK((set_fcol_attr<8, 0>())); CK((set_fcol_attr<8, 1>())); CK((set_fcol_attr<8, 2>()));
+    CK((set_fcol_attr<12, 0>())); CK((set_fcol_attr<12, 1>())); CK((set_fcol_attr<12, 2>()));
+    CK((set_fcol_attr<16, 0>())); CK((set_fcol_attr<16, 1>())); CK((set_fcol_attr<16, 2>()));
+    CK((set_srow_attr<4, 0>())); CK((set_srow_attr<4, 1>())); CK((set_srow_attr<4, 2>()));
+    CK((set_srow_attr<5, 0>())); CK((set_srow_attr<5, 1>())); CK((set_srow_attr<5, 2>()));
+    attr_done = true;
+  }
+  FastPlan *p = new FastPlan();
+  c->fplan = p;
+  for (int k = 0; k < 2; k++) {
+    const Factor &f = k ? c->dw : c->up;
+    p->col_smem[k] = fcol_smem(f.n);
+    p->col_ok[k] = (f.n % 2 == 0) && f.n < (1 << F_COL_BITS) && p->col_smem[k] <= SMEM_LIMIT && f.maxrow <= 16;
+    if (p->col_ok[k]) {
+      int rc = pack_fast(c, f, p->ff[k]);
+      if (rc == EDGPU_ERR_UNSUPPORTED) p->col_ok[k] = false;
+      else if (rc) { fast_plan_free(c); return rc; }
+    }
+  }
+  int rc = build_srow(c, p->sr, 5);
+  if (rc) { fast_plan_free(c); return rc; }
+  return EDGPU_OK;
+}
+
+bool fast_supported_local(edgpu_ctx *c) {
+  if (!c->hstatus || c->dp.jhflag) return false;
+  if (fast_plan_build(c)) return false;
+  return c->fplan->col_ok[0] && c->fplan->sr.ok;
+}
+bool fast_supported_col(edgpu_ctx *c, int k) {
+  if (!c->hstatus || c->dp.jhflag) return false;
+  if (fast_plan_build(c)) return false;
+  return c->fplan->col_ok[k];
+}
+
+template <int WT, int DIAG>
+static void launch_fcol(int uni, bool acc, int grid, size_t smem, cudaStream_t st, const FColArgs &a) {
+  if (acc) {
+    if (uni == 2) k_fcol<WT, DIAG, 2, true><<<grid, FCOL_THREADS, smem, st>>>(a);
+    else if (uni == 1) k_fcol<WT, DIAG, 1, true><<<grid, FCOL_THREADS, smem, st>>>(a);
+    else k_fcol<WT, DIAG, 0, true><<<grid, FCOL_THREADS, smem, st>>>(a);
+  } else {
+    if (uni == 2) k_fcol<WT, DIAG, 2, false><<<grid, FCOL_THREADS, smem, st>>>(a);
+    else if (uni == 1) k_fcol<WT, DIAG, 1, false><<<grid, FCOL_THREADS, smem, st>>>(a);
+    else k_fcol<WT, DIAG, 0, false><<<grid, FCOL_THREADS, smem, st>>>(a);
+  }
+}
+template <int DIAG>
+static void launch_fcol_w(int WT, int uni, bool acc, int grid, size_t smem, cudaStream_t st, const FColArgs &a) {
+  if (WT == 8) launch_fcol<8, DIAG>(uni, acc, grid, smem, st, a);
+  else if (WT == 12) launch_fcol<12, DIAG>(uni, acc, grid, smem, st, a);
+  else launch_fcol<16, DIAG>(uni, acc, grid, smem, st, a);
+}
+
+// y (+)= [Hd o x +] F_k x on a matrix whose contiguous dimension is factor k's index
+int fast_apply_col(edgpu_ctx *c, int k, bool with_diag, bool acc, const double *d_x, double *d_y, int64_t ncols, int64_t coloff) {
+  TRY(fast_plan_build(c));
+  FastPlan *p = c->fplan;
+  if (!p->col_ok[k]) return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "fast column kernel does not cover this factor");
+  if ((reinterpret_cast<uintptr_t>(d_x) & 15) != 0) return edgpu_set_err(EDGPU_ERR_INVALID, "fast H*v needs 16-byte aligned vectors");
+  const FastFactor &ff = p->ff[k];
+  FColArgs a{};
+  a.x = d_x; a.y = d_y; a.n = (int)ff.n; a.ncols = ncols; a.coloff = coloff;
+  a.ell = ff.d_ell; a.ell16 = ff.d_ell16; a.vtab = ff.d_vtab; a.nvals = ff.nvals; a.vuni = ff.vuni;
+  a.diag = c->d_diag;
+  const Factor &fc = k ? c->dw : c->up, &fs = k ? c->up : c->dw;
+  a.dfac_c = fc.d_dfac; a.dfac_s = fs.d_dfac; a.map_c = fc.d_map; a.map_s = fs.d_map;
+  a.norb = c->dp.norb; a.ust = c->dp.ust;
+  for (int i = 0; i < EDGPU_MAX_ORB; i++) a.uloc[i] = c->dp.uloc[i];
+  const int grid = (int)std::min<int64_t>(ncols, c->sm_count);
+  if (grid < 1) return EDGPU_OK;
+  const int diag = !with_diag ? 0 : (c->d_diag ? 1 : 2);
+  // no_uniform: 0 = best available, 1 = force the value-table kernel, 2 = uniform kernel with 4-byte entries
+  int uni = 0;
+  if (ff.uniform && c->opt_no_uniform != 1) uni = (ff.d_ell16 && c->opt_no_uniform != 2) ? 2 : 1;
+  if (diag == 0) launch_fcol_w<0>(ff.WT, uni, acc, grid, p->col_smem[k], c->stream, a);
+  else if (diag == 1) launch_fcol_w<1>(ff.WT, uni, acc, grid, p->col_smem[k], c->stream, a);
+  else launch_fcol_w<2>(ff.WT, uni, acc, grid, p->col_smem[k], c->stream, a);
+  CKL(c);
+  return EDGPU_OK;
+}
+
+template <int LR>
+static void launch_srow(int diag, bool acc, int grid, size_t smem, cudaStream_t st, const CUtensorMap &tmx, const SRowArgs &a) {
+  if (acc) {
+    if (diag == 0) k_srow<LR, 0, true><<<grid, srow_consumers(LR) + 32, smem, st>>>(tmx, a);
+    else if (diag == 1) k_srow<LR, 1, true><<<grid, srow_consumers(LR) + 32, smem, st>>>(tmx, a);
+    else k_srow<LR, 2, true><<<grid, srow_consumers(LR) + 32, smem, st>>>(tmx, a);
+  } else {
+    if (diag == 0) k_srow<LR, 0, false><<<grid, srow_consumers(LR) + 32, smem, st>>>(tmx, a);
+    else if (diag == 1) k_srow<LR, 1, false><<<grid, srow_consumers(LR) + 32, smem, st>>>(tmx, a);
+    else k_srow<LR, 2, false><<<grid, srow_consumers(LR) + 32, smem, st>>>(tmx, a);
+  }
+}
+
+// 2-D tensor map of a column-major double matrix (n0 contiguous), box = b0 x b1 elements
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int make_tmap_2d(CUtensorMap *tm, const double *base, uint64_t n0, uint64_t n1, uint32_t b0, uint32_t b1) {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (!p || q != cudaDriverEntryPointSuccess) return edgpu_set_err(EDGPU_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+    fn = (PFN_encodeTiled)p;
+  }
+  const cuuint64_t dims[2] = {n0, n1};
+  const cuuint64_t strides[1] = {n0 * 8};
+  const cuuint32_t box[2] = {b0, b1};
+  const cuuint32_t es[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(base), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return edgpu_set_err(EDGPU_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return EDGPU_OK;
+}
+
+// y (+)= [Hd o x +] x Hdw^T on the full local matrix (every i_dw column local)
+int fast_apply_row(edgpu_ctx *c, bool with_diag, bool acc, const double *d_x, double *d_y) {
+  TRY(fast_plan_build(c));
+  const SRowPlan &sr = c->fplan->sr;
+  if (!sr.ok) return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "structured row kernel does not cover this model");
+  if ((reinterpret_cast<uintptr_t>(d_x) & 15) != 0) return edgpu_set_err(EDGPU_ERR_INVALID, "fast H*v needs 16-byte aligned vectors");
+  SRowArgs a{};
+  a.x = d_x; a.y = d_y; a.n = (int)c->dimup; a.nf = (int)c->dimdw;
+  a.ndw = c->ndw; a.nhigh = sr.nhigh; a.ngroups = sr.ngroups; a.nchunks = sr.nchunks; a.cmax = sr.cmax;
+  a.jhi = sr.d_jhi; a.grp = sr.d_grp; a.chunks = sr.d_chunks;
+  for (int k = 0; k < EDGPU_MAX_SITES; k++) a.vk[k] = sr.vk[k];
+  a.dbg = (int)c->opt_dbg;
+  a.diag = c->d_diag; a.dr0 = sr.d_dr0; a.dr1 = sr.d_dr1; a.dfac_s = c->dw.d_dfac;
+  const int64_t nitems = ((c->dimup + SROW_R - 1) / SROW_R) * sr.nchunks;
+  const int grid = (int)std::min<int64_t>(nitems, c->sm_count);
+  const int diag = !with_diag ? 0 : (c->d_diag ? 1 : 2);
+  CUtensorMap tmx;
+  TRY(make_tmap_2d(&tmx, d_x, (uint64_t)c->dimup, (uint64_t)c->dimdw, SROW_R, SROW_BC));
+  if (sr.LR == 4) launch_srow<4>(diag, acc, grid, sr.smem, c->stream, tmx, a);
+  else launch_srow<5>(diag, acc, grid, sr.smem, c->stream, tmx, a);
+  CKL(c);
+  return EDGPU_OK;
+}
+
+int fast_apply_local(edgpu_ctx *c, const double *d_x, double *d_y) {
+  if (c->opt_dbg & 8) {                                            // experiment: column pass first
+    TRY(fast_apply_col(c, 0, false, false, d_x, d_y, c->qdw, c->coloff));
+    TRY(fast_apply_row(c, true, true, d_x, d_y));
+    return EDGPU_OK;
+  }
+  // row tiles first (y = Hd o x + x Hdw^T, write only), then whole columns (y += Hup x, contiguous RMW)
+  TRY(fast_apply_row(c, true, false, d_x, d_y));
+  TRY(fast_apply_col(c, 0, false, true, d_x, d_y, c->qdw, c->coloff));
+  return EDGPU_OK;
+}

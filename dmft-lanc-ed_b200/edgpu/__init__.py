@@ -22,7 +22,7 @@ c_ip = C.POINTER(C.c_int)
 c_i32p = C.POINTER(C.c_int32)
 c_i64p = C.POINTER(C.c_int64)
 
-ALGO_AUTO, ALGO_GATHER, ALGO_TILED = 0, 1, 2
+ALGO_AUTO, ALGO_GATHER, ALGO_TILED, ALGO_FAST = 0, 1, 2, 3
 
 # every symbol include/edgpu.h declares (checked by tests/test_abi.py against the header)
 ABI_SYMBOLS = [

@@ -51,9 +51,16 @@ def config(name):
         e, v = init_dmft_bath(2, 4)     # e = -2,-0.1,0.1,2 ; V = 0.5
         return dict(norb=2, nbath=4, nspin=1, uloc=(2.0, 2.0), ust=1.0, jh=0.5, jx=0.5, jp=0.5, xmu=0.0,
                     hfmode=True, bath_e=e, bath_v=v, nup=5, ndw=5)
-    if name.startswith("NS"):           # e.g. NS10 -> single band Ns=10 half filling
-        ns = int(name[2:])
-        return _single_band(ns - 1, ns // 2)
+    if name.startswith("NS"):           # e.g. NS10 -> single band Ns=10 half filling; NS10V: level-dependent V_k
+        vary = name.endswith("V")
+        ns = int(name[2:-1] if vary else name[2:])
+        cfg = _single_band(ns - 1, ns // 2)
+        if vary:                        # a fitted bath: distinct hybridisations and asymmetric levels
+            k = np.arange(ns - 1, dtype=np.float64)
+            cfg["bath_v"] = (0.25 + 0.07 * k - 0.004 * k * k).reshape(1, 1, ns - 1)
+            cfg["bath_e"] = cfg["bath_e"] + 0.013 * (k - 1.5).reshape(1, 1, ns - 1)
+            cfg["xmu"] = 0.1
+        return cfg
     raise KeyError(name)
 
 

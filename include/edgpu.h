@@ -39,7 +39,8 @@ enum {
 enum {
   EDGPU_ALGO_AUTO = 0,
   EDGPU_ALGO_GATHER = 1,      /* one pass, global-memory gathers (reference kernel of the engine) */
-  EDGPU_ALGO_TILED = 2        /* two passes, shared-memory staged column / row-tile kernels */
+  EDGPU_ALGO_TILED = 2,       /* two passes, shared-memory staged column / row-tile kernels (generic factors) */
+  EDGPU_ALGO_FAST = 3         /* two passes, TMA-staged whole-column kernel + structured row kernel */
 };
 
 /* The module-global inputs build_Hv_sector reads (ED_INPUT_VARS.f90:129-208,

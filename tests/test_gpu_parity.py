@@ -344,6 +344,85 @@ def test_tiled_hxv_matches_oracle(name, sec, opts, sparse):
         s.close()
 
 
+FAST_CASES = [("C1", (4, 4), {}), ("C1", (5, 3), {"srow_cmax": 20}), ("C1", (3, 6), {"srow_lr": 4, "srow_cmax": 12}),
+              ("NS10", (5, 5), {"srow_lr": 4, "srow_cmax": 40}), ("NS10", (5, 5), {"srow_lr": 5, "srow_cmax": 30}),
+              ("NS12", (6, 6), {"srow_cmax": 100}), ("NS12", (7, 4), {}), ("NS12", (6, 6), {"no_uniform": 1, "srow_lr": 4}), ("NS12", (6, 6), {"no_uniform": 2}),
+              ("NS6", (3, 3), {}), ("NS6", (3, 3), {"srow_lr": 4, "srow_cmax": 6}), ("NS10V", (5, 5), {"srow_cmax": 50}),
+              ("NS12V", (6, 5), {"srow_lr": 4, "srow_cmax": 64}), ("NS10V", (7, 2), {}), ("NS10", (9, 1), {}),
+              ("NS12", (6, 0), {}), ("NS12", (6, 12), {})]
+
+
+@pytest.mark.parametrize("name,sec,opts", FAST_CASES)
+@pytest.mark.parametrize("sparse", [True, False])
+def test_fast_hxv_matches_oracle(name, sec, opts, sparse):
+    """TMA-staged whole-column kernel + structured row kernel (hxv_fast.cu), including chunkings that
+    force out-of-chunk hops, both low-group widths, level-dependent V_k and edge sectors."""
+    cfg, o = make_oracle(name)
+    s = _solver(cfg, sparse, edgpu.ALGO_FAST)
+    for k, v in opts.items():
+        s.set_option(k, v)
+    try:
+        with o.sector(*sec) as os_:
+            v = configs.bench_vector(os_.dim)
+            v /= np.linalg.norm(v)
+            ref = os_.spmatvec(v)
+            s.build_Hv_sector(s.get_sector(*sec))
+            hv = s.spHtimesV(v)
+            assert np.abs(hv - ref).max() < 1e-13 * max(np.abs(ref).max(), 1e-300)
+            if os_.dim > 1:
+                e_ref, _, a_ref, b_ref = os_.lanc_eigh(v0=np.ones(os_.dim) / np.sqrt(os_.dim))
+                e0, _, a, b = s.sp_lanc_eigh(np.ones(os_.dim) / np.sqrt(os_.dim))
+                assert abs(e0 - e_ref) < 1e-12 * abs(e_ref)
+            s.delete_Hv_sector()
+    finally:
+        s.close()
+
+
+def test_fast_unsupported_is_loud():
+    """Odd DimUp (TMA bulk copies need 16-byte aligned columns): the explicit fast algorithm refuses,
+    AUTO falls back to the generic kernels."""
+    cfg, o = make_oracle("NS7")
+    s = _solver(cfg, True, edgpu.ALGO_FAST)
+    try:
+        s.build_Hv_sector(s.get_sector(3, 3))          # DimUp = C(7,3) = 35
+        v = np.ones(35 * 35)
+        with pytest.raises(Exception):
+            s.spHtimesV(v)
+        s.set_option("hxv_algo", edgpu.ALGO_AUTO)
+        with o.sector(3, 3) as os_:
+            assert np.abs(s.spHtimesV(v) - os_.spmatvec(v)).max() < 1e-12
+        s.delete_Hv_sector()
+    finally:
+        s.close()
+
+
+@pytest.mark.parametrize("name", ["C2", "C3"])
+def test_fast_equals_gather_full_size(name):
+    cfg = configs.config(name)
+    out = {}
+    for algo in (edgpu.ALGO_GATHER, edgpu.ALGO_FAST):
+        for sparse in ((False, True) if algo == edgpu.ALGO_FAST else (False,)):
+            s = _solver(cfg, sparse, algo)
+            try:
+                s.build_Hv_sector(s.get_sector(cfg["nup"], cfg["ndw"]))
+                n = s.nloc
+                dx, dy = s.dev_alloc(8 * n), s.dev_alloc(8 * n)
+                s.dev_fill_bench_vector(dx, n, 0)
+                s.hxv_device(dx, dy)
+                s.sync()
+                out[(algo, sparse)] = np.empty(n)
+                s.dev_download(dy, out[(algo, sparse)])
+                s.dev_free(dx)
+                s.dev_free(dy)
+                s.delete_Hv_sector()
+            finally:
+                s.close()
+    ref = out[(edgpu.ALGO_GATHER, False)]
+    scale = np.abs(ref).max()
+    assert np.abs(ref - out[(edgpu.ALGO_FAST, False)]).max() < 1e-12 * scale
+    assert np.abs(ref - out[(edgpu.ALGO_FAST, True)]).max() < 1e-12 * scale
+
+
 @pytest.mark.parametrize("name", ["C2", "C3"])
 def test_tiled_equals_gather_full_size(name):
     cfg = configs.config(name)
