@@ -166,16 +166,18 @@ def run_reference(args):
 # B200 arm
 # ------------------------------------------------------------------------------------------------
 def run_b200(args):
-    import torch
     import edgpu
     from edgpu import configs
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
+    if edgpu.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
-    torch.cuda.set_device(local)
+    torch = None
+    if world > 1 or not args.hxv_only:                           # torch = distributed plumbing + pinned host buffers only
+        import torch
+        torch.cuda.set_device(local)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -184,7 +186,8 @@ def run_b200(args):
     def barrier():
         if dist is not None:
             dist.barrier()
-        torch.cuda.synchronize()
+        if torch is not None:
+            torch.cuda.synchronize()
 
     cfg = configs.config(args.workload)
     nup, ndw = cfg["nup"], cfg["ndw"]
@@ -225,12 +228,21 @@ def run_b200(args):
     ms_step = ms / args.steps
     value = 1000.0 / ms_step
     if args.hxv_only:
+        kp = s.time_hxv_passes(d_v, d_hv, max(3, min(args.steps, 10))) if world == 1 else []
         if rank == 0:
             print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": ms_step, "hxv_only": True,
-                              "gpu_launches": int(launches)}))
+                              "gpu_launches": int(launches), "kernels": kp}))
         s.delete_Hv_sector()
         s.close()
         return
+
+    # ---- per-kernel split of the same loop (single rank; separate, untimed-for-value pass) ---------
+    passes = []
+    if world == 1:
+        try:
+            passes = s.time_hxv_passes(d_v, d_hv, max(3, min(args.steps, 10)))
+        except Exception:
+            passes = []
 
     # ---- Lanczos iterations per second (device-resident recurrence, no host sync inside) ------------
     s.time_lanczos_device(d_v, 3)
@@ -275,7 +287,42 @@ def run_b200(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    achieved = bytes_per_el * nloc / (ms_step * 1e-3) / 1e9      # per GPU: algorithmic bytes of the local shard
+    step_gbs = bytes_per_el * nloc / (ms_step * 1e-3) / 1e9      # per GPU: algorithmic bytes of the local shard
+    # per-kernel split (CUDA events on the engine's stream between the launches) and the dominant kernel
+    kernels = []
+    if passes:
+        # minimum bytes each launch has to move per element: row kernel reads x and writes y (+ streamed spH0d),
+        # column kernel reads x, reads y, writes y; the whole H*v step is judged against 16 (24) B/element
+        alg = {"k_srow": 16 + (8 if args.stored else 0), "k_fcol": 24, "k_tile_col": 16 + (8 if args.stored else 0),
+               "k_tile_row": 24, "k_hxv_gather": bytes_per_el}
+        tot = sum(ms_k for _, ms_k in passes)
+        for name, ms_k in passes:
+            b = alg.get(name, bytes_per_el)
+            kernels.append({"name": name, "ms": ms_k, "share": ms_k / tot, "algorithmic_bytes_per_element": b,
+                            "achieved_gbs": b * nloc / (ms_k * 1e-3) / 1e9, "frac": b * nloc / (ms_k * 1e-3) / 1e9 / peak})
+    traffic = None
+    dom = max(kernels, key=lambda k: k["ms"]) if kernels else None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_dram_traffic.json")))
+        key = "%s_%s" % (args.workload, "stored" if args.stored else "direct")
+        if dom and world == 1 and key in tr and dom["name"] in tr[key]:
+            traffic = tr[key][dom["name"]]["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    if dom:
+        roof = {"bound": "hbm", "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dom["frac"], "traffic": traffic,
+                "kernel": dom["name"], "ms_per_launch": dom["ms"],
+                "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_element"] * nloc,
+                "algorithmic_bytes_per_element": dom["algorithmic_bytes_per_element"]}
+    else:
+        roof = {"bound": "hbm", "achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak, "traffic": None,
+                "kernel": "whole H*v step (all kernels of one step), per GPU",
+                "algorithmic_bytes_per_element": bytes_per_el}
+    roof.update({"peak_source": peak_src, "elements_per_launch": nloc,
+                 "step": {"algorithmic_bytes_per_element": bytes_per_el, "achieved": step_gbs, "frac": step_gbs / peak,
+                          "note": "north-star roofline: read v + write Hv%s per element over the whole H*v (all launches)"
+                                  % (" + stream spH0d" if args.stored else "; diagonal recomputed")},
+                 "kernels": kernels})
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -284,10 +331,7 @@ def run_b200(args):
                    "algo": args.algo, "l2": "input vector %.0f MB per GPU, larger than the 126 MB L2; no flush" % (8 * nloc / 1e6),
                    "sharding": "i_dw columns, %d rank(s)" % world, "vector": "v_i = sin(0.37 i) + 0.1"},
         "lanczos_iter_per_s": 1000.0 * args.steps / ms_l,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src,
-                     "algorithmic_bytes_per_element": bytes_per_el, "elements_per_launch": nloc,
-                     "kernel": "whole H*v step (all kernels of one step), per GPU"},
+        "roofline": roof,
         "e2e": {"value": 1.0 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * nloc * world, "d2h_bytes_per_step": 8 * nloc * world,
                 "call": "edgpu_hxv == spHtimesV_p(Nloc,v,Hv) with pinned host arrays",
                 "chain_hxv_per_s": nl / chain_s, "chain_call": "edgpu_sp_lanc_tridiag, %d steps, start vector from host" % nl},

@@ -381,6 +381,7 @@ extern "C" int edgpu_destroy(edgpu_ctx *c) {
   cudaFreeHost(c->h_pinned);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  for (int i = 0; i < 6; i++) if (c->pev[i]) cudaEventDestroy(c->pev[i]);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return EDGPU_OK;
@@ -537,6 +538,35 @@ extern "C" int edgpu_sync(edgpu_ctx *c) {
 }
 extern "C" int edgpu_launch_count(const edgpu_ctx *c, int64_t *n) {
   *n = c->launches;
+  return EDGPU_OK;
+}
+// Per-kernel split of a device-resident H*v (single rank): CUDA events between the passes, summed over
+// `reps` applications.  names receives up to 4 NUL-terminated kernel names of 32 bytes each.
+extern "C" int edgpu_time_hxv_passes(edgpu_ctx *c, int64_t nloc, const double *d_v, double *d_hv, int reps,
+                                     int *npasses, double *ms_pass, char *names) {
+  if (!c || !c->hstatus) return edgpu_set_err(EDGPU_ERR_INVALID, "HxV: Hsector NOT set");
+  if (nloc != c->nloc) return edgpu_set_err(EDGPU_ERR_INVALID, "nloc mismatch");
+  if (c->nranks != 1) return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "per-pass timing is single-rank only");
+  CK(cudaSetDevice(c->device));
+  for (int i = 0; i < 6; i++) if (!c->pev[i]) CK(cudaEventCreate(&c->pev[i]));
+  for (int i = 0; i < 4; i++) ms_pass[i] = 0.0;
+  int np = 0;
+  for (int r = 0; r < reps; r++) {
+    c->prof = true; c->prof_n = 0;
+    int rc = hxv_apply(c, d_v, d_hv);
+    if (!rc) prof_mark(c, "end");
+    c->prof = false;
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(c->stream));
+    np = c->prof_n - 1;
+    for (int i = 0; i < np && i < 4; i++) {
+      float ms = 0.f;
+      CK(cudaEventElapsedTime(&ms, c->pev[i], c->pev[i + 1]));
+      ms_pass[i] += ms;
+      if (names) { strncpy(names + 32 * i, c->prof_name[i], 31); names[32 * i + 31] = 0; }
+    }
+  }
+  if (npasses) *npasses = np < 4 ? np : 4;
   return EDGPU_OK;
 }
 extern "C" int edgpu_time_hxv_device(edgpu_ctx *c, int64_t nloc, const double *d_v, double *d_hv,

@@ -78,7 +78,20 @@ struct edgpu_ctx {
   FastPlan *fplan = nullptr;
   int64_t opt_srow_lr = 0, opt_srow_cmax = 0, opt_no_uniform = 0, opt_dbg = 0;
   int64_t launches = 0;
+  // per-pass timing (edgpu_time_hxv_passes): events recorded between the kernels of one H*v
+  bool prof = false;
+  int prof_n = 0;
+  cudaEvent_t pev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  const char *prof_name[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 };
+
+// marks the start of pass `name` (and the end of the previous one) when per-pass timing is on
+static inline void prof_mark(edgpu_ctx *c, const char *name) {
+  if (!c->prof || c->prof_n >= 5) return;
+  cudaEventRecord(c->pev[c->prof_n], c->stream);
+  c->prof_name[c->prof_n] = name;
+  c->prof_n++;
+}
 
 // ---- error plumbing -------------------------------------------------------------------------
 int edgpu_set_err(int code, const char *fmt, ...);

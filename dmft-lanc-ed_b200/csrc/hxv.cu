@@ -172,6 +172,7 @@ int hxv_apply(edgpu_ctx *c, const double *d_x, double *d_y) {
       if (!tiled_supported(c)) return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "tiled H*v does not cover this sector/model");
       return tiled_apply_local(c, d_x, d_y);
     }
+    prof_mark(c, "k_hxv_gather");
     return gather_local(c, d_x, d_y, true, d_x);
   }
   // sharded: diag + up locally; dw through the all-to-all transpose (spMatVec_MPI_main order,

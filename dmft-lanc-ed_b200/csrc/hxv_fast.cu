@@ -834,12 +834,16 @@ int fast_apply_row(edgpu_ctx *c, bool with_diag, bool acc, const double *d_x, do
 
 int fast_apply_local(edgpu_ctx *c, const double *d_x, double *d_y) {
   if (c->opt_dbg & 8) {                                            // experiment: column pass first
+    prof_mark(c, "k_fcol");
     TRY(fast_apply_col(c, 0, false, false, d_x, d_y, c->qdw, c->coloff));
+    prof_mark(c, "k_srow");
     TRY(fast_apply_row(c, true, true, d_x, d_y));
     return EDGPU_OK;
   }
   // row tiles first (y = Hd o x + x Hdw^T, write only), then whole columns (y += Hup x, contiguous RMW)
+  prof_mark(c, "k_srow");
   TRY(fast_apply_row(c, true, false, d_x, d_y));
+  prof_mark(c, "k_fcol");
   TRY(fast_apply_col(c, 0, false, true, d_x, d_y, c->qdw, c->coloff));
   return EDGPU_OK;
 }

@@ -421,7 +421,9 @@ static int tiled_apply_row(edgpu_ctx *c, const double *d_x, double *d_y) {
 
 int tiled_apply_local(edgpu_ctx *c, const double *d_x, double *d_y) {
   TRY(tiled_plan_build(c));
+  prof_mark(c, "k_tile_col");
   TRY(tiled_apply_col(c, 0, true, d_x, d_y, c->qdw, c->coloff));
+  prof_mark(c, "k_tile_row");
   TRY(tiled_apply_row(c, d_x, d_y));
   return EDGPU_OK;
 }

@@ -34,7 +34,7 @@ ABI_SYMBOLS = [
     "edgpu_gf_chains", "edgpu_add_to_lanczos_gf", "edgpu_get_dims", "edgpu_get_sector_map",
     "edgpu_get_csr", "edgpu_get_diag", "edgpu_dev_alloc", "edgpu_dev_free", "edgpu_dev_upload",
     "edgpu_dev_download", "edgpu_dev_fill_bench_vector", "edgpu_sync", "edgpu_time_hxv_device",
-    "edgpu_time_lanczos_device", "edgpu_launch_count",
+    "edgpu_time_lanczos_device", "edgpu_launch_count", "edgpu_time_hxv_passes",
 ]
 
 
@@ -102,6 +102,7 @@ def lib():
         L.edgpu_time_hxv_device.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, c_dp]
         L.edgpu_time_lanczos_device.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, c_dp]
         L.edgpu_launch_count.argtypes = [C.c_void_p, c_i64p]
+        L.edgpu_time_hxv_passes.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, c_ip, c_dp, C.c_char_p]
         _LIB = L
     return _LIB
 
@@ -330,6 +331,14 @@ class Solver:
         ms = C.c_double(0.0)
         _ck(lib().edgpu_time_hxv_device(self.h, self.nloc, d_v, d_hv, reps, C.byref(ms)))
         return ms.value
+
+    def time_hxv_passes(self, d_v, d_hv, reps):
+        """[(kernel name, ms per launch)] of one device-resident H*v, CUDA events between the passes."""
+        n = C.c_int(0)
+        ms = (C.c_double * 4)()
+        names = C.create_string_buffer(128)
+        _ck(lib().edgpu_time_hxv_passes(self.h, self.nloc, d_v, d_hv, int(reps), C.byref(n), ms, names))
+        return [(names.raw[32 * i:32 * i + 32].split(b"\0")[0].decode(), ms[i] / reps) for i in range(n.value)]
 
     def time_lanczos_device(self, d_v0, reps):
         ms = C.c_double(0.0)
