@@ -130,6 +130,7 @@ extern "C" int edgpu_set_option(edgpu_ctx *c, const char *key, int64_t value) {
   if (!strcmp(key, "srow_lr")) { c->opt_srow_lr = value; return EDGPU_OK; }
   if (!strcmp(key, "srow_cmax")) { c->opt_srow_cmax = value; return EDGPU_OK; }
   if (!strcmp(key, "dbg")) { c->opt_dbg = value; return EDGPU_OK; }
+  if (!strcmp(key, "no_peer")) { c->opt_no_peer = value; return EDGPU_OK; }
   if (!strcmp(key, "no_uniform")) { c->opt_no_uniform = value; return EDGPU_OK; }
   return edgpu_set_err(EDGPU_ERR_INVALID, "unknown option %s", key);
 }
@@ -346,6 +347,13 @@ extern "C" int edgpu_build_hv_sector(edgpu_ctx *c, int isector) {
     cudaFree(d_tmp);
   }
   CK(cudaStreamSynchronize(c->stream));
+  if (c->nranks > 1 && !c->opt_no_peer) {
+    // room for the engine's Lanczos vectors, the staging pair and a few user vectors, identical on every rank
+    int64_t qmax = (c->dimdw + c->nranks - 1) / c->nranks;
+    size_t per = (((size_t)(c->dimup * qmax) + 2) * sizeof(double) + 255) & ~(size_t)255;
+    int rc2 = comm_symm_setup(c, per * 10);
+    if (rc2) { edgpu_delete_hv_sector(c); return rc2; }
+  }
   g_current = c;
   return EDGPU_OK;
 }
@@ -363,7 +371,8 @@ extern "C" int edgpu_delete_hv_sector(edgpu_ctx *c) {
   c->d_nd_rowptr = c->d_nd_cols = nullptr; c->d_nd_vals = nullptr; c->nd_nnz = 0;
   double **bufs[] = { &c->d_in, &c->d_out, &c->d_vt, &c->d_hvt, &c->d_send, &c->d_recv, &c->d_full,
                       &c->d_lx, &c->d_lp, &c->d_lt, &c->d_l0, &c->d_lv };
-  for (auto b : bufs) { cudaFree(*b); *b = nullptr; }
+  for (auto b : bufs) vec_free(c, b);
+  comm_symm_teardown(c);
   c->hstatus = false;
   c->isector = 0;
   if (g_current == c) g_current = nullptr;
@@ -407,10 +416,12 @@ extern "C" int edgpu_hxv(edgpu_ctx *c, int64_t nloc, const double *v, double *hv
   if (!c || !c->hstatus) return edgpu_set_err(EDGPU_ERR_INVALID, "HxV: Hsector NOT set");
   if (nloc != c->nloc) return edgpu_set_err(EDGPU_ERR_INVALID, "HxV: Nloc=%lld != vecDim=%lld", (long long)nloc, (long long)c->nloc);
   CK(cudaSetDevice(c->device));
-  TRY(ensure_buf(&c->d_in, c->nloc));
-  TRY(ensure_buf(&c->d_out, c->nloc));
+  TRY(vec_alloc(c, &c->d_in, c->nloc));
+  TRY(vec_alloc(c, &c->d_out, c->nloc));
   CK(cudaMemcpyAsync(c->d_in, v, (size_t)nloc * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (c->sym_ok) TRY(comm_barrier(c));                          // peers read d_in: every upload has landed
   TRY(hxv_apply(c, c->d_in, c->d_out));
+  if (c->sym_ok) TRY(comm_barrier(c));                          // ... and nobody overwrites it while it is read
   CK(cudaMemcpyAsync(hv, c->d_out, (size_t)nloc * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return EDGPU_OK;
@@ -501,11 +512,18 @@ extern "C" int edgpu_get_diag(const edgpu_ctx *cc, double *out, int64_t nloc) {
 // ------------------------------------------------------------------------------------------
 extern "C" int edgpu_dev_alloc(edgpu_ctx *c, int64_t nbytes, void **dptr) {
   CK(cudaSetDevice(c->device));
-  CK(cudaMalloc(dptr, (size_t)nbytes));
+  if (c->sym_ok && c->hstatus) {                                // peer-readable when a sharded sector is live
+    double *p = nullptr;
+    TRY(vec_alloc(c, &p, (nbytes + 7) / 8));
+    *dptr = p;
+    return EDGPU_OK;
+  }
+  CK(cudaMalloc(dptr, (size_t)nbytes + 16));
   return EDGPU_OK;
 }
 extern "C" int edgpu_dev_free(edgpu_ctx *c, void *dptr) {
   CK(cudaSetDevice(c->device));
+  if (sym_offset(c, dptr) >= 0) return EDGPU_OK;                // slab memory goes away with the sector
   CK(cudaFree(dptr));
   return EDGPU_OK;
 }

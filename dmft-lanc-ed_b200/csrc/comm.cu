@@ -12,6 +12,8 @@
 #include <nccl.h>
 #include <string.h>
 
+#include <vector>
+
 #include "engine.h"
 
 namespace {
@@ -21,6 +23,7 @@ struct NcclApi {
   ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
@@ -44,6 +47,7 @@ int nccl_load() {
   SYM(CommInitRank, "ncclCommInitRank");
   SYM(CommDestroy, "ncclCommDestroy");
   SYM(AllReduce, "ncclAllReduce");
+  SYM(AllGather, "ncclAllGather");
   SYM(Send, "ncclSend");
   SYM(Recv, "ncclRecv");
   SYM(GroupStart, "ncclGroupStart");
@@ -96,6 +100,98 @@ extern "C" int edgpu_comm_finalize(edgpu_ctx *c) {
     c->comm = nullptr;
   }
   if (c) { c->rank = 0; c->nranks = 1; }
+  return EDGPU_OK;
+}
+
+// ---- symmetric slab ----------------------------------------------------------------------------------
+int64_t sym_offset(const edgpu_ctx *c, const void *p) {
+  if (!c->sym_ok || !c->sym_slab) return -1;
+  const char *q = reinterpret_cast<const char *>(p);
+  if (q < c->sym_slab || q >= c->sym_slab + c->sym_bytes) return -1;
+  return (int64_t)(q - c->sym_slab);
+}
+int vec_alloc(edgpu_ctx *c, double **p, int64_t n) {
+  if (*p) return EDGPU_OK;
+  const size_t bytes = (((size_t)(n > 0 ? n : 1) + 2) * sizeof(double) + 255) & ~(size_t)255;
+  if (c->sym_ok && c->sym_used + bytes <= c->sym_bytes) {
+    *p = reinterpret_cast<double *>(c->sym_slab + c->sym_used);
+    c->sym_used += bytes;
+    return EDGPU_OK;
+  }
+  CK(cudaMalloc(p, bytes));
+  return EDGPU_OK;
+}
+void vec_free(edgpu_ctx *c, double **p) {
+  if (*p && sym_offset(c, *p) < 0) cudaFree(*p);
+  *p = nullptr;
+}
+int comm_barrier(edgpu_ctx *c) {
+  if (c->nranks == 1) return EDGPU_OK;
+  NK(g_nccl.AllReduce(c->d_partials + 4000, c->d_partials + 4000, 1, ncclDouble, ncclSum, (ncclComm_t)c->comm, c->stream));
+  return EDGPU_OK;
+}
+// Collective.  On any failure (e.g. peers not visible to this process) every rank ends with sym_ok = false
+// and H*v uses the all-to-all transposes instead.
+int comm_symm_setup(edgpu_ctx *c, size_t bytes) {
+  c->sym_ok = false;
+  if (c->nranks == 1 || !c->comm) return EDGPU_OK;
+  const int P = c->nranks, me = c->rank;
+  bytes = (bytes + 255) & ~(size_t)255;
+  int good = 1;
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof(mine));
+  if (cudaMalloc(&c->sym_slab, bytes) != cudaSuccess) { good = 0; c->sym_slab = nullptr; cudaGetLastError(); }
+  if (good && cudaIpcGetMemHandle(&mine, c->sym_slab) != cudaSuccess) { good = 0; cudaGetLastError(); }
+  // exchange the handles (and the success flags) with NCCL: no host-side plumbing needed
+  const size_t rec = sizeof(cudaIpcMemHandle_t) + 8;
+  char *d_all = nullptr;
+  CK(cudaMalloc(&d_all, rec * (size_t)P));
+  std::vector<char> h_all(rec * (size_t)P, 0);
+  memcpy(h_all.data() + rec * me, &mine, sizeof(mine));
+  h_all[rec * me + sizeof(mine)] = (char)good;
+  CK(cudaMemcpyAsync(d_all + rec * me, h_all.data() + rec * me, rec, cudaMemcpyHostToDevice, c->stream));
+  NK(g_nccl.AllGather(d_all + rec * me, d_all, rec, ncclChar, (ncclComm_t)c->comm, c->stream));
+  CK(cudaMemcpyAsync(h_all.data(), d_all, rec * (size_t)P, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  cudaFree(d_all);
+  for (int p = 0; p < P; p++) if (!h_all[rec * p + sizeof(mine)]) good = 0;
+  int opened = 0;
+  if (good) {
+    for (int p = 0; p < P; p++) {
+      if (p == me) { c->sym_peer[p] = c->sym_slab; continue; }
+      cudaIpcMemHandle_t h;
+      memcpy(&h, h_all.data() + rec * p, sizeof(h));
+      void *ptr = nullptr;
+      if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { good = 0; cudaGetLastError(); break; }
+      c->sym_peer[p] = reinterpret_cast<char *>(ptr);
+      opened++;
+    }
+  }
+  // agree on the outcome
+  double flag = good ? 0.0 : 1.0;
+  CK(cudaMemcpyAsync(c->d_partials + 4001, &flag, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  NK(g_nccl.AllReduce(c->d_partials + 4001, c->d_partials + 4001, 1, ncclDouble, ncclSum, (ncclComm_t)c->comm, c->stream));
+  CK(cudaMemcpyAsync(&flag, c->d_partials + 4001, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (flag != 0.0) {
+    for (int p = 0; p < P; p++) { if (p != me && c->sym_peer[p]) cudaIpcCloseMemHandle(c->sym_peer[p]); c->sym_peer[p] = nullptr; }
+    if (c->sym_slab) cudaFree(c->sym_slab);
+    c->sym_slab = nullptr;
+    return EDGPU_OK;
+  }
+  CK(cudaMemsetAsync(c->sym_slab, 0, bytes, c->stream));
+  c->sym_bytes = bytes; c->sym_used = 0; c->sym_ok = true;
+  TRY(comm_barrier(c));
+  CK(cudaStreamSynchronize(c->stream));
+  return EDGPU_OK;
+}
+int comm_symm_teardown(edgpu_ctx *c) {
+  if (!c->sym_slab) { c->sym_ok = false; return EDGPU_OK; }
+  if (c->comm) { comm_barrier(c); cudaStreamSynchronize(c->stream); }   // nobody reads my slab any more
+  for (int p = 0; p < c->nranks; p++) { if (p != c->rank && c->sym_peer[p]) cudaIpcCloseMemHandle(c->sym_peer[p]); c->sym_peer[p] = nullptr; }
+  if (c->comm) { comm_barrier(c); cudaStreamSynchronize(c->stream); }   // every peer has closed its mapping
+  cudaFree(c->sym_slab);
+  c->sym_slab = nullptr; c->sym_bytes = c->sym_used = 0; c->sym_ok = false;
   return EDGPU_OK;
 }
 

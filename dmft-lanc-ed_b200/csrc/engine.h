@@ -76,8 +76,14 @@ struct edgpu_ctx {
   int64_t opt_tile_rows = 0, opt_tile_h = -1, opt_col_h = -1;
   TiledPlan *plan = nullptr;
   FastPlan *fplan = nullptr;
-  int64_t opt_srow_lr = 0, opt_srow_cmax = 0, opt_no_uniform = 0, opt_dbg = 0;
+  int64_t opt_srow_lr = 0, opt_srow_cmax = 0, opt_no_uniform = 0, opt_dbg = 0, opt_no_peer = 0;
   int64_t launches = 0;
+  // symmetric slab (nranks > 1): one allocation per rank at identical offsets, opened by every peer
+  // through CUDA IPC, so that kernels can read a peer's copy of a vector over NVLink
+  char *sym_slab = nullptr;
+  size_t sym_bytes = 0, sym_used = 0;
+  char *sym_peer[64] = {nullptr};
+  bool sym_ok = false;
   // per-pass timing (edgpu_time_hxv_passes): events recorded between the kernels of one H*v
   bool prof = false;
   int prof_n = 0;
@@ -132,12 +138,20 @@ int tiled_apply_col(edgpu_ctx *c, int k, bool with_diag, const double *d_x, doub
 // hxv_fast.cu: TMA-staged whole-column kernel + structured single-band row kernel
 int fast_plan_build(edgpu_ctx *c);
 int fast_plan_free(edgpu_ctx *c);
-bool fast_supported_local(edgpu_ctx *c);          // nranks==1 full operator
+bool fast_supported_local(edgpu_ctx *c);          // full operator on the local shard (peer reads when nranks > 1)
 bool fast_supported_col(edgpu_ctx *c, int k);     // whole-column kernel for factor k
 int fast_apply_local(edgpu_ctx *c, const double *d_x, double *d_y);
 int fast_apply_col(edgpu_ctx *c, int k, bool with_diag, bool acc, const double *d_x, double *d_y, int64_t ncols, int64_t coloff);
-int fast_apply_row(edgpu_ctx *c, bool with_diag, bool acc, const double *d_x, double *d_y);
+int fast_apply_row(edgpu_ctx *c, bool with_diag, bool acc, const double *d_x, double *d_y, const double *const *xpeer);
+bool fast_peer_ready(edgpu_ctx *c, const double *d_x);   // sharded: x lives in the symmetric slab, peers are mapped
 // comm.cu
+int comm_symm_setup(edgpu_ctx *c, size_t bytes);        // collective
+int comm_symm_teardown(edgpu_ctx *c);                   // collective
+int comm_barrier(edgpu_ctx *c);                         // stream-ordered cross-rank barrier (tiny all-reduce)
+// vectors that H*v may read on a peer: carved from the symmetric slab when there is one
+int vec_alloc(edgpu_ctx *c, double **p, int64_t n);
+void vec_free(edgpu_ctx *c, double **p);
+int64_t sym_offset(const edgpu_ctx *c, const void *p);  // byte offset inside the slab, -1 if not in it
 int comm_allreduce_scalar(edgpu_ctx *c, double *d_scalar);
 int comm_transpose_fwd(edgpu_ctx *c, const double *d_x, double *d_vt);          // V(DimUp,qdw) -> Vt(DimDw,qup)
 int comm_transpose_bwd_add(edgpu_ctx *c, const double *d_hvt, double *d_y);     // Hv += (Hvt)^T

@@ -175,6 +175,11 @@ int hxv_apply(edgpu_ctx *c, const double *d_x, double *d_y) {
     prof_mark(c, "k_hxv_gather");
     return gather_local(c, d_x, d_y, true, d_x);
   }
+  // sharded, fast path: the same two kernels as on one GPU; i_dw sources that live on another rank are read
+  // from that rank's copy of x over NVLink (no transposes, no packing)
+  if ((c->algo == EDGPU_ALGO_AUTO || c->algo == EDGPU_ALGO_FAST) && !c->dp.jhflag && fast_peer_ready(c, d_x) &&
+      fast_supported_local(c))
+    return fast_apply_local(c, d_x, d_y);
   // sharded: diag + up locally; dw through the all-to-all transpose (spMatVec_MPI_main order,
   // ED_HAMILTONIAN_SPARSE_HxV.f90:587-644); non-local terms on the all-gathered vector (:673-692)
   const double *d_full = nullptr;

@@ -37,6 +37,9 @@ __host__ __device__ constexpr int srow_consumers(int LR) { return LR >= 5 ? 480 
 #define SROW_R 32
 #define SROW_BC 32                // columns per TMA box (32 rows x 32 columns x 8 B = 8 KB per copy)
 #define SMEM_LIMIT 232448        // 227 KB per CTA on sm_100
+#define JHI_COLMASK 0xFFFFF      // Lin table entry: first column | owner rank << 20 | (cut by a rank boundary) << 30
+#define JHI_CUT 0x40000000
+#define SROW_MAXP 8              // peer reads: ranks of one NVLink domain
 
 struct FastFactor {
   int W = 0, WT = 0, nvals = 0;
@@ -55,6 +58,12 @@ struct SRowPlan {
   uint16_t *d_grp = nullptr;     // [ngroups] high words of the non-empty groups, ascending
   int4 *d_chunks = nullptr;      // [nchunks] (group begin, group end, column begin, column end)
   double *d_dr0 = nullptr, *d_dr1 = nullptr;   // direct mode: dfac_up[row] (+ Uloc when the up impurity is occupied)
+  // sharded vector: hops that touch a low group cut by a rank boundary are left to a small fix-up kernel
+  int nfix = 0;                  // target columns of the fix-up
+  int *d_ftptr = nullptr, *d_ftcol = nullptr, *d_feown = nullptr, *d_fesrc = nullptr;
+  unsigned char *d_ftinit = nullptr;
+  double *d_feval = nullptr;
+  int coloffs[65];
   double vk[EDGPU_MAX_SITES];    // V_k of the dw spin, k = bath bit (1-based site k+1)
   size_t smem = 0;
 };
@@ -285,16 +294,22 @@ struct SRowArgs {
   const double *dr0, *dr1;       // DIAG == 2: per-row tables, dw impurity empty / occupied
   const double *dfac_s;          // DIAG == 2: per-column table (padded by 2 doubles)
   int dbg;                       // timing experiments only (wrong results): 1 = skip far hops, 2 = skip in-chunk hops, 4 = skip y read
+  // sharding: this rank holds the global columns [c0, c0 + nf); x, y, diag point at local column 0
+  int c0;
+  int co[SROW_MAXP + 1];         // first global column of every rank
+  const double *xb[SROW_MAXP];   // every rank's copy of x (peer memory over NVLink; xb[rank] == x)
 };
 
 struct SRowTile {
   const double *tl;              // shared-memory tile of this item + lane: column c at tl[(c - cb) * 32]
   const double *dsc;             // shared: dfac_s[cb ..], DIAG == 2
-  const double *xg;              // x + i0 + (row of this lane, clamped into the matrix)
   double *yg;                    // y + i0 + row
   const double *dgg;             // diag + i0 + row (DIAG == 1)
   const int32_t *jhi;            // shared
   const double *vhigh;           // shared, vhigh[kk] = V_{LR+kk}
+  const double *const *xb;       // shared: per-rank base of x
+  size_t row;                    // row of this lane (clamped into the matrix)
+  const int *co;                 // shared: per-rank first column
   size_t n;                      // column stride in elements
   int cb, csz, nhigh, dbg;
   bool active;                   // this lane's row exists (stores only)
@@ -351,7 +366,8 @@ __device__ __forceinline__ void srow_hop_set(const SRowTile &k, uint32_t h, uint
       const long long vb = __double_as_longlong(k.vhigh[kk]) ^ ((long long)((par >> kk) & 1u) << 63);
       sv[q] = ok ? __longlong_as_double(vb) : 0.0;                  // padding slot: re-reads slot 0's source, weight 0
       const int c2 = k.jhi[h ^ (1u << kk)];
-      const double *p = FAR ? k.xg + (size_t)c2 * k.n : k.tl + (c2 - k.cb) * SROW_R;
+      const int col2 = c2 & JHI_COLMASK, own = (c2 >> 20) & 63;
+      const double *p = FAR ? k.xb[own] + k.row + (size_t)(col2 - k.co[own]) * k.n : k.tl + (col2 - k.cb) * SROW_R;
       src[q] = (ok || q == 0) ? p : src[0];
     }
     srow_hops<LR, N, CNT, BK, FAR, NB>(sv, src, k.n, acc);
@@ -393,11 +409,14 @@ __device__ __forceinline__ void srow_group(const SRowTile &k, const uint32_t h, 
   par ^= par << 2; par ^= par << 4; par ^= par << 8;
   par = (par << 1);
   uint32_t inmask = 0;                                             // high bits whose partner group is in the tile
+  uint32_t farmask = 0;                                            // ... or elsewhere (L2 / a peer GPU)
 #pragma unroll 1
-  for (int kk = 0; kk < k.nhigh; kk++)
-    if ((unsigned)(k.jhi[h ^ (1u << kk)] - k.cb) < (unsigned)k.csz) inmask |= 1u << kk;
-  const uint32_t all = (1u << k.nhigh) - 1u;
-  const uint32_t farmask = all & ~inmask;
+  for (int kk = 0; kk < k.nhigh; kk++) {
+    const int c2 = k.jhi[h ^ (1u << kk)];
+    if (c2 & JHI_CUT) continue;                                    // empty group, or cut by a rank boundary (fix-up kernel)
+    if ((unsigned)((c2 & JHI_COLMASK) - k.cb) < (unsigned)k.csz) inmask |= 1u << kk;
+    else farmask |= 1u << kk;
+  }
   if (!(k.dbg & 1)) {                                              // far sources first: longest latency
     srow_hop_set<LR, N, CNT, true, true, 3>(k, h, par, farmask & h, acc);
     srow_hop_set<LR, N, CNT, false, true, 3>(k, h, par, farmask & ~h, acc);
@@ -406,7 +425,7 @@ __device__ __forceinline__ void srow_group(const SRowTile &k, const uint32_t h, 
     srow_hop_set<LR, N, CNT, true, false, 2>(k, h, par, inmask & h, acc);
     srow_hop_set<LR, N, CNT, false, false, 2>(k, h, par, inmask & ~h, acc);
   }
-  double *yp = k.yg + (size_t)base * k.n;
+  double *yp = k.yg + (size_t)base * k.n;                          // yg / dgg are biased by -c0 columns
   if (DIAG == 1) {
     const double *dp = k.dgg + (size_t)base * k.n;
     double dg[CNT];
@@ -441,7 +460,9 @@ __global__ void __launch_bounds__(srow_consumers(LR) + 32, 1) k_srow(const __gri
   double *vhigh = drw0 + 4 * SROW_R;                              // [32]
   uint64_t *bar = reinterpret_cast<uint64_t *>(vhigh + 32);       // full[2], empty[2]
   int *gctr = reinterpret_cast<int *>(bar + 4);                   // [2] (+2 pad)
-  int32_t *jhi = reinterpret_cast<int32_t *>(gctr + 4);           // [2^nhigh]
+  const double **xbs = reinterpret_cast<const double **>(gctr + 4);   // [SROW_MAXP] per-rank base of x
+  int *cos = reinterpret_cast<int *>(xbs + SROW_MAXP);            // [SROW_MAXP + 1] (+ pad)
+  int32_t *jhi = reinterpret_cast<int32_t *>(cos + SROW_MAXP + 3);   // [2^nhigh]
   uint16_t *grp = reinterpret_cast<uint16_t *>(jhi + (1 << a.nhigh));   // [ngroups]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
@@ -455,6 +476,8 @@ __global__ void __launch_bounds__(srow_consumers(LR) + 32, 1) k_srow(const __gri
   for (int i = tid; i < (1 << a.nhigh); i += blockDim.x) jhi[i] = a.jhi[i];
   for (int i = tid; i < a.ngroups; i += blockDim.x) grp[i] = a.grp[i];
   if (tid < 32) vhigh[tid] = (tid < a.nhigh) ? a.vk[LR + tid] : 0.0;
+  if (tid < SROW_MAXP) xbs[tid] = a.xb[tid];
+  if (tid <= SROW_MAXP) cos[tid] = a.co[tid];
   __syncthreads();
 
   const int64_t nrb = (a.n + SROW_R - 1) / SROW_R;
@@ -484,7 +507,7 @@ __global__ void __launch_bounds__(srow_consumers(LR) + 32, 1) k_srow(const __gri
       }
       __syncwarp();
       if (lane < nops)
-        tma_load_2d(tile0 + (size_t)b * tsz + (size_t)lane * SROW_BC * SROW_R, &tmx, (int)i0, ch.z + lane * SROW_BC, &bar[b]);
+        tma_load_2d(tile0 + (size_t)b * tsz + (size_t)lane * SROW_BC * SROW_R, &tmx, (int)i0, ch.z - a.c0 + lane * SROW_BC, &bar[b]);
       if (DIAG == 2) {
         if (lane == 29) bulk_g2s(dsc0 + (size_t)b * (cpad + 2), a.dfac_s + (ch.z - lead), dsc_bytes, &bar[b]);
         if (lane == 30) bulk_g2s(drw0 + (size_t)b * 2 * SROW_R, a.dr0 + i0, (uint32_t)nr * 8u, &bar[b]);
@@ -508,7 +531,8 @@ __global__ void __launch_bounds__(srow_consumers(LR) + 32, 1) k_srow(const __gri
     const int64_t row = min(i0 + lane, (int64_t)a.n - 1);            // clamp: loads of a ragged last block stay in range
     k.tl = tile0 + (size_t)b * tsz + lane;
     k.dsc = dsc0 + (size_t)b * (cpad + 2) + (ch.z & 1);
-    k.xg = a.x + row; k.yg = a.y + row; k.dgg = a.diag + row;
+    k.yg = a.y + row - (ptrdiff_t)a.c0 * a.n; k.dgg = a.diag + row - (ptrdiff_t)a.c0 * a.n;
+    k.xb = xbs; k.co = cos; k.row = (size_t)row;
     k.jhi = jhi; k.vhigh = vhigh;
     k.n = (size_t)a.n; k.cb = ch.z; k.csz = ch.w - ch.z; k.nhigh = a.nhigh; k.dbg = a.dbg;
     k.active = (i0 + lane) < a.n;
@@ -524,7 +548,7 @@ __global__ void __launch_bounds__(srow_consumers(LR) + 32, 1) k_srow(const __gri
       g = __shfl_sync(0xffffffffu, g, 0) + ch.x;
       if (g >= ch.y) break;
       const uint32_t h = grp[g];
-      const int base = jhi[h];
+      const int base = jhi[h] & JHI_COLMASK;
       const int nlow = a.ndw - __popc(h);
       srow_dispatch<LR, DIAG, ACC>(k, h, base, nlow, vlow, std::make_integer_sequence<int, LR + 1>{});
     }
@@ -582,7 +606,8 @@ static int pack_fast(edgpu_ctx *c, const Factor &f, FastFactor &ff) {
 static size_t fcol_smem(int64_t n) { return (size_t)2 * (n + 2) * 8 + F_MAXVALS * 8 + 16; }
 static size_t srow_smem(int cmax, int nhigh, int ngroups) {
   const size_t cpad = (size_t)((cmax + SROW_BC - 1) / SROW_BC) * SROW_BC;
-  size_t b = (size_t)2 * cpad * SROW_R * 8 + (size_t)2 * (cpad + 2) * 8 + 4 * SROW_R * 8 + 32 * 8 + 32 + 16 + ((size_t)4 << nhigh) + (size_t)2 * ngroups;
+  size_t b = (size_t)2 * cpad * SROW_R * 8 + (size_t)2 * (cpad + 2) * 8 + 4 * SROW_R * 8 + 32 * 8 + 32 + 16 + 8 * SROW_MAXP + 4 * (SROW_MAXP + 3) +
+             ((size_t)4 << nhigh) + (size_t)2 * ngroups;
   return (b + 15) & ~(size_t)15;
 }
 
@@ -591,25 +616,47 @@ static int build_srow(edgpu_ctx *c, SRowPlan &sr, int LR) {
   sr.ok = false;
   if (c->dp.norb != 1 || c->dp.jhflag) return EDGPU_OK;
   if (c->ns <= LR || c->ns - LR > 15 || (c->dimup & 1)) return EDGPU_OK;
+  if (c->nranks > SROW_MAXP || c->dimdw > JHI_COLMASK) return EDGPU_OK;
   if (c->opt_srow_lr == 4 || c->opt_srow_lr == 5) LR = (int)c->opt_srow_lr;
   sr.LR = LR;
   sr.nhigh = c->ns - LR;
+  const int P = c->nranks;
+  for (int p = 0; p <= P; p++) {
+    int64_t q, off;
+    if (p < P) edgpu_split(c->dimdw, P, p, &q, &off); else off = c->dimdw;
+    sr.coloffs[p] = (int)off;
+  }
+  auto owner_of = [&](int col) { int p = 0; while (p + 1 < P && col >= sr.coloffs[p + 1]) p++; return p; };
+  const int c0 = sr.coloffs[c->rank], c1 = sr.coloffs[c->rank + 1];
   const int nh = 1 << sr.nhigh;
   std::vector<int32_t> jhi((size_t)nh, -1);
   std::vector<uint16_t> grp;
-  std::vector<int> gsize;
+  std::vector<int> gsize, gbase;
+  std::vector<char> gcut;
   int64_t col = 0;
   for (int h = 0; h < nh; h++) {
     const int nlow = c->ndw - __builtin_popcount((unsigned)h);
     if (nlow < 0 || nlow > LR) continue;
-    jhi[(size_t)h] = (int32_t)col;
-    grp.push_back((uint16_t)h);
     const int sz = lowtab::binom(LR, nlow);
-    gsize.push_back(sz);
+    const int own = owner_of((int)col);
+    const bool cut = owner_of((int)col + sz - 1) != own;           // the group is split between two ranks
+    jhi[(size_t)h] = (int32_t)col | (own << 20) | (cut ? JHI_CUT : 0);
+    grp.push_back((uint16_t)h);
+    gsize.push_back(sz); gbase.push_back((int)col); gcut.push_back(cut ? 1 : 0);
     col += sz;
   }
   if (col != c->dimdw) return edgpu_set_err(EDGPU_ERR_INVALID, "internal: Lin table does not cover the dw basis");
   sr.ngroups = (int)grp.size();
+  // groups that lie entirely on this rank: a contiguous run [g0, g1) of the global list
+  int g0 = 0, g1 = 0;
+  {
+    int g = 0;
+    while (g < sr.ngroups && (gbase[g] < c0 || gcut[g])) { if (gbase[g] >= c1) break; g++; }
+    g0 = g;
+    while (g < sr.ngroups && !gcut[g] && gbase[g] + gsize[g] <= c1) g++;
+    g1 = g;
+    if (g0 < sr.ngroups && gbase[g0] >= c1) g1 = g0;               // nothing whole on this rank
+  }
   // chunk size from the shared-memory budget (or the option), chunks = runs of whole groups
   int cmax = (int)((SMEM_LIMIT - 4096 - ((size_t)4 << sr.nhigh) - 2 * (size_t)sr.ngroups) / (2 * (SROW_R + 1) * 8));
   cmax = cmax / SROW_BC * SROW_BC;
@@ -620,25 +667,27 @@ static int build_srow(edgpu_ctx *c, SRowPlan &sr, int LR) {
   if (c->opt_srow_cmax > 0 && c->opt_srow_cmax < cmax) cmax = (int)c->opt_srow_cmax;
   if (cmax < lowtab::binom(LR, LR / 2)) return EDGPU_OK;
   // balance: all chunks about the same size
-  const int nch0 = (int)((c->dimdw + cmax - 1) / cmax);
-  const int target = (int)((c->dimdw + nch0 - 1) / nch0);
+  const int nloccols = (g1 > g0) ? gbase[g1 - 1] + gsize[g1 - 1] - gbase[g0] : 0;
+  const int nch0 = std::max(1, (nloccols + cmax - 1) / cmax);
+  const int target = (nloccols + nch0 - 1) / nch0;
   std::vector<int4> chunks;
-  int gb = 0, cb = 0, cur = 0;
-  for (int g = 0; g < sr.ngroups; g++) {
+  int gb = g0, cb = (g1 > g0) ? gbase[g0] : 0, cur = 0;
+  for (int g = g0; g < g1; g++) {
     if (cur > 0 && (cur + gsize[g] > cmax || cur >= target)) {
       chunks.push_back(make_int4(gb, g, cb, cb + cur));
       gb = g; cb += cur; cur = 0;
     }
     cur += gsize[g];
   }
-  if (cur > 0) chunks.push_back(make_int4(gb, sr.ngroups, cb, cb + cur));
+  if (cur > 0) chunks.push_back(make_int4(gb, g1, cb, cb + cur));
   sr.nchunks = (int)chunks.size();
-  sr.cmax = 0;
+  sr.cmax = lowtab::binom(LR, LR / 2);
   for (auto &ch : chunks) sr.cmax = std::max(sr.cmax, ch.w - ch.z);
   sr.smem = srow_smem(sr.cmax, sr.nhigh, sr.ngroups);
   if (sr.smem > SMEM_LIMIT) return EDGPU_OK;
   for (int k = 0; k < EDGPU_MAX_SITES; k++) sr.vk[k] = 0.0;
   for (int k = 1; k < c->ns; k++) sr.vk[k] = c->dp.bv_dw[k - 1];
+  if (chunks.empty()) chunks.push_back(make_int4(0, 0, 0, 0));
   CK(cudaMalloc(&sr.d_jhi, jhi.size() * sizeof(int32_t)));
   CK(cudaMalloc(&sr.d_grp, grp.size() * sizeof(uint16_t)));
   CK(cudaMalloc(&sr.d_chunks, chunks.size() * sizeof(int4)));
@@ -656,6 +705,53 @@ static int build_srow(edgpu_ctx *c, SRowPlan &sr, int LR) {
     CK(cudaMemcpy(sr.d_dr0, d0.data(), d0.size() * sizeof(double), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(sr.d_dr1, d1.data(), d1.size() * sizeof(double), cudaMemcpyHostToDevice));
   }
+  // fix-up list: every dw hop (target <- source) of a LOCAL target column for which the target's or the
+  // source's low group is cut by a rank boundary (the structured kernel skips exactly those), from the
+  // reference-order CSR of spH0dws.  Targets in cut groups are computed entirely here (diagonal included).
+  sr.nfix = 0;
+  if (P > 1) {
+    std::vector<int32_t> rp((size_t)c->dw.n + 1), cc((size_t)std::max<int64_t>(c->dw.nnz, 1));
+    std::vector<double> vv((size_t)std::max<int64_t>(c->dw.nnz, 1));
+    CK(cudaMemcpy(rp.data(), c->dw.d_rowptr, rp.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (c->dw.nnz) {
+      CK(cudaMemcpy(cc.data(), c->dw.d_cols, (size_t)c->dw.nnz * sizeof(int32_t), cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(vv.data(), c->dw.d_vals, (size_t)c->dw.nnz * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    std::vector<char> colcut((size_t)c->dimdw, 0);
+    for (int g = 0; g < sr.ngroups; g++)
+      if (gcut[g]) for (int i = 0; i < gsize[g]; i++) colcut[(size_t)gbase[g] + i] = 1;
+    std::vector<int> tptr(1, 0), tcol, eown, esrc;
+    std::vector<unsigned char> tinit;
+    std::vector<double> eval;
+    for (int t = c0; t < c1; t++) {
+      const bool tc = colcut[(size_t)t] != 0;
+      size_t before = eown.size();
+      for (int32_t q = rp[(size_t)t]; q < rp[(size_t)t + 1]; q++) {
+        const int sc = cc[(size_t)q];
+        if (!tc && !colcut[(size_t)sc]) continue;
+        const int own = owner_of(sc);
+        eown.push_back(own); esrc.push_back(sc - sr.coloffs[own]); eval.push_back(vv[(size_t)q]);
+      }
+      if (tc || eown.size() > before) { tcol.push_back(t - c0); tinit.push_back(tc ? 1 : 0); tptr.push_back((int)eown.size()); }
+    }
+    sr.nfix = (int)tcol.size();
+    if (sr.nfix) {
+      const size_t ne = std::max<size_t>(eown.size(), 1);
+      eown.resize(ne); esrc.resize(ne); eval.resize(ne);
+      CK(cudaMalloc(&sr.d_ftptr, tptr.size() * sizeof(int)));
+      CK(cudaMalloc(&sr.d_ftcol, tcol.size() * sizeof(int)));
+      CK(cudaMalloc(&sr.d_ftinit, tinit.size()));
+      CK(cudaMalloc(&sr.d_feown, ne * sizeof(int)));
+      CK(cudaMalloc(&sr.d_fesrc, ne * sizeof(int)));
+      CK(cudaMalloc(&sr.d_feval, ne * sizeof(double)));
+      CK(cudaMemcpy(sr.d_ftptr, tptr.data(), tptr.size() * sizeof(int), cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(sr.d_ftcol, tcol.data(), tcol.size() * sizeof(int), cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(sr.d_ftinit, tinit.data(), tinit.size(), cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(sr.d_feown, eown.data(), ne * sizeof(int), cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(sr.d_fesrc, esrc.data(), ne * sizeof(int), cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(sr.d_feval, eval.data(), ne * sizeof(double), cudaMemcpyHostToDevice));
+    }
+  }
   sr.ok = true;
   return EDGPU_OK;
 }
@@ -665,6 +761,7 @@ int fast_plan_free(edgpu_ctx *c) {
   for (int k = 0; k < 2; k++) { cudaFree(c->fplan->ff[k].d_ell); cudaFree(c->fplan->ff[k].d_ell16); cudaFree(c->fplan->ff[k].d_vtab); }
   cudaFree(c->fplan->sr.d_jhi); cudaFree(c->fplan->sr.d_grp); cudaFree(c->fplan->sr.d_chunks);
   cudaFree(c->fplan->sr.d_dr0); cudaFree(c->fplan->sr.d_dr1);
+  { SRowPlan &r = c->fplan->sr; cudaFree(r.d_ftptr); cudaFree(r.d_ftcol); cudaFree(r.d_ftinit); cudaFree(r.d_feown); cudaFree(r.d_fesrc); cudaFree(r.d_feval); }
   delete c->fplan;
   c->fplan = nullptr;
   return EDGPU_OK;
@@ -808,28 +905,98 @@ static int make_tmap_2d(CUtensorMap *tm, const double *base, uint64_t n0, uint64
   return EDGPU_OK;
 }
 
-// y (+)= [Hd o x +] x Hdw^T on the full local matrix (every i_dw column local)
-int fast_apply_row(edgpu_ctx *c, bool with_diag, bool acc, const double *d_x, double *d_y) {
+// fix-up for the sharded vector (see build_srow): one CTA per listed local target column
+struct SFixArgs {
+  const double *x;               // local x
+  double *y;
+  int n, c0;
+  const int *tptr, *tcol, *eown, *esrc;
+  const unsigned char *tinit;
+  const double *eval;
+  const double *xb[SROW_MAXP];
+  const double *diag;            // stored: local spH0d
+  const double *dr0, *dr1, *dfac_s;
+  const int32_t *map_s;
+  int diagmode, acc;
+};
+__global__ void __launch_bounds__(256) k_sfix(SFixArgs a) {
+  const int t = blockIdx.x;
+  const int tl = a.tcol[t], e0 = a.tptr[t], e1 = a.tptr[t + 1];
+  const bool init = a.tinit[t] != 0;
+  const size_t off = (size_t)tl * a.n;
+  double dcol = 0.0;
+  bool nd = false;
+  if (init && a.diagmode == 2) { dcol = a.dfac_s[a.c0 + tl]; nd = (a.map_s[a.c0 + tl] & 1) != 0; }
+  for (int r = blockIdx.y * blockDim.x + threadIdx.x; r < a.n; r += gridDim.y * blockDim.x) {
+    double acc;
+    if (init) {
+      double d = 0.0;
+      if (a.diagmode == 1) d = a.diag[off + r];
+      if (a.diagmode == 2) d = (nd ? a.dr1[r] : a.dr0[r]) + dcol;
+      acc = d * a.x[off + r];
+      if (a.acc) acc += a.y[off + r];
+    } else {
+      acc = a.y[off + r];                                           // written by k_srow just before
+    }
+    for (int e = e0; e < e1; e++) acc = fma(a.eval[e], a.xb[a.eown[e]][(size_t)a.esrc[e] * a.n + r], acc);
+    a.y[off + r] = acc;
+  }
+}
+
+// y (+)= [Hd o x +] x Hdw^T on the local shard.  nranks == 1: every column is local.  nranks > 1: sources on
+// other ranks are read from the peers' copies of x (xpeer[p] = rank p's pointer for the same vector).
+int fast_apply_row(edgpu_ctx *c, bool with_diag, bool acc, const double *d_x, double *d_y, const double *const *xpeer) {
   TRY(fast_plan_build(c));
   const SRowPlan &sr = c->fplan->sr;
   if (!sr.ok) return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "structured row kernel does not cover this model");
   if ((reinterpret_cast<uintptr_t>(d_x) & 15) != 0) return edgpu_set_err(EDGPU_ERR_INVALID, "fast H*v needs 16-byte aligned vectors");
+  if (c->nranks > 1 && !xpeer) return edgpu_set_err(EDGPU_ERR_INVALID, "sharded row kernel needs the peers' vectors");
   SRowArgs a{};
-  a.x = d_x; a.y = d_y; a.n = (int)c->dimup; a.nf = (int)c->dimdw;
+  a.x = d_x; a.y = d_y; a.n = (int)c->dimup; a.nf = (int)c->qdw;
   a.ndw = c->ndw; a.nhigh = sr.nhigh; a.ngroups = sr.ngroups; a.nchunks = sr.nchunks; a.cmax = sr.cmax;
   a.jhi = sr.d_jhi; a.grp = sr.d_grp; a.chunks = sr.d_chunks;
   for (int k = 0; k < EDGPU_MAX_SITES; k++) a.vk[k] = sr.vk[k];
   a.dbg = (int)c->opt_dbg;
   a.diag = c->d_diag; a.dr0 = sr.d_dr0; a.dr1 = sr.d_dr1; a.dfac_s = c->dw.d_dfac;
-  const int64_t nitems = ((c->dimup + SROW_R - 1) / SROW_R) * sr.nchunks;
-  const int grid = (int)std::min<int64_t>(nitems, c->sm_count);
+  a.c0 = (int)c->coloff;
+  for (int p = 0; p <= SROW_MAXP; p++) a.co[p] = sr.coloffs[p < c->nranks ? p : c->nranks];
+  for (int p = 0; p < SROW_MAXP; p++) a.xb[p] = (c->nranks == 1 || p >= c->nranks) ? d_x : xpeer[p];
+  a.xb[c->rank] = d_x;
   const int diag = !with_diag ? 0 : (c->d_diag ? 1 : 2);
-  CUtensorMap tmx;
-  TRY(make_tmap_2d(&tmx, d_x, (uint64_t)c->dimup, (uint64_t)c->dimdw, SROW_R, SROW_BC));
-  if (sr.LR == 4) launch_srow<4>(diag, acc, grid, sr.smem, c->stream, tmx, a);
-  else launch_srow<5>(diag, acc, grid, sr.smem, c->stream, tmx, a);
-  CKL(c);
+  const int64_t nitems = ((c->dimup + SROW_R - 1) / SROW_R) * sr.nchunks;
+  if (sr.nchunks > 0 && c->fplan->sr.cmax > 0 && nitems > 0 && !(sr.nchunks == 1 && c->qdw == 0)) {
+    const int grid = (int)std::min<int64_t>(nitems, c->sm_count);
+    CUtensorMap tmx;
+    TRY(make_tmap_2d(&tmx, d_x, (uint64_t)c->dimup, (uint64_t)c->qdw, SROW_R, SROW_BC));
+    // a rank may own no whole group at all (tiny sectors): the chunk table then holds one empty chunk
+    if (sr.LR == 4) launch_srow<4>(diag, acc, grid, sr.smem, c->stream, tmx, a);
+    else launch_srow<5>(diag, acc, grid, sr.smem, c->stream, tmx, a);
+    CKL(c);
+  }
+  if (sr.nfix > 0) {
+    SFixArgs f{};
+    f.x = d_x; f.y = d_y; f.n = (int)c->dimup; f.c0 = (int)c->coloff;
+    f.tptr = sr.d_ftptr; f.tcol = sr.d_ftcol; f.eown = sr.d_feown; f.esrc = sr.d_fesrc; f.tinit = sr.d_ftinit; f.eval = sr.d_feval;
+    for (int p = 0; p < SROW_MAXP; p++) f.xb[p] = a.xb[p];
+    f.diag = c->d_diag; f.dr0 = sr.d_dr0; f.dr1 = sr.d_dr1; f.dfac_s = c->dw.d_dfac; f.map_s = c->dw.d_map;
+    f.diagmode = diag; f.acc = acc ? 1 : 0;
+    dim3 grid((unsigned)sr.nfix, (unsigned)std::max<int64_t>(1, std::min<int64_t>(32, (c->dimup + 1023) / 1024)));
+    k_sfix<<<grid, 256, 0, c->stream>>>(f);
+    CKL(c);
+  }
   return EDGPU_OK;
+}
+
+// peers' pointers of a vector that lives in the symmetric slab (nullptr if it does not)
+static const double *const *peer_ptrs(edgpu_ctx *c, const double *d_x, const double **buf) {
+  if (c->nranks == 1) return nullptr;
+  const int64_t off = sym_offset(c, d_x);
+  if (off < 0) return nullptr;
+  for (int p = 0; p < c->nranks; p++) buf[p] = reinterpret_cast<const double *>(c->sym_peer[p] + off);
+  return buf;
+}
+bool fast_peer_ready(edgpu_ctx *c, const double *d_x) {
+  return c->nranks > 1 && c->nranks <= SROW_MAXP && c->sym_ok && sym_offset(c, d_x) >= 0;
 }
 
 int fast_apply_local(edgpu_ctx *c, const double *d_x, double *d_y) {
@@ -837,12 +1004,15 @@ int fast_apply_local(edgpu_ctx *c, const double *d_x, double *d_y) {
     prof_mark(c, "k_fcol");
     TRY(fast_apply_col(c, 0, false, false, d_x, d_y, c->qdw, c->coloff));
     prof_mark(c, "k_srow");
-    TRY(fast_apply_row(c, true, true, d_x, d_y));
+    TRY(fast_apply_row(c, true, true, d_x, d_y, nullptr));
     return EDGPU_OK;
   }
   // row tiles first (y = Hd o x + x Hdw^T, write only), then whole columns (y += Hup x, contiguous RMW)
+  const double *pb[64];
+  const double *const *xpeer = peer_ptrs(c, d_x, pb);
+  if (c->nranks > 1 && !xpeer) return edgpu_set_err(EDGPU_ERR_INVALID, "sharded fast H*v: the vector is not in the symmetric slab");
   prof_mark(c, "k_srow");
-  TRY(fast_apply_row(c, true, false, d_x, d_y));
+  TRY(fast_apply_row(c, true, false, d_x, d_y, xpeer));
   prof_mark(c, "k_fcol");
   TRY(fast_apply_col(c, 0, false, true, d_x, d_y, c->qdw, c->coloff));
   return EDGPU_OK;

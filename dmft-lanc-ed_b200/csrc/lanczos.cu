@@ -147,9 +147,9 @@ static int lanczos_step(edgpu_ctx *c, int k /*0-based*/) {
   return EDGPU_OK;
 }
 static int lanczos_begin(edgpu_ctx *c, int ncoef) {
-  TRY(ensure(&c->d_lx, c->nloc));
-  TRY(ensure(&c->d_lp, c->nloc));
-  TRY(ensure(&c->d_lt, c->nloc));
+  TRY(vec_alloc(c, &c->d_lx, c->nloc));
+  TRY(vec_alloc(c, &c->d_lp, c->nloc));
+  TRY(vec_alloc(c, &c->d_lt, c->nloc));
   TRY(ensure_coeffs(c, ncoef));
   CK(cudaMemsetAsync(c->d_alanc, 0, (size_t)c->lanc_cap * sizeof(double), c->stream));
   CK(cudaMemsetAsync(c->d_blanc, 0, (size_t)c->lanc_cap * sizeof(double), c->stream));
@@ -253,8 +253,8 @@ extern "C" int edgpu_sp_lanc_eigh(edgpu_ctx *c, double *egs, double *vect, int64
   if (ncheck <= 0) ncheck = 10;
   CK(cudaSetDevice(c->device));
   TRY(lanczos_begin(c, nitermax));
-  TRY(ensure(&c->d_l0, c->nloc));
-  TRY(ensure(&c->d_lv, c->nloc));
+  TRY(vec_alloc(c, &c->d_l0, c->nloc));
+  TRY(vec_alloc(c, &c->d_lv, c->nloc));
   // start vector
   CK(cudaMemcpyAsync(c->d_lx, vect, (size_t)nloc * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   TRY(lanczos_norm_start(c));

@@ -21,25 +21,36 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
-    if rank == 0:
-        idt.copy_(torch.frombuffer(bytearray(edgpu.comm_unique_id()), dtype=torch.uint8))
-    dist.broadcast(idt, 0)
-    uid = bytes(idt.cpu().numpy().tobytes())
+    def fresh_uid():
+        """A NCCL unique id serves ONE communicator: every Solver gets its own (rank 0 draws, broadcast)."""
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(edgpu.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        return bytes(idt.cpu().numpy().tobytes())
+
     fails = []
 
     def check(name, ok, detail=""):
         if not ok:
             fails.append("%s rank %d %s" % (name, rank, detail))
 
-    cases = [("C1", (4, 4), True), ("C1", (4, 4), False), ("C1", (5, 3), True), ("NS10", (5, 5), False),
-             ("NS10", (6, 4), True), ("C4", (5, 5), True), ("C4", (5, 5), False), ("C4", (6, 5), True)]
-    for name, sec, sparse in cases:
+    # (config, sector, stored?, engine options).  Single-band cases run the peer-read fast path (k_srow reads
+    # other ranks' columns over NVLink + fix-up of the low groups cut by a rank boundary); "no_peer" forces the
+    # all-to-all transposes; C4 (spin-exchange / pair-hopping) uses the all-gather path.
+    cases = [("C1", (4, 4), True, {}), ("C1", (4, 4), False, {}), ("C1", (5, 3), True, {"srow_cmax": 12}),
+             ("NS10", (5, 5), False, {"srow_lr": 4, "srow_cmax": 24}), ("NS10", (6, 4), True, {}),
+             ("NS12", (6, 6), False, {}), ("NS12", (7, 5), True, {"srow_cmax": 64}), ("NS10V", (5, 5), False, {}),
+             ("NS10", (5, 5), True, {"no_peer": 1}), ("NS12", (6, 6), False, {"no_peer": 1, "hxv_algo": 1}),
+             ("C4", (5, 5), True, {}), ("C4", (5, 5), False, {}), ("C4", (6, 5), True, {})]
+    for name, sec, sparse, opts in cases:
         cfg = configs.config(name)
         kw = configs.solver_kwargs(cfg)
         o = O.Oracle(**kw)
         s = edgpu.Solver(ed_sparse_h=sparse, device=local, **kw)
-        s.set_comm(rank, world, uid)
+        for k_, v_ in opts.items():
+            s.set_option(k_, v_)
+        s.set_comm(rank, world, fresh_uid())
         with o.sector(*sec) as full, o.sector(sec[0], sec[1], rank, world) as mine:
             v = configs.bench_vector(full.dim)
             v /= np.linalg.norm(v)
@@ -63,10 +74,13 @@ def main():
             e_ref, vec_ref, a_ref, b_ref = full.lanc_eigh(v0=v0)
             e0, vec, a, b = s.sp_lanc_eigh(v0[sl])
             check("E0", abs(e0 - e_ref) < 1e-12 * abs(e_ref), "%.15g vs %.15g" % (e0, e_ref))
-            n = min(50, len(a), len(a_ref))
+            n = min(20, len(a), len(a_ref))          # well inside the numerically stable prefix (tests/test_gpu_parity.py)
             check("alanc", np.abs(a[:n] - a_ref[:n]).max() < 1e-8 and np.abs(b[:n] - b_ref[:n]).max() < 1e-8)
-            sgn = np.sign(vec[0] * vec_ref[sl][0]) if vec[0] != 0 else 1.0
-            check("vec", np.abs(sgn * vec - vec_ref[sl]).max() < 1e-6)
+            # same eigenvector up to a global sign: overlap of the sharded vector with the oracle's (second order in
+            # the vector error, like the single-GPU test)
+            ov = torch.tensor([float(vec @ vec_ref[sl]), float(vec @ vec)], dtype=torch.float64, device="cuda")
+            dist.all_reduce(ov)
+            check("vec", abs(abs(ov[0].item()) - 1) < 1e-10 and abs(ov[1].item() - 1) < 1e-12, "overlap %.3e" % (abs(ov[0].item()) - 1))
             s.delete_Hv_sector()
             # GF chains from the sharded ground state
             s.gf_set_state(isec, vec_ref[sl], e_ref)
@@ -80,7 +94,7 @@ def main():
                     k += 1
                     check("gf nlanc", r["nlanc"] == rc["nlanc"])
                     if rc["nlanc"]:
-                        m = min(50, rc["nlanc"])
+                        m = min(20, rc["nlanc"])
                         check("gf norm2", abs(r["norm2"] - rc["norm2"]) < 1e-12)
                         check("gf a", np.abs(r["alanc"][:m] - rc["alanc"][:m]).max() < 1e-8)
                         check("gf b", np.abs(r["blanc"][:m] - rc["blanc"][:m]).max() < 1e-8)
