@@ -125,6 +125,8 @@ int edgpu_set_err(int code, const char *fmt, ...);
 // ---- cross-file entry points ------------------------------------------------------------------
 // hxv.cu: y = H x on the local shard (device pointers), all terms, any nranks
 int hxv_apply(edgpu_ctx *c, const double *d_x, double *d_y);
+// true when hxv_apply would take the fast two-kernel path for this vector (then the Lanczos epilogue can be fused)
+bool hxv_fast_path(edgpu_ctx *c, const double *d_x);
 // Lanczos-fused form: w = sx*(H x) - cprev*xp (written over xp), partial sums of (sx*x).w go to
 // c->d_partials; scalars are read from c->d_st on device.
 int hxv_release_plan(edgpu_ctx *c);
@@ -140,8 +142,9 @@ int fast_plan_build(edgpu_ctx *c);
 int fast_plan_free(edgpu_ctx *c);
 bool fast_supported_local(edgpu_ctx *c);          // full operator on the local shard (peer reads when nranks > 1)
 bool fast_supported_col(edgpu_ctx *c, int k);     // whole-column kernel for factor k
-int fast_apply_local(edgpu_ctx *c, const double *d_x, double *d_y);
-int fast_apply_col(edgpu_ctx *c, int k, bool with_diag, bool acc, const double *d_x, double *d_y, int64_t ncols, int64_t coloff);
+int fast_apply_local(edgpu_ctx *c, const double *d_x, double *d_y, double *d_xp = nullptr, int *npartials = nullptr);
+int fast_apply_col(edgpu_ctx *c, int k, bool with_diag, bool acc, const double *d_x, double *d_y, int64_t ncols, int64_t coloff,
+                   double *d_xp = nullptr, int *npartials = nullptr);
 int fast_apply_row(edgpu_ctx *c, bool with_diag, bool acc, const double *d_x, double *d_y, const double *const *xpeer);
 bool fast_peer_ready(edgpu_ctx *c, const double *d_x);   // sharded: x lives in the symmetric slab, peers are mapped
 // comm.cu

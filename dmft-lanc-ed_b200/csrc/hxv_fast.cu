@@ -138,18 +138,27 @@ struct FColArgs {
   int norb;
   double uloc[EDGPU_MAX_ORB];
   double ust;
+  // MODE == 2 (Lanczos epilogue): w = sx*(y + F x) - cprev*xp, written over xp; partials of (sx*x).w
+  double *xp;
+  const LancState *st;
+  double *partials;
 };
 
+// MODE: 0 = y = F x, 1 = y += F x, 2 = y += F x fused with the first Lanczos vector update (y is only read)
 // UNI: 0 = general (value table), 1 = uniform magnitude with 4-byte entries, 2 = uniform with 2-byte entries
-template <int WT, int DIAG, int UNI, bool ACC>
+template <int WT, int DIAG, int UNI, int MODE>
 __global__ void __launch_bounds__(FCOL_THREADS, 1) k_fcol(FColArgs a) {
+  constexpr bool ACC = MODE >= 1;
   extern __shared__ __align__(128) unsigned char smraw[];
   const int n = a.n, ld = n + 2;
   double *buf0 = reinterpret_cast<double *>(smraw);
   double *buf1 = buf0 + ld;
   double *vtab = buf1 + ld;
   uint64_t *bar = reinterpret_cast<uint64_t *>(vtab + F_MAXVALS);
+  double *red = reinterpret_cast<double *>(bar + 2);             // [32] block reduction (MODE == 2)
   const int tid = threadIdx.x;
+  double lsx = 0.0, lcp = 0.0, lsum = 0.0;
+  if (MODE == 2) { lsx = a.st->sx; lcp = a.st->cprev; }
   if (tid == 0) {
     mbar_init(&bar[0], 1);
     mbar_init(&bar[1], 1);
@@ -222,7 +231,14 @@ __global__ void __launch_bounds__(FCOL_THREADS, 1) k_fcol(FColArgs a) {
       }
       if (UNI) acc0 = fma(a.vuni, acc, acc0); else acc0 += acc;
       if (ACC) acc0 += yold;
-      __stcs(yc + r, acc0);
+      if (MODE == 2) {
+        double *wp = a.xp + j * (int64_t)n + r;
+        const double w = lsx * acc0 - lcp * __ldcs(wp);
+        __stcs(wp, w);
+        lsum = fma(lsx * xs[r], w, lsum);
+      } else {
+        __stcs(yc + r, acc0);
+      }
     }
     __syncthreads();                           // every thread is done reading this buffer
     const int64_t j2 = j + 2 * G;
@@ -233,6 +249,16 @@ __global__ void __launch_bounds__(FCOL_THREADS, 1) k_fcol(FColArgs a) {
       char *dst = reinterpret_cast<char *>(b ? buf1 : buf0);
       for (uint32_t off = 0; off < colbytes; off += 32768u)
         bulk_g2s(dst + off, src + off, min(32768u, colbytes - off), &bar[b]);
+    }
+  }
+  if (MODE == 2) {                                               // deterministic: fixed order inside the CTA, one partial per CTA
+    for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+    if ((tid & 31) == 0) red[tid >> 5] = lsum;
+    __syncthreads();
+    if (tid < 32) {
+      double r2 = red[tid];
+      for (int o = 16; o > 0; o >>= 1) r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+      if (tid == 0) a.partials[blockIdx.x] = r2;
     }
   }
 }
@@ -309,6 +335,8 @@ struct SRowTile {
   const double *vhigh;           // shared, vhigh[kk] = V_{LR+kk}
   const double *const *xb;       // shared: per-rank base of x
   size_t row;                    // row of this lane (clamped into the matrix)
+  const double *x0;              // single rank: x (column 0, row 0)
+  const double *tile;            // shared-memory tile of this item (column cb, row 0)
   const int *co;                 // shared: per-rank first column
   size_t n;                      // column stride in elements
   int cb, csz, nhigh, dbg;
@@ -316,66 +344,90 @@ struct SRowTile {
   double drow0, drow1;
 };
 
-// One high-bit hop applied to the register block.  BK = the hopped bath bit is occupied in the target
-// group: targets are the columns with the impurity empty, sources lo|1 in class N+1; otherwise targets
-// have the impurity occupied and sources are lo&~1 in class N-1.  NB hops are fused so that all their
-// loads are in flight before the first use (far sources come from L2 with ~1 us latency).
-template <int LR, int N, int CNT, bool BK, bool FAR, int NB>
-__device__ __forceinline__ void srow_hops(const double (&sv)[NB], const double *const (&src)[NB], size_t ss, double (&acc)[CNT]) {
-  constexpr int HB = lowtab::imax(1, BK ? lowtab::binom(LR - 1, N) : lowtab::binom(LR - 1, N - 1));
-  double v[NB][HB];
-  static_for<NB>([&](auto bc) {
-    constexpr int q = decltype(bc)::value;
-    static_for<CNT>([&](auto ic) {
-      constexpr int i = decltype(ic)::value;
-      constexpr int lo = lowtab::pat(LR, N, i);
-      if constexpr (((lo & 1) == 0) == BK) {
-        constexpr int j = lowtab::rank(BK ? (lo | 1) : (lo & ~1));
-        constexpr int hi = lowtab::half_index(LR, N, i, BK ? 0 : 1);
-        v[q][hi] = FAR ? __ldg(src[q] + j * ss) : src[q][j * SROW_R];
-      }
-    });
-  });
-  static_for<NB>([&](auto bc) {
-    constexpr int q = decltype(bc)::value;
-    static_for<CNT>([&](auto ic) {
-      constexpr int i = decltype(ic)::value;
-      constexpr int lo = lowtab::pat(LR, N, i);
-      if constexpr (((lo & 1) == 0) == BK) {
-        constexpr int par = lowtab::popc(lo >> 1) & 1;
-        constexpr int hi = lowtab::half_index(LR, N, i, BK ? 0 : 1);
-        if constexpr (par) acc[i] = fma(-sv[q], v[q][hi], acc[i]);
-        else acc[i] = fma(sv[q], v[q][hi], acc[i]);
-      }
-    });
-  });
-}
+// Per-group hop descriptors, built once per group by class-independent code (srow_prepare) and kept in
+// shared memory (one slot per high bit and warp): where the partner group's first column is (a GENERIC
+// pointer: the shared-memory tile, this GPU's L2, or a peer GPU over NVLink) and the signed hopping amplitude.
+struct HopDesc {
+  const double *p;
+  double v;
+};
 
-// all hops of one kind (BK, FAR) of a group: the set bits of `m`, NB at a time
-template <int LR, int N, int CNT, bool BK, bool FAR, int NB>
-__device__ __forceinline__ void srow_hop_set(const SRowTile &k, uint32_t h, uint32_t par, uint32_t m, double (&acc)[CNT]) {
+// NB hops of one kind fused so that all their loads are in flight before the first use (far sources have
+// ~1 us latency).  BK = the hopped bath bit is occupied in the target group: targets are the columns with the
+// impurity empty, sources lo|1 in class N+1; otherwise targets have the impurity occupied, sources lo&~1 in N-1.
+template <int LR, int N, int CNT, bool BK, int NB>
+__device__ __forceinline__ void srow_hop_set(const HopDesc *desc, uint32_t m, size_t ss, size_t loff, double (&acc)[CNT]) {
   if constexpr ((BK && N == LR) || (!BK && N == 0)) return;        // no such targets in this class
+  constexpr int HB = lowtab::imax(1, BK ? lowtab::binom(LR - 1, N) : lowtab::binom(LR - 1, N - 1));
   while (m) {
-    double sv[NB];
-    const double *src[NB];
+    HopDesc d[NB];
 #pragma unroll
     for (int q = 0; q < NB; q++) {
-      const bool ok = m != 0;                                     // q == 0 is always a real hop
-      const int kk = ok ? __ffs((int)m) - 1 : 0;
+      if (m == 0) { d[q].p = d[0].p; d[q].v = 0.0; continue; }     // padding slot: re-reads slot 0's source, weight 0
+      d[q] = desc[__ffs((int)m) - 1];                              // warp-uniform base; this lane's row is added here
+      d[q].p += loff;
       m &= m - 1;
-      const long long vb = __double_as_longlong(k.vhigh[kk]) ^ ((long long)((par >> kk) & 1u) << 63);
-      sv[q] = ok ? __longlong_as_double(vb) : 0.0;                  // padding slot: re-reads slot 0's source, weight 0
-      const int c2 = k.jhi[h ^ (1u << kk)];
-      const int col2 = c2 & JHI_COLMASK, own = (c2 >> 20) & 63;
-      const double *p = FAR ? k.xb[own] + k.row + (size_t)(col2 - k.co[own]) * k.n : k.tl + (col2 - k.cb) * SROW_R;
-      src[q] = (ok || q == 0) ? p : src[0];
     }
-    srow_hops<LR, N, CNT, BK, FAR, NB>(sv, src, k.n, acc);
+    double v[NB][HB];
+    static_for<NB>([&](auto bc) {
+      constexpr int q = decltype(bc)::value;
+      static_for<CNT>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        constexpr int lo = lowtab::pat(LR, N, i);
+        if constexpr (((lo & 1) == 0) == BK) {
+          constexpr int j = lowtab::rank(BK ? (lo | 1) : (lo & ~1));
+          constexpr int hi = lowtab::half_index(LR, N, i, BK ? 0 : 1);
+          v[q][hi] = d[q].p[j * ss];
+        }
+      });
+    });
+    static_for<NB>([&](auto bc) {
+      constexpr int q = decltype(bc)::value;
+      static_for<CNT>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        constexpr int lo = lowtab::pat(LR, N, i);
+        if constexpr (((lo & 1) == 0) == BK) {
+          constexpr int par = lowtab::popc(lo >> 1) & 1;
+          constexpr int hi = lowtab::half_index(LR, N, i, BK ? 0 : 1);
+          if constexpr (par) acc[i] = fma(-d[q].v, v[q][hi], acc[i]);
+          else acc[i] = fma(d[q].v, v[q][hi], acc[i]);
+        }
+      });
+    });
   }
 }
 
+// class-independent part of a group: descriptors of its high-bit hops; returns the masks of the hops whose
+// source lies in the tile (stride 32 elements) and elsewhere (stride n elements)
+template <bool SH>
+__device__ __forceinline__ void srow_prepare(const SRowTile &k, uint32_t h, HopDesc *desc, uint32_t &inmask, uint32_t &farmask) {
+  uint32_t par = h ^ (h << 1);                                     // bit kk of par = parity of h below bit kk
+  par ^= par << 2; par ^= par << 4; par ^= par << 8;
+  par <<= 1;
+  inmask = 0; farmask = 0;
+#pragma unroll 1
+  for (int kk = 0; kk < k.nhigh; kk++) {
+    const int c2 = k.jhi[h ^ (1u << kk)];
+    if (c2 & JHI_CUT) continue;                                    // empty group, or cut by a rank boundary (fix-up kernel)
+    const int col2 = c2 & JHI_COLMASK;
+    HopDesc d;
+    d.v = __longlong_as_double(__double_as_longlong(k.vhigh[kk]) ^ ((long long)((par >> kk) & 1u) << 63));
+    if ((unsigned)(col2 - k.cb) < (unsigned)k.csz) {
+      d.p = k.tile + (col2 - k.cb) * SROW_R;
+      inmask |= 1u << kk;
+    } else {
+      if (SH) { const int own = (c2 >> 20) & 63; d.p = k.xb[own] + (size_t)(col2 - k.co[own]) * k.n; }
+      else d.p = k.x0 + (size_t)col2 * k.n;
+      farmask |= 1u << kk;
+    }
+    if ((threadIdx.x & 31) == 0) desc[kk] = d;
+  }
+  __syncwarp();
+}
+
 template <int LR, int N, int DIAG, bool ACC>
-__device__ __forceinline__ void srow_group(const SRowTile &k, const uint32_t h, const int base, const double (&vlow)[LR]) {
+__device__ __forceinline__ void srow_group(const SRowTile &k, const uint32_t h, const int base, const double (&vlow)[LR],
+                                           const HopDesc *desc, uint32_t inmask, uint32_t farmask) {
   constexpr int CNT = lowtab::binom(LR, N);
   double xv[CNT], acc[CNT];
   const int lb = base - k.cb;
@@ -403,27 +455,15 @@ __device__ __forceinline__ void srow_group(const SRowTile &k, const uint32_t h, 
       }
     });
   });
-  // hops on the high bits: the whole group maps onto ONE other group (Lin table jhi).  Sources inside
-  // the chunk come from the shared-memory tile, the others straight from L2.
-  uint32_t par = h ^ (h << 1);                                     // bit kk of par = parity of h below bit kk
-  par ^= par << 2; par ^= par << 4; par ^= par << 8;
-  par = (par << 1);
-  uint32_t inmask = 0;                                             // high bits whose partner group is in the tile
-  uint32_t farmask = 0;                                            // ... or elsewhere (L2 / a peer GPU)
-#pragma unroll 1
-  for (int kk = 0; kk < k.nhigh; kk++) {
-    const int c2 = k.jhi[h ^ (1u << kk)];
-    if (c2 & JHI_CUT) continue;                                    // empty group, or cut by a rank boundary (fix-up kernel)
-    if ((unsigned)((c2 & JHI_COLMASK) - k.cb) < (unsigned)k.csz) inmask |= 1u << kk;
-    else farmask |= 1u << kk;
-  }
-  if (!(k.dbg & 1)) {                                              // far sources first: longest latency
-    srow_hop_set<LR, N, CNT, true, true, 3>(k, h, par, farmask & h, acc);
-    srow_hop_set<LR, N, CNT, false, true, 3>(k, h, par, farmask & ~h, acc);
+  // hops on the high bits: the whole group maps onto ONE other group (descriptors from srow_prepare).  Far
+  // sources first (longest latency, three hops' loads in flight), then the ones in the shared-memory tile.
+  if (!(k.dbg & 1)) {
+    srow_hop_set<LR, N, CNT, true, 3>(desc, farmask & h, k.n, k.row, acc);
+    srow_hop_set<LR, N, CNT, false, 3>(desc, farmask & ~h, k.n, k.row, acc);
   }
   if (!(k.dbg & 2)) {
-    srow_hop_set<LR, N, CNT, true, false, 2>(k, h, par, inmask & h, acc);
-    srow_hop_set<LR, N, CNT, false, false, 2>(k, h, par, inmask & ~h, acc);
+    srow_hop_set<LR, N, CNT, true, 1>(desc, inmask & h, SROW_R, (size_t)(threadIdx.x & 31), acc);
+    srow_hop_set<LR, N, CNT, false, 1>(desc, inmask & ~h, SROW_R, (size_t)(threadIdx.x & 31), acc);
   }
   double *yp = k.yg + (size_t)base * k.n;                          // yg / dgg are biased by -c0 columns
   if (DIAG == 1) {
@@ -442,14 +482,14 @@ __device__ __forceinline__ void srow_group(const SRowTile &k, const uint32_t h, 
 
 template <int LR, int DIAG, bool ACC, int... NS>
 __device__ __forceinline__ void srow_dispatch(const SRowTile &k, uint32_t h, int base, int nlow, const double (&vlow)[LR],
-                                              std::integer_sequence<int, NS...>) {
-  ((nlow == NS ? (srow_group<LR, NS, DIAG, ACC>(k, h, base, vlow), 0) : 0), ...);
+                                              const HopDesc *desc, uint32_t inmask, uint32_t farmask, std::integer_sequence<int, NS...>) {
+  ((nlow == NS ? (srow_group<LR, NS, DIAG, ACC>(k, h, base, vlow, desc, inmask, farmask), 0) : 0), ...);
 }
 
 // 16 consumer warps + 1 producer warp.  full[b]: the TMA copies of buffer b have landed; empty[b]: every
 // consumer warp is done with buffer b.  Consumer warps take the low groups of the tile from a shared
 // counter and run ahead into the next buffer without a CTA-wide barrier.
-template <int LR, int DIAG, bool ACC>
+template <int LR, int DIAG, bool ACC, bool SH>
 __global__ void __launch_bounds__(srow_consumers(LR) + 32, 1) k_srow(const __grid_constant__ CUtensorMap tmx, SRowArgs a) {
   extern __shared__ __align__(128) unsigned char smraw[];
   const int cpad = ((a.cmax + SROW_BC - 1) / SROW_BC) * SROW_BC;
@@ -462,9 +502,11 @@ __global__ void __launch_bounds__(srow_consumers(LR) + 32, 1) k_srow(const __gri
   int *gctr = reinterpret_cast<int *>(bar + 4);                   // [2] (+2 pad)
   const double **xbs = reinterpret_cast<const double **>(gctr + 4);   // [SROW_MAXP] per-rank base of x
   int *cos = reinterpret_cast<int *>(xbs + SROW_MAXP);            // [SROW_MAXP + 1] (+ pad)
-  int32_t *jhi = reinterpret_cast<int32_t *>(cos + SROW_MAXP + 3);   // [2^nhigh]
+  HopDesc *desc0 = reinterpret_cast<HopDesc *>(cos + SROW_MAXP + 4);   // 16-byte aligned: every table before it is   // [24 warps][16] hop descriptors of the group in flight
+  int32_t *jhi = reinterpret_cast<int32_t *>(desc0 + 24 * 16);    // [2^nhigh]
   uint16_t *grp = reinterpret_cast<uint16_t *>(jhi + (1 << a.nhigh));   // [ngroups]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  HopDesc *desc = desc0 + warp * 16;
   if (tid == 0) {
     mbar_init(&bar[0], 1);
     mbar_init(&bar[1], 1);
@@ -532,7 +574,7 @@ __global__ void __launch_bounds__(srow_consumers(LR) + 32, 1) k_srow(const __gri
     k.tl = tile0 + (size_t)b * tsz + lane;
     k.dsc = dsc0 + (size_t)b * (cpad + 2) + (ch.z & 1);
     k.yg = a.y + row - (ptrdiff_t)a.c0 * a.n; k.dgg = a.diag + row - (ptrdiff_t)a.c0 * a.n;
-    k.xb = xbs; k.co = cos; k.row = (size_t)row;
+    k.xb = xbs; k.co = cos; k.row = (size_t)row; k.x0 = a.x; k.tile = tile0 + (size_t)b * tsz;
     k.jhi = jhi; k.vhigh = vhigh;
     k.n = (size_t)a.n; k.cb = ch.z; k.csz = ch.w - ch.z; k.nhigh = a.nhigh; k.dbg = a.dbg;
     k.active = (i0 + lane) < a.n;
@@ -550,7 +592,10 @@ __global__ void __launch_bounds__(srow_consumers(LR) + 32, 1) k_srow(const __gri
       const uint32_t h = grp[g];
       const int base = jhi[h] & JHI_COLMASK;
       const int nlow = a.ndw - __popc(h);
-      srow_dispatch<LR, DIAG, ACC>(k, h, base, nlow, vlow, std::make_integer_sequence<int, LR + 1>{});
+      uint32_t inmask, farmask;
+      srow_prepare<SH>(k, h, desc, inmask, farmask);
+      srow_dispatch<LR, DIAG, ACC>(k, h, base, nlow, vlow, desc, inmask, farmask, std::make_integer_sequence<int, LR + 1>{});
+      __syncwarp();                                                 // descriptors are rewritten for the next group
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&bar[2 + b]);                       // this warp is done with buffer b
@@ -603,11 +648,11 @@ static int pack_fast(edgpu_ctx *c, const Factor &f, FastFactor &ff) {
   return EDGPU_OK;
 }
 
-static size_t fcol_smem(int64_t n) { return (size_t)2 * (n + 2) * 8 + F_MAXVALS * 8 + 16; }
+static size_t fcol_smem(int64_t n) { return (size_t)2 * (n + 2) * 8 + F_MAXVALS * 8 + 16 + 32 * 8; }
 static size_t srow_smem(int cmax, int nhigh, int ngroups) {
   const size_t cpad = (size_t)((cmax + SROW_BC - 1) / SROW_BC) * SROW_BC;
-  size_t b = (size_t)2 * cpad * SROW_R * 8 + (size_t)2 * (cpad + 2) * 8 + 4 * SROW_R * 8 + 32 * 8 + 32 + 16 + 8 * SROW_MAXP + 4 * (SROW_MAXP + 3) +
-             ((size_t)4 << nhigh) + (size_t)2 * ngroups;
+  size_t b = (size_t)2 * cpad * SROW_R * 8 + (size_t)2 * (cpad + 2) * 8 + 4 * SROW_R * 8 + 32 * 8 + 32 + 16 + 8 * SROW_MAXP + 4 * (SROW_MAXP + 4) +
+             24 * 16 * 16 + ((size_t)4 << nhigh) + (size_t)2 * ngroups;
   return (b + 15) & ~(size_t)15;
 }
 
@@ -658,12 +703,12 @@ static int build_srow(edgpu_ctx *c, SRowPlan &sr, int LR) {
     if (g0 < sr.ngroups && gbase[g0] >= c1) g1 = g0;               // nothing whole on this rank
   }
   // chunk size from the shared-memory budget (or the option), chunks = runs of whole groups
-  int cmax = (int)((SMEM_LIMIT - 4096 - ((size_t)4 << sr.nhigh) - 2 * (size_t)sr.ngroups) / (2 * (SROW_R + 1) * 8));
+  int cmax = (int)((SMEM_LIMIT - 12288 - ((size_t)4 << sr.nhigh) - 2 * (size_t)sr.ngroups) / (2 * (SROW_R + 1) * 8));
   cmax = cmax / SROW_BC * SROW_BC;
   if (cmax > 32 * SROW_BC) cmax = 32 * SROW_BC;             // one tensor copy per lane of the producer warp
-  // measured on B200 (C3): tiles of ~288 columns beat the largest that fits; the L1 that is left over
-  // (228 KB - shared memory) serves the out-of-tile sources
-  if (c->opt_srow_cmax <= 0 && cmax > 288) cmax = 288;
+  // measured on B200 (C3, chunk sweep 96..352): tiles of ~160 columns beat the largest that fits by 25 %;
+  // the L1 that is left over (228 KB - shared memory) serves the out-of-tile sources
+  if (c->opt_srow_cmax <= 0 && cmax > 160) cmax = 160;
   if (c->opt_srow_cmax > 0 && c->opt_srow_cmax < cmax) cmax = (int)c->opt_srow_cmax;
   if (cmax < lowtab::binom(LR, LR / 2)) return EDGPU_OK;
   // balance: all chunks about the same size
@@ -771,15 +816,18 @@ template <int WT, int DIAG>
 static cudaError_t set_fcol_attr() {
   cudaError_t e = cudaSuccess;
 #define SETF(U, A) if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fcol<WT, DIAG, U, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT)
-  SETF(0, false); SETF(1, false); SETF(2, false); SETF(0, true); SETF(1, true); SETF(2, true);
+  SETF(0, 0); SETF(1, 0); SETF(2, 0); SETF(0, 1); SETF(1, 1); SETF(2, 1);
+  if (DIAG == 0) { SETF(0, 2); SETF(1, 2); SETF(2, 2); }
 #undef SETF
   return e;
 }
 template <int LR, int DIAG>
 static cudaError_t set_srow_attr() {
-  cudaError_t e = cudaFuncSetAttribute(k_srow<LR, DIAG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(k_srow<LR, DIAG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+  cudaError_t e = cudaFuncSetAttribute(k_srow<LR, DIAG, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_srow<LR, DIAG, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_srow<LR, DIAG, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_srow<LR, DIAG, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+  return e;
 }
 
 int fast_plan_build(edgpu_ctx *c) {
@@ -821,27 +869,28 @@ bool fast_supported_col(edgpu_ctx *c, int k) {
   return c->fplan->col_ok[k];
 }
 
+template <int WT, int DIAG, int MODE>
+static void launch_fcol_m(int uni, int grid, size_t smem, cudaStream_t st, const FColArgs &a) {
+  if (uni == 2) k_fcol<WT, DIAG, 2, MODE><<<grid, FCOL_THREADS, smem, st>>>(a);
+  else if (uni == 1) k_fcol<WT, DIAG, 1, MODE><<<grid, FCOL_THREADS, smem, st>>>(a);
+  else k_fcol<WT, DIAG, 0, MODE><<<grid, FCOL_THREADS, smem, st>>>(a);
+}
 template <int WT, int DIAG>
-static void launch_fcol(int uni, bool acc, int grid, size_t smem, cudaStream_t st, const FColArgs &a) {
-  if (acc) {
-    if (uni == 2) k_fcol<WT, DIAG, 2, true><<<grid, FCOL_THREADS, smem, st>>>(a);
-    else if (uni == 1) k_fcol<WT, DIAG, 1, true><<<grid, FCOL_THREADS, smem, st>>>(a);
-    else k_fcol<WT, DIAG, 0, true><<<grid, FCOL_THREADS, smem, st>>>(a);
-  } else {
-    if (uni == 2) k_fcol<WT, DIAG, 2, false><<<grid, FCOL_THREADS, smem, st>>>(a);
-    else if (uni == 1) k_fcol<WT, DIAG, 1, false><<<grid, FCOL_THREADS, smem, st>>>(a);
-    else k_fcol<WT, DIAG, 0, false><<<grid, FCOL_THREADS, smem, st>>>(a);
-  }
+static void launch_fcol(int uni, int mode, int grid, size_t smem, cudaStream_t st, const FColArgs &a) {
+  if (mode == 2) { if constexpr (DIAG == 0) launch_fcol_m<WT, 0, 2>(uni, grid, smem, st, a); }
+  else if (mode == 1) launch_fcol_m<WT, DIAG, 1>(uni, grid, smem, st, a);
+  else launch_fcol_m<WT, DIAG, 0>(uni, grid, smem, st, a);
 }
 template <int DIAG>
-static void launch_fcol_w(int WT, int uni, bool acc, int grid, size_t smem, cudaStream_t st, const FColArgs &a) {
-  if (WT == 8) launch_fcol<8, DIAG>(uni, acc, grid, smem, st, a);
-  else if (WT == 12) launch_fcol<12, DIAG>(uni, acc, grid, smem, st, a);
-  else launch_fcol<16, DIAG>(uni, acc, grid, smem, st, a);
+static void launch_fcol_w(int WT, int uni, int mode, int grid, size_t smem, cudaStream_t st, const FColArgs &a) {
+  if (WT == 8) launch_fcol<8, DIAG>(uni, mode, grid, smem, st, a);
+  else if (WT == 12) launch_fcol<12, DIAG>(uni, mode, grid, smem, st, a);
+  else launch_fcol<16, DIAG>(uni, mode, grid, smem, st, a);
 }
 
 // y (+)= [Hd o x +] F_k x on a matrix whose contiguous dimension is factor k's index
-int fast_apply_col(edgpu_ctx *c, int k, bool with_diag, bool acc, const double *d_x, double *d_y, int64_t ncols, int64_t coloff) {
+int fast_apply_col(edgpu_ctx *c, int k, bool with_diag, bool acc, const double *d_x, double *d_y, int64_t ncols, int64_t coloff,
+                   double *d_xp, int *npartials) {
   TRY(fast_plan_build(c));
   FastPlan *p = c->fplan;
   if (!p->col_ok[k]) return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "fast column kernel does not cover this factor");
@@ -858,27 +907,37 @@ int fast_apply_col(edgpu_ctx *c, int k, bool with_diag, bool acc, const double *
   const int grid = (int)std::min<int64_t>(ncols, c->sm_count);
   if (grid < 1) return EDGPU_OK;
   const int diag = !with_diag ? 0 : (c->d_diag ? 1 : 2);
+  const int mode = d_xp ? 2 : (acc ? 1 : 0);
+  if (mode == 2 && (diag != 0 || !acc)) return edgpu_set_err(EDGPU_ERR_INVALID, "Lanczos epilogue needs the accumulate form without diagonal");
+  a.xp = d_xp; a.st = c->d_st; a.partials = c->d_partials;
+  if (npartials) *npartials = grid;
   // no_uniform: 0 = best available, 1 = force the value-table kernel, 2 = uniform kernel with 4-byte entries
   int uni = 0;
   if (ff.uniform && c->opt_no_uniform != 1) uni = (ff.d_ell16 && c->opt_no_uniform != 2) ? 2 : 1;
-  if (diag == 0) launch_fcol_w<0>(ff.WT, uni, acc, grid, p->col_smem[k], c->stream, a);
-  else if (diag == 1) launch_fcol_w<1>(ff.WT, uni, acc, grid, p->col_smem[k], c->stream, a);
-  else launch_fcol_w<2>(ff.WT, uni, acc, grid, p->col_smem[k], c->stream, a);
+  if (diag == 0) launch_fcol_w<0>(ff.WT, uni, mode, grid, p->col_smem[k], c->stream, a);
+  else if (diag == 1) launch_fcol_w<1>(ff.WT, uni, mode, grid, p->col_smem[k], c->stream, a);
+  else launch_fcol_w<2>(ff.WT, uni, mode, grid, p->col_smem[k], c->stream, a);
   CKL(c);
   return EDGPU_OK;
 }
 
-template <int LR>
-static void launch_srow(int diag, bool acc, int grid, size_t smem, cudaStream_t st, const CUtensorMap &tmx, const SRowArgs &a) {
+template <int LR, bool SH>
+static void launch_srow_s(int diag, bool acc, int grid, size_t smem, cudaStream_t st, const CUtensorMap &tmx, const SRowArgs &a) {
+  const int nt = srow_consumers(LR) + 32;
   if (acc) {
-    if (diag == 0) k_srow<LR, 0, true><<<grid, srow_consumers(LR) + 32, smem, st>>>(tmx, a);
-    else if (diag == 1) k_srow<LR, 1, true><<<grid, srow_consumers(LR) + 32, smem, st>>>(tmx, a);
-    else k_srow<LR, 2, true><<<grid, srow_consumers(LR) + 32, smem, st>>>(tmx, a);
+    if (diag == 0) k_srow<LR, 0, true, SH><<<grid, nt, smem, st>>>(tmx, a);
+    else if (diag == 1) k_srow<LR, 1, true, SH><<<grid, nt, smem, st>>>(tmx, a);
+    else k_srow<LR, 2, true, SH><<<grid, nt, smem, st>>>(tmx, a);
   } else {
-    if (diag == 0) k_srow<LR, 0, false><<<grid, srow_consumers(LR) + 32, smem, st>>>(tmx, a);
-    else if (diag == 1) k_srow<LR, 1, false><<<grid, srow_consumers(LR) + 32, smem, st>>>(tmx, a);
-    else k_srow<LR, 2, false><<<grid, srow_consumers(LR) + 32, smem, st>>>(tmx, a);
+    if (diag == 0) k_srow<LR, 0, false, SH><<<grid, nt, smem, st>>>(tmx, a);
+    else if (diag == 1) k_srow<LR, 1, false, SH><<<grid, nt, smem, st>>>(tmx, a);
+    else k_srow<LR, 2, false, SH><<<grid, nt, smem, st>>>(tmx, a);
   }
+}
+template <int LR>
+static void launch_srow(bool sharded, int diag, bool acc, int grid, size_t smem, cudaStream_t st, const CUtensorMap &tmx, const SRowArgs &a) {
+  if (sharded) launch_srow_s<LR, true>(diag, acc, grid, smem, st, tmx, a);
+  else launch_srow_s<LR, false>(diag, acc, grid, smem, st, tmx, a);
 }
 
 // 2-D tensor map of a column-major double matrix (n0 contiguous), box = b0 x b1 elements
@@ -969,8 +1028,8 @@ int fast_apply_row(edgpu_ctx *c, bool with_diag, bool acc, const double *d_x, do
     CUtensorMap tmx;
     TRY(make_tmap_2d(&tmx, d_x, (uint64_t)c->dimup, (uint64_t)c->qdw, SROW_R, SROW_BC));
     // a rank may own no whole group at all (tiny sectors): the chunk table then holds one empty chunk
-    if (sr.LR == 4) launch_srow<4>(diag, acc, grid, sr.smem, c->stream, tmx, a);
-    else launch_srow<5>(diag, acc, grid, sr.smem, c->stream, tmx, a);
+    if (sr.LR == 4) launch_srow<4>(c->nranks > 1, diag, acc, grid, sr.smem, c->stream, tmx, a);
+    else launch_srow<5>(c->nranks > 1, diag, acc, grid, sr.smem, c->stream, tmx, a);
     CKL(c);
   }
   if (sr.nfix > 0) {
@@ -999,10 +1058,12 @@ bool fast_peer_ready(edgpu_ctx *c, const double *d_x) {
   return c->nranks > 1 && c->nranks <= SROW_MAXP && c->sym_ok && sym_offset(c, d_x) >= 0;
 }
 
-int fast_apply_local(edgpu_ctx *c, const double *d_x, double *d_y) {
+// d_xp != nullptr: Lanczos form -- d_y only holds the row-pass partial result, w = sx*(H x) - cprev*xp goes to
+// d_xp and the per-CTA partial sums of (sx*x).w to c->d_partials (*npartials of them)
+int fast_apply_local(edgpu_ctx *c, const double *d_x, double *d_y, double *d_xp, int *npartials) {
   if (c->opt_dbg & 8) {                                            // experiment: column pass first
     prof_mark(c, "k_fcol");
-    TRY(fast_apply_col(c, 0, false, false, d_x, d_y, c->qdw, c->coloff));
+    TRY(fast_apply_col(c, 0, false, false, d_x, d_y, c->qdw, c->coloff, nullptr, nullptr));
     prof_mark(c, "k_srow");
     TRY(fast_apply_row(c, true, true, d_x, d_y, nullptr));
     return EDGPU_OK;
@@ -1014,6 +1075,6 @@ int fast_apply_local(edgpu_ctx *c, const double *d_x, double *d_y) {
   prof_mark(c, "k_srow");
   TRY(fast_apply_row(c, true, false, d_x, d_y, xpeer));
   prof_mark(c, "k_fcol");
-  TRY(fast_apply_col(c, 0, false, true, d_x, d_y, c->qdw, c->coloff));
+  TRY(fast_apply_col(c, 0, false, true, d_x, d_y, c->qdw, c->coloff, d_xp, npartials));
   return EDGPU_OK;
 }

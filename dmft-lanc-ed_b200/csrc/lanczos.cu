@@ -124,18 +124,25 @@ static int ensure_coeffs(edgpu_ctx *c, int n) {
   c->lanc_cap = n + 2;
   return EDGPU_OK;
 }
-static int reduce_to_state(edgpu_ctx *c) {   // partials -> st->red, all-reduced over ranks
-  k_finalize<<<1, RED_THREADS, 0, c->stream>>>(c->d_partials, RED_BLOCKS, c->d_st);
+static int reduce_to_state(edgpu_ctx *c, int nb = RED_BLOCKS) {   // partials -> st->red, all-reduced over ranks
+  k_finalize<<<1, RED_THREADS, 0, c->stream>>>(c->d_partials, nb, c->d_st);
   CKL(c);
   return comm_allreduce_scalar(c, &c->d_st->red);
 }
 
 // one Lanczos step on device; on entry X = c->d_lx (scale st->sx), Xp = c->d_lp; on exit rotated
 static int lanczos_step(edgpu_ctx *c, int k /*0-based*/) {
-  TRY(hxv_apply(c, c->d_lx, c->d_lt));
-  k_lanc_a<<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(c->d_lt, c->d_lx, c->d_lp, c->nloc, c->d_st, c->d_partials);
-  CKL(c);
-  TRY(reduce_to_state(c));
+  if (hxv_fast_path(c, c->d_lx)) {
+    // w = sx*(H x) - cprev*xp and the alpha partials come out of the column kernel's epilogue
+    int nb = 0;
+    TRY(fast_apply_local(c, c->d_lx, c->d_lt, c->d_lp, &nb));
+    TRY(reduce_to_state(c, nb));
+  } else {
+    TRY(hxv_apply(c, c->d_lx, c->d_lt));
+    k_lanc_a<<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(c->d_lt, c->d_lx, c->d_lp, c->nloc, c->d_st, c->d_partials);
+    CKL(c);
+    TRY(reduce_to_state(c));
+  }
   k_post_alpha<<<1, 1, 0, c->stream>>>(c->d_st, c->d_alanc, k);
   CKL(c);
   k_lanc_b<<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(c->d_lp, c->d_lx, c->nloc, c->d_st, c->d_partials);

@@ -1,12 +1,8 @@
 #!/bin/bash
-# One GPU-box call: the whole GPU parity suite, smoke, the default bench line, a launch list.
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
-nproc > gpurun_out/nproc.txt; free -g >> gpurun_out/nproc.txt
-timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -30 > gpurun_out/pytest_gpu.log
-tail -8 gpurun_out/pytest_gpu.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
-timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_C3.json 2> gpurun_out/bench_C3.err; cat gpurun_out/bench_C3.json; tail -3 gpurun_out/bench_C3.err
-CMD="python bench.py --workload C3 --steps 2 --warmup 3 --hxv-only"
-date +%s; $CMD > gpurun_out/plain.log 2>&1 && timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/launches_C3.csv $CMD > gpurun_out/ncu1.log 2>&1; date +%s
-tail -2 gpurun_out/ncu1.log
+timeout 900 python -m pytest tests -m gpu -q -x -k "fast_hxv" 2>&1 | grep -E "Error|error|passed|failed|FAILED" | head -12
+run() { name=$1; shift; timeout 300 python bench.py --steps 10 --warmup 3 --hxv-only "$@" > gpurun_out/hxv_$name.json 2> gpurun_out/hxv_$name.err; echo "$name: $(cut -c40-250 gpurun_out/hxv_$name.json)"; tail -2 gpurun_out/hxv_$name.err; }
+run C3_cmax288 --workload C3 --algo fast --opt srow_cmax=288
+run C3_cmax224 --workload C3 --algo fast --opt srow_cmax=224
+run C3_cmax160 --workload C3 --algo fast --opt srow_cmax=160
+run C3_lr4_224 --workload C3 --algo fast --opt srow_cmax=224 --opt srow_lr=4
