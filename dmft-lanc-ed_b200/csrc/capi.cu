@@ -419,7 +419,6 @@ extern "C" int edgpu_hxv(edgpu_ctx *c, int64_t nloc, const double *v, double *hv
   TRY(vec_alloc(c, &c->d_in, c->nloc));
   TRY(vec_alloc(c, &c->d_out, c->nloc));
   CK(cudaMemcpyAsync(c->d_in, v, (size_t)nloc * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  if (c->sym_ok) TRY(comm_barrier(c));                          // peers read d_in: every upload has landed
   TRY(hxv_apply(c, c->d_in, c->d_out));
   if (c->sym_ok) TRY(comm_barrier(c));                          // ... and nobody overwrites it while it is read
   CK(cudaMemcpyAsync(hv, c->d_out, (size_t)nloc * sizeof(double), cudaMemcpyDeviceToHost, c->stream));

@@ -1072,6 +1072,10 @@ int fast_apply_local(edgpu_ctx *c, const double *d_x, double *d_y, double *d_xp,
   const double *pb[64];
   const double *const *xpeer = peer_ptrs(c, d_x, pb);
   if (c->nranks > 1 && !xpeer) return edgpu_set_err(EDGPU_ERR_INVALID, "sharded fast H*v: the vector is not in the symmetric slab");
+  // Peers read x while this rank reads theirs.  One stream-ordered barrier per application orders every rank's
+  // earlier writes of x before the reads (RAW) and, because each rank enqueues it after its previous H*v, every
+  // rank's previous remote reads before anybody's later overwrite of those buffers (WAR).
+  if (c->nranks > 1) TRY(comm_barrier(c));
   prof_mark(c, "k_srow");
   TRY(fast_apply_row(c, true, false, d_x, d_y, xpeer));
   prof_mark(c, "k_fcol");
