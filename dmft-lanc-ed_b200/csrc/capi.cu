@@ -351,7 +351,7 @@ extern "C" int edgpu_build_hv_sector(edgpu_ctx *c, int isector) {
     // room for the engine's Lanczos vectors, the staging pair and a few user vectors, identical on every rank
     int64_t qmax = (c->dimdw + c->nranks - 1) / c->nranks;
     size_t per = (((size_t)(c->dimup * qmax) + 2) * sizeof(double) + 255) & ~(size_t)255;
-    int rc2 = comm_symm_setup(c, per * 10);
+    int rc2 = comm_symm_setup(c, per, 10);
     if (rc2) { edgpu_delete_hv_sector(c); return rc2; }
   }
   g_current = c;

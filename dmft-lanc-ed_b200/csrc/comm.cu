@@ -113,10 +113,15 @@ int64_t sym_offset(const edgpu_ctx *c, const void *p) {
 int vec_alloc(edgpu_ctx *c, double **p, int64_t n) {
   if (*p) return EDGPU_OK;
   const size_t bytes = (((size_t)(n > 0 ? n : 1) + 2) * sizeof(double) + 255) & ~(size_t)255;
-  if (c->sym_ok && c->sym_used + bytes <= c->sym_bytes) {
-    *p = reinterpret_cast<double *>(c->sym_slab + c->sym_used);
-    c->sym_used += bytes;
-    return EDGPU_OK;
+  if (c->sym_ok && c->sym_unit) {
+    // nloc differs by one column between ranks: carve in rank-independent units so that the same vector
+    // sits at the same offset on every rank
+    const size_t need = (bytes + c->sym_unit - 1) / c->sym_unit * c->sym_unit;
+    if (c->sym_used + need <= c->sym_bytes) {
+      *p = reinterpret_cast<double *>(c->sym_slab + c->sym_used);
+      c->sym_used += need;
+      return EDGPU_OK;
+    }
   }
   CK(cudaMalloc(p, bytes));
   return EDGPU_OK;
@@ -126,14 +131,16 @@ void vec_free(edgpu_ctx *c, double **p) {
   *p = nullptr;
 }
 int comm_barrier(edgpu_ctx *c) {
-  if (c->nranks == 1) return EDGPU_OK;
+  if (c->nranks == 1 || !c->comm) return EDGPU_OK;
   NK(g_nccl.AllReduce(c->d_partials + 4000, c->d_partials + 4000, 1, ncclDouble, ncclSum, (ncclComm_t)c->comm, c->stream));
   return EDGPU_OK;
 }
 // Collective.  On any failure (e.g. peers not visible to this process) every rank ends with sym_ok = false
 // and H*v uses the all-to-all transposes instead.
-int comm_symm_setup(edgpu_ctx *c, size_t bytes) {
+int comm_symm_setup(edgpu_ctx *c, size_t unit, int nunits) {
   c->sym_ok = false;
+  c->sym_unit = (unit + 255) & ~(size_t)255;
+  size_t bytes = c->sym_unit * (size_t)nunits;
   if (c->nranks == 1 || !c->comm) return EDGPU_OK;
   const int P = c->nranks, me = c->rank;
   bytes = (bytes + 255) & ~(size_t)255;

@@ -81,7 +81,7 @@ struct edgpu_ctx {
   // symmetric slab (nranks > 1): one allocation per rank at identical offsets, opened by every peer
   // through CUDA IPC, so that kernels can read a peer's copy of a vector over NVLink
   char *sym_slab = nullptr;
-  size_t sym_bytes = 0, sym_used = 0;
+  size_t sym_bytes = 0, sym_used = 0, sym_unit = 0;
   char *sym_peer[64] = {nullptr};
   bool sym_ok = false;
   // per-pass timing (edgpu_time_hxv_passes): events recorded between the kernels of one H*v
@@ -148,7 +148,7 @@ int fast_apply_col(edgpu_ctx *c, int k, bool with_diag, bool acc, const double *
 int fast_apply_row(edgpu_ctx *c, bool with_diag, bool acc, const double *d_x, double *d_y, const double *const *xpeer);
 bool fast_peer_ready(edgpu_ctx *c, const double *d_x);   // sharded: x lives in the symmetric slab, peers are mapped
 // comm.cu
-int comm_symm_setup(edgpu_ctx *c, size_t bytes);        // collective
+int comm_symm_setup(edgpu_ctx *c, size_t unit, int nunits);   // collective: nunits vectors of `unit` bytes
 int comm_symm_teardown(edgpu_ctx *c);                   // collective
 int comm_barrier(edgpu_ctx *c);                         // stream-ordered cross-rank barrier (tiny all-reduce)
 // vectors that H*v may read on a peer: carved from the symmetric slab when there is one

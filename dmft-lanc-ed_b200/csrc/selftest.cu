@@ -81,3 +81,54 @@ extern "C" int edgpu_selftest_nonlocal_row(const edgpu_params *p, uint32_t mup, 
   DevParams d = make_dp(p);
   return hd_nonlocal_row(d, mup, mdw, cup, cdw, val);
 }
+
+// Sharded fast path on ONE device: `nranks` contexts stand in for the ranks (no NCCL; each "rank" reads the
+// others' shards through ordinary device pointers).  Exercises exactly the kernels and plans of the multi-GPU
+// path -- rank-aware Lin table, low groups cut by a rank boundary, the fix-up kernel, per-owner source pointers
+// -- so that a single-GPU box can check them for any rank count.  x, y: full host vectors.
+extern "C" int edgpu_selftest_sharded_hxv(const edgpu_params *p, int nup, int ndw, int nranks, int64_t srow_lr,
+                                          int64_t srow_cmax, const double *x, double *y) {
+  if (nranks < 1 || nranks > 8) return edgpu_set_err(EDGPU_ERR_INVALID, "selftest: 1 <= nranks <= 8");
+  std::vector<edgpu_ctx *> cs((size_t)nranks, nullptr);
+  std::vector<double *> dx((size_t)nranks, nullptr), dy((size_t)nranks, nullptr);
+  int rc = EDGPU_OK;
+  auto cleanup = [&]() {
+    for (int r = 0; r < nranks; r++) {
+      if (dx[r]) cudaFree(dx[r]);
+      if (dy[r]) cudaFree(dy[r]);
+      if (cs[r]) { cs[r]->rank = 0; cs[r]->nranks = 1; edgpu_destroy(cs[r]); }
+    }
+  };
+  for (int r = 0; r < nranks && !rc; r++) {
+    rc = edgpu_create(p, -1, &cs[r]);
+    if (rc) break;
+    cs[r]->rank = r; cs[r]->nranks = nranks;                       // no communicator: peers are plain pointers here
+    edgpu_set_option(cs[r], "srow_lr", srow_lr);
+    edgpu_set_option(cs[r], "srow_cmax", srow_cmax);
+    int isec = 0;
+    rc = edgpu_get_sector(cs[r], nup, ndw, &isec);
+    if (!rc) rc = edgpu_build_hv_sector(cs[r], isec);
+    if (rc) break;
+    const size_t nb = ((size_t)cs[r]->nloc + 2) * sizeof(double);
+    if (cudaMalloc(&dx[r], nb) != cudaSuccess || cudaMalloc(&dy[r], nb) != cudaSuccess) { rc = edgpu_set_err(EDGPU_ERR_CUDA, "selftest: cudaMalloc"); break; }
+    cudaMemset(dy[r], 0, nb);
+    if (cudaMemcpy(dx[r], x + cs[r]->coloff * cs[r]->dimup, (size_t)cs[r]->nloc * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+      rc = edgpu_set_err(EDGPU_ERR_CUDA, "selftest: upload");
+      break;
+    }
+  }
+  if (!rc) cudaDeviceSynchronize();
+  for (int r = 0; r < nranks && !rc; r++) {
+    if (!fast_supported_local(cs[r])) { rc = edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "selftest: fast path does not cover this sector"); break; }
+    const double *peers[8];
+    for (int q = 0; q < 8; q++) peers[q] = dx[q < nranks ? q : 0];
+    rc = fast_apply_row(cs[r], true, false, dx[r], dy[r], nranks > 1 ? peers : nullptr);
+    if (!rc) rc = fast_apply_col(cs[r], 0, false, true, dx[r], dy[r], cs[r]->qdw, cs[r]->coloff);
+  }
+  if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = edgpu_set_err(EDGPU_ERR_CUDA, "selftest: kernels: %s", cudaGetErrorString(cudaGetLastError()));
+  for (int r = 0; r < nranks && !rc; r++)
+    if (cudaMemcpy(y + cs[r]->coloff * cs[r]->dimup, dy[r], (size_t)cs[r]->nloc * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess)
+      rc = edgpu_set_err(EDGPU_ERR_CUDA, "selftest: download");
+  cleanup();
+  return rc;
+}

@@ -23,6 +23,10 @@ double edgpu_selftest_diag(const edgpu_params *p, uint32_t mup, uint32_t mdw, in
 /* one row of spH0nd: returns the entry count, outputs column words and values */
 int edgpu_selftest_nonlocal_row(const edgpu_params *p, uint32_t mup, uint32_t mdw, uint32_t *cup, uint32_t *cdw,
                                 double *val);
+/* GPU: the sharded fast H*v path with `nranks` ranks emulated by `nranks` contexts on ONE device (peers are plain
+ * device pointers instead of NVLink mappings); x, y are full host vectors.  Test instrumentation only. */
+int edgpu_selftest_sharded_hxv(const edgpu_params *p, int nup, int ndw, int nranks, int64_t srow_lr, int64_t srow_cmax,
+                               const double *x, double *y);
 #ifdef __cplusplus
 }
 #endif

@@ -378,6 +378,38 @@ def test_fast_hxv_matches_oracle(name, sec, opts, sparse):
         s.close()
 
 
+SHARD_CASES = [("C1", (4, 4), 2, 0, 0), ("C1", (4, 4), 3, 0, 0), ("C1", (4, 4), 4, 0, 0), ("C1", (5, 3), 4, 0, 12),
+               ("NS10", (5, 5), 3, 4, 24), ("NS10", (5, 5), 8, 0, 0), ("NS10", (6, 4), 5, 0, 0), ("NS12", (6, 6), 7, 0, 64),
+               ("NS12", (7, 5), 4, 4, 0), ("NS10V", (5, 5), 6, 0, 0), ("NS12V", (6, 5), 8, 4, 48), ("C1", (3, 6), 8, 4, 12)]
+
+
+@pytest.mark.parametrize("name,sec,nranks,lr,cmax", SHARD_CASES)
+@pytest.mark.parametrize("sparse", [True, False])
+def test_sharded_fast_path_emulated_on_one_gpu(name, sec, nranks, lr, cmax, sparse):
+    """The kernels and plans of the multi-GPU fast path (rank-aware Lin table, low groups cut by a rank boundary,
+    fix-up kernel, per-owner source pointers) with the ranks emulated by contexts on ONE device
+    (edgpu_selftest_sharded_hxv): any rank count 1..8, including splits where DimDw is not a multiple of P and
+    ranks that own no whole low group."""
+    import ctypes as C
+    cfg, o = make_oracle(name)
+    s = _solver(cfg, sparse)
+    try:
+        with o.sector(*sec) as os_:
+            v = configs.bench_vector(os_.dim)
+            v /= np.linalg.norm(v)
+            ref = os_.spmatvec(v)
+            out = np.zeros(os_.dim)
+            L = edgpu.lib()
+            L.edgpu_selftest_sharded_hxv.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64,
+                                                     C.c_void_p, C.c_void_p]
+            rc = L.edgpu_selftest_sharded_hxv(C.byref(s._keep[0]), sec[0], sec[1], nranks, lr, cmax,
+                                              v.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+            assert rc == 0, L.edgpu_last_error().decode()
+            assert np.abs(out - ref).max() < 1e-13 * np.abs(ref).max()
+    finally:
+        s.close()
+
+
 def test_fast_unsupported_is_loud():
     """Odd DimUp (TMA bulk copies need 16-byte aligned columns): the explicit fast algorithm refuses,
     AUTO falls back to the generic kernels."""
