@@ -46,7 +46,8 @@ struct FastFactor {
   int64_t n = 0;
   uint32_t *d_ell = nullptr;     // [WT][n] slot-major, padding entries point at column n (zero slot)
   double *d_vtab = nullptr;      // [nvals] magnitudes, vtab[0] = 0
-  uint16_t *d_ell16 = nullptr;   // [WT][n] uniform factors with n < 32768: column | sign << 15 (halves the L2 index traffic)
+  uint16_t *d_ell16 = nullptr;   // uniform factors with n < 32768: column | sign << 15 (halves the L2 index traffic);
+                                 // [n][8] row-major when WT == 8 (one 16-byte load per row), else [WT][n]
   bool uniform = false;          // every stored magnitude identical -> y = v * sum(+-x)
   double vuni = 0.0;
 };
@@ -195,21 +196,24 @@ __global__ void __launch_bounds__(FCOL_THREADS, 1) k_fcol(FColArgs a) {
     if (DIAG == 2) { dcol = a.dfac_s[a.coloff + j]; ms = (uint32_t)a.map_s[a.coloff + j]; }
     double *yc = a.y + j * (int64_t)n;
     uint32_t en[WT];
-    if (tid < n) {
+    auto load_ell = [&](int row) {
+      if (UNI == 2 && WT == 8) {                                 // 8 two-byte entries = one LDG.128
+        const uint4 q = __ldg(reinterpret_cast<const uint4 *>(a.ell16) + row);
+        en[0] = q.x & 0xFFFFu; en[1] = q.x >> 16; en[2] = q.y & 0xFFFFu; en[3] = q.y >> 16;
+        en[4 % WT] = q.z & 0xFFFFu; en[5 % WT] = q.z >> 16; en[6 % WT] = q.w & 0xFFFFu; en[7 % WT] = q.w >> 16;
+      } else {
 #pragma unroll
-      for (int s = 0; s < WT; s++) en[s] = (UNI == 2) ? (uint32_t)__ldg(a.ell16 + (size_t)s * n + tid) : __ldg(a.ell + (size_t)s * n + tid);
-    }
+        for (int s = 0; s < WT; s++) en[s] = (UNI == 2) ? (uint32_t)__ldg(a.ell16 + (size_t)s * n + row) : __ldg(a.ell + (size_t)s * n + row);
+      }
+    };
+    if (tid < n) load_ell(tid);
     for (int r = tid; r < n; r += FCOL_THREADS) {
       uint32_t e[WT];
 #pragma unroll
       for (int s = 0; s < WT; s++) e[s] = en[s];
       double yold = 0.0;
       if (ACC) yold = __ldcs(yc + r);
-      if (r + FCOL_THREADS < n) {                // software prefetch of the next row's ELL entries
-#pragma unroll
-        for (int s = 0; s < WT; s++)
-          en[s] = (UNI == 2) ? (uint32_t)__ldg(a.ell16 + (size_t)s * n + r + FCOL_THREADS) : __ldg(a.ell + (size_t)s * n + r + FCOL_THREADS);
-      }
+      if (r + FCOL_THREADS < n) load_ell(r + FCOL_THREADS);      // software prefetch of the next row's ELL entries
       double acc0 = 0.0;
       if (DIAG == 1) acc0 = __ldcs(a.diag + j * (int64_t)n + r) * xs[r];
       if (DIAG == 2) {
@@ -641,7 +645,12 @@ static int pack_fast(edgpu_ctx *c, const Factor &f, FastFactor &ff) {
   CK(cudaMemcpy(ff.d_vtab, vtab.data(), vtab.size() * sizeof(double), cudaMemcpyHostToDevice));
   if (ff.uniform && f.n < 32768) {
     std::vector<uint16_t> e16(ell.size());
-    for (size_t i = 0; i < ell.size(); i++) e16[i] = (uint16_t)((ell[i] & 0x7FFFu) | ((ell[i] >> 31) << 15));
+    for (int k = 0; k < ff.WT; k++)
+      for (int64_t i = 0; i < f.n; i++) {
+        const uint32_t e = ell[(size_t)k * f.n + i];
+        const size_t at = (ff.WT == 8) ? (size_t)i * 8 + k : (size_t)k * f.n + i;
+        e16[at] = (uint16_t)((e & 0x7FFFu) | ((e >> 31) << 15));
+      }
     CK(cudaMalloc(&ff.d_ell16, e16.size() * sizeof(uint16_t)));
     CK(cudaMemcpy(ff.d_ell16, e16.data(), e16.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
   }

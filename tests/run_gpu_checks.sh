@@ -1,3 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q -k "sharded_fast_path" 2>&1 | grep -E "^E  .*(assert|Error|error)|passed|failed|FAILED" | head -40
+timeout 900 python -m pytest tests -m gpu -q -x -k "fast_hxv or fast_equals" 2>&1 | grep -E "passed|failed|FAILED" | head -5
+run() { name=$1; shift; timeout 300 python bench.py --steps 10 --warmup 3 --hxv-only "$@" > gpurun_out/hxv_$name.json 2> gpurun_out/hxv_$name.err; echo "$name: $(cut -c40-250 gpurun_out/hxv_$name.json)"; tail -2 gpurun_out/hxv_$name.err; }
+run C3_base --workload C3 --algo fast
