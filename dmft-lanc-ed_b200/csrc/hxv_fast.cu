@@ -35,6 +35,12 @@
 // consumer threads per CTA (+1 producer warp): LR=5 -> 512 threads x 128 registers, LR=4 -> 768 x 85
 __host__ __device__ constexpr int srow_consumers(int LR) { return LR >= 5 ? 480 : 736; }
 #define SROW_R 32
+#ifndef SROW_NB_FAR
+#define SROW_NB_FAR 3             // high-bit hops whose loads are fused (far sources: L2 / peer GPU)
+#endif
+#ifndef SROW_NB_IN
+#define SROW_NB_IN 1              // ... for sources inside the shared-memory tile
+#endif
 #define SROW_BC 32                // columns per TMA box (32 rows x 32 columns x 8 B = 8 KB per copy)
 #define SMEM_LIMIT 232448        // 227 KB per CTA on sm_100
 #define JHI_COLMASK 0xFFFFF      // Lin table entry: first column | owner rank << 20 | (cut by a rank boundary) << 30
@@ -462,12 +468,12 @@ __device__ __forceinline__ void srow_group(const SRowTile &k, const uint32_t h, 
   // hops on the high bits: the whole group maps onto ONE other group (descriptors from srow_prepare).  Far
   // sources first (longest latency, three hops' loads in flight), then the ones in the shared-memory tile.
   if (!(k.dbg & 1)) {
-    srow_hop_set<LR, N, CNT, true, 3>(desc, farmask & h, k.n, k.row, acc);
-    srow_hop_set<LR, N, CNT, false, 3>(desc, farmask & ~h, k.n, k.row, acc);
+    srow_hop_set<LR, N, CNT, true, SROW_NB_FAR>(desc, farmask & h, k.n, k.row, acc);
+    srow_hop_set<LR, N, CNT, false, SROW_NB_FAR>(desc, farmask & ~h, k.n, k.row, acc);
   }
   if (!(k.dbg & 2)) {
-    srow_hop_set<LR, N, CNT, true, 1>(desc, inmask & h, SROW_R, (size_t)(threadIdx.x & 31), acc);
-    srow_hop_set<LR, N, CNT, false, 1>(desc, inmask & ~h, SROW_R, (size_t)(threadIdx.x & 31), acc);
+    srow_hop_set<LR, N, CNT, true, SROW_NB_IN>(desc, inmask & h, SROW_R, (size_t)(threadIdx.x & 31), acc);
+    srow_hop_set<LR, N, CNT, false, SROW_NB_IN>(desc, inmask & ~h, SROW_R, (size_t)(threadIdx.x & 31), acc);
   }
   double *yp = k.yg + (size_t)base * k.n;                          // yg / dgg are biased by -c0 columns
   if (DIAG == 1) {

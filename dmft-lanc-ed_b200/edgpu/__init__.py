@@ -14,7 +14,8 @@ import numpy as np
 from . import configs  # noqa: F401
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-_LIBPATH = os.path.join(os.path.dirname(_PKG), "libedgpu.so")
+# EDGPU_LIB: an alternative build of the same library (kernel-variant experiments, tools/variants.sh)
+_LIBPATH = os.environ.get("EDGPU_LIB") or os.path.join(os.path.dirname(_PKG), "libedgpu.so")
 _LIB = None
 
 c_dp = C.POINTER(C.c_double)
