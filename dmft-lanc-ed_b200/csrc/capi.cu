@@ -131,6 +131,7 @@ extern "C" int edgpu_set_option(edgpu_ctx *c, const char *key, int64_t value) {
   if (!strcmp(key, "srow_cmax")) { c->opt_srow_cmax = value; return EDGPU_OK; }
   if (!strcmp(key, "dbg")) { c->opt_dbg = value; return EDGPU_OK; }
   if (!strcmp(key, "no_peer")) { c->opt_no_peer = value; return EDGPU_OK; }
+  if (!strcmp(key, "col_cluster")) { c->opt_col_cluster = value; return EDGPU_OK; }
   if (!strcmp(key, "no_uniform")) { c->opt_no_uniform = value; return EDGPU_OK; }
   return edgpu_set_err(EDGPU_ERR_INVALID, "unknown option %s", key);
 }

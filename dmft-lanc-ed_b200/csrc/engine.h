@@ -76,7 +76,7 @@ struct edgpu_ctx {
   int64_t opt_tile_rows = 0, opt_tile_h = -1, opt_col_h = -1;
   TiledPlan *plan = nullptr;
   FastPlan *fplan = nullptr;
-  int64_t opt_srow_lr = 0, opt_srow_cmax = 0, opt_no_uniform = 0, opt_dbg = 0, opt_no_peer = 0;
+  int64_t opt_srow_lr = 0, opt_srow_cmax = 0, opt_no_uniform = 0, opt_dbg = 0, opt_no_peer = 0, opt_col_cluster = 0;
   int64_t launches = 0;
   // symmetric slab (nranks > 1): one allocation per rank at identical offsets, opened by every peer
   // through CUDA IPC, so that kernels can read a peer's copy of a vector over NVLink

@@ -79,6 +79,8 @@ struct FastPlan {
   FastFactor ff[2];
   bool col_ok[2] = {false, false};
   size_t col_smem[2] = {0, 0};
+  bool col2_ok[2] = {false, false};   // two-CTA cluster variant (half a column per SM)
+  size_t col2_smem[2] = {0, 0};
   SRowPlan sr;
 };
 
@@ -156,19 +158,23 @@ struct FColArgs {
 template <int WT, int DIAG, int UNI, int MODE>
 __global__ void __launch_bounds__(FCOL_THREADS, 1) k_fcol(FColArgs a) {
   constexpr bool ACC = MODE >= 1;
+  constexpr int NCW = FCOL_THREADS / 32 - 1;                      // 31 consumer warps + 1 producer warp
+  constexpr int NCT = NCW * 32;
   extern __shared__ __align__(128) unsigned char smraw[];
   const int n = a.n, ld = n + 2;
   double *buf0 = reinterpret_cast<double *>(smraw);
   double *buf1 = buf0 + ld;
   double *vtab = buf1 + ld;
-  uint64_t *bar = reinterpret_cast<uint64_t *>(vtab + F_MAXVALS);
-  double *red = reinterpret_cast<double *>(bar + 2);             // [32] block reduction (MODE == 2)
-  const int tid = threadIdx.x;
+  uint64_t *bar = reinterpret_cast<uint64_t *>(vtab + F_MAXVALS);  // full[2], empty[2]
+  double *red = reinterpret_cast<double *>(bar + 4);             // [32] block reduction (MODE == 2)
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   double lsx = 0.0, lcp = 0.0, lsum = 0.0;
   if (MODE == 2) { lsx = a.st->sx; lcp = a.st->cprev; }
   if (tid == 0) {
     mbar_init(&bar[0], 1);
     mbar_init(&bar[1], 1);
+    mbar_init(&bar[2], NCW);
+    mbar_init(&bar[3], NCW);
     fence_barrier_init();
     buf0[n] = 0.0; buf0[n + 1] = 0.0;      // zero slot for the ELL padding entries
     buf1[n] = 0.0; buf1[n + 1] = 0.0;
@@ -178,11 +184,16 @@ __global__ void __launch_bounds__(FCOL_THREADS, 1) k_fcol(FColArgs a) {
   __syncthreads();
   const uint32_t colbytes = (uint32_t)n * 8u;
   const int64_t G = gridDim.x;
-  if (tid == 0) {
-    fence_proxy_async();
-    for (int b = 0; b < 2; b++) {
-      const int64_t j = blockIdx.x + b * G;
-      if (j < a.ncols) {
+  if (warp == NCW) {
+    // ---- producer warp: one whole column per stage; a stage is refilled as soon as every consumer warp
+    // has released it (no CTA-wide barrier anywhere in the loop)
+    if (lane == 0) {
+      for (int64_t it = 0;; it++) {
+        const int64_t j = blockIdx.x + it * G;
+        if (j >= a.ncols) break;
+        const int b = (int)(it & 1);
+        if (it >= 2) mbar_wait(&bar[2 + b], (uint32_t)(((it >> 1) - 1) & 1));
+        fence_proxy_async();
         mbar_expect_tx(&bar[b], colbytes);
         const char *src = reinterpret_cast<const char *>(a.x + j * (int64_t)n);
         char *dst = reinterpret_cast<char *>(b ? buf1 : buf0);
@@ -190,78 +201,177 @@ __global__ void __launch_bounds__(FCOL_THREADS, 1) k_fcol(FColArgs a) {
           bulk_g2s(dst + off, src + off, min(32768u, colbytes - off), &bar[b]);
       }
     }
-  }
-  for (int64_t it = 0;; it++) {
-    const int64_t j = blockIdx.x + it * G;
-    if (j >= a.ncols) break;
-    const int b = (int)(it & 1);
-    const double *xs = b ? buf1 : buf0;
-    mbar_wait(&bar[b], (uint32_t)((it >> 1) & 1));
-    double dcol = 0.0;
-    uint32_t ms = 0;
-    if (DIAG == 2) { dcol = a.dfac_s[a.coloff + j]; ms = (uint32_t)a.map_s[a.coloff + j]; }
-    double *yc = a.y + j * (int64_t)n;
-    uint32_t en[WT];
-    auto load_ell = [&](int row) {
-      if (UNI == 2 && WT == 8) {                                 // 8 two-byte entries = one LDG.128
-        const uint4 q = __ldg(reinterpret_cast<const uint4 *>(a.ell16) + row);
-        en[0] = q.x & 0xFFFFu; en[1] = q.x >> 16; en[2] = q.y & 0xFFFFu; en[3] = q.y >> 16;
-        en[4 % WT] = q.z & 0xFFFFu; en[5 % WT] = q.z >> 16; en[6 % WT] = q.w & 0xFFFFu; en[7 % WT] = q.w >> 16;
-      } else {
+  } else {
+    for (int64_t it = 0;; it++) {
+      const int64_t j = blockIdx.x + it * G;
+      if (j >= a.ncols) break;
+      const int b = (int)(it & 1);
+      const double *xs = b ? buf1 : buf0;
+      double dcol = 0.0;
+      uint32_t ms = 0;
+      if (DIAG == 2) { dcol = a.dfac_s[a.coloff + j]; ms = (uint32_t)a.map_s[a.coloff + j]; }
+      double *yc = a.y + j * (int64_t)n;
+      uint32_t en[WT];
+      auto load_ell = [&](int row) {
+        if (UNI == 2 && WT == 8) {                                 // 8 two-byte entries = one LDG.128
+          const uint4 q = __ldg(reinterpret_cast<const uint4 *>(a.ell16) + row);
+          en[0] = q.x & 0xFFFFu; en[1] = q.x >> 16; en[2] = q.y & 0xFFFFu; en[3] = q.y >> 16;
+          en[4 % WT] = q.z & 0xFFFFu; en[5 % WT] = q.z >> 16; en[6 % WT] = q.w & 0xFFFFu; en[7 % WT] = q.w >> 16;
+        } else {
 #pragma unroll
-        for (int s = 0; s < WT; s++) en[s] = (UNI == 2) ? (uint32_t)__ldg(a.ell16 + (size_t)s * n + row) : __ldg(a.ell + (size_t)s * n + row);
+          for (int s = 0; s < WT; s++) en[s] = (UNI == 2) ? (uint32_t)__ldg(a.ell16 + (size_t)s * n + row) : __ldg(a.ell + (size_t)s * n + row);
+        }
+      };
+      if (tid < n) load_ell(tid);                                  // independent of the column: issued before the wait
+      double ynext = 0.0;
+      if (ACC && tid < n) ynext = __ldcs(yc + tid);
+      mbar_wait(&bar[b], (uint32_t)((it >> 1) & 1));
+      for (int r = tid; r < n; r += NCT) {
+        uint32_t e[WT];
+#pragma unroll
+        for (int s = 0; s < WT; s++) e[s] = en[s];
+        const double yold = ynext;
+        if (r + NCT < n) {                                         // software prefetch of the next row's inputs
+          load_ell(r + NCT);
+          if (ACC) ynext = __ldcs(yc + r + NCT);
+        }
+        double acc0 = 0.0;
+        if (DIAG == 1) acc0 = __ldcs(a.diag + j * (int64_t)n + r) * xs[r];
+        if (DIAG == 2) {
+          double d = __ldg(a.dfac_c + r) + dcol;
+          const uint32_t mc = (uint32_t)__ldg(a.map_c + r);
+          for (int o = 0; o < a.norb; o++)
+            if ((mc >> o) & 1u)
+              for (int q = 0; q < a.norb; q++)
+                if ((ms >> q) & 1u) d += (o == q) ? a.uloc[o] : a.ust;
+          acc0 = d * xs[r];
+        }
+        double acc = 0.0;
+#pragma unroll
+        for (int s = 0; s < WT; s++) {
+          if (UNI == 2) { acc += flip_sign(xs[e[s] & 0x7FFFu], (e[s] & 0x8000u) << 16); continue; }
+          const double xv = xs[e[s] & F_COL_MASK];
+          if (UNI) acc += flip_sign(xv, e[s] & 0x80000000u);
+          else acc = fma(flip_sign(vtab[(e[s] >> F_COL_BITS) & F_VID_MASK], e[s] & 0x80000000u), xv, acc);
+        }
+        if (UNI) acc0 = fma(a.vuni, acc, acc0); else acc0 += acc;
+        if (ACC) acc0 += yold;
+        if (MODE == 2) {
+          double *wp = a.xp + j * (int64_t)n + r;
+          const double w = lsx * acc0 - lcp * __ldcs(wp);
+          __stcs(wp, w);
+          lsum = fma(lsx * xs[r], w, lsum);
+        } else {
+          __stcs(yc + r, acc0);
+        }
       }
-    };
-    if (tid < n) load_ell(tid);
-    for (int r = tid; r < n; r += FCOL_THREADS) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar[2 + b]);                     // this warp is done with the stage
+    }
+  }
+  if (MODE == 2) {                                               // deterministic: fixed order inside the CTA, one partial per CTA
+    for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+    if (lane == 0) red[warp] = lsum;
+    __syncthreads();
+    if (tid < 32) {
+      double r2 = red[tid];
+      for (int o = 16; o > 0; o >>= 1) r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+      if (tid == 0) a.partials[blockIdx.x] = r2;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass 1 for columns that do not fit one SM's shared memory (Ns = 18: 389 KB): a CLUSTER of two CTAs holds
+// the column, one half each; a source in the other half is read through distributed shared memory
+// (mapa + ld.shared::cluster).  In the sorted basis the halves are (nearly) the two values of the top bit, so
+// only the hops on that bit cross (1/17 of the gathers at Ns = 18).  Single stage per CTA: the half fills the SM.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local, uint32_t rank) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local), "r"(rank));
+  return ra;
+}
+__device__ __forceinline__ double ld_dsmem(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+template <int WT, int UNI, int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FCOL_THREADS, 1) k_fcol2(FColArgs a) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  constexpr bool ACC = MODE >= 1;
+  const int n = a.n;
+  const int nh0 = ((n >> 1) + 1) & ~1;                            // rows [0, nh0) on CTA 0, [nh0, n) on CTA 1
+  const uint32_t me = cluster_ctarank();
+  const int r0 = me ? nh0 : 0, nr = me ? n - nh0 : nh0;
+  const int r0p = me ? 0 : nh0, nrp = me ? nh0 : n - nh0;         // the partner's rows
+  const int hmax = nh0 + 2;
+  double *buf = reinterpret_cast<double *>(smraw);                // [hmax]; buf[nr] = 0 serves the ELL padding
+  double *vtab = buf + hmax;
+  uint64_t *bar = reinterpret_cast<uint64_t *>(vtab + F_MAXVALS);
+  double *red = reinterpret_cast<double *>(bar + 2);
+  const int tid = threadIdx.x;
+  double lsx = 0.0, lcp = 0.0, lsum = 0.0;
+  if (MODE == 2) { lsx = a.st->sx; lcp = a.st->cprev; }
+  if (tid == 0) { mbar_init(&bar[0], 1); fence_barrier_init(); }
+  if (UNI == 0)
+    for (int i = tid; i < a.nvals; i += FCOL_THREADS) vtab[i] = a.vtab[i];
+  __syncthreads();
+  const uint32_t peer_base = mapa_u32(smem_u32(buf), me ^ 1u);
+  const int64_t G = gridDim.x >> 1, pair = blockIdx.x >> 1;
+  const uint32_t bytes = (uint32_t)nr * 8u;
+  for (int64_t it = 0;; it++) {
+    const int64_t j = pair + it * G;
+    if (j >= a.ncols) break;
+    if (tid == 0) {
+      fence_proxy_async();
+      mbar_expect_tx(&bar[0], bytes);
+      const char *src = reinterpret_cast<const char *>(a.x + j * (int64_t)n + r0);
+      for (uint32_t off = 0; off < bytes; off += 32768u) bulk_g2s(reinterpret_cast<char *>(buf) + off, src + off, min(32768u, bytes - off), &bar[0]);
+      buf[nr] = 0.0;
+    }
+    mbar_wait(&bar[0], (uint32_t)(it & 1));
+    cluster_sync_all();                                            // both halves of column j are in place
+    double *yc = a.y + j * (int64_t)n + r0;
+    for (int r = tid; r < nr; r += FCOL_THREADS) {
       uint32_t e[WT];
 #pragma unroll
-      for (int s = 0; s < WT; s++) e[s] = en[s];
+      for (int s = 0; s < WT; s++) e[s] = __ldg(a.ell + (size_t)s * n + r0 + r);
       double yold = 0.0;
       if (ACC) yold = __ldcs(yc + r);
-      if (r + FCOL_THREADS < n) load_ell(r + FCOL_THREADS);      // software prefetch of the next row's ELL entries
-      double acc0 = 0.0;
-      if (DIAG == 1) acc0 = __ldcs(a.diag + j * (int64_t)n + r) * xs[r];
-      if (DIAG == 2) {
-        double d = __ldg(a.dfac_c + r) + dcol;
-        const uint32_t mc = (uint32_t)__ldg(a.map_c + r);
-        for (int o = 0; o < a.norb; o++)
-          if ((mc >> o) & 1u)
-            for (int q = 0; q < a.norb; q++)
-              if ((ms >> q) & 1u) d += (o == q) ? a.uloc[o] : a.ust;
-        acc0 = d * xs[r];
-      }
       double acc = 0.0;
 #pragma unroll
       for (int s = 0; s < WT; s++) {
-        if (UNI == 2) { acc += flip_sign(xs[e[s] & 0x7FFFu], (e[s] & 0x8000u) << 16); continue; }
-        const double xv = xs[e[s] & F_COL_MASK];
+        const int col = (int)(e[s] & F_COL_MASK);
+        const uint32_t lc = (uint32_t)(col - r0);
+        double xv;
+        if (lc < (uint32_t)nr || col >= n) xv = buf[col >= n ? nr : (int)lc];
+        else xv = ld_dsmem(peer_base + (uint32_t)(col - r0p) * 8u);
         if (UNI) acc += flip_sign(xv, e[s] & 0x80000000u);
         else acc = fma(flip_sign(vtab[(e[s] >> F_COL_BITS) & F_VID_MASK], e[s] & 0x80000000u), xv, acc);
       }
-      if (UNI) acc0 = fma(a.vuni, acc, acc0); else acc0 += acc;
+      double acc0 = UNI ? a.vuni * acc : acc;
       if (ACC) acc0 += yold;
       if (MODE == 2) {
-        double *wp = a.xp + j * (int64_t)n + r;
+        double *wp = a.xp + j * (int64_t)n + r0 + r;
         const double w = lsx * acc0 - lcp * __ldcs(wp);
         __stcs(wp, w);
-        lsum = fma(lsx * xs[r], w, lsum);
+        lsum = fma(lsx * buf[r], w, lsum);
       } else {
         __stcs(yc + r, acc0);
       }
     }
-    __syncthreads();                           // every thread is done reading this buffer
-    const int64_t j2 = j + 2 * G;
-    if (tid == 0 && j2 < a.ncols) {
-      fence_proxy_async();
-      mbar_expect_tx(&bar[b], colbytes);
-      const char *src = reinterpret_cast<const char *>(a.x + j2 * (int64_t)n);
-      char *dst = reinterpret_cast<char *>(b ? buf1 : buf0);
-      for (uint32_t off = 0; off < colbytes; off += 32768u)
-        bulk_g2s(dst + off, src + off, min(32768u, colbytes - off), &bar[b]);
-    }
+    cluster_sync_all();                                            // nobody reads this column any more
   }
-  if (MODE == 2) {                                               // deterministic: fixed order inside the CTA, one partial per CTA
+  (void)nrp;
+  if (MODE == 2) {
     for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
     if ((tid & 31) == 0) red[tid >> 5] = lsum;
     __syncthreads();
@@ -663,7 +773,8 @@ static int pack_fast(edgpu_ctx *c, const Factor &f, FastFactor &ff) {
   return EDGPU_OK;
 }
 
-static size_t fcol_smem(int64_t n) { return (size_t)2 * (n + 2) * 8 + F_MAXVALS * 8 + 16 + 32 * 8; }
+static size_t fcol_smem(int64_t n) { return (size_t)2 * (n + 2) * 8 + F_MAXVALS * 8 + 32 + 32 * 8; }
+static size_t fcol2_smem(int64_t n) { return (size_t)((((n >> 1) + 1) & ~(int64_t)1) + 2) * 8 + F_MAXVALS * 8 + 16 + 32 * 8; }
 static size_t srow_smem(int cmax, int nhigh, int ngroups) {
   const size_t cpad = (size_t)((cmax + SROW_BC - 1) / SROW_BC) * SROW_BC;
   size_t b = (size_t)2 * cpad * SROW_R * 8 + (size_t)2 * (cpad + 2) * 8 + 4 * SROW_R * 8 + 32 * 8 + 32 + 16 + 8 * SROW_MAXP + 4 * (SROW_MAXP + 4) +
@@ -858,13 +969,26 @@ int fast_plan_build(edgpu_ctx *c) {
   }
   FastPlan *p = new FastPlan();
   c->fplan = p;
+  {
+    static bool attr2_done = false;
+    if (!attr2_done) {
+#define SET2(W, U, M) CK(cudaFuncSetAttribute(k_fcol2<W, U, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT))
+      SET2(8, 0, 0); SET2(8, 1, 0); SET2(8, 0, 1); SET2(8, 1, 1); SET2(8, 0, 2); SET2(8, 1, 2);
+      SET2(12, 0, 0); SET2(12, 1, 0); SET2(12, 0, 1); SET2(12, 1, 1); SET2(12, 0, 2); SET2(12, 1, 2);
+      SET2(16, 0, 0); SET2(16, 1, 0); SET2(16, 0, 1); SET2(16, 1, 1); SET2(16, 0, 2); SET2(16, 1, 2);
+#undef SET2
+      attr2_done = true;
+    }
+  }
   for (int k = 0; k < 2; k++) {
     const Factor &f = k ? c->dw : c->up;
     p->col_smem[k] = fcol_smem(f.n);
     p->col_ok[k] = (f.n % 2 == 0) && f.n < (1 << F_COL_BITS) && p->col_smem[k] <= SMEM_LIMIT && f.maxrow <= 16;
-    if (p->col_ok[k]) {
+    p->col2_smem[k] = fcol2_smem(f.n);
+    p->col2_ok[k] = (f.n % 2 == 0) && f.n >= 8 && f.n < (1 << F_COL_BITS) && p->col2_smem[k] <= SMEM_LIMIT && f.maxrow <= 16 && c->sm_count >= 2;
+    if (p->col_ok[k] || p->col2_ok[k]) {
       int rc = pack_fast(c, f, p->ff[k]);
-      if (rc == EDGPU_ERR_UNSUPPORTED) p->col_ok[k] = false;
+      if (rc == EDGPU_ERR_UNSUPPORTED) { p->col_ok[k] = false; p->col2_ok[k] = false; }
       else if (rc) { fast_plan_free(c); return rc; }
     }
   }
@@ -876,12 +1000,12 @@ int fast_plan_build(edgpu_ctx *c) {
 bool fast_supported_local(edgpu_ctx *c) {
   if (!c->hstatus || c->dp.jhflag) return false;
   if (fast_plan_build(c)) return false;
-  return c->fplan->col_ok[0] && c->fplan->sr.ok;
+  return (c->fplan->col_ok[0] || c->fplan->col2_ok[0]) && c->fplan->sr.ok;
 }
 bool fast_supported_col(edgpu_ctx *c, int k) {
   if (!c->hstatus || c->dp.jhflag) return false;
   if (fast_plan_build(c)) return false;
-  return c->fplan->col_ok[k];
+  return c->fplan->col_ok[k] || c->fplan->col2_ok[k];
 }
 
 template <int WT, int DIAG, int MODE>
@@ -903,12 +1027,31 @@ static void launch_fcol_w(int WT, int uni, int mode, int grid, size_t smem, cuda
   else launch_fcol<16, DIAG>(uni, mode, grid, smem, st, a);
 }
 
+template <int WT>
+static void launch_fcol2_w(int uni, int mode, int grid, size_t smem, cudaStream_t st, const FColArgs &a) {
+  if (uni) {
+    if (mode == 2) k_fcol2<WT, 1, 2><<<grid, FCOL_THREADS, smem, st>>>(a);
+    else if (mode == 1) k_fcol2<WT, 1, 1><<<grid, FCOL_THREADS, smem, st>>>(a);
+    else k_fcol2<WT, 1, 0><<<grid, FCOL_THREADS, smem, st>>>(a);
+  } else {
+    if (mode == 2) k_fcol2<WT, 0, 2><<<grid, FCOL_THREADS, smem, st>>>(a);
+    else if (mode == 1) k_fcol2<WT, 0, 1><<<grid, FCOL_THREADS, smem, st>>>(a);
+    else k_fcol2<WT, 0, 0><<<grid, FCOL_THREADS, smem, st>>>(a);
+  }
+}
+static void launch_fcol2(int WT, int uni, int mode, int grid, size_t smem, cudaStream_t st, const FColArgs &a) {
+  if (WT == 8) launch_fcol2_w<8>(uni, mode, grid, smem, st, a);
+  else if (WT == 12) launch_fcol2_w<12>(uni, mode, grid, smem, st, a);
+  else launch_fcol2_w<16>(uni, mode, grid, smem, st, a);
+}
+
 // y (+)= [Hd o x +] F_k x on a matrix whose contiguous dimension is factor k's index
 int fast_apply_col(edgpu_ctx *c, int k, bool with_diag, bool acc, const double *d_x, double *d_y, int64_t ncols, int64_t coloff,
                    double *d_xp, int *npartials) {
   TRY(fast_plan_build(c));
   FastPlan *p = c->fplan;
-  if (!p->col_ok[k]) return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "fast column kernel does not cover this factor");
+  const bool use2 = p->col2_ok[k] && (!p->col_ok[k] || c->opt_col_cluster);
+  if (!p->col_ok[k] && !use2) return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "fast column kernel does not cover this factor");
   if ((reinterpret_cast<uintptr_t>(d_x) & 15) != 0) return edgpu_set_err(EDGPU_ERR_INVALID, "fast H*v needs 16-byte aligned vectors");
   const FastFactor &ff = p->ff[k];
   FColArgs a{};
@@ -926,6 +1069,15 @@ int fast_apply_col(edgpu_ctx *c, int k, bool with_diag, bool acc, const double *
   if (mode == 2 && (diag != 0 || !acc)) return edgpu_set_err(EDGPU_ERR_INVALID, "Lanczos epilogue needs the accumulate form without diagonal");
   a.xp = d_xp; a.st = c->d_st; a.partials = c->d_partials;
   if (npartials) *npartials = grid;
+  if (use2) {
+    if (diag != 0) return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "cluster column kernel has no fused diagonal");
+    const int pairs = (int)std::min<int64_t>(ncols, c->sm_count / 2);
+    const int uni2 = (ff.uniform && c->opt_no_uniform != 1) ? 1 : 0;
+    if (npartials) *npartials = 2 * pairs;
+    launch_fcol2(ff.WT, uni2, mode, 2 * pairs, p->col2_smem[k], c->stream, a);
+    CKL(c);
+    return EDGPU_OK;
+  }
   // no_uniform: 0 = best available, 1 = force the value-table kernel, 2 = uniform kernel with 4-byte entries
   int uni = 0;
   if (ff.uniform && c->opt_no_uniform != 1) uni = (ff.d_ell16 && c->opt_no_uniform != 2) ? 2 : 1;

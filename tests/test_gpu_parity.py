@@ -349,7 +349,10 @@ FAST_CASES = [("C1", (4, 4), {}), ("C1", (5, 3), {"srow_cmax": 20}), ("C1", (3, 
               ("NS12", (6, 6), {"srow_cmax": 100}), ("NS12", (7, 4), {}), ("NS12", (6, 6), {"no_uniform": 1, "srow_lr": 4}), ("NS12", (6, 6), {"no_uniform": 2}),
               ("NS6", (3, 3), {}), ("NS6", (3, 3), {"srow_lr": 4, "srow_cmax": 6}), ("NS10V", (5, 5), {"srow_cmax": 50}),
               ("NS12V", (6, 5), {"srow_lr": 4, "srow_cmax": 64}), ("NS10V", (7, 2), {}), ("NS10", (9, 1), {}),
-              ("NS12", (6, 0), {}), ("NS12", (6, 12), {})]
+              ("NS12", (6, 0), {}), ("NS12", (6, 12), {}),
+              # two-CTA cluster column kernel (columns too long for one SM; forced here on small ones)
+              ("C1", (4, 4), {"col_cluster": 1}), ("NS12", (6, 6), {"col_cluster": 1}), ("NS12", (7, 4), {"col_cluster": 1, "no_uniform": 1}),
+              ("NS10V", (5, 5), {"col_cluster": 1}), ("NS12", (5, 6), {"col_cluster": 1, "srow_lr": 4})]
 
 
 @pytest.mark.parametrize("name,sec,opts", FAST_CASES)
