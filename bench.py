@@ -21,6 +21,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "dmft-lanc-ed_b200"))
+# stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...") goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 METRIC = "lanczos_hxv_per_s"
 UNIT = "H*v/s"
