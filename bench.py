@@ -356,6 +356,17 @@ def run_b200(args):
 
 
 if __name__ == "__main__":
+    # stdout carries exactly ONE JSON line: everything else any library writes to fd 1 (NCCL's version banner,
+    # warnings) is sent to stderr for the whole run, and the line goes to a private copy of the real stdout
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    _print = print
+
+    def print(*args, **kw):                                      # noqa: A001 -- the module's only stdout writer
+        kw.setdefault("file", _OUT)
+        _print(*args, **kw)
+        _OUT.flush()
+
     a = parse()
     if a.impl == "reference":
         run_reference(a)
