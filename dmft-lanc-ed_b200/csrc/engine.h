@@ -137,6 +137,24 @@ bool tiled_supported(const edgpu_ctx *c);
 int tiled_apply_local(edgpu_ctx *c, const double *d_x, double *d_y);   // nranks==1: full operator
 // y = [Hd o x +] F_k x, contiguous dimension = index of factor k (0 up, 1 dw), ncols local columns
 int tiled_apply_col(edgpu_ctx *c, int k, bool with_diag, const double *d_x, double *d_y, int64_t ncols, int64_t coloff);
+// hxv_fast.cu: host arithmetic of the structured row kernel's plan (no device needed; see selftest.cu)
+struct SRowHostPlan {
+  bool ok = false;
+  int LR = 0, nhigh = 0, cmax = 0, g0 = 0, g1 = 0;
+  size_t smem = 0;
+  std::vector<int> coloffs;            // [P+1] first global column of every rank
+  std::vector<int32_t> jhi;            // [2^nhigh] first column | owner << 20 | cut << 30, -1 = empty group
+  std::vector<uint16_t> grp;           // high words of the non-empty groups, ascending
+  std::vector<int> gsize, gbase;
+  std::vector<char> gcut;
+  std::vector<int4> chunks;            // (group begin, group end, column begin, column end), whole local groups only
+  std::vector<int> tptr, tcol, eown, esrc;   // fix-up list (srow_fix_host)
+  std::vector<unsigned char> tinit;
+  std::vector<double> eval;
+};
+// returns 1 = plan built, 0 = the structured kernel does not apply, -1 = internal inconsistency
+int srow_plan_host(int ns, int ndw, int64_t dimdw, int nranks, int rank, int lr, int64_t cmax_opt, SRowHostPlan &hp);
+void srow_fix_host(SRowHostPlan &hp, int rank, int64_t dimdw, const int32_t *rp, const int32_t *cc, const double *vv);
 // hxv_fast.cu: TMA-staged whole-column kernel + structured single-band row kernel
 int fast_plan_build(edgpu_ctx *c);
 int fast_plan_free(edgpu_ctx *c);

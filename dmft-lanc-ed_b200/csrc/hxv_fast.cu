@@ -782,88 +782,126 @@ static size_t srow_smem(int cmax, int nhigh, int ngroups) {
   return (b + 15) & ~(size_t)15;
 }
 
-static int build_srow(edgpu_ctx *c, SRowPlan &sr, int LR) {
-  // single band, star geometry, no inter-orbital terms: every dw hop is bit 0 <-> bit k
-  sr.ok = false;
-  if (c->dp.norb != 1 || c->dp.jhflag) return EDGPU_OK;
-  if (c->ns <= LR || c->ns - LR > 15 || (c->dimup & 1)) return EDGPU_OK;
-  if (c->nranks > SROW_MAXP || c->dimdw > JHI_COLMASK) return EDGPU_OK;
-  if (c->opt_srow_lr == 4 || c->opt_srow_lr == 5) LR = (int)c->opt_srow_lr;
-  sr.LR = LR;
-  sr.nhigh = c->ns - LR;
-  const int P = c->nranks;
+// ---- pure host arithmetic of the row-kernel plan (also reachable without a GPU through
+// edgpu_selftest_srow_plan, so that the CPU-only tests can check the sharding logic) -----------------
+int srow_plan_host(int ns, int ndw, int64_t dimdw, int nranks, int rank, int lr, int64_t cmax_opt, SRowHostPlan &hp) {
+  hp = SRowHostPlan();
+  const int LR = (lr == 4 || lr == 5) ? lr : 5;
+  if (ns <= LR || ns - LR > 15 || nranks > SROW_MAXP || dimdw > JHI_COLMASK) return 0;
+  hp.LR = LR;
+  hp.nhigh = ns - LR;
+  const int P = nranks;
+  hp.coloffs.assign((size_t)P + 1, 0);
   for (int p = 0; p <= P; p++) {
-    int64_t q, off;
-    if (p < P) edgpu_split(c->dimdw, P, p, &q, &off); else off = c->dimdw;
-    sr.coloffs[p] = (int)off;
+    int64_t q = 0, off = dimdw;
+    if (p < P) edgpu_split(dimdw, P, p, &q, &off);
+    hp.coloffs[(size_t)p] = (int)off;
   }
-  auto owner_of = [&](int col) { int p = 0; while (p + 1 < P && col >= sr.coloffs[p + 1]) p++; return p; };
-  const int c0 = sr.coloffs[c->rank], c1 = sr.coloffs[c->rank + 1];
-  const int nh = 1 << sr.nhigh;
-  std::vector<int32_t> jhi((size_t)nh, -1);
-  std::vector<uint16_t> grp;
-  std::vector<int> gsize, gbase;
-  std::vector<char> gcut;
+  auto owner_of = [&](int col) { int p = 0; while (p + 1 < P && col >= hp.coloffs[(size_t)p + 1]) p++; return p; };
+  const int c0 = hp.coloffs[(size_t)rank], c1 = hp.coloffs[(size_t)rank + 1];
+  const int nh = 1 << hp.nhigh;
+  hp.jhi.assign((size_t)nh, -1);
   int64_t col = 0;
   for (int h = 0; h < nh; h++) {
-    const int nlow = c->ndw - __builtin_popcount((unsigned)h);
+    const int nlow = ndw - __builtin_popcount((unsigned)h);
     if (nlow < 0 || nlow > LR) continue;
     const int sz = lowtab::binom(LR, nlow);
     const int own = owner_of((int)col);
     const bool cut = owner_of((int)col + sz - 1) != own;           // the group is split between two ranks
-    jhi[(size_t)h] = (int32_t)col | (own << 20) | (cut ? JHI_CUT : 0);
-    grp.push_back((uint16_t)h);
-    gsize.push_back(sz); gbase.push_back((int)col); gcut.push_back(cut ? 1 : 0);
+    hp.jhi[(size_t)h] = (int32_t)col | (own << 20) | (cut ? JHI_CUT : 0);
+    hp.grp.push_back((uint16_t)h);
+    hp.gsize.push_back(sz); hp.gbase.push_back((int)col); hp.gcut.push_back(cut ? 1 : 0);
     col += sz;
   }
-  if (col != c->dimdw) return edgpu_set_err(EDGPU_ERR_INVALID, "internal: Lin table does not cover the dw basis");
-  sr.ngroups = (int)grp.size();
+  if (col != dimdw) return -1;                                     // the Lin table must cover the basis exactly
+  const int ngroups = (int)hp.grp.size();
   // groups that lie entirely on this rank: a contiguous run [g0, g1) of the global list
   int g0 = 0, g1 = 0;
   {
     int g = 0;
-    while (g < sr.ngroups && (gbase[g] < c0 || gcut[g])) { if (gbase[g] >= c1) break; g++; }
+    while (g < ngroups && (hp.gbase[(size_t)g] < c0 || hp.gcut[(size_t)g])) { if (hp.gbase[(size_t)g] >= c1) break; g++; }
     g0 = g;
-    while (g < sr.ngroups && !gcut[g] && gbase[g] + gsize[g] <= c1) g++;
+    while (g < ngroups && !hp.gcut[(size_t)g] && hp.gbase[(size_t)g] + hp.gsize[(size_t)g] <= c1) g++;
     g1 = g;
-    if (g0 < sr.ngroups && gbase[g0] >= c1) g1 = g0;               // nothing whole on this rank
+    if (g0 < ngroups && hp.gbase[(size_t)g0] >= c1) g1 = g0;       // nothing whole on this rank
   }
+  hp.g0 = g0; hp.g1 = g1;
   // chunk size from the shared-memory budget (or the option), chunks = runs of whole groups
-  int cmax = (int)((SMEM_LIMIT - 12288 - ((size_t)4 << sr.nhigh) - 2 * (size_t)sr.ngroups) / (2 * (SROW_R + 1) * 8));
+  int cmax = (int)((SMEM_LIMIT - 12288 - ((size_t)4 << hp.nhigh) - 2 * (size_t)ngroups) / (2 * (SROW_R + 1) * 8));
   cmax = cmax / SROW_BC * SROW_BC;
   if (cmax > 32 * SROW_BC) cmax = 32 * SROW_BC;             // one tensor copy per lane of the producer warp
   // measured on B200 (C3, chunk sweep 96..352): tiles of ~160 columns beat the largest that fits by 25 %;
   // the L1 that is left over (228 KB - shared memory) serves the out-of-tile sources
-  if (c->opt_srow_cmax <= 0 && cmax > 160) cmax = 160;
-  if (c->opt_srow_cmax > 0 && c->opt_srow_cmax < cmax) cmax = (int)c->opt_srow_cmax;
-  if (cmax < lowtab::binom(LR, LR / 2)) return EDGPU_OK;
+  if (cmax_opt <= 0 && cmax > 160) cmax = 160;
+  if (cmax_opt > 0 && cmax_opt < cmax) cmax = (int)cmax_opt;
+  if (cmax < lowtab::binom(LR, LR / 2)) return 0;
   // balance: all chunks about the same size
-  const int nloccols = (g1 > g0) ? gbase[g1 - 1] + gsize[g1 - 1] - gbase[g0] : 0;
+  const int nloccols = (g1 > g0) ? hp.gbase[(size_t)g1 - 1] + hp.gsize[(size_t)g1 - 1] - hp.gbase[(size_t)g0] : 0;
   const int nch0 = std::max(1, (nloccols + cmax - 1) / cmax);
   const int target = (nloccols + nch0 - 1) / nch0;
-  std::vector<int4> chunks;
-  int gb = g0, cb = (g1 > g0) ? gbase[g0] : 0, cur = 0;
+  int gb = g0, cb = (g1 > g0) ? hp.gbase[(size_t)g0] : 0, cur = 0;
   for (int g = g0; g < g1; g++) {
-    if (cur > 0 && (cur + gsize[g] > cmax || cur >= target)) {
-      chunks.push_back(make_int4(gb, g, cb, cb + cur));
+    if (cur > 0 && (cur + hp.gsize[(size_t)g] > cmax || cur >= target)) {
+      hp.chunks.push_back(make_int4(gb, g, cb, cb + cur));
       gb = g; cb += cur; cur = 0;
     }
-    cur += gsize[g];
+    cur += hp.gsize[(size_t)g];
   }
-  if (cur > 0) chunks.push_back(make_int4(gb, g1, cb, cb + cur));
-  sr.nchunks = (int)chunks.size();
-  sr.cmax = lowtab::binom(LR, LR / 2);
-  for (auto &ch : chunks) sr.cmax = std::max(sr.cmax, ch.w - ch.z);
-  sr.smem = srow_smem(sr.cmax, sr.nhigh, sr.ngroups);
-  if (sr.smem > SMEM_LIMIT) return EDGPU_OK;
+  if (cur > 0) hp.chunks.push_back(make_int4(gb, g1, cb, cb + cur));
+  hp.cmax = lowtab::binom(LR, LR / 2);
+  for (auto &ch : hp.chunks) hp.cmax = std::max(hp.cmax, ch.w - ch.z);
+  hp.smem = srow_smem(hp.cmax, hp.nhigh, ngroups);
+  if (hp.smem > SMEM_LIMIT) return 0;
+  hp.ok = true;
+  return 1;
+}
+
+// fix-up list: every dw hop (target <- source) of a LOCAL target column for which the target's or the source's
+// low group is cut by a rank boundary (the structured kernel skips exactly those), from the reference-order CSR
+// of spH0dws.  Targets in cut groups are computed entirely by the fix-up kernel (diagonal included).
+void srow_fix_host(SRowHostPlan &hp, int rank, int64_t dimdw, const int32_t *rp, const int32_t *cc, const double *vv) {
+  const int P = (int)hp.coloffs.size() - 1;
+  hp.tptr.assign(1, 0); hp.tcol.clear(); hp.tinit.clear(); hp.eown.clear(); hp.esrc.clear(); hp.eval.clear();
+  if (P <= 1) return;
+  auto owner_of = [&](int col) { int p = 0; while (p + 1 < P && col >= hp.coloffs[(size_t)p + 1]) p++; return p; };
+  const int c0 = hp.coloffs[(size_t)rank], c1 = hp.coloffs[(size_t)rank + 1];
+  std::vector<char> colcut((size_t)dimdw, 0);
+  for (size_t g = 0; g < hp.grp.size(); g++)
+    if (hp.gcut[g]) for (int i = 0; i < hp.gsize[g]; i++) colcut[(size_t)hp.gbase[g] + i] = 1;
+  for (int t = c0; t < c1; t++) {
+    const bool tc = colcut[(size_t)t] != 0;
+    const size_t before = hp.eown.size();
+    for (int32_t q = rp[(size_t)t]; q < rp[(size_t)t + 1]; q++) {
+      const int sc = cc[(size_t)q];
+      if (!tc && !colcut[(size_t)sc]) continue;
+      const int own = owner_of(sc);
+      hp.eown.push_back(own); hp.esrc.push_back(sc - hp.coloffs[(size_t)own]); hp.eval.push_back(vv[(size_t)q]);
+    }
+    if (tc || hp.eown.size() > before) { hp.tcol.push_back(t - c0); hp.tinit.push_back(tc ? 1 : 0); hp.tptr.push_back((int)hp.eown.size()); }
+  }
+}
+
+static int build_srow(edgpu_ctx *c, SRowPlan &sr, int LR) {
+  // single band, star geometry, no inter-orbital terms: every dw hop is bit 0 <-> bit k
+  sr.ok = false;
+  if (c->dp.norb != 1 || c->dp.jhflag || (c->dimup & 1)) return EDGPU_OK;
+  if (c->opt_srow_lr == 4 || c->opt_srow_lr == 5) LR = (int)c->opt_srow_lr;
+  SRowHostPlan hp;
+  const int prc = srow_plan_host(c->ns, c->ndw, c->dimdw, c->nranks, c->rank, LR, c->opt_srow_cmax, hp);
+  if (prc < 0) return edgpu_set_err(EDGPU_ERR_INVALID, "internal: Lin table does not cover the dw basis");
+  if (prc == 0) return EDGPU_OK;
+  sr.LR = hp.LR; sr.nhigh = hp.nhigh; sr.ngroups = (int)hp.grp.size(); sr.nchunks = (int)hp.chunks.size();
+  sr.cmax = hp.cmax; sr.smem = hp.smem;
+  for (size_t p = 0; p < hp.coloffs.size(); p++) sr.coloffs[p] = hp.coloffs[p];
   for (int k = 0; k < EDGPU_MAX_SITES; k++) sr.vk[k] = 0.0;
   for (int k = 1; k < c->ns; k++) sr.vk[k] = c->dp.bv_dw[k - 1];
+  std::vector<int4> chunks = hp.chunks;
   if (chunks.empty()) chunks.push_back(make_int4(0, 0, 0, 0));
-  CK(cudaMalloc(&sr.d_jhi, jhi.size() * sizeof(int32_t)));
-  CK(cudaMalloc(&sr.d_grp, grp.size() * sizeof(uint16_t)));
+  CK(cudaMalloc(&sr.d_jhi, hp.jhi.size() * sizeof(int32_t)));
+  CK(cudaMalloc(&sr.d_grp, std::max<size_t>(hp.grp.size(), 1) * sizeof(uint16_t)));
   CK(cudaMalloc(&sr.d_chunks, chunks.size() * sizeof(int4)));
-  CK(cudaMemcpy(sr.d_jhi, jhi.data(), jhi.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(sr.d_grp, grp.data(), grp.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(sr.d_jhi, hp.jhi.data(), hp.jhi.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(sr.d_grp, hp.grp.data(), hp.grp.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(sr.d_chunks, chunks.data(), chunks.size() * sizeof(int4), cudaMemcpyHostToDevice));
   if (c->up.d_dfac) {                                              // direct mode: per-row diagonal tables
     std::vector<double> d0((size_t)c->dimup + 32, 0.0), d1((size_t)c->dimup + 32, 0.0);
@@ -876,11 +914,8 @@ static int build_srow(edgpu_ctx *c, SRowPlan &sr, int LR) {
     CK(cudaMemcpy(sr.d_dr0, d0.data(), d0.size() * sizeof(double), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(sr.d_dr1, d1.data(), d1.size() * sizeof(double), cudaMemcpyHostToDevice));
   }
-  // fix-up list: every dw hop (target <- source) of a LOCAL target column for which the target's or the
-  // source's low group is cut by a rank boundary (the structured kernel skips exactly those), from the
-  // reference-order CSR of spH0dws.  Targets in cut groups are computed entirely here (diagonal included).
   sr.nfix = 0;
-  if (P > 1) {
+  if (c->nranks > 1) {
     std::vector<int32_t> rp((size_t)c->dw.n + 1), cc((size_t)std::max<int64_t>(c->dw.nnz, 1));
     std::vector<double> vv((size_t)std::max<int64_t>(c->dw.nnz, 1));
     CK(cudaMemcpy(rp.data(), c->dw.d_rowptr, rp.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
@@ -888,39 +923,23 @@ static int build_srow(edgpu_ctx *c, SRowPlan &sr, int LR) {
       CK(cudaMemcpy(cc.data(), c->dw.d_cols, (size_t)c->dw.nnz * sizeof(int32_t), cudaMemcpyDeviceToHost));
       CK(cudaMemcpy(vv.data(), c->dw.d_vals, (size_t)c->dw.nnz * sizeof(double), cudaMemcpyDeviceToHost));
     }
-    std::vector<char> colcut((size_t)c->dimdw, 0);
-    for (int g = 0; g < sr.ngroups; g++)
-      if (gcut[g]) for (int i = 0; i < gsize[g]; i++) colcut[(size_t)gbase[g] + i] = 1;
-    std::vector<int> tptr(1, 0), tcol, eown, esrc;
-    std::vector<unsigned char> tinit;
-    std::vector<double> eval;
-    for (int t = c0; t < c1; t++) {
-      const bool tc = colcut[(size_t)t] != 0;
-      size_t before = eown.size();
-      for (int32_t q = rp[(size_t)t]; q < rp[(size_t)t + 1]; q++) {
-        const int sc = cc[(size_t)q];
-        if (!tc && !colcut[(size_t)sc]) continue;
-        const int own = owner_of(sc);
-        eown.push_back(own); esrc.push_back(sc - sr.coloffs[own]); eval.push_back(vv[(size_t)q]);
-      }
-      if (tc || eown.size() > before) { tcol.push_back(t - c0); tinit.push_back(tc ? 1 : 0); tptr.push_back((int)eown.size()); }
-    }
-    sr.nfix = (int)tcol.size();
+    srow_fix_host(hp, c->rank, c->dimdw, rp.data(), cc.data(), vv.data());
+    sr.nfix = (int)hp.tcol.size();
     if (sr.nfix) {
-      const size_t ne = std::max<size_t>(eown.size(), 1);
-      eown.resize(ne); esrc.resize(ne); eval.resize(ne);
-      CK(cudaMalloc(&sr.d_ftptr, tptr.size() * sizeof(int)));
-      CK(cudaMalloc(&sr.d_ftcol, tcol.size() * sizeof(int)));
-      CK(cudaMalloc(&sr.d_ftinit, tinit.size()));
+      const size_t ne = std::max<size_t>(hp.eown.size(), 1);
+      hp.eown.resize(ne); hp.esrc.resize(ne); hp.eval.resize(ne);
+      CK(cudaMalloc(&sr.d_ftptr, hp.tptr.size() * sizeof(int)));
+      CK(cudaMalloc(&sr.d_ftcol, hp.tcol.size() * sizeof(int)));
+      CK(cudaMalloc(&sr.d_ftinit, hp.tinit.size()));
       CK(cudaMalloc(&sr.d_feown, ne * sizeof(int)));
       CK(cudaMalloc(&sr.d_fesrc, ne * sizeof(int)));
       CK(cudaMalloc(&sr.d_feval, ne * sizeof(double)));
-      CK(cudaMemcpy(sr.d_ftptr, tptr.data(), tptr.size() * sizeof(int), cudaMemcpyHostToDevice));
-      CK(cudaMemcpy(sr.d_ftcol, tcol.data(), tcol.size() * sizeof(int), cudaMemcpyHostToDevice));
-      CK(cudaMemcpy(sr.d_ftinit, tinit.data(), tinit.size(), cudaMemcpyHostToDevice));
-      CK(cudaMemcpy(sr.d_feown, eown.data(), ne * sizeof(int), cudaMemcpyHostToDevice));
-      CK(cudaMemcpy(sr.d_fesrc, esrc.data(), ne * sizeof(int), cudaMemcpyHostToDevice));
-      CK(cudaMemcpy(sr.d_feval, eval.data(), ne * sizeof(double), cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(sr.d_ftptr, hp.tptr.data(), hp.tptr.size() * sizeof(int), cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(sr.d_ftcol, hp.tcol.data(), hp.tcol.size() * sizeof(int), cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(sr.d_ftinit, hp.tinit.data(), hp.tinit.size(), cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(sr.d_feown, hp.eown.data(), ne * sizeof(int), cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(sr.d_fesrc, hp.esrc.data(), ne * sizeof(int), cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(sr.d_feval, hp.eval.data(), ne * sizeof(double), cudaMemcpyHostToDevice));
     }
   }
   sr.ok = true;

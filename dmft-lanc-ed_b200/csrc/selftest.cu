@@ -132,3 +132,47 @@ extern "C" int edgpu_selftest_sharded_hxv(const edgpu_params *p, int nup, int nd
   cleanup();
   return rc;
 }
+
+// HOST ONLY (no device): the plan of the structured row kernel for `rank` of `nranks` -- Lin table with owner /
+// cut flags, chunk table, fix-up list -- exactly as build_srow computes it, so that the CPU-only tests can
+// check the sharding logic.  info[8] = {ok, LR, nhigh, ngroups, nchunks, cmax, nfix targets, nfix edges};
+// arrays may be NULL; capacities in entries.  Returns 0, or 1 when a capacity was too small.
+extern "C" int edgpu_selftest_srow_plan(const edgpu_params *p, int ndw, int nranks, int rank, int64_t lr, int64_t cmax,
+                                        int32_t *info, int32_t *jhi, int cap_jhi, int32_t *chunks, int cap_chunks,
+                                        int32_t *tcol, int32_t *tinit, int32_t *tptr, int cap_t,
+                                        int32_t *eown, int32_t *esrc, double *eval, int cap_e) {
+  DevParams d = make_dp(p);
+  const int64_t n = edgpu_selftest_map(d.ns, ndw, nullptr);
+  SRowHostPlan hp;
+  for (int k = 0; k < 8; k++) info[k] = 0;
+  const int rc = srow_plan_host(d.ns, ndw, n, nranks, rank, (int)lr, cmax, hp);
+  if (rc <= 0) { info[0] = rc; return 0; }
+  std::vector<int32_t> map((size_t)n), rp((size_t)n + 1), cc;
+  std::vector<double> vv;
+  edgpu_selftest_map(d.ns, ndw, map.data());
+  int32_t c[EDGPU_MAX_ROW_NNZ]; double v[EDGPU_MAX_ROW_NNZ];
+  for (int64_t i = 0; i < n; i++) {
+    rp[(size_t)i] = (int32_t)cc.size();
+    const int m = hd_factor_row(d, 1, map.data(), n, (uint32_t)map[(size_t)i], c, v);
+    for (int k = 0; k < m; k++) { cc.push_back(c[k]); vv.push_back(v[k]); }
+  }
+  rp[(size_t)n] = (int32_t)cc.size();
+  srow_fix_host(hp, rank, n, rp.data(), cc.data(), vv.data());
+  info[0] = 1; info[1] = hp.LR; info[2] = hp.nhigh; info[3] = (int32_t)hp.grp.size(); info[4] = (int32_t)hp.chunks.size();
+  info[5] = hp.cmax; info[6] = (int32_t)hp.tcol.size(); info[7] = (int32_t)hp.eown.size();
+  int small = 0;
+  if (jhi) { if ((int)hp.jhi.size() > cap_jhi) small = 1; else memcpy(jhi, hp.jhi.data(), hp.jhi.size() * sizeof(int32_t)); }
+  if (chunks) {
+    if ((int)hp.chunks.size() > cap_chunks) small = 1;
+    else for (size_t k = 0; k < hp.chunks.size(); k++) { chunks[4 * k] = hp.chunks[k].x; chunks[4 * k + 1] = hp.chunks[k].y; chunks[4 * k + 2] = hp.chunks[k].z; chunks[4 * k + 3] = hp.chunks[k].w; }
+  }
+  if (tcol) {
+    if ((int)hp.tcol.size() > cap_t) small = 1;
+    else for (size_t k = 0; k < hp.tcol.size(); k++) { tcol[k] = hp.tcol[k]; tinit[k] = hp.tinit[k]; tptr[k] = hp.tptr[k]; tptr[k + 1] = hp.tptr[k + 1]; }
+  }
+  if (eown) {
+    if ((int)hp.eown.size() > cap_e) small = 1;
+    else for (size_t k = 0; k < hp.eown.size(); k++) { eown[k] = hp.eown[k]; esrc[k] = hp.esrc[k]; eval[k] = hp.eval[k]; }
+  }
+  return small;
+}

@@ -23,6 +23,13 @@ double edgpu_selftest_diag(const edgpu_params *p, uint32_t mup, uint32_t mdw, in
 /* one row of spH0nd: returns the entry count, outputs column words and values */
 int edgpu_selftest_nonlocal_row(const edgpu_params *p, uint32_t mup, uint32_t mdw, uint32_t *cup, uint32_t *cdw,
                                 double *val);
+/* HOST: plan of the structured row kernel for `rank` of `nranks` (Lin table with owner / cut flags, chunk table,
+ * fix-up list of the hops that touch a low group cut by a rank boundary), as build_Hv_sector computes it.
+ * info[8] = {ok, LR, nhigh, ngroups, nchunks, cmax, fix targets, fix edges}; arrays may be NULL. */
+int edgpu_selftest_srow_plan(const edgpu_params *p, int ndw, int nranks, int rank, int64_t lr, int64_t cmax,
+                             int32_t *info, int32_t *jhi, int cap_jhi, int32_t *chunks, int cap_chunks,
+                             int32_t *tcol, int32_t *tinit, int32_t *tptr, int cap_t,
+                             int32_t *eown, int32_t *esrc, double *eval, int cap_e);
 /* GPU: the sharded fast H*v path with `nranks` ranks emulated by `nranks` contexts on ONE device (peers are plain
  * device pointers instead of NVLink mappings); x, y are full host vectors.  Test instrumentation only. */
 int edgpu_selftest_sharded_hxv(const edgpu_params *p, int nup, int ndw, int nranks, int64_t srow_lr, int64_t srow_cmax,

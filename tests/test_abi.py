@@ -1,6 +1,7 @@
 """The C-ABI library loads, exports every symbol include/*.h declares, fails loudly without a GPU,
 and its host-evaluable bit logic (hd_funcs.h, shared with the kernels) matches the oracle."""
 import ctypes as C
+import math
 import os
 import re
 
@@ -121,3 +122,88 @@ def test_host_side_gf_accumulation_matches_oracle():
     cfg = configs.config("C1")
     sig, _ = edgpu.sigma_normal(z, g, cfg["xmu"], 0.0, cfg["bath_e"], cfg["bath_v"])
     assert np.abs(sig - gold["smats"]).max() < 1e-10
+
+
+ROWPLAN_CASES = [("C1", 4, 1, 0, 0), ("C1", 4, 2, 0, 0), ("C1", 4, 3, 0, 0), ("C1", 4, 4, 0, 12), ("C1", 3, 4, 4, 12),
+                 ("NS10", 5, 3, 4, 24), ("NS10", 5, 8, 0, 0), ("NS12", 6, 7, 0, 64), ("NS12", 5, 8, 4, 48),
+                 ("NS14", 7, 8, 0, 0), ("NS16", 8, 8, 0, 0), ("NS16", 9, 5, 0, 0)]
+
+
+@pytest.mark.parametrize("name,ndw,nranks,lr,cmax", ROWPLAN_CASES)
+def test_row_kernel_plan_covers_every_hop_exactly_once(name, ndw, nranks, lr, cmax):
+    """Host arithmetic behind the sharded structured row kernel (hxv_fast.cu: srow_plan_host / srow_fix_host),
+    checked without a GPU for every rank of a split: the chunks tile the whole low groups of the rank, the
+    fix-up list holds exactly the hops whose target or source group is cut by a rank boundary (with the oracle's
+    matrix elements), every other hop is left to the kernel, and the Lin table is the closed-form rank."""
+    L = edgpu.lib()
+    cfg, o = make_oracle(name)
+    keep = _params(cfg)
+    p = keep[0]
+    i32p, dp = C.POINTER(C.c_int32), C.POINTER(C.c_double)
+    with o.sector(cfg["nup"], ndw) as s:
+        rp, cc, vv = s.hdw()
+        md = s.map_dw()
+        dimdw = len(md)
+    handled = np.zeros(len(cc), dtype=np.int32)          # how many times each CSR entry (target <- source) is covered
+    colcov = np.zeros(dimdw, dtype=np.int32)
+    for rank in range(nranks):
+        info = np.zeros(8, np.int32)
+        cap_j, cap_c, cap_t, cap_e = 1 << 15, 4096, dimdw + 8, len(cc) + 8
+        jhi = np.zeros(cap_j, np.int32); chunks = np.zeros(4 * cap_c, np.int32)
+        tcol = np.zeros(cap_t, np.int32); tinit = np.zeros(cap_t, np.int32); tptr = np.zeros(cap_t + 1, np.int32)
+        eown = np.zeros(cap_e, np.int32); esrc = np.zeros(cap_e, np.int32); ev = np.zeros(cap_e)
+        rc = L.edgpu_selftest_srow_plan(C.byref(p), ndw, nranks, rank, C.c_int64(lr), C.c_int64(cmax),
+                                        info.ctypes.data_as(i32p), jhi.ctypes.data_as(i32p), cap_j,
+                                        chunks.ctypes.data_as(i32p), cap_c, tcol.ctypes.data_as(i32p),
+                                        tinit.ctypes.data_as(i32p), tptr.ctypes.data_as(i32p), cap_t,
+                                        eown.ctypes.data_as(i32p), esrc.ctypes.data_as(i32p), ev.ctypes.data_as(dp), cap_e)
+        assert rc == 0 and info[0] == 1, (rc, info)
+        LR, nhigh, nchunks, nfix = int(info[1]), int(info[2]), int(info[4]), int(info[6])
+        q, off = edgpu.split(dimdw, nranks, rank)
+        coloffs = [edgpu.split(dimdw, nranks, r)[1] for r in range(nranks)] + [dimdw]
+        # Lin table: first column of every group = rank of its smallest word; owner / cut flags from the split
+        lowmask = (1 << LR) - 1
+        gcut = {}
+        for h in range(1 << nhigh):
+            e = int(jhi[h])
+            nlow = ndw - bin(h).count("1")
+            if nlow < 0 or nlow > LR:
+                assert e == -1
+                continue
+            words = md[(md >> LR) == h]
+            base = int(np.searchsorted(md, words[0]))
+            assert (e & 0xFFFFF) == base and len(words) == math.comb(LR, nlow)
+            own = max(r for r in range(nranks) if coloffs[r] <= base)
+            cut = base + len(words) > coloffs[own + 1]
+            assert ((e >> 20) & 63) == own and bool(e & 0x40000000) == cut
+            gcut[h] = cut
+        colcut = np.array([gcut[int(w) >> LR] for w in md])
+        # chunks: whole, uncut local groups, contiguous, within the size limit
+        ch = chunks[:4 * nchunks].reshape(-1, 4)
+        for k in range(nchunks):
+            assert off <= ch[k, 2] < ch[k, 3] <= off + q and ch[k, 3] - ch[k, 2] <= info[5]
+            assert not colcut[ch[k, 2]:ch[k, 3]].any()
+            colcov[ch[k, 2]:ch[k, 3]] += 1
+            if k:
+                assert ch[k, 2] == ch[k - 1, 3] and ch[k, 0] == ch[k - 1, 1]
+        inchunk = np.zeros(dimdw, bool)
+        for k in range(nchunks):
+            inchunk[ch[k, 2]:ch[k, 3]] = True
+        # the kernel's rule: a hop is applied by k_srow iff its target is in a chunk and its source group is not cut
+        for t in range(off, off + q):
+            for e in range(rp[t], rp[t + 1]):
+                if inchunk[t] and not colcut[cc[e]]:
+                    handled[e] += 1
+        # fix-up list: targets in cut groups are initialised there, every listed edge is a real matrix element
+        for k in range(nfix):
+            t = off + int(tcol[k])
+            assert bool(tinit[k]) == bool(colcut[t])
+            if tinit[k]:
+                colcov[t] += 1
+            for e in range(tptr[k], tptr[k + 1]):
+                src = coloffs[int(eown[e])] + int(esrc[e])
+                hit = [x for x in range(rp[t], rp[t + 1]) if cc[x] == src]
+                assert len(hit) == 1 and vv[hit[0]] == ev[e]
+                handled[hit[0]] += 1
+    assert (colcov == 1).all()                                # every column written by exactly one kernel
+    assert (handled == 1).all()                               # every hop applied exactly once
