@@ -400,12 +400,6 @@ extern "C" int edgpu_destroy(edgpu_ctx *c) {
 // ------------------------------------------------------------------------------------------
 // the operator through host pointers (spHtimesV_p)
 // ------------------------------------------------------------------------------------------
-static int ensure_buf(double **p, int64_t n) {
-  if (*p) return EDGPU_OK;
-  CK(cudaMalloc(p, (size_t)n * sizeof(double)));
-  return EDGPU_OK;
-}
-
 extern "C" int edgpu_hxv_device(edgpu_ctx *c, int64_t nloc, const double *d_v, double *d_hv) {
   if (!c || !c->hstatus) return edgpu_set_err(EDGPU_ERR_INVALID, "HxV: Hsector NOT set");
   if (nloc != c->nloc) return edgpu_set_err(EDGPU_ERR_INVALID, "HxV: Nloc=%lld != vecDim=%lld", (long long)nloc, (long long)c->nloc);

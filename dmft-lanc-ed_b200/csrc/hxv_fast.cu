@@ -1,20 +1,25 @@
-// hxv_fast.cu -- the engine's fast H*v path: two HBM passes, each staged through shared memory by
-// TMA bulk copies (cp.async.bulk + mbarrier, double buffered, persistent CTAs, one CTA per SM).
+// hxv_fast.cu -- the engine's fast H*v path: two HBM passes, each staged through shared memory by the TMA
+// engine (cp.async.bulk / cp.async.bulk.tensor + mbarrier, double buffered, persistent CTAs, one CTA per SM,
+// a dedicated producer warp and full/empty barriers instead of CTA-wide barriers).
 //
 //   y = Hd o x + Hup x + x Hdw^T       x(i_up, i_dw) column-major, i_up contiguous
 //
-//   pass 1  k_fcol : one WHOLE column x(:, j) per stage in shared memory (a contiguous 8*DimUp byte
-//                    bulk copy), y(:, j) = [Hd o x +] F x(:, j).  F is any one-spin factor
-//                    (spH0ups / spH0dws, ED_HAMILTONIAN/stored/H_up.f90, H_dw.f90) in a packed
-//                    4-byte ELL form streamed from L2; every gather hits shared memory.
-//   pass 2  k_srow : tile = 32 consecutive i_up rows x one chunk of i_dw columns; lanes run along
-//                    i_up so every shared-memory access is unit stride, and the dw hops are
-//                    generated from the bit structure of the star geometry (Norb = 1: every hop
-//                    is impurity bit 0 <-> bath bit k): the columns of one "low group" (same high
-//                    bits, LR low bits) live in registers, hops among the low bits are register
-//                    to register, a hop on a high bit moves the whole group to ONE other group
-//                    whose base column comes from a Lin table.  No per-element index data at all.
-//                    y += Hd o x + x Hdw^T.
+//   pass 1  k_srow : y = Hd o x + x Hdw^T (write only).  Tile = 32 consecutive i_up rows x one chunk of i_dw
+//                    columns (2-D tensor-map TMA boxes); lanes run along i_up so every shared-memory access is
+//                    unit stride, and the dw hops are generated from the bit structure of the star geometry
+//                    (Norb = 1: every hop is impurity bit 0 <-> bath bit k): the columns of one "low group"
+//                    (same high bits, LR low bits) live in registers, hops among the low bits are register to
+//                    register, a hop on a high bit moves the whole group to ONE other group whose base column
+//                    comes from a Lin table.  No per-element index data at all.  Sources outside the tile come
+//                    from L2 -- or, when the vector is sharded over GPUs, from the owner rank's copy over NVLink
+//                    (peer-mapped symmetric slab, comm.cu); the few hops that touch a low group cut by a rank
+//                    boundary are left to k_sfix.
+//   pass 2  k_fcol : y += F x(:, j) with one WHOLE column per stage in shared memory (a contiguous 8*DimUp byte
+//                    bulk copy).  F is any one-spin factor (spH0ups / spH0dws, ED_HAMILTONIAN/stored/H_up.f90,
+//                    H_dw.f90) in a packed ELL form streamed from L2; every gather hits shared memory.  MODE 2
+//                    fuses the first Lanczos vector update (w = s*Hx - c*x_prev, alpha partials) into the epilogue.
+//           k_fcol2: the same for columns that exceed one SM (Ns = 18): a 2-CTA cluster holds the column, the
+//                    other half is read through distributed shared memory.
 //
 // The factor values are exactly the reference's V_k * sg1 * sg2 (stored/H_up.f90:55-81); only the
 // order of the floating-point sums differs.

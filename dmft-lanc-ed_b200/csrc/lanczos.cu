@@ -111,11 +111,6 @@ __global__ void k_random_start(double *__restrict__ x, int64_t n, int64_t goff) 
   }
 }
 
-static int ensure(double **p, int64_t n) {
-  if (*p) return EDGPU_OK;
-  CK(cudaMalloc(p, (size_t)(n > 0 ? n : 1) * sizeof(double)));
-  return EDGPU_OK;
-}
 static int ensure_coeffs(edgpu_ctx *c, int n) {
   if (c->lanc_cap >= n + 2) return EDGPU_OK;
   cudaFree(c->d_alanc); cudaFree(c->d_blanc);
