@@ -207,3 +207,54 @@ def test_row_kernel_plan_covers_every_hop_exactly_once(name, ndw, nranks, lr, cm
                 handled[hit[0]] += 1
     assert (colcov == 1).all()                                # every column written by exactly one kernel
     assert (handled == 1).all()                               # every hop applied exactly once
+
+
+@pytest.mark.parametrize("name,ndw,lr", [("C1", 4, 5), ("C1", 5, 4), ("NS10", 5, 5), ("NS10V", 4, 4), ("NS12V", 6, 5), ("NS14", 7, 5)])
+def test_structured_hop_enumeration_reproduces_spH0dws(name, ndw, lr):
+    """The algebra k_srow relies on (hxv_fast.cu: srow_group / srow_prepare), restated in Python on top of the
+    engine's own Lin table: low group = (high word h, LR low bits), hop = impurity bit 0 <-> bath bit k, partner
+    column = jhi[h'] + rank of the partner's low pattern in its class, sign = parity of the occupied bits strictly
+    between the two.  Enumerated that way, the (target, source, value) triples must be EXACTLY spH0dws(1) of the
+    oracle (stored/H_dw.f90:8-80) -- structure bit-exact, values bit-exact."""
+    L = edgpu.lib()
+    cfg, o = make_oracle(name)
+    keep = _params(cfg)
+    i32p = C.POINTER(C.c_int32)
+    with o.sector(cfg["nup"], ndw) as s:
+        rp, cc, vv = s.hdw()
+    info = np.zeros(8, np.int32)
+    jhi = np.zeros(1 << 15, np.int32)
+    rc = L.edgpu_selftest_srow_plan(C.byref(keep[0]), ndw, 1, 0, C.c_int64(lr), C.c_int64(0), info.ctypes.data_as(i32p),
+                                    jhi.ctypes.data_as(i32p), len(jhi), None, 0, None, None, None, 0, None, None, None, 0)
+    assert rc == 0 and info[0] == 1
+    LR, nhigh = int(info[1]), int(info[2])
+    ns = LR + nhigh
+    vk = [0.0] + [float(cfg["bath_v"].reshape(-1)[k]) for k in range(ns - 1)]      # V_k of the dw spin (Nspin = 1)
+    popc = lambda x: bin(x).count("1")
+    pats = {n: [q for q in range(1 << LR) if popc(q) == n] for n in range(LR + 1)}
+    rank = lambda lo: pats[popc(lo)].index(lo)
+    trip = {}
+    for h in range(1 << nhigh):
+        n = ndw - popc(h)
+        if n < 0 or n > LR:
+            continue
+        base = int(jhi[h]) & 0xFFFFF
+        for i, lo in enumerate(pats[n]):
+            t = base + i
+            for kb in range(1, LR):                                   # hops among the low bits (register to register)
+                if ((lo >> kb) & 1) != (lo & 1):
+                    lo2 = lo ^ (1 | (1 << kb))
+                    sgn = -1.0 if popc(lo & ((1 << kb) - 2)) & 1 else 1.0
+                    trip[(t, base + rank(lo2))] = sgn * vk[kb]
+            for kk in range(nhigh):                                   # hops on the high bits (whole group -> one group)
+                bit = 1 << kk
+                if bool(h & bit) == bool(lo & 1):
+                    continue                                          # bath bit and impurity bit must differ
+                lo2 = lo ^ 1
+                base2 = int(jhi[h ^ bit]) & 0xFFFFF
+                sgn = -1.0 if (popc(lo >> 1) + popc(h & (bit - 1))) & 1 else 1.0
+                trip[(t, base2 + rank(lo2))] = sgn * vk[LR + kk]
+    ref = {(t, int(cc[e])): float(vv[e]) for t in range(len(rp) - 1) for e in range(rp[t], rp[t + 1])}
+    trip = {k: v for k, v in trip.items() if v != 0.0}                # the reference stores no entry for V_k = 0
+    assert trip.keys() == ref.keys()
+    assert all(trip[k] == ref[k] for k in ref)
