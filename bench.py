@@ -296,7 +296,7 @@ def run_b200(args):
         # minimum bytes each launch has to move per element: row kernel reads x and writes y (+ streamed spH0d),
         # column kernel reads x, reads y, writes y; the whole H*v step is judged against 16 (24) B/element
         alg = {"k_srow": 16 + (8 if args.stored else 0), "k_fcol": 24, "k_tile_col": 16 + (8 if args.stored else 0),
-               "k_tile_row": 24, "k_hxv_gather": bytes_per_el}
+               "k_tile_row": 24, "k_hxv_gather": bytes_per_el, "k_halo_pull": 0}
         tot = sum(ms_k for _, ms_k in passes)
         for name, ms_k in passes:
             b = alg.get(name, bytes_per_el)

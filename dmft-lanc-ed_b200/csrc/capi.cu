@@ -76,25 +76,17 @@ static int load_params(edgpu_ctx *c, const edgpu_params *p) {
   return EDGPU_OK;
 }
 
-extern "C" int edgpu_create(const edgpu_params *p, int device, edgpu_ctx **out) {
-  if (!out) return edgpu_set_err(EDGPU_ERR_INVALID, "out == NULL");
-  *out = nullptr;
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
-    return edgpu_set_err(EDGPU_ERR_NO_DEVICE, "no CUDA device: this engine has no CPU fallback");
-  edgpu_ctx *c = new edgpu_ctx();
-  int rc = load_params(c, p);
-  if (rc) { delete c; return rc; }
-  if (device < 0) cudaGetDevice(&device);
-  c->device = device;
-  if (cudaSetDevice(device) != cudaSuccess) { delete c; return edgpu_set_err(EDGPU_ERR_NO_DEVICE, "cudaSetDevice(%d) failed", device); }
+static int create_device_state(edgpu_ctx *c) {
   cudaDeviceProp prop;
-  CK(cudaGetDeviceProperties(&prop, device));
-  if (prop.major < 10) { delete c; return edgpu_set_err(EDGPU_ERR_NO_DEVICE, "device %s is sm_%d%d; this engine is built for sm_100a only", prop.name, prop.major, prop.minor); }
+  CK(cudaGetDeviceProperties(&prop, c->device));
+  if (prop.major < 10) return edgpu_set_err(EDGPU_ERR_NO_DEVICE, "device %s is sm_%d%d; this engine is built for sm_100a only", prop.name, prop.major, prop.minor);
   c->sm_count = prop.multiProcessorCount;
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
   CK(cudaEventCreate(&c->ev0));
   CK(cudaEventCreate(&c->ev1));
+  CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   // exact binomials by Pascal's rule (== binomial(), ED_SETUP.f90:1017-1035, for these sizes)
   memset(c->h_binom, 0, sizeof(c->h_binom));
   for (int n = 0; n < EDGPU_BINOM_LD; n++) {
@@ -108,9 +100,27 @@ extern "C" int edgpu_create(const edgpu_params *p, int device, edgpu_ctx **out) 
   CK(cudaMalloc(&c->d_binom, sizeof(c->h_binom)));
   CK(cudaMemcpy(c->d_binom, c->h_binom, sizeof(c->h_binom), cudaMemcpyHostToDevice));
   CK(cudaMalloc(&c->d_partials, 4096 * sizeof(double)));
+  CK(cudaMemset(c->d_partials, 0, 4096 * sizeof(double)));
   CK(cudaMalloc(&c->d_st, sizeof(LancState)));
   CK(cudaMemset(c->d_st, 0, sizeof(LancState)));
   CK(cudaMallocHost(&c->h_pinned, 4096 * sizeof(double)));
+  return EDGPU_OK;
+}
+
+extern "C" int edgpu_create(const edgpu_params *p, int device, edgpu_ctx **out) {
+  if (!out) return edgpu_set_err(EDGPU_ERR_INVALID, "out == NULL");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return edgpu_set_err(EDGPU_ERR_NO_DEVICE, "no CUDA device: this engine has no CPU fallback");
+  edgpu_ctx *c = new edgpu_ctx();
+  int rc = load_params(c, p);
+  if (rc) { delete c; return rc; }
+  if (device < 0) cudaGetDevice(&device);
+  c->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) { delete c; return edgpu_set_err(EDGPU_ERR_NO_DEVICE, "cudaSetDevice(%d) failed", device); }
+  rc = create_device_state(c);
+  if (rc) { edgpu_destroy(c); return rc; }                       // one cleanup path: destroy frees whatever exists
   *out = c;
   return EDGPU_OK;
 }
@@ -128,8 +138,10 @@ extern "C" int edgpu_set_option(edgpu_ctx *c, const char *key, int64_t value) {
   if (!strcmp(key, "tile_h")) { c->opt_tile_h = value; return EDGPU_OK; }
   if (!strcmp(key, "col_h")) { c->opt_col_h = value; return EDGPU_OK; }
   if (!strcmp(key, "srow_lr")) { c->opt_srow_lr = value; return EDGPU_OK; }
-  if (!strcmp(key, "srow_cmax")) { c->opt_srow_cmax = value; return EDGPU_OK; }
-  if (!strcmp(key, "dbg")) { c->opt_dbg = value; return EDGPU_OK; }
+  if (!strcmp(key, "srow_t")) { c->opt_srow_t = value; return EDGPU_OK; }      // t + 1 forces chunks of 2^t low groups
+  if (!strcmp(key, "no_fuse")) { c->opt_no_fuse = value; return EDGPU_OK; }    // Lanczos update as a separate pass
+  if (!strcmp(key, "halo_ctas")) { c->opt_halo_ctas = value; return EDGPU_OK; }
+  if (!strcmp(key, "no_overlap")) { c->opt_no_overlap = value; return EDGPU_OK; }
   if (!strcmp(key, "no_peer")) { c->opt_no_peer = value; return EDGPU_OK; }
   if (!strcmp(key, "col_cluster")) { c->opt_col_cluster = value; return EDGPU_OK; }
   if (!strcmp(key, "no_uniform")) { c->opt_no_uniform = value; return EDGPU_OK; }
@@ -145,8 +157,9 @@ extern "C" int edgpu_get_sector(const edgpu_ctx *c, int nup, int ndw, int *isect
   return EDGPU_OK;
 }
 extern "C" int edgpu_get_nup_ndw(const edgpu_ctx *c, int isector, int *nup, int *ndw) {
+  if (!c) return edgpu_set_err(EDGPU_ERR_INVALID, "ctx == NULL");
   int nsec = (c->ns + 1) * (c->ns + 1);                     // Nsectors, ED_SETUP.f90:134
-  if (!c || isector < 1 || isector > nsec) return edgpu_set_err(EDGPU_ERR_INVALID, "isector out of range");
+  if (isector < 1 || isector > nsec) return edgpu_set_err(EDGPU_ERR_INVALID, "isector out of range");
   int count = isector - 1;                                  // get_Nup/get_Ndw, ED_SETUP.f90:477-500
   *ndw = count % (c->ns + 1);
   *nup = count / (c->ns + 1);
@@ -326,15 +339,17 @@ extern "C" int edgpu_build_hv_sector(edgpu_ctx *c, int isector) {
     int64_t *d_counts = nullptr;
     CK(cudaMalloc(&d_counts, (size_t)(c->nloc + 1) * sizeof(int64_t)));
     CK(cudaMemsetAsync(d_counts, 0, (size_t)(c->nloc + 1) * sizeof(int64_t), c->stream));
-    int blocks = (int)((c->nloc + 127) / 128);
+    if (c->nloc + 1 > (int64_t)0x7fffffff * 128)
+      return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "spH0nd: local dimension %lld exceeds the builder's grid", (long long)c->nloc);
+    const unsigned blocks = (unsigned)((c->nloc + 127) / 128);
     k_nd_count<<<blocks, 128, 0, c->stream>>>(c->dp, c->up.d_map, c->dw.d_map, c->dimup, c->coloff, c->nloc, d_counts);
     CKL(c);
     CK(cudaMalloc(&c->d_nd_rowptr, (size_t)(c->nloc + 1) * sizeof(int64_t)));
     size_t tmp_bytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_counts, c->d_nd_rowptr, (int)(c->nloc + 1), c->stream);
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_counts, c->d_nd_rowptr, (int64_t)(c->nloc + 1), c->stream);
     void *d_tmp = nullptr;
     CK(cudaMalloc(&d_tmp, tmp_bytes));
-    cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_counts, c->d_nd_rowptr, (int)(c->nloc + 1), c->stream);
+    cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_counts, c->d_nd_rowptr, (int64_t)(c->nloc + 1), c->stream);
     c->launches++;
     CK(cudaMemcpyAsync(&c->nd_nnz, c->d_nd_rowptr + c->nloc, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -391,6 +406,9 @@ extern "C" int edgpu_destroy(edgpu_ctx *c) {
   cudaFreeHost(c->h_pinned);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
+  if (c->stream2) cudaStreamDestroy(c->stream2);
   for (int i = 0; i < 6; i++) if (c->pev[i]) cudaEventDestroy(c->pev[i]);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -404,7 +422,11 @@ extern "C" int edgpu_hxv_device(edgpu_ctx *c, int64_t nloc, const double *d_v, d
   if (!c || !c->hstatus) return edgpu_set_err(EDGPU_ERR_INVALID, "HxV: Hsector NOT set");
   if (nloc != c->nloc) return edgpu_set_err(EDGPU_ERR_INVALID, "HxV: Nloc=%lld != vecDim=%lld", (long long)nloc, (long long)c->nloc);
   CK(cudaSetDevice(c->device));
-  return hxv_apply(c, d_v, d_hv);
+  TRY(hxv_apply(c, d_v, d_hv));
+  // sharded fast path: peers pull columns of d_v during the call.  The caller owns d_v and may overwrite it as soon
+  // as this returns, so every rank's reads are ordered before the return of anybody's next stream operation.
+  if (c->sym_ok && sym_offset(c, d_v) >= 0) TRY(comm_barrier(c));
+  return EDGPU_OK;
 }
 
 extern "C" int edgpu_hxv(edgpu_ctx *c, int64_t nloc, const double *v, double *hv) {
@@ -509,15 +531,24 @@ extern "C" int edgpu_dev_alloc(edgpu_ctx *c, int64_t nbytes, void **dptr) {
   if (c->sym_ok && c->hstatus) {                                // peer-readable when a sharded sector is live
     double *p = nullptr;
     TRY(vec_alloc(c, &p, (nbytes + 7) / 8));
+    if (sym_offset(c, p) >= 0) c->slab_ptrs.push_back(p);       // remembered: dies with the sector
     *dptr = p;
     return EDGPU_OK;
   }
   CK(cudaMalloc(dptr, (size_t)nbytes + 16));
+  for (size_t i = 0; i < c->slab_ptrs.size(); i++)               // an address of a released slab may come back
+    if (c->slab_ptrs[i] == *dptr) { c->slab_ptrs.erase(c->slab_ptrs.begin() + (long)i); break; }
   return EDGPU_OK;
 }
 extern "C" int edgpu_dev_free(edgpu_ctx *c, void *dptr) {
+  if (!c) return edgpu_set_err(EDGPU_ERR_INVALID, "ctx == NULL");
+  if (!dptr) return EDGPU_OK;
   CK(cudaSetDevice(c->device));
-  if (sym_offset(c, dptr) >= 0) return EDGPU_OK;                // slab memory goes away with the sector
+  // buffers carved from the symmetric slab (edgpu_dev_alloc while a sharded sector is live) belong to that sector:
+  // they are released by delete_Hv_sector, and freeing one -- before or after -- is a no-op
+  if (sym_offset(c, dptr) >= 0) return EDGPU_OK;
+  for (size_t i = 0; i < c->slab_ptrs.size(); i++)
+    if (c->slab_ptrs[i] == dptr) { c->slab_ptrs.erase(c->slab_ptrs.begin() + (long)i); return EDGPU_OK; }
   CK(cudaFree(dptr));
   return EDGPU_OK;
 }
@@ -558,7 +589,6 @@ extern "C" int edgpu_time_hxv_passes(edgpu_ctx *c, int64_t nloc, const double *d
                                      int *npasses, double *ms_pass, char *names) {
   if (!c || !c->hstatus) return edgpu_set_err(EDGPU_ERR_INVALID, "HxV: Hsector NOT set");
   if (nloc != c->nloc) return edgpu_set_err(EDGPU_ERR_INVALID, "nloc mismatch");
-  if (c->nranks != 1) return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "per-pass timing is single-rank only");
   CK(cudaSetDevice(c->device));
   for (int i = 0; i < 6; i++) if (!c->pev[i]) CK(cudaEventCreate(&c->pev[i]));
   for (int i = 0; i < 4; i++) ms_pass[i] = 0.0;

@@ -26,13 +26,28 @@ struct LancState {              // device-resident Lanczos scalars (no host sync
   double norm2;
 };
 
+#define EDGPU_MAXP 8            // ranks of one NVLink domain (peer-mapped symmetric slab)
+
+// One low group of the structured row kernel (hxv_fast.cu), precomputed per sector: 80 bytes, bulk-copied next
+// to the tile.  hx = high word h | (mask of the high-bit hops the kernel applies) << 16; par bit kk = parity of
+// the occupied high bits below kk; pc[kk] = first column of the partner group of hop kk (tile-local for the T
+// lowest high bits, shard-local otherwise).
+struct SRowRec {
+  int32_t lb, N;
+  uint32_t hx, par;
+  int32_t pc[16];
+};
+static_assert(sizeof(SRowRec) == 80, "SRowRec is copied in 16-byte units");
+
 struct TiledPlan;               // hxv_tiled.cu
 struct FastPlan;                // hxv_fast.cu
 
 struct edgpu_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t stream2 = nullptr;             // halo copy next to the row kernel (sharded fast path)
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
+  bool fast_attrs_set = false, tiled_attrs_set = false;   // per-device function attributes (this context's device)
   int sm_count = 148;
   // inputs
   edgpu_params hp{};
@@ -76,7 +91,9 @@ struct edgpu_ctx {
   int64_t opt_tile_rows = 0, opt_tile_h = -1, opt_col_h = -1;
   TiledPlan *plan = nullptr;
   FastPlan *fplan = nullptr;
-  int64_t opt_srow_lr = 0, opt_srow_cmax = 0, opt_no_uniform = 0, opt_dbg = 0, opt_no_peer = 0, opt_col_cluster = 0;
+  int64_t opt_srow_lr = 0, opt_srow_t = 0, opt_no_uniform = 0, opt_no_fuse = 0, opt_no_peer = 0, opt_col_cluster = 0;
+  int64_t opt_halo_ctas = 0, opt_no_overlap = 0;
+  const double *const *peer_override = nullptr;   // selftest only: the ranks emulated on one device
   int64_t launches = 0;
   // symmetric slab (nranks > 1): one allocation per rank at identical offsets, opened by every peer
   // through CUDA IPC, so that kernels can read a peer's copy of a vector over NVLink
@@ -84,6 +101,7 @@ struct edgpu_ctx {
   size_t sym_bytes = 0, sym_used = 0, sym_unit = 0;
   char *sym_peer[64] = {nullptr};
   bool sym_ok = false;
+  std::vector<void *> slab_ptrs;              // edgpu_dev_alloc buffers carved from the slab (die with the sector)
   // per-pass timing (edgpu_time_hxv_passes): events recorded between the kernels of one H*v
   bool prof = false;
   int prof_n = 0;
@@ -127,9 +145,6 @@ int edgpu_set_err(int code, const char *fmt, ...);
 int hxv_apply(edgpu_ctx *c, const double *d_x, double *d_y);
 // true when hxv_apply would take the fast two-kernel path for this vector (then the Lanczos epilogue can be fused)
 bool hxv_fast_path(edgpu_ctx *c, const double *d_x);
-// Lanczos-fused form: w = sx*(H x) - cprev*xp (written over xp), partial sums of (sx*x).w go to
-// c->d_partials; scalars are read from c->d_st on device.
-int hxv_release_plan(edgpu_ctx *c);
 // hxv_tiled.cu
 int tiled_plan_build(edgpu_ctx *c);
 int tiled_plan_free(edgpu_ctx *c);
@@ -140,21 +155,21 @@ int tiled_apply_col(edgpu_ctx *c, int k, bool with_diag, const double *d_x, doub
 // hxv_fast.cu: host arithmetic of the structured row kernel's plan (no device needed; see selftest.cu)
 struct SRowHostPlan {
   bool ok = false;
-  int LR = 0, nhigh = 0, cmax = 0, g0 = 0, g1 = 0;
+  int LR = 0, T = 0, nhigh = 0, cmax = 0, cpad = 0, maxg = 0;
   size_t smem = 0;
   std::vector<int> coloffs;            // [P+1] first global column of every rank
-  std::vector<int32_t> jhi;            // [2^nhigh] first column | owner << 20 | cut << 30, -1 = empty group
-  std::vector<uint16_t> grp;           // high words of the non-empty groups, ascending
-  std::vector<int> gsize, gbase;
-  std::vector<char> gcut;
-  std::vector<int4> chunks;            // (group begin, group end, column begin, column end), whole local groups only
-  std::vector<int> tptr, tcol, eown, esrc;   // fix-up list (srow_fix_host)
-  std::vector<unsigned char> tinit;
-  std::vector<double> eval;
+  std::vector<int32_t> jhi;            // [2^nhigh] first global column of group h, -1 = empty group
+  std::vector<char> gwhole;            // [2^nhigh] every column of the group is on this rank
+  std::vector<int4> chunks;            // (first record, groups, local column begin, local column end)
+  std::vector<SRowRec> recs;
+  std::vector<int> lptr, lloc;         // column-pass source lists (srow_lists_host)
+  std::vector<double> lamp;
+  std::vector<unsigned char> linit;
+  std::vector<int> hown, hcol;         // halo slots
 };
 // returns 1 = plan built, 0 = the structured kernel does not apply, -1 = internal inconsistency
-int srow_plan_host(int ns, int ndw, int64_t dimdw, int nranks, int rank, int lr, int64_t cmax_opt, SRowHostPlan &hp);
-void srow_fix_host(SRowHostPlan &hp, int rank, int64_t dimdw, const int32_t *rp, const int32_t *cc, const double *vv);
+int srow_plan_host(int ns, int ndw, int64_t dimdw, int nranks, int rank, int lr, int tbits_opt, SRowHostPlan &hp);
+void srow_lists_host(SRowHostPlan &hp, int rank, int64_t dimdw, const int32_t *map, const int32_t *rp, const int32_t *cc, const double *vv);
 // hxv_fast.cu: TMA-staged whole-column kernel + structured single-band row kernel
 int fast_plan_build(edgpu_ctx *c);
 int fast_plan_free(edgpu_ctx *c);
@@ -162,8 +177,9 @@ bool fast_supported_local(edgpu_ctx *c);          // full operator on the local 
 bool fast_supported_col(edgpu_ctx *c, int k);     // whole-column kernel for factor k
 int fast_apply_local(edgpu_ctx *c, const double *d_x, double *d_y, double *d_xp = nullptr, int *npartials = nullptr);
 int fast_apply_col(edgpu_ctx *c, int k, bool with_diag, bool acc, const double *d_x, double *d_y, int64_t ncols, int64_t coloff,
-                   double *d_xp = nullptr, int *npartials = nullptr);
-int fast_apply_row(edgpu_ctx *c, bool with_diag, bool acc, const double *d_x, double *d_y, const double *const *xpeer);
+                   double *d_xp = nullptr, int *npartials = nullptr, bool dw_lists = false);
+int fast_apply_row(edgpu_ctx *c, const double *d_x, double *d_y, int grid_limit = 0);
+int fast_halo_pull(edgpu_ctx *c, const double *const *xpeer, cudaStream_t st, int ctas);
 bool fast_peer_ready(edgpu_ctx *c, const double *d_x);   // sharded: x lives in the symmetric slab, peers are mapped
 // comm.cu
 int comm_symm_setup(edgpu_ctx *c, size_t unit, int nunits);   // collective: nunits vectors of `unit` bytes

@@ -162,7 +162,7 @@ static int pick_col(edgpu_ctx *c) {
 }
 
 bool hxv_fast_path(edgpu_ctx *c, const double *d_x) {
-  if (c->dp.jhflag || (c->opt_dbg & 16)) return false;
+  if (c->dp.jhflag || c->opt_no_fuse) return false;
   if (c->nranks == 1) return pick_local(c) == EDGPU_ALGO_FAST && fast_supported_local(c);
   return (c->algo == EDGPU_ALGO_AUTO || c->algo == EDGPU_ALGO_FAST) && fast_peer_ready(c, d_x) && fast_supported_local(c);
 }

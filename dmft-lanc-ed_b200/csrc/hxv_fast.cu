@@ -1,25 +1,31 @@
 // hxv_fast.cu -- the engine's fast H*v path: two HBM passes, each staged through shared memory by the TMA
-// engine (cp.async.bulk / cp.async.bulk.tensor + mbarrier, double buffered, persistent CTAs, one CTA per SM,
+// engine (cp.async.bulk / cp.async.bulk.tensor + mbarrier, multi-buffered, persistent CTAs, one CTA per SM,
 // a dedicated producer warp and full/empty barriers instead of CTA-wide barriers).
 //
 //   y = Hd o x + Hup x + x Hdw^T       x(i_up, i_dw) column-major, i_up contiguous
 //
-//   pass 1  k_srow : y = Hd o x + x Hdw^T (write only).  Tile = 32 consecutive i_up rows x one chunk of i_dw
-//                    columns (2-D tensor-map TMA boxes); lanes run along i_up so every shared-memory access is
-//                    unit stride, and the dw hops are generated from the bit structure of the star geometry
-//                    (Norb = 1: every hop is impurity bit 0 <-> bath bit k): the columns of one "low group"
-//                    (same high bits, LR low bits) live in registers, hops among the low bits are register to
-//                    register, a hop on a high bit moves the whole group to ONE other group whose base column
-//                    comes from a Lin table.  No per-element index data at all.  Sources outside the tile come
-//                    from L2 -- or, when the vector is sharded over GPUs, from the owner rank's copy over NVLink
-//                    (peer-mapped symmetric slab, comm.cu); the few hops that touch a low group cut by a rank
-//                    boundary are left to k_sfix.
+//   pass 1  k_srow : y = Hd o x + x Hdw^T (write only).  Tile = 32 consecutive i_up rows x one ALIGNED chunk of
+//                    i_dw columns (2-D tensor-map TMA boxes); lanes run along i_up so every shared-memory access
+//                    is unit stride, and the dw hops are generated from the bit structure of the star geometry
+//                    (Norb = 1: every hop is impurity bit 0 <-> bath bit k).  The columns of one "low group"
+//                    (same high word h, LR low bits) live in registers; hops among the low bits are register to
+//                    register; a hop on a high bit moves the whole group onto ONE other group.  A chunk is the set
+//                    of groups that share the top bits of h, so it is closed under the T lowest high bits: those
+//                    hops read the shared-memory tile, only the hops on the remaining top bits read L2.  Everything
+//                    about a group (tile offset, class, parities, partner columns) is precomputed once per sector
+//                    in an 80-byte record that the producer warp bulk-copies next to the tile.
 //   pass 2  k_fcol : y += F x(:, j) with one WHOLE column per stage in shared memory (a contiguous 8*DimUp byte
 //                    bulk copy).  F is any one-spin factor (spH0ups / spH0dws, ED_HAMILTONIAN/stored/H_up.f90,
 //                    H_dw.f90) in a packed ELL form streamed from L2; every gather hits shared memory.  MODE 2
 //                    fuses the first Lanczos vector update (w = s*Hx - c*x_prev, alpha partials) into the epilogue.
 //           k_fcol2: the same for columns that exceed one SM (Ns = 18): a 2-CTA cluster holds the column, the
 //                    other half is read through distributed shared memory.
+//
+// Sharded vector (i_dw columns split over the GPUs of one NVLink domain, ED_HAMILTONIAN.f90:96-110): k_srow only
+// touches local memory.  The dw hops whose source column lives on another rank -- and the few that touch a low
+// group cut by a rank boundary -- are applied by pass 2 from per-column source lists; their sources are copied
+// once per H*v from the owners' copies of x (peer-mapped symmetric slab, comm.cu) into a local halo buffer by
+// k_halo_pull, which runs on a second stream and on its own SMs while k_srow works.
 //
 // The factor values are exactly the reference's V_k * sg1 * sg2 (stored/H_up.f90:55-81); only the
 // order of the floating-point sums differs.
@@ -37,20 +43,22 @@
 #define F_VID_MASK 0x7FFu
 #define F_MAXVALS 256
 #define FCOL_THREADS 1024
-// consumer threads per CTA (+1 producer warp): LR=5 -> 512 threads x 128 registers, LR=4 -> 768 x 85
-__host__ __device__ constexpr int srow_consumers(int LR) { return LR >= 5 ? 480 : 736; }
-#define SROW_R 32
+#define SROW_R 32                 // rows per tile = lanes of a warp
+#define SROW_BC 32                // columns per TMA box (32 rows x 32 columns x 8 B = 8 KB per copy)
+#define SROW_THREADS 512          // 15 consumer warps + 1 producer warp, 128 registers each
+#define SROW_CONSUMERS (SROW_THREADS - 32)
+#ifndef SROW_STAGES
+#define SROW_STAGES 2
+#endif
 #ifndef SROW_NB_FAR
-#define SROW_NB_FAR 3             // high-bit hops whose loads are fused (far sources: L2 / peer GPU)
+#define SROW_NB_FAR 4             // far (L2) hops of one kind whose loads are in flight together
 #endif
 #ifndef SROW_NB_IN
-#define SROW_NB_IN 1              // ... for sources inside the shared-memory tile
+#define SROW_NB_IN 2              // ... for sources inside the shared-memory tile
 #endif
-#define SROW_BC 32                // columns per TMA box (32 rows x 32 columns x 8 B = 8 KB per copy)
+#define SROW_MAXG 64              // groups per chunk: 2^T, T <= 6
 #define SMEM_LIMIT 232448        // 227 KB per CTA on sm_100
-#define JHI_COLMASK 0xFFFFF      // Lin table entry: first column | owner rank << 20 | (cut by a rank boundary) << 30
-#define JHI_CUT 0x40000000
-#define SROW_MAXP 8              // peer reads: ranks of one NVLink domain
+#define HALO_CHUNK 8192           // doubles per work item of the halo copy kernel
 
 struct FastFactor {
   int W = 0, WT = 0, nvals = 0;
@@ -65,19 +73,21 @@ struct FastFactor {
 
 struct SRowPlan {
   bool ok = false;
-  int LR = 0, nhigh = 0, ngroups = 0, nchunks = 0, cmax = 0;
-  int32_t *d_jhi = nullptr;      // [2^nhigh] first column of group h, -1 if the group is empty
-  uint16_t *d_grp = nullptr;     // [ngroups] high words of the non-empty groups, ascending
-  int4 *d_chunks = nullptr;      // [nchunks] (group begin, group end, column begin, column end)
+  int LR = 0, T = 0, nhigh = 0, nchunks = 0, cmax = 0, maxg = 0;
+  SRowRec *d_recs = nullptr;     // group records, chunk by chunk
+  int4 *d_chunks = nullptr;      // [nchunks] (first record, groups, local column begin, local column end)
   double *d_dr0 = nullptr, *d_dr1 = nullptr;   // direct mode: dfac_up[row] (+ Uloc when the up impurity is occupied)
-  // sharded vector: hops that touch a low group cut by a rank boundary are left to a small fix-up kernel
-  int nfix = 0;                  // target columns of the fix-up
-  int *d_ftptr = nullptr, *d_ftcol = nullptr, *d_feown = nullptr, *d_fesrc = nullptr;
-  unsigned char *d_ftinit = nullptr;
-  double *d_feval = nullptr;
-  int coloffs[65];
   double vk[EDGPU_MAX_SITES];    // V_k of the dw spin, k = bath bit (1-based site k+1)
+  double *d_vk = nullptr;
   size_t smem = 0;
+  // sharded vector: dw hops left to the column pass (source on another rank, or a low group cut by a boundary)
+  bool lists = false;
+  int *d_lptr = nullptr, *d_lloc = nullptr;    // per local column: entry range; entry: local column (>= 0) or -1 - halo slot
+  double *d_lamp = nullptr;
+  unsigned char *d_linit = nullptr;            // column is not written by k_srow at all (cut group): diagonal added here
+  int nslots = 0;                              // halo columns
+  int *d_hown = nullptr, *d_hcol = nullptr;    // owner rank, column inside the owner's shard
+  double *d_halo = nullptr;                    // [nslots][DimUp]
 };
 
 struct FastPlan {
@@ -133,8 +143,9 @@ __device__ __forceinline__ double flip_sign(double v, uint32_t signbit31) {
   return __hiloint2double(__double2hiint(v) ^ (int)signbit31, __double2loint(v));
 }
 
+
 // ---------------------------------------------------------------------------------------------
-// pass 1: whole-column kernel
+// pass 2: whole-column kernel
 // ---------------------------------------------------------------------------------------------
 struct FColArgs {
   const double *x;
@@ -156,11 +167,41 @@ struct FColArgs {
   double *xp;
   const LancState *st;
   double *partials;
+  // LISTS (sharded vector): dw hops that the row pass leaves to this one (source on another rank, or a low group
+  // cut by a rank boundary).  Entry e of local column j, lptr[j] <= e < lptr[j+1]: y(:, j) += lamp[e] * src(:),
+  // src = local column lloc[e] of x when lloc[e] >= 0, else halo column -1 - lloc[e].  linit[j]: the row pass did
+  // not write column j at all, so y(:, j) starts from the diagonal term here (diagmode 1 stored, 2 recomputed).
+  const int *lptr, *lloc;
+  const double *lamp;
+  const unsigned char *linit;
+  const double *halo;
+  int diagmode;
 };
+
+// diagonal of element (r, local column j) for the columns the row pass skipped (runtime form of DIAG 1 / 2)
+__device__ __forceinline__ double fcol_init_diag(const FColArgs &a, int64_t j, int r) {
+  if (a.diagmode == 1) return __ldcs(a.diag + j * (int64_t)a.n + r);
+  double d = __ldg(a.dfac_c + r) + __ldg(a.dfac_s + a.coloff + j);
+  const uint32_t mc = (uint32_t)__ldg(a.map_c + r), ms = (uint32_t)__ldg(a.map_s + a.coloff + j);
+  for (int o = 0; o < a.norb; o++)
+    if ((mc >> o) & 1u)
+      for (int q = 0; q < a.norb; q++)
+        if ((ms >> q) & 1u) d += (o == q) ? a.uloc[o] : a.ust;
+  return d;
+}
+// the listed hops of one element
+__device__ __forceinline__ double fcol_lists(const FColArgs &a, int l0, int l1, int r, double acc) {
+  for (int e = l0; e < l1; e++) {
+    const int loc = __ldg(a.lloc + e);
+    const double *sp = loc >= 0 ? a.x + (size_t)loc * a.n : a.halo + (size_t)(-1 - loc) * a.n;
+    acc = fma(__ldg(a.lamp + e), __ldcs(sp + r), acc);
+  }
+  return acc;
+}
 
 // MODE: 0 = y = F x, 1 = y += F x, 2 = y += F x fused with the first Lanczos vector update (y is only read)
 // UNI: 0 = general (value table), 1 = uniform magnitude with 4-byte entries, 2 = uniform with 2-byte entries
-template <int WT, int DIAG, int UNI, int MODE>
+template <int WT, int DIAG, int UNI, int MODE, bool LISTS>
 __global__ void __launch_bounds__(FCOL_THREADS, 1) k_fcol(FColArgs a) {
   constexpr bool ACC = MODE >= 1;
   constexpr int NCW = FCOL_THREADS / 32 - 1;                      // 31 consumer warps + 1 producer warp
@@ -216,6 +257,9 @@ __global__ void __launch_bounds__(FCOL_THREADS, 1) k_fcol(FColArgs a) {
       uint32_t ms = 0;
       if (DIAG == 2) { dcol = a.dfac_s[a.coloff + j]; ms = (uint32_t)a.map_s[a.coloff + j]; }
       double *yc = a.y + j * (int64_t)n;
+      int l0 = 0, l1 = 0;
+      bool init = false;
+      if (LISTS) { l0 = __ldg(a.lptr + j); l1 = __ldg(a.lptr + j + 1); init = __ldg(a.linit + j) != 0; }
       uint32_t en[WT];
       auto load_ell = [&](int row) {
         if (UNI == 2 && WT == 8) {                                 // 8 two-byte entries = one LDG.128
@@ -260,7 +304,12 @@ __global__ void __launch_bounds__(FCOL_THREADS, 1) k_fcol(FColArgs a) {
           else acc = fma(flip_sign(vtab[(e[s] >> F_COL_BITS) & F_VID_MASK], e[s] & 0x80000000u), xv, acc);
         }
         if (UNI) acc0 = fma(a.vuni, acc, acc0); else acc0 += acc;
-        if (ACC) acc0 += yold;
+        if (LISTS) {
+          acc0 += init ? fcol_init_diag(a, j, r) * xs[r] : yold;
+          acc0 = fcol_lists(a, l0, l1, r, acc0);
+        } else if (ACC) {
+          acc0 += yold;
+        }
         if (MODE == 2) {
           double *wp = a.xp + j * (int64_t)n + r;
           const double w = lsx * acc0 - lcp * __ldcs(wp);
@@ -287,7 +336,7 @@ __global__ void __launch_bounds__(FCOL_THREADS, 1) k_fcol(FColArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// pass 1 for columns that do not fit one SM's shared memory (Ns = 18: 389 KB): a CLUSTER of two CTAs holds
+// pass 2 for columns that do not fit one SM's shared memory (Ns = 18: 389 KB): a CLUSTER of two CTAs holds
 // the column, one half each; a source in the other half is read through distributed shared memory
 // (mapa + ld.shared::cluster).  In the sorted basis the halves are (nearly) the two values of the top bit, so
 // only the hops on that bit cross (1/17 of the gathers at Ns = 18).  Single stage per CTA: the half fills the SM.
@@ -308,7 +357,7 @@ __device__ __forceinline__ double ld_dsmem(uint32_t addr) {
   return v;
 }
 
-template <int WT, int UNI, int MODE>
+template <int WT, int UNI, int MODE, bool LISTS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FCOL_THREADS, 1) k_fcol2(FColArgs a) {
   extern __shared__ __align__(128) unsigned char smraw[];
   constexpr bool ACC = MODE >= 1;
@@ -345,6 +394,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FCOL_THREADS, 1) k_f
     mbar_wait(&bar[0], (uint32_t)(it & 1));
     cluster_sync_all();                                            // both halves of column j are in place
     double *yc = a.y + j * (int64_t)n + r0;
+    int l0 = 0, l1 = 0;
+    bool init = false;
+    if (LISTS) { l0 = __ldg(a.lptr + j); l1 = __ldg(a.lptr + j + 1); init = __ldg(a.linit + j) != 0; }
     for (int r = tid; r < nr; r += FCOL_THREADS) {
       uint32_t e[WT];
 #pragma unroll
@@ -363,7 +415,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FCOL_THREADS, 1) k_f
         else acc = fma(flip_sign(vtab[(e[s] >> F_COL_BITS) & F_VID_MASK], e[s] & 0x80000000u), xv, acc);
       }
       double acc0 = UNI ? a.vuni * acc : acc;
-      if (ACC) acc0 += yold;
+      if (LISTS) {
+        acc0 += init ? fcol_init_diag(a, j, r0 + r) * buf[r] : yold;
+        acc0 = fcol_lists(a, l0, l1, r0 + r, acc0);
+      } else if (ACC) {
+        acc0 += yold;
+      }
       if (MODE == 2) {
         double *wp = a.xp + j * (int64_t)n + r0 + r;
         const double w = lsx * acc0 - lcp * __ldcs(wp);
@@ -388,8 +445,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FCOL_THREADS, 1) k_f
   }
 }
 
+
 // ---------------------------------------------------------------------------------------------
-// pass 2: structured row-tile kernel for the single-band star geometry
+// pass 1: structured row-tile kernel for the single-band star geometry
 // ---------------------------------------------------------------------------------------------
 namespace lowtab {
 __host__ __device__ constexpr int popc(int v) { int c = 0; for (; v; v &= v - 1) c++; return c; }
@@ -432,251 +490,236 @@ __device__ __forceinline__ void static_for(F &&f) {
 }
 
 struct SRowArgs {
-  const double *x;
+  const double *x;               // local shard, column 0
   double *y;
   int n;                         // DimUp (contiguous, even)
-  int nf;                        // DimDw (all columns local)
-  int ndw, nhigh, ngroups, nchunks, cmax;
-  const int32_t *jhi;
-  const uint16_t *grp;
+  uint32_t n8;                   // column stride in bytes
+  int nchunks, tbits, nhigh, cpad;
   const int4 *chunks;
-  double vk[EDGPU_MAX_SITES];    // vk[k], k = 1 .. Ns-1
-  const double *diag;            // DIAG == 1: spH0d, one value per element
+  const SRowRec *recs;
+  double vk[EDGPU_MAX_SITES];    // vk[k], k = 1 .. Ns-1 (compile-time indices only: constant-bank operands)
+  const double *vkd;             // the same table in global memory (run-time indices)
+  const double *diag;            // DIAG == 1: local spH0d, one value per element
   const double *dr0, *dr1;       // DIAG == 2: per-row tables, dw impurity empty / occupied
-  const double *dfac_s;          // DIAG == 2: per-column table (padded by 2 doubles)
-  int dbg;                       // timing experiments only (wrong results): 1 = skip far hops, 2 = skip in-chunk hops, 4 = skip y read
-  // sharding: this rank holds the global columns [c0, c0 + nf); x, y, diag point at local column 0
-  int c0;
-  int co[SROW_MAXP + 1];         // first global column of every rank
-  const double *xb[SROW_MAXP];   // every rank's copy of x (peer memory over NVLink; xb[rank] == x)
+  const double *dfac_s;          // DIAG == 2: per-column table of the WHOLE dw basis (padded by 2 doubles)
+  int c0;                        // first global column of this shard
 };
 
+// what a consumer warp knows about the tile it works on
 struct SRowTile {
-  const double *tl;              // shared-memory tile of this item + lane: column c at tl[(c - cb) * 32]
-  const double *dsc;             // shared: dfac_s[cb ..], DIAG == 2
-  double *yg;                    // y + i0 + row
-  const double *dgg;             // diag + i0 + row (DIAG == 1)
-  const int32_t *jhi;            // shared
-  const double *vhigh;           // shared, vhigh[kk] = V_{LR+kk}
-  const double *const *xb;       // shared: per-rank base of x
-  size_t row;                    // row of this lane (clamped into the matrix)
-  const double *x0;              // single rank: x (column 0, row 0)
-  const double *tile;            // shared-memory tile of this item (column cb, row 0)
-  const int *co;                 // shared: per-rank first column
-  size_t n;                      // column stride in elements
-  int cb, csz, nhigh, dbg;
+  const double *tl;              // shared-memory tile + lane: local column cb + c at tl[c * 32]
+  const double *dsc;             // shared: dfac_s of the tile's columns (DIAG == 2)
+  const double *xrow;            // x + row of this lane (row clamped into the matrix)
+  double *yrow;                  // y + row of this lane + first column of the tile
+  const double *dgrow;           // diag + row + first column of the tile (DIAG == 1)
+  const double *vhigh;           // shared: vhigh[kk] = V_{LR+kk}
+  uint32_t n8, inmask, farmask;
   bool active;                   // this lane's row exists (stores only)
   double drow0, drow1;
 };
 
-// Per-group hop descriptors, built once per group by class-independent code (srow_prepare) and kept in
-// shared memory (one slot per high bit and warp): where the partner group's first column is (a GENERIC
-// pointer: the shared-memory tile, this GPU's L2, or a peer GPU over NVLink) and the signed hopping amplitude.
-struct HopDesc {
-  const double *p;
+// p + j columns (column stride n8 bytes); one IMAD.WIDE.U32
+__device__ __forceinline__ const double *col_at(const double *p, uint32_t n8, uint32_t j) {
+  return reinterpret_cast<const double *>(reinterpret_cast<const char *>(p) + (uint64_t)n8 * (uint64_t)j);
+}
+__device__ __forceinline__ double *col_at(double *p, uint32_t n8, uint32_t j) {
+  return reinterpret_cast<double *>(reinterpret_cast<char *>(p) + (uint64_t)n8 * (uint64_t)j);
+}
+
+// predicated loads (no control flow around the loads of a hop slot that is switched off)
+__device__ __forceinline__ double ldg_if(const double *p, int on) {
   double v;
-};
+  asm("{\n.reg .pred q;\nsetp.ne.s32 q, %2, 0;\nmov.f64 %0, 0d0000000000000000;\n@q ld.global.f64 %0, [%1];\n}" : "=d"(v) : "l"(p), "r"(on));
+  return v;
+}
+template <int OFF>
+__device__ __forceinline__ double lds_if(uint32_t saddr, int on) {
+  double v;
+  asm("{\n.reg .pred q;\nsetp.ne.s32 q, %2, 0;\nmov.f64 %0, 0d0000000000000000;\n@q ld.shared.f64 %0, [%1+%3];\n}" : "=d"(v) : "r"(saddr), "r"(on), "n"(OFF));
+  return v;
+}
 
-// NB hops of one kind fused so that all their loads are in flight before the first use (far sources have
-// ~1 us latency).  BK = the hopped bath bit is occupied in the target group: targets are the columns with the
-// impurity empty, sources lo|1 in class N+1; otherwise targets have the impurity occupied, sources lo&~1 in N-1.
-template <int LR, int N, int CNT, bool BK, int NB>
-__device__ __forceinline__ void srow_hop_set(const HopDesc *desc, uint32_t m, size_t ss, size_t loff, double (&acc)[CNT]) {
-  if constexpr ((BK && N == LR) || (!BK && N == 0)) return;        // no such targets in this class
-  constexpr int HB = lowtab::imax(1, BK ? lowtab::binom(LR - 1, N) : lowtab::binom(LR - 1, N - 1));
-  while (m) {
-    HopDesc d[NB];
+// All hops of ONE kind of a low group, NB at a time so that their loads are in flight together.  m: the hopped
+// high bits.  BK = the bath bit is occupied in the target group: targets are the columns with the impurity
+// empty, sources lo|1 in class N+1 of the partner group; otherwise targets have the impurity occupied, sources
+// lo&~1 in class N-1.  SM = the partner group is in the shared-memory tile (column stride 32 doubles, immediate
+// offsets), else in global memory (column stride n8 bytes).  pc[kk] = first column of the partner group (tile-local
+// resp. shard-local), par bit kk = parity of the occupied high bits below kk.  Slots beyond the last hop are
+// switched off by predicated loads and a zero amplitude (no divergent control flow, no wasted traffic).
+template <int LR, int N, bool BK, bool SM, int NB>
+__device__ __forceinline__ void srow_hops(uint32_t m, const int32_t *pc, const double *vhigh, uint32_t par, const double *src0,
+                                          uint32_t n8, double (&acc)[lowtab::binom(LR, N)]) {
+  if constexpr ((BK && N == LR) || (!BK && N == 0)) {
+    return;                                                        // no such targets in this class
+  } else {
+    constexpr int CNT = lowtab::binom(LR, N);
+    constexpr int HB = BK ? lowtab::binom(LR - 1, N) : lowtab::binom(LR - 1, N - 1);
+    while (m) {
+      const double *p[NB];
+      uint32_t sp[NB];
+      double amp[NB];
+      int on[NB];
 #pragma unroll
-    for (int q = 0; q < NB; q++) {
-      if (m == 0) { d[q].p = d[0].p; d[q].v = 0.0; continue; }     // padding slot: re-reads slot 0's source, weight 0
-      d[q] = desc[__ffs((int)m) - 1];                              // warp-uniform base; this lane's row is added here
-      d[q].p += loff;
-      m &= m - 1;
-    }
-    double v[NB][HB];
-    static_for<NB>([&](auto bc) {
-      constexpr int q = decltype(bc)::value;
-      static_for<CNT>([&](auto ic) {
-        constexpr int i = decltype(ic)::value;
-        constexpr int lo = lowtab::pat(LR, N, i);
-        if constexpr (((lo & 1) == 0) == BK) {
-          constexpr int j = lowtab::rank(BK ? (lo | 1) : (lo & ~1));
-          constexpr int hi = lowtab::half_index(LR, N, i, BK ? 0 : 1);
-          v[q][hi] = d[q].p[j * ss];
-        }
-      });
-    });
-    static_for<NB>([&](auto bc) {
-      constexpr int q = decltype(bc)::value;
-      static_for<CNT>([&](auto ic) {
-        constexpr int i = decltype(ic)::value;
-        constexpr int lo = lowtab::pat(LR, N, i);
-        if constexpr (((lo & 1) == 0) == BK) {
-          constexpr int par = lowtab::popc(lo >> 1) & 1;
-          constexpr int hi = lowtab::half_index(LR, N, i, BK ? 0 : 1);
-          if constexpr (par) acc[i] = fma(-d[q].v, v[q][hi], acc[i]);
-          else acc[i] = fma(d[q].v, v[q][hi], acc[i]);
-        }
-      });
-    });
-  }
-}
-
-// class-independent part of a group: descriptors of its high-bit hops; returns the masks of the hops whose
-// source lies in the tile (stride 32 elements) and elsewhere (stride n elements)
-template <bool SH>
-__device__ __forceinline__ void srow_prepare(const SRowTile &k, uint32_t h, HopDesc *desc, uint32_t &inmask, uint32_t &farmask) {
-  uint32_t par = h ^ (h << 1);                                     // bit kk of par = parity of h below bit kk
-  par ^= par << 2; par ^= par << 4; par ^= par << 8;
-  par <<= 1;
-  inmask = 0; farmask = 0;
-#pragma unroll 1
-  for (int kk = 0; kk < k.nhigh; kk++) {
-    const int c2 = k.jhi[h ^ (1u << kk)];
-    if (c2 & JHI_CUT) continue;                                    // empty group, or cut by a rank boundary (fix-up kernel)
-    const int col2 = c2 & JHI_COLMASK;
-    HopDesc d;
-    d.v = __longlong_as_double(__double_as_longlong(k.vhigh[kk]) ^ ((long long)((par >> kk) & 1u) << 63));
-    if ((unsigned)(col2 - k.cb) < (unsigned)k.csz) {
-      d.p = k.tile + (col2 - k.cb) * SROW_R;
-      inmask |= 1u << kk;
-    } else {
-      if (SH) { const int own = (c2 >> 20) & 63; d.p = k.xb[own] + (size_t)(col2 - k.co[own]) * k.n; }
-      else d.p = k.x0 + (size_t)col2 * k.n;
-      farmask |= 1u << kk;
-    }
-    if ((threadIdx.x & 31) == 0) desc[kk] = d;
-  }
-  __syncwarp();
-}
-
-template <int LR, int N, int DIAG, bool ACC>
-__device__ __forceinline__ void srow_group(const SRowTile &k, const uint32_t h, const int base, const double (&vlow)[LR],
-                                           const HopDesc *desc, uint32_t inmask, uint32_t farmask) {
-  constexpr int CNT = lowtab::binom(LR, N);
-  double xv[CNT], acc[CNT];
-  const int lb = base - k.cb;
-  const double *tl = k.tl + lb * SROW_R;
-  static_for<CNT>([&](auto ic) { constexpr int i = decltype(ic)::value; xv[i] = tl[i * SROW_R]; });
-  // diagonal (direct mode: factorised tables staged in shared memory); streamed inputs are read at the end
-  static_for<CNT>([&](auto ic) {
-    constexpr int i = decltype(ic)::value;
-    constexpr int lo = lowtab::pat(LR, N, i);
-    if (DIAG == 2) acc[i] = (((lo & 1) ? k.drow1 : k.drow0) + k.dsc[lb + i]) * xv[i];
-    else acc[i] = 0.0;
-  });
-  // hops among the low bits: register to register
-  static_for<CNT>([&](auto ic) {
-    constexpr int i = decltype(ic)::value;
-    constexpr int lo = lowtab::pat(LR, N, i);
-    static_for<LR - 1>([&](auto kc) {
-      constexpr int kb = decltype(kc)::value + 1;
-      if constexpr (((lo >> kb) & 1) != (lo & 1)) {
-        constexpr int lo2 = lo ^ (1 | (1 << kb));
-        constexpr int j = lowtab::rank(lo2);
-        constexpr int par = lowtab::popc(lo & ((1 << kb) - 2)) & 1;
-        if constexpr (par) acc[i] = fma(-vlow[kb], xv[j], acc[i]);
-        else acc[i] = fma(vlow[kb], xv[j], acc[i]);
+      for (int q = 0; q < NB; q++) {
+        on[q] = m != 0;
+        const int kk = on[q] ? __ffs((int)m) - 1 : 0;
+        m &= m - 1;
+        const uint32_t col = (uint32_t)pc[kk];
+        if (SM) { sp[q] = smem_u32(src0) + col * (SROW_R * 8); p[q] = nullptr; }
+        else { p[q] = col_at(src0, n8, col); sp[q] = 0; }
+        const double v = vhigh[kk];
+        amp[q] = on[q] ? (((par >> kk) & 1u) ? -v : v) : 0.0;
       }
+      double v[NB][HB];
+      static_for<NB>([&](auto bc) {
+        constexpr int q = decltype(bc)::value;
+        static_for<CNT>([&](auto ic) {
+          constexpr int i = decltype(ic)::value;
+          constexpr int lo = lowtab::pat(LR, N, i);
+          if constexpr (((lo & 1) == 0) == BK) {
+            constexpr int j = lowtab::rank(BK ? (lo | 1) : (lo & ~1));
+            constexpr int hi = lowtab::half_index(LR, N, i, BK ? 0 : 1);
+            if constexpr (SM) v[q][hi] = lds_if<j * SROW_R * 8>(sp[q], on[q]);
+            else v[q][hi] = ldg_if(col_at(p[q], n8, j), on[q]);
+          }
+        });
+      });
+      static_for<NB>([&](auto bc) {
+        constexpr int q = decltype(bc)::value;
+        static_for<CNT>([&](auto ic) {
+          constexpr int i = decltype(ic)::value;
+          constexpr int lo = lowtab::pat(LR, N, i);
+          if constexpr (((lo & 1) == 0) == BK) {
+            constexpr int par_lo = lowtab::popc(lo >> 1) & 1;
+            constexpr int hi = lowtab::half_index(LR, N, i, BK ? 0 : 1);
+            if constexpr (par_lo) acc[i] = fma(-amp[q], v[q][hi], acc[i]);
+            else acc[i] = fma(amp[q], v[q][hi], acc[i]);
+          }
+        });
+      });
+    }
+  }
+}
+
+// one low group of class N (N electrons in the LR low bits): record hd + partner columns pc (shared memory).
+// vk: the hybridisations as kernel-parameter constants (vk[kb] with a compile-time kb is a constant-bank operand).
+template <int LR, int N, int DIAG>
+__device__ __forceinline__ void srow_group(const SRowTile &k, const int4 hd, const int32_t *pc, const double (&vk)[EDGPU_MAX_SITES]) {
+  constexpr int CNT = lowtab::binom(LR, N);
+  double acc[CNT];
+  const int lb = hd.x;
+  const uint32_t h = (uint32_t)hd.z & 0xFFFFu, ex = (uint32_t)hd.z >> 16, par = (uint32_t)hd.w;
+  const double *tl = k.tl + lb * SROW_R;
+  {
+    // diagonal (direct mode: factorised tables staged in shared memory) and the hops among the low bits, register
+    // to register; the group's own values are dead after this block
+    double xv[CNT];
+    static_for<CNT>([&](auto ic) { constexpr int i = decltype(ic)::value; xv[i] = tl[i * SROW_R]; });
+    static_for<CNT>([&](auto ic) {
+      constexpr int i = decltype(ic)::value;
+      constexpr int lo = lowtab::pat(LR, N, i);
+      if (DIAG == 2) acc[i] = (((lo & 1) ? k.drow1 : k.drow0) + k.dsc[lb + i]) * xv[i];
+      else acc[i] = 0.0;
     });
-  });
-  // hops on the high bits: the whole group maps onto ONE other group (descriptors from srow_prepare).  Far
-  // sources first (longest latency, three hops' loads in flight), then the ones in the shared-memory tile.
-  if (!(k.dbg & 1)) {
-    srow_hop_set<LR, N, CNT, true, SROW_NB_FAR>(desc, farmask & h, k.n, k.row, acc);
-    srow_hop_set<LR, N, CNT, false, SROW_NB_FAR>(desc, farmask & ~h, k.n, k.row, acc);
+    static_for<CNT>([&](auto ic) {
+      constexpr int i = decltype(ic)::value;
+      constexpr int lo = lowtab::pat(LR, N, i);
+      static_for<LR - 1>([&](auto kc) {
+        constexpr int kb = decltype(kc)::value + 1;
+        if constexpr (((lo >> kb) & 1) != (lo & 1)) {
+          constexpr int lo2 = lo ^ (1 | (1 << kb));
+          constexpr int j = lowtab::rank(lo2);
+          constexpr int par_lo = lowtab::popc(lo & ((1 << kb) - 2)) & 1;
+          if constexpr (par_lo) acc[i] = fma(-vk[kb], xv[j], acc[i]);
+          else acc[i] = fma(vk[kb], xv[j], acc[i]);
+        }
+      });
+    });
   }
-  if (!(k.dbg & 2)) {
-    srow_hop_set<LR, N, CNT, true, SROW_NB_IN>(desc, inmask & h, SROW_R, (size_t)(threadIdx.x & 31), acc);
-    srow_hop_set<LR, N, CNT, false, SROW_NB_IN>(desc, inmask & ~h, SROW_R, (size_t)(threadIdx.x & 31), acc);
-  }
-  double *yp = k.yg + (size_t)base * k.n;                          // yg / dgg are biased by -c0 columns
-  if (DIAG == 1) {
-    const double *dp = k.dgg + (size_t)base * k.n;
+  // hops on the top bits: sources in L2
+  srow_hops<LR, N, true, false, SROW_NB_FAR>(ex & h & k.farmask, pc, k.vhigh, par, k.xrow, k.n8, acc);
+  srow_hops<LR, N, false, false, SROW_NB_FAR>(ex & ~h & k.farmask, pc, k.vhigh, par, k.xrow, k.n8, acc);
+  // hops on the T lowest high bits: the partner group is in the tile
+  srow_hops<LR, N, true, true, SROW_NB_IN>(ex & h & k.inmask, pc, k.vhigh, par, k.tl, k.n8, acc);
+  srow_hops<LR, N, false, true, SROW_NB_IN>(ex & ~h & k.inmask, pc, k.vhigh, par, k.tl, k.n8, acc);
+  if (DIAG == 1) {                                                 // streamed spH0d: one more pass over the group
+    const double *dp = col_at(k.dgrow, k.n8, (uint32_t)lb);
     double dg[CNT];
-    static_for<CNT>([&](auto ic) { constexpr int i = decltype(ic)::value; dg[i] = __ldcs(dp + i * k.n); });
-    static_for<CNT>([&](auto ic) { constexpr int i = decltype(ic)::value; acc[i] = fma(dg[i], xv[i], acc[i]); });
+    static_for<CNT>([&](auto ic) { constexpr int i = decltype(ic)::value; dg[i] = __ldcs(col_at(dp, k.n8, i)); });
+    static_for<CNT>([&](auto ic) { constexpr int i = decltype(ic)::value; acc[i] = fma(dg[i], tl[i * SROW_R], acc[i]); });
   }
-  if (ACC && !(k.dbg & 4)) {
-    double yold[CNT];
-    static_for<CNT>([&](auto ic) { constexpr int i = decltype(ic)::value; yold[i] = __ldcs(yp + i * k.n); });
-    static_for<CNT>([&](auto ic) { constexpr int i = decltype(ic)::value; acc[i] += yold[i]; });
+  if (k.active) {
+    double *yp = col_at(k.yrow, k.n8, (uint32_t)lb);
+    static_for<CNT>([&](auto ic) { constexpr int i = decltype(ic)::value; __stcs(col_at(yp, k.n8, i), acc[i]); });
   }
-  if (k.active) static_for<CNT>([&](auto ic) { constexpr int i = decltype(ic)::value; __stcs(yp + i * k.n, acc[i]); });
 }
 
-template <int LR, int DIAG, bool ACC, int... NS>
-__device__ __forceinline__ void srow_dispatch(const SRowTile &k, uint32_t h, int base, int nlow, const double (&vlow)[LR],
-                                              const HopDesc *desc, uint32_t inmask, uint32_t farmask, std::integer_sequence<int, NS...>) {
-  ((nlow == NS ? (srow_group<LR, NS, DIAG, ACC>(k, h, base, vlow, desc, inmask, farmask), 0) : 0), ...);
+template <int LR, int DIAG, int... NS>
+__device__ __forceinline__ void srow_dispatch(const SRowTile &k, const int4 hd, const int32_t *pc, const double (&vk)[EDGPU_MAX_SITES],
+                                              std::integer_sequence<int, NS...>) {
+  ((hd.y == NS ? (srow_group<LR, NS, DIAG>(k, hd, pc, vk), 0) : 0), ...);
 }
 
-// 16 consumer warps + 1 producer warp.  full[b]: the TMA copies of buffer b have landed; empty[b]: every
+// 15 consumer warps + 1 producer warp.  full[b]: the TMA copies of buffer b have landed; empty[b]: every
 // consumer warp is done with buffer b.  Consumer warps take the low groups of the tile from a shared
-// counter and run ahead into the next buffer without a CTA-wide barrier.
-template <int LR, int DIAG, bool ACC, bool SH>
-__global__ void __launch_bounds__(srow_consumers(LR) + 32, 1) k_srow(const __grid_constant__ CUtensorMap tmx, SRowArgs a) {
+// counter (largest first) and run ahead into the next buffer without a CTA-wide barrier.
+template <int LR, int DIAG>
+__global__ void __launch_bounds__(SROW_THREADS, 1) k_srow(const __grid_constant__ CUtensorMap tmx, SRowArgs a) {
   extern __shared__ __align__(128) unsigned char smraw[];
-  const int cpad = ((a.cmax + SROW_BC - 1) / SROW_BC) * SROW_BC;
-  const int tsz = cpad * SROW_R;                                  // doubles per tile buffer
-  double *tile0 = reinterpret_cast<double *>(smraw);
-  double *dsc0 = tile0 + 2 * tsz;                                 // [2][cpad + 2]
-  double *drw0 = dsc0 + 2 * (cpad + 2);                           // [2][2][32]
-  double *vhigh = drw0 + 4 * SROW_R;                              // [32]
-  uint64_t *bar = reinterpret_cast<uint64_t *>(vhigh + 32);       // full[2], empty[2]
-  int *gctr = reinterpret_cast<int *>(bar + 4);                   // [2] (+2 pad)
-  const double **xbs = reinterpret_cast<const double **>(gctr + 4);   // [SROW_MAXP] per-rank base of x
-  int *cos = reinterpret_cast<int *>(xbs + SROW_MAXP);            // [SROW_MAXP + 1] (+ pad)
-  HopDesc *desc0 = reinterpret_cast<HopDesc *>(cos + SROW_MAXP + 4);   // 16-byte aligned: every table before it is   // [24 warps][16] hop descriptors of the group in flight
-  int32_t *jhi = reinterpret_cast<int32_t *>(desc0 + 24 * 16);    // [2^nhigh]
-  uint16_t *grp = reinterpret_cast<uint16_t *>(jhi + (1 << a.nhigh));   // [ngroups]
+  constexpr int S = SROW_STAGES;
+  const int tsz = a.cpad * SROW_R;                                // doubles per tile buffer
+  double *tile0 = reinterpret_cast<double *>(smraw);              // [S][cpad * 32]
+  double *dsc0 = tile0 + (size_t)S * tsz;                         // [S][cpad + 2]
+  double *drw0 = dsc0 + S * (a.cpad + 2);                         // [S][2][32]
+  double *vhigh = drw0 + S * 2 * SROW_R;                          // [32]
+  SRowRec *rec0 = reinterpret_cast<SRowRec *>(vhigh + 32);        // [S][SROW_MAXG], 16-byte aligned
+  uint64_t *bar = reinterpret_cast<uint64_t *>(rec0 + S * SROW_MAXG);   // full[S], empty[S]
+  int *gctr = reinterpret_cast<int *>(bar + 2 * S);               // [S]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  HopDesc *desc = desc0 + warp * 16;
   if (tid == 0) {
-    mbar_init(&bar[0], 1);
-    mbar_init(&bar[1], 1);
-    mbar_init(&bar[2], srow_consumers(LR) / 32);
-    mbar_init(&bar[3], srow_consumers(LR) / 32);
+    for (int b = 0; b < S; b++) {
+      mbar_init(&bar[b], 1);
+      mbar_init(&bar[S + b], SROW_CONSUMERS / 32);
+      gctr[b] = 0;
+    }
     fence_barrier_init();
-    gctr[0] = 0; gctr[1] = 0;
   }
-  for (int i = tid; i < (1 << a.nhigh); i += blockDim.x) jhi[i] = a.jhi[i];
-  for (int i = tid; i < a.ngroups; i += blockDim.x) grp[i] = a.grp[i];
-  if (tid < 32) vhigh[tid] = (tid < a.nhigh) ? a.vk[LR + tid] : 0.0;
-  if (tid < SROW_MAXP) xbs[tid] = a.xb[tid];
-  if (tid <= SROW_MAXP) cos[tid] = a.co[tid];
+  if (tid < 32) vhigh[tid] = (tid < a.nhigh) ? __ldg(a.vkd + LR + tid) : 0.0;
   __syncthreads();
 
-  const int64_t nrb = (a.n + SROW_R - 1) / SROW_R;
-  const int64_t nitems = nrb * a.nchunks;
-  const int64_t G = gridDim.x;
-  if (warp == srow_consumers(LR) / 32) {
+  const int nrb = (a.n + SROW_R - 1) / SROW_R;
+  const int nitems = nrb * a.nchunks;                             // < 2^31: at most 2^19 items at Ns = 18
+  const int G = (int)gridDim.x;
+  if (warp == SROW_CONSUMERS / 32) {
     // ---- producer warp ----
-    for (int64_t it = 0;; it++) {
-      const int64_t t = blockIdx.x + it * G;
+    for (int it = 0;; it++) {
+      const int t = (int)blockIdx.x + it * G;
       if (t >= nitems) break;
-      const int b = (int)(it & 1);
-      if (it >= 2) mbar_wait(&bar[2 + b], (uint32_t)(((it >> 1) - 1) & 1));
-      const int64_t rb = t / a.nchunks;
-      const int4 ch = __ldg(a.chunks + (int)(t % a.nchunks));
+      const int b = it % S;
+      const int use = it / S;
+      if (use >= 1) mbar_wait(&bar[S + b], (uint32_t)((use - 1) & 1));
+      const int rb = t / a.nchunks;
+      const int4 ch = __ldg(a.chunks + (t % a.nchunks));
       const int nc = ch.w - ch.z;
       const int nops = (nc + SROW_BC - 1) / SROW_BC;
-      const int64_t i0 = rb * SROW_R;
-      const int nr = (int)min((int64_t)SROW_R, (int64_t)a.n - i0);
-      const int lead = ch.z & 1;
+      const int i0 = rb * SROW_R;
+      const int nr = min(SROW_R, a.n - i0);
+      const int lead = (a.c0 + ch.z) & 1;                          // bulk copies start on a 16-byte boundary
       const uint32_t dsc_bytes = (uint32_t)((lead + nc + 1) & ~1) * 8u;
+      const uint32_t rec_bytes = (uint32_t)ch.y * (uint32_t)sizeof(SRowRec);
       if (lane == 0) {
         gctr[b] = 0;
         fence_proxy_async();
-        uint32_t bytes = (uint32_t)nops * (uint32_t)(SROW_BC * SROW_R * 8);
+        uint32_t bytes = (uint32_t)nops * (uint32_t)(SROW_BC * SROW_R * 8) + rec_bytes;
         if (DIAG == 2) bytes += dsc_bytes + 2u * (uint32_t)nr * 8u;
         mbar_expect_tx(&bar[b], bytes);
       }
       __syncwarp();
       if (lane < nops)
-        tma_load_2d(tile0 + (size_t)b * tsz + (size_t)lane * SROW_BC * SROW_R, &tmx, (int)i0, ch.z - a.c0 + lane * SROW_BC, &bar[b]);
+        tma_load_2d(tile0 + (size_t)b * tsz + (size_t)lane * SROW_BC * SROW_R, &tmx, i0, ch.z + lane * SROW_BC, &bar[b]);
+      if (lane == 28) bulk_g2s(rec0 + b * SROW_MAXG, a.recs + ch.x, rec_bytes, &bar[b]);
       if (DIAG == 2) {
-        if (lane == 29) bulk_g2s(dsc0 + (size_t)b * (cpad + 2), a.dfac_s + (ch.z - lead), dsc_bytes, &bar[b]);
+        if (lane == 29) bulk_g2s(dsc0 + (size_t)b * (a.cpad + 2), a.dfac_s + (a.c0 + ch.z - lead), dsc_bytes, &bar[b]);
         if (lane == 30) bulk_g2s(drw0 + (size_t)b * 2 * SROW_R, a.dr0 + i0, (uint32_t)nr * 8u, &bar[b]);
         if (lane == 31) bulk_g2s(drw0 + (size_t)b * 2 * SROW_R + SROW_R, a.dr1 + i0, (uint32_t)nr * 8u, &bar[b]);
       }
@@ -684,26 +727,27 @@ __global__ void __launch_bounds__(srow_consumers(LR) + 32, 1) k_srow(const __gri
     return;
   }
   // ---- consumer warps ----
-  double vlow[LR];
-#pragma unroll
-  for (int q = 0; q < LR; q++) vlow[q] = a.vk[q];                 // vlow[0] unused
-  for (int64_t it = 0;; it++) {
-    const int64_t t = blockIdx.x + it * G;
+  SRowTile k;
+  k.vhigh = vhigh;
+  k.n8 = a.n8;
+  k.inmask = (1u << a.tbits) - 1u;
+  k.farmask = ((1u << a.nhigh) - 1u) & ~k.inmask;
+  for (int it = 0;; it++) {
+    const int t = (int)blockIdx.x + it * G;
     if (t >= nitems) break;
-    const int b = (int)(it & 1);
-    const int64_t rb = t / a.nchunks;
-    const int4 ch = __ldg(a.chunks + (int)(t % a.nchunks));
-    SRowTile k;
-    const int64_t i0 = rb * SROW_R;
-    const int64_t row = min(i0 + lane, (int64_t)a.n - 1);            // clamp: loads of a ragged last block stay in range
+    const int b = it % S;
+    const int rb = t / a.nchunks;
+    const int4 ch = __ldg(a.chunks + (t % a.nchunks));
+    const int i0 = rb * SROW_R;
+    const int row = min(i0 + lane, a.n - 1);                         // clamp: loads of a ragged last block stay in range
     k.tl = tile0 + (size_t)b * tsz + lane;
-    k.dsc = dsc0 + (size_t)b * (cpad + 2) + (ch.z & 1);
-    k.yg = a.y + row - (ptrdiff_t)a.c0 * a.n; k.dgg = a.diag + row - (ptrdiff_t)a.c0 * a.n;
-    k.xb = xbs; k.co = cos; k.row = (size_t)row; k.x0 = a.x; k.tile = tile0 + (size_t)b * tsz;
-    k.jhi = jhi; k.vhigh = vhigh;
-    k.n = (size_t)a.n; k.cb = ch.z; k.csz = ch.w - ch.z; k.nhigh = a.nhigh; k.dbg = a.dbg;
+    k.dsc = dsc0 + (size_t)b * (a.cpad + 2) + ((a.c0 + ch.z) & 1);
+    k.xrow = a.x + row;
+    k.yrow = col_at(a.y + row, a.n8, (uint32_t)ch.z);
+    k.dgrow = col_at(a.diag + row, a.n8, (uint32_t)ch.z);
     k.active = (i0 + lane) < a.n;
-    mbar_wait(&bar[b], (uint32_t)((it >> 1) & 1));
+    const SRowRec *recs = rec0 + b * SROW_MAXG;
+    mbar_wait(&bar[b], (uint32_t)((it / S) & 1));
     k.drow0 = 0.0; k.drow1 = 0.0;
     if (DIAG == 2) {
       k.drow0 = drw0[b * 2 * SROW_R + lane];
@@ -712,18 +756,51 @@ __global__ void __launch_bounds__(srow_consumers(LR) + 32, 1) k_srow(const __gri
     for (;;) {
       int g = 0;
       if (lane == 0) g = atomicAdd(&gctr[b], 1);
-      g = __shfl_sync(0xffffffffu, g, 0) + ch.x;
+      g = __shfl_sync(0xffffffffu, g, 0);
       if (g >= ch.y) break;
-      const uint32_t h = grp[g];
-      const int base = jhi[h] & JHI_COLMASK;
-      const int nlow = a.ndw - __popc(h);
-      uint32_t inmask, farmask;
-      srow_prepare<SH>(k, h, desc, inmask, farmask);
-      srow_dispatch<LR, DIAG, ACC>(k, h, base, nlow, vlow, desc, inmask, farmask, std::make_integer_sequence<int, LR + 1>{});
-      __syncwarp();                                                 // descriptors are rewritten for the next group
+      const int4 hd = *reinterpret_cast<const int4 *>(&recs[g]);
+      srow_dispatch<LR, DIAG>(k, hd, recs[g].pc, a.vk, std::make_integer_sequence<int, LR + 1>{});
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&bar[2 + b]);                       // this warp is done with buffer b
+    if (lane == 0) mbar_arrive(&bar[S + b]);                       // this warp is done with buffer b
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// halo: copies of the remote source columns, pulled from the owners' shards over NVLink
+// ---------------------------------------------------------------------------------------------
+struct HaloArgs {
+  double *halo;                  // [nslots][n]
+  int n, nslots;
+  const int *hown, *hcol;
+  const double *xb[EDGPU_MAXP];  // every rank's copy of x (peer-mapped)
+};
+__global__ void __launch_bounds__(512) k_halo_pull(HaloArgs a) {
+  __shared__ const double *xb[EDGPU_MAXP];
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int p = 0; p < EDGPU_MAXP; p++) xb[p] = a.xb[p];
+  }
+  __syncthreads();
+  const int nrc = (a.n + HALO_CHUNK - 1) / HALO_CHUNK;
+  const int64_t nitems = (int64_t)a.nslots * nrc;
+  for (int64_t it = blockIdx.x; it < nitems; it += gridDim.x) {
+    const int slot = (int)(it / nrc), rc = (int)(it % nrc);
+    const int r0 = rc * HALO_CHUNK;
+    const int cnt2 = (min(HALO_CHUNK, a.n - r0)) >> 1;             // n is even: whole double2
+    const double2 *src = reinterpret_cast<const double2 *>(xb[__ldg(a.hown + slot)] + (size_t)__ldg(a.hcol + slot) * a.n + r0);
+    double2 *dst = reinterpret_cast<double2 *>(a.halo + (size_t)slot * a.n + r0);
+    double2 v[HALO_CHUNK / 2 / 512];
+#pragma unroll
+    for (int q = 0; q < HALO_CHUNK / 2 / 512; q++) {
+      const int i = threadIdx.x + q * 512;
+      if (i < cnt2) v[q] = src[i];
+    }
+#pragma unroll
+    for (int q = 0; q < HALO_CHUNK / 2 / 512; q++) {
+      const int i = threadIdx.x + q * 512;
+      if (i < cnt2) dst[i] = v[q];
+    }
   }
 }
 
@@ -780,19 +857,22 @@ static int pack_fast(edgpu_ctx *c, const Factor &f, FastFactor &ff) {
 
 static size_t fcol_smem(int64_t n) { return (size_t)2 * (n + 2) * 8 + F_MAXVALS * 8 + 32 + 32 * 8; }
 static size_t fcol2_smem(int64_t n) { return (size_t)((((n >> 1) + 1) & ~(int64_t)1) + 2) * 8 + F_MAXVALS * 8 + 16 + 32 * 8; }
-static size_t srow_smem(int cmax, int nhigh, int ngroups) {
-  const size_t cpad = (size_t)((cmax + SROW_BC - 1) / SROW_BC) * SROW_BC;
-  size_t b = (size_t)2 * cpad * SROW_R * 8 + (size_t)2 * (cpad + 2) * 8 + 4 * SROW_R * 8 + 32 * 8 + 32 + 16 + 8 * SROW_MAXP + 4 * (SROW_MAXP + 4) +
-             24 * 16 * 16 + ((size_t)4 << nhigh) + (size_t)2 * ngroups;
+static size_t srow_smem(int cpad) {
+  size_t b = (size_t)SROW_STAGES * ((size_t)cpad * SROW_R * 8 + (size_t)(cpad + 2) * 8 + 2 * SROW_R * 8 + SROW_MAXG * sizeof(SRowRec) + 16 + 4) +
+             32 * 8 + 64;
   return (b + 15) & ~(size_t)15;
 }
 
 // ---- pure host arithmetic of the row-kernel plan (also reachable without a GPU through
-// edgpu_selftest_srow_plan, so that the CPU-only tests can check the sharding logic) -----------------
-int srow_plan_host(int ns, int ndw, int64_t dimdw, int nranks, int rank, int lr, int64_t cmax_opt, SRowHostPlan &hp) {
+// edgpu_selftest_srow_plan, so that the CPU-only tests can check the chunk / record / list logic) ----------
+//
+// dw word = (h << LR) | lo.  Group = all words with the same h (class N = ndw - popc(h) electrons in the low bits),
+// chunk = all groups with the same h >> T.  The basis is sorted by word, so groups and chunks are runs of columns.
+// On rank `rank` of `nranks` a group is "whole" when all its columns are local; the kernel works on whole groups only.
+int srow_plan_host(int ns, int ndw, int64_t dimdw, int nranks, int rank, int lr, int tbits_opt, SRowHostPlan &hp) {
   hp = SRowHostPlan();
   const int LR = (lr == 4 || lr == 5) ? lr : 5;
-  if (ns <= LR || ns - LR > 15 || nranks > SROW_MAXP || dimdw > JHI_COLMASK) return 0;
+  if (ns <= LR || ns - LR > 16 || nranks > EDGPU_MAXP || dimdw >= (1 << 30)) return 0;
   hp.LR = LR;
   hp.nhigh = ns - LR;
   const int P = nranks;
@@ -802,150 +882,158 @@ int srow_plan_host(int ns, int ndw, int64_t dimdw, int nranks, int rank, int lr,
     if (p < P) edgpu_split(dimdw, P, p, &q, &off);
     hp.coloffs[(size_t)p] = (int)off;
   }
-  auto owner_of = [&](int col) { int p = 0; while (p + 1 < P && col >= hp.coloffs[(size_t)p + 1]) p++; return p; };
   const int c0 = hp.coloffs[(size_t)rank], c1 = hp.coloffs[(size_t)rank + 1];
   const int nh = 1 << hp.nhigh;
   hp.jhi.assign((size_t)nh, -1);
+  hp.gwhole.assign((size_t)nh, 0);
   int64_t col = 0;
   for (int h = 0; h < nh; h++) {
     const int nlow = ndw - __builtin_popcount((unsigned)h);
     if (nlow < 0 || nlow > LR) continue;
     const int sz = lowtab::binom(LR, nlow);
-    const int own = owner_of((int)col);
-    const bool cut = owner_of((int)col + sz - 1) != own;           // the group is split between two ranks
-    hp.jhi[(size_t)h] = (int32_t)col | (own << 20) | (cut ? JHI_CUT : 0);
-    hp.grp.push_back((uint16_t)h);
-    hp.gsize.push_back(sz); hp.gbase.push_back((int)col); hp.gcut.push_back(cut ? 1 : 0);
+    hp.jhi[(size_t)h] = (int32_t)col;
+    hp.gwhole[(size_t)h] = (col >= c0 && col + sz <= c1) ? 1 : 0;
     col += sz;
   }
   if (col != dimdw) return -1;                                     // the Lin table must cover the basis exactly
-  const int ngroups = (int)hp.grp.size();
-  // groups that lie entirely on this rank: a contiguous run [g0, g1) of the global list
-  int g0 = 0, g1 = 0;
-  {
-    int g = 0;
-    while (g < ngroups && (hp.gbase[(size_t)g] < c0 || hp.gcut[(size_t)g])) { if (hp.gbase[(size_t)g] >= c1) break; g++; }
-    g0 = g;
-    while (g < ngroups && !hp.gcut[(size_t)g] && hp.gbase[(size_t)g] + hp.gsize[(size_t)g] <= c1) g++;
-    g1 = g;
-    if (g0 < ngroups && hp.gbase[(size_t)g0] >= c1) g1 = g0;       // nothing whole on this rank
+  // chunk width: the largest T whose tiles (two buffers of 32 rows) fit the shared memory, at most 2^T = SROW_MAXG groups
+  int T = 0;
+  for (int t = 0; t <= hp.nhigh && (1 << t) <= SROW_MAXG; t++) {
+    const int cmax = lowtab::binom(LR + t, (LR + t) / 2);
+    const int cpad = (cmax + SROW_BC - 1) / SROW_BC * SROW_BC;
+    if (srow_smem(cpad) <= SMEM_LIMIT && t <= 5) T = t;            // T = 6 needs 16-row tiles: not built
   }
-  hp.g0 = g0; hp.g1 = g1;
-  // chunk size from the shared-memory budget (or the option), chunks = runs of whole groups
-  int cmax = (int)((SMEM_LIMIT - 12288 - ((size_t)4 << hp.nhigh) - 2 * (size_t)ngroups) / (2 * (SROW_R + 1) * 8));
-  cmax = cmax / SROW_BC * SROW_BC;
-  if (cmax > 32 * SROW_BC) cmax = 32 * SROW_BC;             // one tensor copy per lane of the producer warp
-  // measured on B200 (C3, chunk sweep 96..352): tiles of ~160 columns beat the largest that fits by 25 %;
-  // the L1 that is left over (228 KB - shared memory) serves the out-of-tile sources
-  if (cmax_opt <= 0 && cmax > 160) cmax = 160;
-  if (cmax_opt > 0 && cmax_opt < cmax) cmax = (int)cmax_opt;
-  if (cmax < lowtab::binom(LR, LR / 2)) return 0;
-  // balance: all chunks about the same size
-  const int nloccols = (g1 > g0) ? hp.gbase[(size_t)g1 - 1] + hp.gsize[(size_t)g1 - 1] - hp.gbase[(size_t)g0] : 0;
-  const int nch0 = std::max(1, (nloccols + cmax - 1) / cmax);
-  const int target = (nloccols + nch0 - 1) / nch0;
-  int gb = g0, cb = (g1 > g0) ? hp.gbase[(size_t)g0] : 0, cur = 0;
-  for (int g = g0; g < g1; g++) {
-    if (cur > 0 && (cur + hp.gsize[(size_t)g] > cmax || cur >= target)) {
-      hp.chunks.push_back(make_int4(gb, g, cb, cb + cur));
-      gb = g; cb += cur; cur = 0;
+  if (tbits_opt > 0 && tbits_opt - 1 <= T) T = tbits_opt - 1;      // option value t+1 forces T = t (tests: small chunks)
+  hp.T = T;
+  const int nchunk_ids = 1 << (hp.nhigh - T);
+  hp.cmax = 0; hp.maxg = 0;
+  for (int ci = 0; ci < nchunk_ids; ci++) {
+    // whole local groups of this chunk: a run of consecutive h (local columns are one interval)
+    std::vector<int> hs;
+    for (int u = 0; u < (1 << T); u++) {
+      const int h = (ci << T) | u;
+      if (hp.jhi[(size_t)h] >= 0 && hp.gwhole[(size_t)h]) hs.push_back(h);
     }
-    cur += hp.gsize[(size_t)g];
+    if (hs.empty()) continue;
+    auto gsize = [&](int h) { return lowtab::binom(LR, ndw - __builtin_popcount((unsigned)h)); };
+    const int cb = hp.jhi[(size_t)hs.front()], ce = hp.jhi[(size_t)hs.back()] + gsize(hs.back());
+    std::stable_sort(hs.begin(), hs.end(), [&](int a, int b) { return gsize(a) > gsize(b); });   // largest first
+    const int rec_begin = (int)hp.recs.size();
+    for (int h : hs) {
+      SRowRec r;
+      r.lb = hp.jhi[(size_t)h] - cb;
+      r.N = ndw - __builtin_popcount((unsigned)h);
+      uint32_t ex = 0, par = 0;
+      for (int kk = 0; kk < 16; kk++) r.pc[kk] = 0;
+      for (int kk = 0; kk < hp.nhigh; kk++) {
+        const int h2 = h ^ (1 << kk);
+        if (__builtin_popcount((unsigned)(h & ((1 << kk) - 1))) & 1) par |= 1u << kk;
+        if (hp.jhi[(size_t)h2] < 0 || !hp.gwhole[(size_t)h2]) continue;   // no such group, or not (wholly) on this rank
+        ex |= 1u << kk;
+        r.pc[kk] = kk < T ? hp.jhi[(size_t)h2] - cb : hp.jhi[(size_t)h2] - c0;
+      }
+      r.hx = (uint32_t)h | (ex << 16);
+      r.par = par;
+      hp.recs.push_back(r);
+    }
+    hp.chunks.push_back(make_int4(rec_begin, (int)hs.size(), cb - c0, ce - c0));
+    hp.cmax = std::max(hp.cmax, ce - cb);
+    hp.maxg = std::max(hp.maxg, (int)hs.size());
   }
-  if (cur > 0) hp.chunks.push_back(make_int4(gb, g1, cb, cb + cur));
-  hp.cmax = lowtab::binom(LR, LR / 2);
-  for (auto &ch : hp.chunks) hp.cmax = std::max(hp.cmax, ch.w - ch.z);
-  hp.smem = srow_smem(hp.cmax, hp.nhigh, ngroups);
-  if (hp.smem > SMEM_LIMIT) return 0;
+  hp.cpad = std::max(SROW_BC, (hp.cmax + SROW_BC - 1) / SROW_BC * SROW_BC);
+  hp.smem = srow_smem(hp.cpad);
+  if (hp.smem > SMEM_LIMIT || hp.maxg > SROW_MAXG) return 0;
   hp.ok = true;
   return 1;
 }
 
-// fix-up list: every dw hop (target <- source) of a LOCAL target column for which the target's or the source's
-// low group is cut by a rank boundary (the structured kernel skips exactly those), from the reference-order CSR
-// of spH0dws.  Targets in cut groups are computed entirely by the fix-up kernel (diagonal included).
-void srow_fix_host(SRowHostPlan &hp, int rank, int64_t dimdw, const int32_t *rp, const int32_t *cc, const double *vv) {
+// Source lists of the column pass: every dw hop (target <- source) of a LOCAL target column that the row kernel does
+// not apply, i.e. the target's or the source's low group is not whole on this rank, from the reference-order CSR of
+// spH0dws (stored/H_dw.f90).  Columns of groups that are not whole are computed entirely here (linit).  Remote
+// sources get a halo slot each.  map: Hs(2)%map.
+void srow_lists_host(SRowHostPlan &hp, int rank, int64_t dimdw, const int32_t *map, const int32_t *rp, const int32_t *cc, const double *vv) {
   const int P = (int)hp.coloffs.size() - 1;
-  hp.tptr.assign(1, 0); hp.tcol.clear(); hp.tinit.clear(); hp.eown.clear(); hp.esrc.clear(); hp.eval.clear();
-  if (P <= 1) return;
-  auto owner_of = [&](int col) { int p = 0; while (p + 1 < P && col >= hp.coloffs[(size_t)p + 1]) p++; return p; };
   const int c0 = hp.coloffs[(size_t)rank], c1 = hp.coloffs[(size_t)rank + 1];
-  std::vector<char> colcut((size_t)dimdw, 0);
-  for (size_t g = 0; g < hp.grp.size(); g++)
-    if (hp.gcut[g]) for (int i = 0; i < hp.gsize[g]; i++) colcut[(size_t)hp.gbase[g] + i] = 1;
+  hp.lptr.assign(1, 0); hp.lloc.clear(); hp.lamp.clear(); hp.linit.clear(); hp.hown.clear(); hp.hcol.clear();
+  if (P <= 1) return;
+  (void)dimdw;
+  auto owner_of = [&](int col) { int p = 0; while (p + 1 < P && col >= hp.coloffs[(size_t)p + 1]) p++; return p; };
+  std::map<int, int> slot;                                         // global source column -> halo slot
   for (int t = c0; t < c1; t++) {
-    const bool tc = colcut[(size_t)t] != 0;
-    const size_t before = hp.eown.size();
+    const bool tw = hp.gwhole[(size_t)((uint32_t)map[t] >> hp.LR)] != 0;
     for (int32_t q = rp[(size_t)t]; q < rp[(size_t)t + 1]; q++) {
-      const int sc = cc[(size_t)q];
-      if (!tc && !colcut[(size_t)sc]) continue;
-      const int own = owner_of(sc);
-      hp.eown.push_back(own); hp.esrc.push_back(sc - hp.coloffs[(size_t)own]); hp.eval.push_back(vv[(size_t)q]);
+      const int s = cc[(size_t)q];
+      if (tw && hp.gwhole[(size_t)((uint32_t)map[s] >> hp.LR)]) continue;      // k_srow applies it
+      int loc;
+      if (s >= c0 && s < c1) loc = s - c0;
+      else {
+        auto it = slot.find(s);
+        if (it == slot.end()) {
+          const int own = owner_of(s);
+          it = slot.emplace(s, (int)hp.hown.size()).first;
+          hp.hown.push_back(own); hp.hcol.push_back(s - hp.coloffs[(size_t)own]);
+        }
+        loc = -1 - it->second;
+      }
+      hp.lloc.push_back(loc); hp.lamp.push_back(vv[(size_t)q]);
     }
-    if (tc || hp.eown.size() > before) { hp.tcol.push_back(t - c0); hp.tinit.push_back(tc ? 1 : 0); hp.tptr.push_back((int)hp.eown.size()); }
+    hp.lptr.push_back((int)hp.lloc.size());
+    hp.linit.push_back(tw ? 0 : 1);
   }
 }
 
-static int build_srow(edgpu_ctx *c, SRowPlan &sr, int LR) {
+template <typename T>
+static int to_device(T **d, const std::vector<T> &h) {
+  const size_t n = std::max<size_t>(h.size(), 1);
+  CK(cudaMalloc(d, n * sizeof(T)));
+  if (!h.empty()) CK(cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return EDGPU_OK;
+}
+
+static int build_srow(edgpu_ctx *c, SRowPlan &sr) {
   // single band, star geometry, no inter-orbital terms: every dw hop is bit 0 <-> bit k
   sr.ok = false;
   if (c->dp.norb != 1 || c->dp.jhflag || (c->dimup & 1)) return EDGPU_OK;
-  if (c->opt_srow_lr == 4 || c->opt_srow_lr == 5) LR = (int)c->opt_srow_lr;
   SRowHostPlan hp;
-  const int prc = srow_plan_host(c->ns, c->ndw, c->dimdw, c->nranks, c->rank, LR, c->opt_srow_cmax, hp);
+  const int prc = srow_plan_host(c->ns, c->ndw, c->dimdw, c->nranks, c->rank, (int)c->opt_srow_lr, (int)c->opt_srow_t, hp);
   if (prc < 0) return edgpu_set_err(EDGPU_ERR_INVALID, "internal: Lin table does not cover the dw basis");
   if (prc == 0) return EDGPU_OK;
-  sr.LR = hp.LR; sr.nhigh = hp.nhigh; sr.ngroups = (int)hp.grp.size(); sr.nchunks = (int)hp.chunks.size();
-  sr.cmax = hp.cmax; sr.smem = hp.smem;
-  for (size_t p = 0; p < hp.coloffs.size(); p++) sr.coloffs[p] = hp.coloffs[p];
+  sr.LR = hp.LR; sr.T = hp.T; sr.nhigh = hp.nhigh; sr.nchunks = (int)hp.chunks.size();
+  sr.cmax = hp.cpad; sr.maxg = hp.maxg; sr.smem = hp.smem;
   for (int k = 0; k < EDGPU_MAX_SITES; k++) sr.vk[k] = 0.0;
   for (int k = 1; k < c->ns; k++) sr.vk[k] = c->dp.bv_dw[k - 1];
-  std::vector<int4> chunks = hp.chunks;
-  if (chunks.empty()) chunks.push_back(make_int4(0, 0, 0, 0));
-  CK(cudaMalloc(&sr.d_jhi, hp.jhi.size() * sizeof(int32_t)));
-  CK(cudaMalloc(&sr.d_grp, std::max<size_t>(hp.grp.size(), 1) * sizeof(uint16_t)));
-  CK(cudaMalloc(&sr.d_chunks, chunks.size() * sizeof(int4)));
-  CK(cudaMemcpy(sr.d_jhi, hp.jhi.data(), hp.jhi.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(sr.d_grp, hp.grp.data(), hp.grp.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(sr.d_chunks, chunks.data(), chunks.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  TRY(to_device(&sr.d_vk, std::vector<double>(sr.vk, sr.vk + EDGPU_MAX_SITES)));
+  TRY(to_device(&sr.d_recs, hp.recs));
+  TRY(to_device(&sr.d_chunks, hp.chunks));
   if (c->up.d_dfac) {                                              // direct mode: per-row diagonal tables
     std::vector<double> d0((size_t)c->dimup + 32, 0.0), d1((size_t)c->dimup + 32, 0.0);
     std::vector<int32_t> mu((size_t)c->dimup);
     CK(cudaMemcpy(d0.data(), c->up.d_dfac, (size_t)c->dimup * sizeof(double), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(mu.data(), c->up.d_map, (size_t)c->dimup * sizeof(int32_t), cudaMemcpyDeviceToHost));
     for (int64_t i = 0; i < c->dimup; i++) d1[(size_t)i] = d0[(size_t)i] + ((mu[(size_t)i] & 1) ? c->dp.uloc[0] : 0.0);
-    CK(cudaMalloc(&sr.d_dr0, d0.size() * sizeof(double)));
-    CK(cudaMalloc(&sr.d_dr1, d1.size() * sizeof(double)));
-    CK(cudaMemcpy(sr.d_dr0, d0.data(), d0.size() * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(sr.d_dr1, d1.data(), d1.size() * sizeof(double), cudaMemcpyHostToDevice));
+    TRY(to_device(&sr.d_dr0, d0));
+    TRY(to_device(&sr.d_dr1, d1));
   }
-  sr.nfix = 0;
+  sr.lists = false; sr.nslots = 0;
   if (c->nranks > 1) {
-    std::vector<int32_t> rp((size_t)c->dw.n + 1), cc((size_t)std::max<int64_t>(c->dw.nnz, 1));
+    std::vector<int32_t> map((size_t)c->dw.n), rp((size_t)c->dw.n + 1), cc((size_t)std::max<int64_t>(c->dw.nnz, 1));
     std::vector<double> vv((size_t)std::max<int64_t>(c->dw.nnz, 1));
+    CK(cudaMemcpy(map.data(), c->dw.d_map, map.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(rp.data(), c->dw.d_rowptr, rp.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
     if (c->dw.nnz) {
       CK(cudaMemcpy(cc.data(), c->dw.d_cols, (size_t)c->dw.nnz * sizeof(int32_t), cudaMemcpyDeviceToHost));
       CK(cudaMemcpy(vv.data(), c->dw.d_vals, (size_t)c->dw.nnz * sizeof(double), cudaMemcpyDeviceToHost));
     }
-    srow_fix_host(hp, c->rank, c->dimdw, rp.data(), cc.data(), vv.data());
-    sr.nfix = (int)hp.tcol.size();
-    if (sr.nfix) {
-      const size_t ne = std::max<size_t>(hp.eown.size(), 1);
-      hp.eown.resize(ne); hp.esrc.resize(ne); hp.eval.resize(ne);
-      CK(cudaMalloc(&sr.d_ftptr, hp.tptr.size() * sizeof(int)));
-      CK(cudaMalloc(&sr.d_ftcol, hp.tcol.size() * sizeof(int)));
-      CK(cudaMalloc(&sr.d_ftinit, hp.tinit.size()));
-      CK(cudaMalloc(&sr.d_feown, ne * sizeof(int)));
-      CK(cudaMalloc(&sr.d_fesrc, ne * sizeof(int)));
-      CK(cudaMalloc(&sr.d_feval, ne * sizeof(double)));
-      CK(cudaMemcpy(sr.d_ftptr, hp.tptr.data(), hp.tptr.size() * sizeof(int), cudaMemcpyHostToDevice));
-      CK(cudaMemcpy(sr.d_ftcol, hp.tcol.data(), hp.tcol.size() * sizeof(int), cudaMemcpyHostToDevice));
-      CK(cudaMemcpy(sr.d_ftinit, hp.tinit.data(), hp.tinit.size(), cudaMemcpyHostToDevice));
-      CK(cudaMemcpy(sr.d_feown, hp.eown.data(), ne * sizeof(int), cudaMemcpyHostToDevice));
-      CK(cudaMemcpy(sr.d_fesrc, hp.esrc.data(), ne * sizeof(int), cudaMemcpyHostToDevice));
-      CK(cudaMemcpy(sr.d_feval, hp.eval.data(), ne * sizeof(double), cudaMemcpyHostToDevice));
-    }
+    srow_lists_host(hp, c->rank, c->dimdw, map.data(), rp.data(), cc.data(), vv.data());
+    sr.lists = true;
+    sr.nslots = (int)hp.hown.size();
+    TRY(to_device(&sr.d_lptr, hp.lptr));
+    TRY(to_device(&sr.d_lloc, hp.lloc));
+    TRY(to_device(&sr.d_lamp, hp.lamp));
+    TRY(to_device(&sr.d_linit, hp.linit));
+    TRY(to_device(&sr.d_hown, hp.hown));
+    TRY(to_device(&sr.d_hcol, hp.hcol));
+    if (sr.nslots) CK(cudaMalloc(&sr.d_halo, (size_t)sr.nslots * (size_t)c->dimup * sizeof(double)));
   }
   sr.ok = true;
   return EDGPU_OK;
@@ -954,56 +1042,56 @@ static int build_srow(edgpu_ctx *c, SRowPlan &sr, int LR) {
 int fast_plan_free(edgpu_ctx *c) {
   if (!c->fplan) return EDGPU_OK;
   for (int k = 0; k < 2; k++) { cudaFree(c->fplan->ff[k].d_ell); cudaFree(c->fplan->ff[k].d_ell16); cudaFree(c->fplan->ff[k].d_vtab); }
-  cudaFree(c->fplan->sr.d_jhi); cudaFree(c->fplan->sr.d_grp); cudaFree(c->fplan->sr.d_chunks);
-  cudaFree(c->fplan->sr.d_dr0); cudaFree(c->fplan->sr.d_dr1);
-  { SRowPlan &r = c->fplan->sr; cudaFree(r.d_ftptr); cudaFree(r.d_ftcol); cudaFree(r.d_ftinit); cudaFree(r.d_feown); cudaFree(r.d_fesrc); cudaFree(r.d_feval); }
+  SRowPlan &r = c->fplan->sr;
+  cudaFree(r.d_recs); cudaFree(r.d_chunks); cudaFree(r.d_vk); cudaFree(r.d_dr0); cudaFree(r.d_dr1);
+  cudaFree(r.d_lptr); cudaFree(r.d_lloc); cudaFree(r.d_lamp); cudaFree(r.d_linit); cudaFree(r.d_hown); cudaFree(r.d_hcol); cudaFree(r.d_halo);
   delete c->fplan;
   c->fplan = nullptr;
   return EDGPU_OK;
 }
 
+// the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute: set once per context
 template <int WT, int DIAG>
 static cudaError_t set_fcol_attr() {
   cudaError_t e = cudaSuccess;
-#define SETF(U, A) if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fcol<WT, DIAG, U, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT)
-  SETF(0, 0); SETF(1, 0); SETF(2, 0); SETF(0, 1); SETF(1, 1); SETF(2, 1);
-  if (DIAG == 0) { SETF(0, 2); SETF(1, 2); SETF(2, 2); }
+#define SETF(U, A, L) if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fcol<WT, DIAG, U, A, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT)
+  SETF(0, 0, false); SETF(1, 0, false); SETF(2, 0, false); SETF(0, 1, false); SETF(1, 1, false); SETF(2, 1, false);
+  if (DIAG == 0) {
+    SETF(0, 2, false); SETF(1, 2, false); SETF(2, 2, false);
+    SETF(0, 1, true); SETF(1, 1, true); SETF(2, 1, true); SETF(0, 2, true); SETF(1, 2, true); SETF(2, 2, true);
+  }
 #undef SETF
   return e;
 }
-template <int LR, int DIAG>
-static cudaError_t set_srow_attr() {
-  cudaError_t e = cudaFuncSetAttribute(k_srow<LR, DIAG, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_srow<LR, DIAG, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_srow<LR, DIAG, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_srow<LR, DIAG, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+template <int WT>
+static cudaError_t set_fcol2_attr() {
+  cudaError_t e = cudaSuccess;
+#define SET2(U, M, L) if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fcol2<WT, U, M, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT)
+  SET2(0, 0, false); SET2(1, 0, false); SET2(0, 1, false); SET2(1, 1, false); SET2(0, 2, false); SET2(1, 2, false);
+  SET2(0, 1, true); SET2(1, 1, true); SET2(0, 2, true); SET2(1, 2, true);
+#undef SET2
   return e;
+}
+static int set_kernel_attrs(edgpu_ctx *c) {
+  if (c->fast_attrs_set) return EDGPU_OK;
+  CK(cudaSetDevice(c->device));
+  CK((set_fcol_attr<8, 0>())); CK((set_fcol_attr<8, 1>())); CK((set_fcol_attr<8, 2>()));
+  CK((set_fcol_attr<12, 0>())); CK((set_fcol_attr<12, 1>())); CK((set_fcol_attr<12, 2>()));
+  CK((set_fcol_attr<16, 0>())); CK((set_fcol_attr<16, 1>())); CK((set_fcol_attr<16, 2>()));
+  CK(set_fcol2_attr<8>()); CK(set_fcol2_attr<12>()); CK(set_fcol2_attr<16>());
+  CK(cudaFuncSetAttribute(k_srow<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+  CK(cudaFuncSetAttribute(k_srow<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+  CK(cudaFuncSetAttribute(k_srow<5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+  CK(cudaFuncSetAttribute(k_srow<5, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+  c->fast_attrs_set = true;
+  return EDGPU_OK;
 }
 
 int fast_plan_build(edgpu_ctx *c) {
   if (c->fplan) return EDGPU_OK;
-  static bool attr_done = false;
-  if (!attr_done) {
-    CK((set_fcol_attr<8, 0>())); CK((set_fcol_attr<8, 1>())); CK((set_fcol_attr<8, 2>()));
-    CK((set_fcol_attr<12, 0>())); CK((set_fcol_attr<12, 1>())); CK((set_fcol_attr<12, 2>()));
-    CK((set_fcol_attr<16, 0>())); CK((set_fcol_attr<16, 1>())); CK((set_fcol_attr<16, 2>()));
-    CK((set_srow_attr<4, 0>())); CK((set_srow_attr<4, 1>())); CK((set_srow_attr<4, 2>()));
-    CK((set_srow_attr<5, 0>())); CK((set_srow_attr<5, 1>())); CK((set_srow_attr<5, 2>()));
-    attr_done = true;
-  }
+  TRY(set_kernel_attrs(c));
   FastPlan *p = new FastPlan();
   c->fplan = p;
-  {
-    static bool attr2_done = false;
-    if (!attr2_done) {
-#define SET2(W, U, M) CK(cudaFuncSetAttribute(k_fcol2<W, U, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT))
-      SET2(8, 0, 0); SET2(8, 1, 0); SET2(8, 0, 1); SET2(8, 1, 1); SET2(8, 0, 2); SET2(8, 1, 2);
-      SET2(12, 0, 0); SET2(12, 1, 0); SET2(12, 0, 1); SET2(12, 1, 1); SET2(12, 0, 2); SET2(12, 1, 2);
-      SET2(16, 0, 0); SET2(16, 1, 0); SET2(16, 0, 1); SET2(16, 1, 1); SET2(16, 0, 2); SET2(16, 1, 2);
-#undef SET2
-      attr2_done = true;
-    }
-  }
   for (int k = 0; k < 2; k++) {
     const Factor &f = k ? c->dw : c->up;
     p->col_smem[k] = fcol_smem(f.n);
@@ -1016,7 +1104,7 @@ int fast_plan_build(edgpu_ctx *c) {
       else if (rc) { fast_plan_free(c); return rc; }
     }
   }
-  int rc = build_srow(c, p->sr, 5);
+  int rc = build_srow(c, p->sr);
   if (rc) { fast_plan_free(c); return rc; }
   return EDGPU_OK;
 }
@@ -1032,46 +1120,53 @@ bool fast_supported_col(edgpu_ctx *c, int k) {
   return c->fplan->col_ok[k] || c->fplan->col2_ok[k];
 }
 
-template <int WT, int DIAG, int MODE>
+template <int WT, int DIAG, int MODE, bool LISTS>
 static void launch_fcol_m(int uni, int grid, size_t smem, cudaStream_t st, const FColArgs &a) {
-  if (uni == 2) k_fcol<WT, DIAG, 2, MODE><<<grid, FCOL_THREADS, smem, st>>>(a);
-  else if (uni == 1) k_fcol<WT, DIAG, 1, MODE><<<grid, FCOL_THREADS, smem, st>>>(a);
-  else k_fcol<WT, DIAG, 0, MODE><<<grid, FCOL_THREADS, smem, st>>>(a);
+  if (uni == 2) k_fcol<WT, DIAG, 2, MODE, LISTS><<<grid, FCOL_THREADS, smem, st>>>(a);
+  else if (uni == 1) k_fcol<WT, DIAG, 1, MODE, LISTS><<<grid, FCOL_THREADS, smem, st>>>(a);
+  else k_fcol<WT, DIAG, 0, MODE, LISTS><<<grid, FCOL_THREADS, smem, st>>>(a);
 }
 template <int WT, int DIAG>
-static void launch_fcol(int uni, int mode, int grid, size_t smem, cudaStream_t st, const FColArgs &a) {
-  if (mode == 2) { if constexpr (DIAG == 0) launch_fcol_m<WT, 0, 2>(uni, grid, smem, st, a); }
-  else if (mode == 1) launch_fcol_m<WT, DIAG, 1>(uni, grid, smem, st, a);
-  else launch_fcol_m<WT, DIAG, 0>(uni, grid, smem, st, a);
+static void launch_fcol(int uni, int mode, bool lists, int grid, size_t smem, cudaStream_t st, const FColArgs &a) {
+  if constexpr (DIAG == 0) {
+    if (lists) {
+      if (mode == 2) launch_fcol_m<WT, 0, 2, true>(uni, grid, smem, st, a);
+      else launch_fcol_m<WT, 0, 1, true>(uni, grid, smem, st, a);
+      return;
+    }
+    if (mode == 2) { launch_fcol_m<WT, 0, 2, false>(uni, grid, smem, st, a); return; }
+  }
+  if (mode == 1) launch_fcol_m<WT, DIAG, 1, false>(uni, grid, smem, st, a);
+  else launch_fcol_m<WT, DIAG, 0, false>(uni, grid, smem, st, a);
 }
 template <int DIAG>
-static void launch_fcol_w(int WT, int uni, int mode, int grid, size_t smem, cudaStream_t st, const FColArgs &a) {
-  if (WT == 8) launch_fcol<8, DIAG>(uni, mode, grid, smem, st, a);
-  else if (WT == 12) launch_fcol<12, DIAG>(uni, mode, grid, smem, st, a);
-  else launch_fcol<16, DIAG>(uni, mode, grid, smem, st, a);
+static void launch_fcol_w(int WT, int uni, int mode, bool lists, int grid, size_t smem, cudaStream_t st, const FColArgs &a) {
+  if (WT == 8) launch_fcol<8, DIAG>(uni, mode, lists, grid, smem, st, a);
+  else if (WT == 12) launch_fcol<12, DIAG>(uni, mode, lists, grid, smem, st, a);
+  else launch_fcol<16, DIAG>(uni, mode, lists, grid, smem, st, a);
 }
 
-template <int WT>
-static void launch_fcol2_w(int uni, int mode, int grid, size_t smem, cudaStream_t st, const FColArgs &a) {
-  if (uni) {
-    if (mode == 2) k_fcol2<WT, 1, 2><<<grid, FCOL_THREADS, smem, st>>>(a);
-    else if (mode == 1) k_fcol2<WT, 1, 1><<<grid, FCOL_THREADS, smem, st>>>(a);
-    else k_fcol2<WT, 1, 0><<<grid, FCOL_THREADS, smem, st>>>(a);
+template <int WT, int UNI>
+static void launch_fcol2_u(int mode, bool lists, int grid, size_t smem, cudaStream_t st, const FColArgs &a) {
+  if (lists) {
+    if (mode == 2) k_fcol2<WT, UNI, 2, true><<<grid, FCOL_THREADS, smem, st>>>(a);
+    else k_fcol2<WT, UNI, 1, true><<<grid, FCOL_THREADS, smem, st>>>(a);
   } else {
-    if (mode == 2) k_fcol2<WT, 0, 2><<<grid, FCOL_THREADS, smem, st>>>(a);
-    else if (mode == 1) k_fcol2<WT, 0, 1><<<grid, FCOL_THREADS, smem, st>>>(a);
-    else k_fcol2<WT, 0, 0><<<grid, FCOL_THREADS, smem, st>>>(a);
+    if (mode == 2) k_fcol2<WT, UNI, 2, false><<<grid, FCOL_THREADS, smem, st>>>(a);
+    else if (mode == 1) k_fcol2<WT, UNI, 1, false><<<grid, FCOL_THREADS, smem, st>>>(a);
+    else k_fcol2<WT, UNI, 0, false><<<grid, FCOL_THREADS, smem, st>>>(a);
   }
 }
-static void launch_fcol2(int WT, int uni, int mode, int grid, size_t smem, cudaStream_t st, const FColArgs &a) {
-  if (WT == 8) launch_fcol2_w<8>(uni, mode, grid, smem, st, a);
-  else if (WT == 12) launch_fcol2_w<12>(uni, mode, grid, smem, st, a);
-  else launch_fcol2_w<16>(uni, mode, grid, smem, st, a);
+static void launch_fcol2(int WT, int uni, int mode, bool lists, int grid, size_t smem, cudaStream_t st, const FColArgs &a) {
+  if (WT == 8) { if (uni) launch_fcol2_u<8, 1>(mode, lists, grid, smem, st, a); else launch_fcol2_u<8, 0>(mode, lists, grid, smem, st, a); }
+  else if (WT == 12) { if (uni) launch_fcol2_u<12, 1>(mode, lists, grid, smem, st, a); else launch_fcol2_u<12, 0>(mode, lists, grid, smem, st, a); }
+  else { if (uni) launch_fcol2_u<16, 1>(mode, lists, grid, smem, st, a); else launch_fcol2_u<16, 0>(mode, lists, grid, smem, st, a); }
 }
 
-// y (+)= [Hd o x +] F_k x on a matrix whose contiguous dimension is factor k's index
+// y (+)= [Hd o x +] F_k x on a matrix whose contiguous dimension is factor k's index.  dw_lists: also apply the dw
+// hops the row pass left to this one (sharded vector, k == 0, accumulate form).
 int fast_apply_col(edgpu_ctx *c, int k, bool with_diag, bool acc, const double *d_x, double *d_y, int64_t ncols, int64_t coloff,
-                   double *d_xp, int *npartials) {
+                   double *d_xp, int *npartials, bool dw_lists) {
   TRY(fast_plan_build(c));
   FastPlan *p = c->fplan;
   const bool use2 = p->col2_ok[k] && (!p->col_ok[k] || c->opt_col_cluster);
@@ -1091,6 +1186,12 @@ int fast_apply_col(edgpu_ctx *c, int k, bool with_diag, bool acc, const double *
   const int diag = !with_diag ? 0 : (c->d_diag ? 1 : 2);
   const int mode = d_xp ? 2 : (acc ? 1 : 0);
   if (mode == 2 && (diag != 0 || !acc)) return edgpu_set_err(EDGPU_ERR_INVALID, "Lanczos epilogue needs the accumulate form without diagonal");
+  const bool lists = dw_lists && p->sr.lists;
+  if (lists) {
+    if (k != 0 || diag != 0 || !acc) return edgpu_set_err(EDGPU_ERR_INVALID, "dw source lists belong to the accumulating up pass");
+    a.lptr = p->sr.d_lptr; a.lloc = p->sr.d_lloc; a.lamp = p->sr.d_lamp; a.linit = p->sr.d_linit; a.halo = p->sr.d_halo;
+    a.diagmode = c->d_diag ? 1 : 2;
+  }
   a.xp = d_xp; a.st = c->d_st; a.partials = c->d_partials;
   if (npartials) *npartials = grid;
   if (use2) {
@@ -1098,37 +1199,18 @@ int fast_apply_col(edgpu_ctx *c, int k, bool with_diag, bool acc, const double *
     const int pairs = (int)std::min<int64_t>(ncols, c->sm_count / 2);
     const int uni2 = (ff.uniform && c->opt_no_uniform != 1) ? 1 : 0;
     if (npartials) *npartials = 2 * pairs;
-    launch_fcol2(ff.WT, uni2, mode, 2 * pairs, p->col2_smem[k], c->stream, a);
+    launch_fcol2(ff.WT, uni2, mode, lists, 2 * pairs, p->col2_smem[k], c->stream, a);
     CKL(c);
     return EDGPU_OK;
   }
   // no_uniform: 0 = best available, 1 = force the value-table kernel, 2 = uniform kernel with 4-byte entries
   int uni = 0;
   if (ff.uniform && c->opt_no_uniform != 1) uni = (ff.d_ell16 && c->opt_no_uniform != 2) ? 2 : 1;
-  if (diag == 0) launch_fcol_w<0>(ff.WT, uni, mode, grid, p->col_smem[k], c->stream, a);
-  else if (diag == 1) launch_fcol_w<1>(ff.WT, uni, mode, grid, p->col_smem[k], c->stream, a);
-  else launch_fcol_w<2>(ff.WT, uni, mode, grid, p->col_smem[k], c->stream, a);
+  if (diag == 0) launch_fcol_w<0>(ff.WT, uni, mode, lists, grid, p->col_smem[k], c->stream, a);
+  else if (diag == 1) launch_fcol_w<1>(ff.WT, uni, mode, false, grid, p->col_smem[k], c->stream, a);
+  else launch_fcol_w<2>(ff.WT, uni, mode, false, grid, p->col_smem[k], c->stream, a);
   CKL(c);
   return EDGPU_OK;
-}
-
-template <int LR, bool SH>
-static void launch_srow_s(int diag, bool acc, int grid, size_t smem, cudaStream_t st, const CUtensorMap &tmx, const SRowArgs &a) {
-  const int nt = srow_consumers(LR) + 32;
-  if (acc) {
-    if (diag == 0) k_srow<LR, 0, true, SH><<<grid, nt, smem, st>>>(tmx, a);
-    else if (diag == 1) k_srow<LR, 1, true, SH><<<grid, nt, smem, st>>>(tmx, a);
-    else k_srow<LR, 2, true, SH><<<grid, nt, smem, st>>>(tmx, a);
-  } else {
-    if (diag == 0) k_srow<LR, 0, false, SH><<<grid, nt, smem, st>>>(tmx, a);
-    else if (diag == 1) k_srow<LR, 1, false, SH><<<grid, nt, smem, st>>>(tmx, a);
-    else k_srow<LR, 2, false, SH><<<grid, nt, smem, st>>>(tmx, a);
-  }
-}
-template <int LR>
-static void launch_srow(bool sharded, int diag, bool acc, int grid, size_t smem, cudaStream_t st, const CUtensorMap &tmx, const SRowArgs &a) {
-  if (sharded) launch_srow_s<LR, true>(diag, acc, grid, smem, st, tmx, a);
-  else launch_srow_s<LR, false>(diag, acc, grid, smem, st, tmx, a);
 }
 
 // 2-D tensor map of a column-major double matrix (n0 contiguous), box = b0 x b1 elements
@@ -1155,121 +1237,103 @@ static int make_tmap_2d(CUtensorMap *tm, const double *base, uint64_t n0, uint64
   return EDGPU_OK;
 }
 
-// fix-up for the sharded vector (see build_srow): one CTA per listed local target column
-struct SFixArgs {
-  const double *x;               // local x
-  double *y;
-  int n, c0;
-  const int *tptr, *tcol, *eown, *esrc;
-  const unsigned char *tinit;
-  const double *eval;
-  const double *xb[SROW_MAXP];
-  const double *diag;            // stored: local spH0d
-  const double *dr0, *dr1, *dfac_s;
-  const int32_t *map_s;
-  int diagmode, acc;
-};
-__global__ void __launch_bounds__(256) k_sfix(SFixArgs a) {
-  const int t = blockIdx.x;
-  const int tl = a.tcol[t], e0 = a.tptr[t], e1 = a.tptr[t + 1];
-  const bool init = a.tinit[t] != 0;
-  const size_t off = (size_t)tl * a.n;
-  double dcol = 0.0;
-  bool nd = false;
-  if (init && a.diagmode == 2) { dcol = a.dfac_s[a.c0 + tl]; nd = (a.map_s[a.c0 + tl] & 1) != 0; }
-  for (int r = blockIdx.y * blockDim.x + threadIdx.x; r < a.n; r += gridDim.y * blockDim.x) {
-    double acc;
-    if (init) {
-      double d = 0.0;
-      if (a.diagmode == 1) d = a.diag[off + r];
-      if (a.diagmode == 2) d = (nd ? a.dr1[r] : a.dr0[r]) + dcol;
-      acc = d * a.x[off + r];
-      if (a.acc) acc += a.y[off + r];
-    } else {
-      acc = a.y[off + r];                                           // written by k_srow just before
-    }
-    for (int e = e0; e < e1; e++) acc = fma(a.eval[e], a.xb[a.eown[e]][(size_t)a.esrc[e] * a.n + r], acc);
-    a.y[off + r] = acc;
-  }
-}
-
-// y (+)= [Hd o x +] x Hdw^T on the local shard.  nranks == 1: every column is local.  nranks > 1: sources on
-// other ranks are read from the peers' copies of x (xpeer[p] = rank p's pointer for the same vector).
-int fast_apply_row(edgpu_ctx *c, bool with_diag, bool acc, const double *d_x, double *d_y, const double *const *xpeer) {
+// y = Hd o x + x Hdw^T on the whole low groups of the local shard (every source local).  grid_limit > 0: leave the
+// other SMs to a kernel that runs next to this one (the halo copy).
+int fast_apply_row(edgpu_ctx *c, const double *d_x, double *d_y, int grid_limit) {
   TRY(fast_plan_build(c));
   const SRowPlan &sr = c->fplan->sr;
   if (!sr.ok) return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "structured row kernel does not cover this model");
   if ((reinterpret_cast<uintptr_t>(d_x) & 15) != 0) return edgpu_set_err(EDGPU_ERR_INVALID, "fast H*v needs 16-byte aligned vectors");
-  if (c->nranks > 1 && !xpeer) return edgpu_set_err(EDGPU_ERR_INVALID, "sharded row kernel needs the peers' vectors");
+  if (sr.nchunks == 0 || c->qdw == 0) return EDGPU_OK;            // this rank owns no whole group: all left to the lists
   SRowArgs a{};
-  a.x = d_x; a.y = d_y; a.n = (int)c->dimup; a.nf = (int)c->qdw;
-  a.ndw = c->ndw; a.nhigh = sr.nhigh; a.ngroups = sr.ngroups; a.nchunks = sr.nchunks; a.cmax = sr.cmax;
-  a.jhi = sr.d_jhi; a.grp = sr.d_grp; a.chunks = sr.d_chunks;
+  a.x = d_x; a.y = d_y; a.n = (int)c->dimup; a.n8 = (uint32_t)(c->dimup * 8);
+  a.nchunks = sr.nchunks; a.tbits = sr.T; a.nhigh = sr.nhigh; a.cpad = sr.cmax;
+  a.chunks = sr.d_chunks; a.recs = sr.d_recs;
   for (int k = 0; k < EDGPU_MAX_SITES; k++) a.vk[k] = sr.vk[k];
-  a.dbg = (int)c->opt_dbg;
+  a.vkd = sr.d_vk;
   a.diag = c->d_diag; a.dr0 = sr.d_dr0; a.dr1 = sr.d_dr1; a.dfac_s = c->dw.d_dfac;
   a.c0 = (int)c->coloff;
-  for (int p = 0; p <= SROW_MAXP; p++) a.co[p] = sr.coloffs[p < c->nranks ? p : c->nranks];
-  for (int p = 0; p < SROW_MAXP; p++) a.xb[p] = (c->nranks == 1 || p >= c->nranks) ? d_x : xpeer[p];
-  a.xb[c->rank] = d_x;
-  const int diag = !with_diag ? 0 : (c->d_diag ? 1 : 2);
+  const int diag = c->d_diag ? 1 : 2;
   const int64_t nitems = ((c->dimup + SROW_R - 1) / SROW_R) * sr.nchunks;
-  if (sr.nchunks > 0 && c->fplan->sr.cmax > 0 && nitems > 0 && !(sr.nchunks == 1 && c->qdw == 0)) {
-    const int grid = (int)std::min<int64_t>(nitems, c->sm_count);
-    CUtensorMap tmx;
-    TRY(make_tmap_2d(&tmx, d_x, (uint64_t)c->dimup, (uint64_t)c->qdw, SROW_R, SROW_BC));
-    // a rank may own no whole group at all (tiny sectors): the chunk table then holds one empty chunk
-    if (sr.LR == 4) launch_srow<4>(c->nranks > 1, diag, acc, grid, sr.smem, c->stream, tmx, a);
-    else launch_srow<5>(c->nranks > 1, diag, acc, grid, sr.smem, c->stream, tmx, a);
-    CKL(c);
+  int grid = (int)std::min<int64_t>(nitems, c->sm_count);
+  if (grid_limit > 0 && grid > grid_limit) grid = grid_limit;
+  CUtensorMap tmx;
+  TRY(make_tmap_2d(&tmx, d_x, (uint64_t)c->dimup, (uint64_t)c->qdw, SROW_R, SROW_BC));
+  if (sr.LR == 4) {
+    if (diag == 1) k_srow<4, 1><<<grid, SROW_THREADS, sr.smem, c->stream>>>(tmx, a);
+    else k_srow<4, 2><<<grid, SROW_THREADS, sr.smem, c->stream>>>(tmx, a);
+  } else {
+    if (diag == 1) k_srow<5, 1><<<grid, SROW_THREADS, sr.smem, c->stream>>>(tmx, a);
+    else k_srow<5, 2><<<grid, SROW_THREADS, sr.smem, c->stream>>>(tmx, a);
   }
-  if (sr.nfix > 0) {
-    SFixArgs f{};
-    f.x = d_x; f.y = d_y; f.n = (int)c->dimup; f.c0 = (int)c->coloff;
-    f.tptr = sr.d_ftptr; f.tcol = sr.d_ftcol; f.eown = sr.d_feown; f.esrc = sr.d_fesrc; f.tinit = sr.d_ftinit; f.eval = sr.d_feval;
-    for (int p = 0; p < SROW_MAXP; p++) f.xb[p] = a.xb[p];
-    f.diag = c->d_diag; f.dr0 = sr.d_dr0; f.dr1 = sr.d_dr1; f.dfac_s = c->dw.d_dfac; f.map_s = c->dw.d_map;
-    f.diagmode = diag; f.acc = acc ? 1 : 0;
-    dim3 grid((unsigned)sr.nfix, (unsigned)std::max<int64_t>(1, std::min<int64_t>(32, (c->dimup + 1023) / 1024)));
-    k_sfix<<<grid, 256, 0, c->stream>>>(f);
-    CKL(c);
-  }
+  CKL(c);
+  return EDGPU_OK;
+}
+
+// copies the remote source columns of this H*v into the halo buffer (stream st); xpeer[p] = rank p's pointer of x
+int fast_halo_pull(edgpu_ctx *c, const double *const *xpeer, cudaStream_t st, int ctas) {
+  const SRowPlan &sr = c->fplan->sr;
+  if (!sr.lists || sr.nslots == 0) return EDGPU_OK;
+  HaloArgs h{};
+  h.halo = sr.d_halo; h.n = (int)c->dimup; h.nslots = sr.nslots; h.hown = sr.d_hown; h.hcol = sr.d_hcol;
+  for (int p = 0; p < EDGPU_MAXP; p++) h.xb[p] = xpeer[p < c->nranks ? p : 0];
+  const int64_t nitems = (int64_t)sr.nslots * ((c->dimup + HALO_CHUNK - 1) / HALO_CHUNK);
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(nitems, ctas));
+  k_halo_pull<<<grid, 512, 0, st>>>(h);
+  CKL(c);
   return EDGPU_OK;
 }
 
 // peers' pointers of a vector that lives in the symmetric slab (nullptr if it does not)
 static const double *const *peer_ptrs(edgpu_ctx *c, const double *d_x, const double **buf) {
   if (c->nranks == 1) return nullptr;
+  if (c->peer_override) return c->peer_override;                   // one-device emulation of the ranks (selftest)
   const int64_t off = sym_offset(c, d_x);
   if (off < 0) return nullptr;
   for (int p = 0; p < c->nranks; p++) buf[p] = reinterpret_cast<const double *>(c->sym_peer[p] + off);
   return buf;
 }
 bool fast_peer_ready(edgpu_ctx *c, const double *d_x) {
-  return c->nranks > 1 && c->nranks <= SROW_MAXP && c->sym_ok && sym_offset(c, d_x) >= 0;
+  if (c->nranks > 1 && c->peer_override) return true;
+  return c->nranks > 1 && c->nranks <= EDGPU_MAXP && c->sym_ok && sym_offset(c, d_x) >= 0;
 }
 
 // d_xp != nullptr: Lanczos form -- d_y only holds the row-pass partial result, w = sx*(H x) - cprev*xp goes to
 // d_xp and the per-CTA partial sums of (sx*x).w to c->d_partials (*npartials of them)
 int fast_apply_local(edgpu_ctx *c, const double *d_x, double *d_y, double *d_xp, int *npartials) {
-  if (c->opt_dbg & 8) {                                            // experiment: column pass first
-    prof_mark(c, "k_fcol");
-    TRY(fast_apply_col(c, 0, false, false, d_x, d_y, c->qdw, c->coloff, nullptr, nullptr));
-    prof_mark(c, "k_srow");
-    TRY(fast_apply_row(c, true, true, d_x, d_y, nullptr));
-    return EDGPU_OK;
-  }
-  // row tiles first (y = Hd o x + x Hdw^T, write only), then whole columns (y += Hup x, contiguous RMW)
+  TRY(fast_plan_build(c));
+  const SRowPlan &sr = c->fplan->sr;
   const double *pb[64];
   const double *const *xpeer = peer_ptrs(c, d_x, pb);
   if (c->nranks > 1 && !xpeer) return edgpu_set_err(EDGPU_ERR_INVALID, "sharded fast H*v: the vector is not in the symmetric slab");
-  // Peers read x while this rank reads theirs.  One stream-ordered barrier per application orders every rank's
-  // earlier writes of x before the reads (RAW) and, because each rank enqueues it after its previous H*v, every
-  // rank's previous remote reads before anybody's later overwrite of those buffers (WAR).
-  if (c->nranks > 1) TRY(comm_barrier(c));
+  int grid_limit = 0;
+  bool forked = false;
+  if (c->nranks > 1) {
+    // Peers read x while this rank reads theirs.  One stream-ordered barrier per application orders every rank's
+    // earlier writes of x before the reads (RAW) and, because each rank enqueues it after its previous H*v, every
+    // rank's previous remote reads before anybody's later overwrite of those buffers (WAR).
+    TRY(comm_barrier(c));
+    if (sr.nslots > 0) {
+      const int hctas = (int)std::max<int64_t>(1, std::min<int64_t>(c->opt_halo_ctas > 0 ? c->opt_halo_ctas : 32, c->sm_count / 2));
+      if (c->stream2 && !c->opt_no_overlap) {
+        // the copy runs on its own stream and SMs, next to the row kernel (both only read x)
+        CK(cudaEventRecord(c->ev_fork, c->stream));
+        CK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+        TRY(fast_halo_pull(c, xpeer, c->stream2, hctas));
+        CK(cudaEventRecord(c->ev_join, c->stream2));
+        grid_limit = c->sm_count - hctas;
+        forked = true;
+      } else {
+        prof_mark(c, "k_halo_pull");
+        TRY(fast_halo_pull(c, xpeer, c->stream, c->sm_count * 2));
+      }
+    }
+  }
+  // row tiles first (y = Hd o x + x Hdw^T, write only), then whole columns (y += Hup x, contiguous RMW)
   prof_mark(c, "k_srow");
-  TRY(fast_apply_row(c, true, false, d_x, d_y, xpeer));
+  TRY(fast_apply_row(c, d_x, d_y, grid_limit));
+  if (forked) CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
   prof_mark(c, "k_fcol");
-  TRY(fast_apply_col(c, 0, false, true, d_x, d_y, c->qdw, c->coloff, d_xp, npartials));
+  TRY(fast_apply_col(c, 0, false, true, d_x, d_y, c->qdw, c->coloff, d_xp, npartials, true));
   return EDGPU_OK;
 }

@@ -352,8 +352,7 @@ int tiled_plan_build(edgpu_ctx *c) {
     p->b_nchunks = (int)((n + p->b_chunk - 1) / p->b_chunk);
     p->b_smem = row_smem(R, W, p->b_chunk);
   }
-  static bool attr_done = false;
-  if (!attr_done) {
+  if (!c->tiled_attrs_set) {                                      // per-device function attribute: once per context
     const int mx = (int)SMEM_BUDGET;
 #define SETA(k) CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, mx))
     SETA((k_tile_col<1, 0>)); SETA((k_tile_col<2, 0>)); SETA((k_tile_col<4, 0>)); SETA((k_tile_col<8, 0>));
@@ -361,7 +360,7 @@ int tiled_plan_build(edgpu_ctx *c) {
     SETA((k_tile_col<1, 2>)); SETA((k_tile_col<2, 2>)); SETA((k_tile_col<4, 2>)); SETA((k_tile_col<8, 2>));
     SETA((k_tile_row<8>)); SETA((k_tile_row<16>));
 #undef SETA
-    attr_done = true;
+    c->tiled_attrs_set = true;
   }
   return EDGPU_OK;
 }

@@ -1,7 +1,8 @@
-// selftest.cu -- HOST evaluation of the __host__ __device__ integer/bit logic in hd_funcs.h, so
-// that the CPU-only test-suite can check the exact code the kernels run (rank formula, factor rows,
-// diagonal order) against the oracle without a GPU.  These hooks are test instrumentation
-// (include/edgpu_selftest.h); no product entry point calls them and they are not a compute path.
+// selftest.cu -- test instrumentation, built into its OWN library (libedgpu_selftest.so, linked against
+// libedgpu.so; include/edgpu_selftest.h): HOST evaluation of the __host__ __device__ integer/bit logic in
+// hd_funcs.h and of the row-kernel plan, so that the CPU-only test-suite can check the exact code the kernels run
+// (rank formula, factor rows, diagonal order, chunk / record / list arithmetic) against the oracle without a GPU,
+// plus the one-device emulation of the sharded path.  The product library exports none of this.
 #include <string.h>
 
 #include <vector>
@@ -82,13 +83,13 @@ extern "C" int edgpu_selftest_nonlocal_row(const edgpu_params *p, uint32_t mup, 
   return hd_nonlocal_row(d, mup, mdw, cup, cdw, val);
 }
 
-// Sharded fast path on ONE device: `nranks` contexts stand in for the ranks (no NCCL; each "rank" reads the
-// others' shards through ordinary device pointers).  Exercises exactly the kernels and plans of the multi-GPU
-// path -- rank-aware Lin table, low groups cut by a rank boundary, the fix-up kernel, per-owner source pointers
-// -- so that a single-GPU box can check them for any rank count.  x, y: full host vectors.
+// Sharded fast path on ONE device: `nranks` contexts stand in for the ranks (no NCCL; each "rank" pulls its halo
+// from the others' shards through ordinary device pointers).  Exercises exactly the kernels and plans of the
+// multi-GPU path -- whole / cut low groups, group records, the halo copy kernel, the source lists of the column
+// pass -- so that a single-GPU box can check them for any rank count.  x, y: full host vectors.
 extern "C" int edgpu_selftest_sharded_hxv(const edgpu_params *p, int nup, int ndw, int nranks, int64_t srow_lr,
-                                          int64_t srow_cmax, const double *x, double *y) {
-  if (nranks < 1 || nranks > 8) return edgpu_set_err(EDGPU_ERR_INVALID, "selftest: 1 <= nranks <= 8");
+                                          int64_t srow_t, int64_t col_cluster, const double *x, double *y) {
+  if (nranks < 1 || nranks > EDGPU_MAXP) return edgpu_set_err(EDGPU_ERR_INVALID, "selftest: 1 <= nranks <= 8");
   std::vector<edgpu_ctx *> cs((size_t)nranks, nullptr);
   std::vector<double *> dx((size_t)nranks, nullptr), dy((size_t)nranks, nullptr);
   int rc = EDGPU_OK;
@@ -96,7 +97,7 @@ extern "C" int edgpu_selftest_sharded_hxv(const edgpu_params *p, int nup, int nd
     for (int r = 0; r < nranks; r++) {
       if (dx[r]) cudaFree(dx[r]);
       if (dy[r]) cudaFree(dy[r]);
-      if (cs[r]) { cs[r]->rank = 0; cs[r]->nranks = 1; edgpu_destroy(cs[r]); }
+      if (cs[r]) { cs[r]->peer_override = nullptr; cs[r]->rank = 0; cs[r]->nranks = 1; edgpu_destroy(cs[r]); }
     }
   };
   for (int r = 0; r < nranks && !rc; r++) {
@@ -104,28 +105,30 @@ extern "C" int edgpu_selftest_sharded_hxv(const edgpu_params *p, int nup, int nd
     if (rc) break;
     cs[r]->rank = r; cs[r]->nranks = nranks;                       // no communicator: peers are plain pointers here
     edgpu_set_option(cs[r], "srow_lr", srow_lr);
-    edgpu_set_option(cs[r], "srow_cmax", srow_cmax);
+    edgpu_set_option(cs[r], "srow_t", srow_t);
+    edgpu_set_option(cs[r], "col_cluster", col_cluster);
+    edgpu_set_option(cs[r], "no_peer", 1);                         // no symmetric slab without a communicator
     int isec = 0;
     rc = edgpu_get_sector(cs[r], nup, ndw, &isec);
     if (!rc) rc = edgpu_build_hv_sector(cs[r], isec);
     if (rc) break;
     const size_t nb = ((size_t)cs[r]->nloc + 2) * sizeof(double);
     if (cudaMalloc(&dx[r], nb) != cudaSuccess || cudaMalloc(&dy[r], nb) != cudaSuccess) { rc = edgpu_set_err(EDGPU_ERR_CUDA, "selftest: cudaMalloc"); break; }
-    cudaMemset(dy[r], 0, nb);
+    cudaMemset(dy[r], 0xff, nb);                                   // NaN pattern: every element must be written
     if (cudaMemcpy(dx[r], x + cs[r]->coloff * cs[r]->dimup, (size_t)cs[r]->nloc * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
       rc = edgpu_set_err(EDGPU_ERR_CUDA, "selftest: upload");
       break;
     }
   }
   if (!rc) cudaDeviceSynchronize();
+  const double *peers[EDGPU_MAXP];
+  for (int q = 0; q < EDGPU_MAXP; q++) peers[q] = dx[q < nranks ? q : 0];
   for (int r = 0; r < nranks && !rc; r++) {
     if (!fast_supported_local(cs[r])) { rc = edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "selftest: fast path does not cover this sector"); break; }
-    const double *peers[8];
-    for (int q = 0; q < 8; q++) peers[q] = dx[q < nranks ? q : 0];
-    rc = fast_apply_row(cs[r], true, false, dx[r], dy[r], nranks > 1 ? peers : nullptr);
-    if (!rc) rc = fast_apply_col(cs[r], 0, false, true, dx[r], dy[r], cs[r]->qdw, cs[r]->coloff);
+    cs[r]->peer_override = peers;
+    rc = fast_apply_local(cs[r], dx[r], dy[r], nullptr, nullptr);
+    if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = edgpu_set_err(EDGPU_ERR_CUDA, "selftest: kernels: %s", cudaGetErrorString(cudaGetLastError()));
   }
-  if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = edgpu_set_err(EDGPU_ERR_CUDA, "selftest: kernels: %s", cudaGetErrorString(cudaGetLastError()));
   for (int r = 0; r < nranks && !rc; r++)
     if (cudaMemcpy(y + cs[r]->coloff * cs[r]->dimup, dy[r], (size_t)cs[r]->nloc * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess)
       rc = edgpu_set_err(EDGPU_ERR_CUDA, "selftest: download");
@@ -133,19 +136,20 @@ extern "C" int edgpu_selftest_sharded_hxv(const edgpu_params *p, int nup, int nd
   return rc;
 }
 
-// HOST ONLY (no device): the plan of the structured row kernel for `rank` of `nranks` -- Lin table with owner /
-// cut flags, chunk table, fix-up list -- exactly as build_srow computes it, so that the CPU-only tests can
-// check the sharding logic.  info[8] = {ok, LR, nhigh, ngroups, nchunks, cmax, nfix targets, nfix edges};
-// arrays may be NULL; capacities in entries.  Returns 0, or 1 when a capacity was too small.
-extern "C" int edgpu_selftest_srow_plan(const edgpu_params *p, int ndw, int nranks, int rank, int64_t lr, int64_t cmax,
+// HOST ONLY (no device): the plan of the structured row kernel for `rank` of `nranks` -- Lin table, chunk table,
+// group records, column-pass source lists and halo slots -- exactly as build_Hv_sector computes it, so that the
+// CPU-only tests can check the chunking / sharding logic.  info[8] = {ok, LR, T, nhigh, nchunks, nrecs, list
+// entries, halo slots}; arrays may be NULL; capacities in entries.  recs: 20 int32 per record (lb, N, hx, par,
+// pc[16]).  lptr has qdw+1 entries, linit qdw.  Returns 0, or 1 when a capacity was too small.
+extern "C" int edgpu_selftest_srow_plan(const edgpu_params *p, int ndw, int nranks, int rank, int64_t lr, int64_t tbits_opt,
                                         int32_t *info, int32_t *jhi, int cap_jhi, int32_t *chunks, int cap_chunks,
-                                        int32_t *tcol, int32_t *tinit, int32_t *tptr, int cap_t,
-                                        int32_t *eown, int32_t *esrc, double *eval, int cap_e) {
+                                        int32_t *recs, int cap_recs, int32_t *lptr, int32_t *linit, int cap_cols,
+                                        int32_t *lloc, double *lamp, int cap_e, int32_t *hown, int32_t *hcol, int cap_slots) {
   DevParams d = make_dp(p);
   const int64_t n = edgpu_selftest_map(d.ns, ndw, nullptr);
   SRowHostPlan hp;
   for (int k = 0; k < 8; k++) info[k] = 0;
-  const int rc = srow_plan_host(d.ns, ndw, n, nranks, rank, (int)lr, cmax, hp);
+  const int rc = srow_plan_host(d.ns, ndw, n, nranks, rank, (int)lr, (int)tbits_opt, hp);
   if (rc <= 0) { info[0] = rc; return 0; }
   std::vector<int32_t> map((size_t)n), rp((size_t)n + 1), cc;
   std::vector<double> vv;
@@ -157,22 +161,27 @@ extern "C" int edgpu_selftest_srow_plan(const edgpu_params *p, int ndw, int nran
     for (int k = 0; k < m; k++) { cc.push_back(c[k]); vv.push_back(v[k]); }
   }
   rp[(size_t)n] = (int32_t)cc.size();
-  srow_fix_host(hp, rank, n, rp.data(), cc.data(), vv.data());
-  info[0] = 1; info[1] = hp.LR; info[2] = hp.nhigh; info[3] = (int32_t)hp.grp.size(); info[4] = (int32_t)hp.chunks.size();
-  info[5] = hp.cmax; info[6] = (int32_t)hp.tcol.size(); info[7] = (int32_t)hp.eown.size();
+  srow_lists_host(hp, rank, n, map.data(), rp.data(), cc.data(), vv.data());
+  info[0] = 1; info[1] = hp.LR; info[2] = hp.T; info[3] = hp.nhigh; info[4] = (int32_t)hp.chunks.size();
+  info[5] = (int32_t)hp.recs.size(); info[6] = (int32_t)hp.lloc.size(); info[7] = (int32_t)hp.hown.size();
   int small = 0;
   if (jhi) { if ((int)hp.jhi.size() > cap_jhi) small = 1; else memcpy(jhi, hp.jhi.data(), hp.jhi.size() * sizeof(int32_t)); }
   if (chunks) {
     if ((int)hp.chunks.size() > cap_chunks) small = 1;
     else for (size_t k = 0; k < hp.chunks.size(); k++) { chunks[4 * k] = hp.chunks[k].x; chunks[4 * k + 1] = hp.chunks[k].y; chunks[4 * k + 2] = hp.chunks[k].z; chunks[4 * k + 3] = hp.chunks[k].w; }
   }
-  if (tcol) {
-    if ((int)hp.tcol.size() > cap_t) small = 1;
-    else for (size_t k = 0; k < hp.tcol.size(); k++) { tcol[k] = hp.tcol[k]; tinit[k] = hp.tinit[k]; tptr[k] = hp.tptr[k]; tptr[k + 1] = hp.tptr[k + 1]; }
+  if (recs) { if ((int)hp.recs.size() > cap_recs) small = 1; else if (!hp.recs.empty()) memcpy(recs, hp.recs.data(), hp.recs.size() * sizeof(SRowRec)); }
+  if (lptr) {
+    if ((int)hp.linit.size() > cap_cols) small = 1;
+    else { for (size_t k = 0; k < hp.lptr.size(); k++) lptr[k] = hp.lptr[k]; for (size_t k = 0; k < hp.linit.size(); k++) linit[k] = hp.linit[k]; }
   }
-  if (eown) {
-    if ((int)hp.eown.size() > cap_e) small = 1;
-    else for (size_t k = 0; k < hp.eown.size(); k++) { eown[k] = hp.eown[k]; esrc[k] = hp.esrc[k]; eval[k] = hp.eval[k]; }
+  if (lloc) {
+    if ((int)hp.lloc.size() > cap_e) small = 1;
+    else for (size_t k = 0; k < hp.lloc.size(); k++) { lloc[k] = hp.lloc[k]; lamp[k] = hp.lamp[k]; }
+  }
+  if (hown) {
+    if ((int)hp.hown.size() > cap_slots) small = 1;
+    else for (size_t k = 0; k < hp.hown.size(); k++) { hown[k] = hp.hown[k]; hcol[k] = hp.hcol[k]; }
   }
   return small;
 }

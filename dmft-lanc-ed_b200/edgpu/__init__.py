@@ -17,6 +17,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 # EDGPU_LIB: an alternative build of the same library (kernel-variant experiments, tools/variants.sh)
 _LIBPATH = os.environ.get("EDGPU_LIB") or os.path.join(os.path.dirname(_PKG), "libedgpu.so")
 _LIB = None
+_TESTLIB = None
 
 c_dp = C.POINTER(C.c_double)
 c_ip = C.POINTER(C.c_int)
@@ -106,6 +107,19 @@ def lib():
         L.edgpu_time_hxv_passes.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, c_ip, c_dp, C.c_char_p]
         _LIB = L
     return _LIB
+
+
+def selftest_lib():
+    """libedgpu_selftest.so: test instrumentation only (include/edgpu_selftest.h), a separate library linked
+    against libedgpu.so.  Nothing in the product path loads it."""
+    global _TESTLIB
+    if _TESTLIB is None:
+        lib()
+        path = os.path.join(os.path.dirname(_LIBPATH), "libedgpu_selftest.so")
+        if not os.path.exists(path):
+            raise ImportError("%s not found: build it with make -C dmft-lanc-ed_b200/csrc" % path)
+        _TESTLIB = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    return _TESTLIB
 
 
 def _ck(rc):

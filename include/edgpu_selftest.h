@@ -1,5 +1,6 @@
 /*
- * edgpu_selftest.h -- test instrumentation exported by libedgpu.so: HOST evaluation of the
+ * edgpu_selftest.h -- test instrumentation exported by libedgpu_selftest.so (a separate library linked against
+ * libedgpu.so; the product library exports none of it): HOST evaluation of the
  * __host__ __device__ bit logic shared with the kernels (dmft-lanc-ed_b200/csrc/hd_funcs.h).
  * Not part of the drop-in boundary; no product entry point calls these and they do not compute
  * H*v.  They let the CPU-only test-suite compare the kernels' index/sign/diagonal code with the
@@ -23,17 +24,19 @@ double edgpu_selftest_diag(const edgpu_params *p, uint32_t mup, uint32_t mdw, in
 /* one row of spH0nd: returns the entry count, outputs column words and values */
 int edgpu_selftest_nonlocal_row(const edgpu_params *p, uint32_t mup, uint32_t mdw, uint32_t *cup, uint32_t *cdw,
                                 double *val);
-/* HOST: plan of the structured row kernel for `rank` of `nranks` (Lin table with owner / cut flags, chunk table,
- * fix-up list of the hops that touch a low group cut by a rank boundary), as build_Hv_sector computes it.
- * info[8] = {ok, LR, nhigh, ngroups, nchunks, cmax, fix targets, fix edges}; arrays may be NULL. */
-int edgpu_selftest_srow_plan(const edgpu_params *p, int ndw, int nranks, int rank, int64_t lr, int64_t cmax,
+/* HOST: plan of the structured row kernel for `rank` of `nranks` (Lin table, chunk table, group records, the
+ * column-pass source lists of the hops the row kernel leaves out on a sharded vector, halo slots), as
+ * build_Hv_sector computes it.  tbits_opt = t + 1 forces chunks of 2^t low groups (0 = automatic).
+ * info[8] = {ok, LR, T, nhigh, nchunks, nrecs, list entries, halo slots}; arrays may be NULL; recs: 20 int32 per
+ * record (lb, N, hx, par, pc[16]); lptr: qdw+1 entries, linit: qdw. */
+int edgpu_selftest_srow_plan(const edgpu_params *p, int ndw, int nranks, int rank, int64_t lr, int64_t tbits_opt,
                              int32_t *info, int32_t *jhi, int cap_jhi, int32_t *chunks, int cap_chunks,
-                             int32_t *tcol, int32_t *tinit, int32_t *tptr, int cap_t,
-                             int32_t *eown, int32_t *esrc, double *eval, int cap_e);
+                             int32_t *recs, int cap_recs, int32_t *lptr, int32_t *linit, int cap_cols,
+                             int32_t *lloc, double *lamp, int cap_e, int32_t *hown, int32_t *hcol, int cap_slots);
 /* GPU: the sharded fast H*v path with `nranks` ranks emulated by `nranks` contexts on ONE device (peers are plain
  * device pointers instead of NVLink mappings); x, y are full host vectors.  Test instrumentation only. */
-int edgpu_selftest_sharded_hxv(const edgpu_params *p, int nup, int ndw, int nranks, int64_t srow_lr, int64_t srow_cmax,
-                               const double *x, double *y);
+int edgpu_selftest_sharded_hxv(const edgpu_params *p, int nup, int ndw, int nranks, int64_t srow_lr, int64_t srow_t,
+                               int64_t col_cluster, const double *x, double *y);
 #ifdef __cplusplus
 }
 #endif

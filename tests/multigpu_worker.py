@@ -35,12 +35,12 @@ def main():
         if not ok:
             fails.append("%s rank %d %s" % (name, rank, detail))
 
-    # (config, sector, stored?, engine options).  Single-band cases run the peer-read fast path (k_srow reads
-    # other ranks' columns over NVLink + fix-up of the low groups cut by a rank boundary); "no_peer" forces the
+    # (config, sector, stored?, engine options).  Single-band cases run the sharded fast path (halo pulled from the
+    # peers over NVLink next to k_srow, remote / boundary hops applied by the column pass); "no_peer" forces the
     # all-to-all transposes; C4 (spin-exchange / pair-hopping) uses the all-gather path.
-    cases = [("C1", (4, 4), True, {}), ("C1", (4, 4), False, {}), ("C1", (5, 3), True, {"srow_cmax": 12}),
-             ("NS10", (5, 5), False, {"srow_lr": 4, "srow_cmax": 24}), ("NS10", (6, 4), True, {}),
-             ("NS12", (6, 6), False, {}), ("NS12", (7, 5), True, {"srow_cmax": 64}), ("NS10V", (5, 5), False, {}),
+    cases = [("C1", (4, 4), True, {}), ("C1", (4, 4), False, {}), ("C1", (5, 3), True, {"srow_t": 1}),
+             ("NS10", (5, 5), False, {"srow_lr": 4, "srow_t": 3}), ("NS10", (6, 4), True, {}),
+             ("NS12", (6, 6), False, {}), ("NS12", (7, 5), True, {"srow_t": 4}), ("NS10V", (5, 5), False, {}),
              ("NS10", (5, 5), True, {"no_peer": 1}), ("NS12", (6, 6), False, {"no_peer": 1, "hxv_algo": 1}),
              ("C4", (5, 5), True, {}), ("C4", (5, 5), False, {}), ("C4", (6, 5), True, {})]
     for name, sec, sparse, opts in cases:

@@ -26,8 +26,13 @@ def test_library_exports_every_declared_symbol():
     names = _declared("edgpu.h")
     assert len(names) >= 30
     assert sorted(edgpu.ABI_SYMBOLS) == names
-    for n in names + _declared("edgpu_selftest.h"):
+    for n in names:
         assert hasattr(L, n), n
+    # the test instrumentation lives in its own library; the product library exports none of it
+    T = edgpu.selftest_lib()
+    for n in _declared("edgpu_selftest.h"):
+        assert hasattr(T, n), n
+        assert not hasattr(L, n), n
 
 
 def test_no_torch_or_cxx_types_in_header():
@@ -67,7 +72,7 @@ def _params(cfg, sparse=True):
 def test_kernel_bit_logic_on_host_matches_oracle(name):
     """hd_funcs.h evaluated on the host through the self-test hooks: sector maps, factor CSR and the
     stored diagonal are BIT-EXACT against the oracle; the factorised diagonal agrees to 1e-14."""
-    L = edgpu.lib()
+    L = edgpu.selftest_lib()
     L.edgpu_selftest_map.restype = C.c_int64
     L.edgpu_selftest_factor.restype = C.c_int64
     L.edgpu_selftest_diag.restype = C.c_double
@@ -124,137 +129,126 @@ def test_host_side_gf_accumulation_matches_oracle():
     assert np.abs(sig - gold["smats"]).max() < 1e-10
 
 
-ROWPLAN_CASES = [("C1", 4, 1, 0, 0), ("C1", 4, 2, 0, 0), ("C1", 4, 3, 0, 0), ("C1", 4, 4, 0, 12), ("C1", 3, 4, 4, 12),
-                 ("NS10", 5, 3, 4, 24), ("NS10", 5, 8, 0, 0), ("NS12", 6, 7, 0, 64), ("NS12", 5, 8, 4, 48),
-                 ("NS14", 7, 8, 0, 0), ("NS16", 8, 8, 0, 0), ("NS16", 9, 5, 0, 0)]
+ROWPLAN_CASES = [("C1", 4, 1, 0, 0), ("C1", 4, 2, 0, 0), ("C1", 4, 3, 0, 1), ("C1", 4, 4, 0, 2), ("C1", 3, 4, 4, 1),
+                 ("NS10", 5, 3, 4, 3), ("NS10", 5, 8, 0, 0), ("NS12", 6, 7, 0, 4), ("NS12", 5, 8, 4, 2),
+                 ("NS14", 7, 8, 0, 0), ("NS16", 8, 8, 0, 0), ("NS16", 9, 5, 0, 0), ("NS16", 8, 1, 0, 0), ("NS18", 9, 8, 0, 0)]
 
 
-@pytest.mark.parametrize("name,ndw,nranks,lr,cmax", ROWPLAN_CASES)
-def test_row_kernel_plan_covers_every_hop_exactly_once(name, ndw, nranks, lr, cmax):
-    """Host arithmetic behind the sharded structured row kernel (hxv_fast.cu: srow_plan_host / srow_fix_host),
-    checked without a GPU for every rank of a split: the chunks tile the whole low groups of the rank, the
-    fix-up list holds exactly the hops whose target or source group is cut by a rank boundary (with the oracle's
-    matrix elements), every other hop is left to the kernel, and the Lin table is the closed-form rank."""
-    L = edgpu.lib()
-    cfg, o = make_oracle(name)
-    keep = _params(cfg)
-    p = keep[0]
+def _row_plan(p, ndw, nranks, rank, lr, st, dimdw, nnz):
+    """edgpu_selftest_srow_plan -> dict of numpy arrays."""
+    L = edgpu.selftest_lib()
     i32p, dp = C.POINTER(C.c_int32), C.POINTER(C.c_double)
-    with o.sector(cfg["nup"], ndw) as s:
-        rp, cc, vv = s.hdw()
-        md = s.map_dw()
-        dimdw = len(md)
-    handled = np.zeros(len(cc), dtype=np.int32)          # how many times each CSR entry (target <- source) is covered
-    colcov = np.zeros(dimdw, dtype=np.int32)
-    for rank in range(nranks):
-        info = np.zeros(8, np.int32)
-        cap_j, cap_c, cap_t, cap_e = 1 << 15, 4096, dimdw + 8, len(cc) + 8
-        jhi = np.zeros(cap_j, np.int32); chunks = np.zeros(4 * cap_c, np.int32)
-        tcol = np.zeros(cap_t, np.int32); tinit = np.zeros(cap_t, np.int32); tptr = np.zeros(cap_t + 1, np.int32)
-        eown = np.zeros(cap_e, np.int32); esrc = np.zeros(cap_e, np.int32); ev = np.zeros(cap_e)
-        rc = L.edgpu_selftest_srow_plan(C.byref(p), ndw, nranks, rank, C.c_int64(lr), C.c_int64(cmax),
-                                        info.ctypes.data_as(i32p), jhi.ctypes.data_as(i32p), cap_j,
-                                        chunks.ctypes.data_as(i32p), cap_c, tcol.ctypes.data_as(i32p),
-                                        tinit.ctypes.data_as(i32p), tptr.ctypes.data_as(i32p), cap_t,
-                                        eown.ctypes.data_as(i32p), esrc.ctypes.data_as(i32p), ev.ctypes.data_as(dp), cap_e)
-        assert rc == 0 and info[0] == 1, (rc, info)
-        LR, nhigh, nchunks, nfix = int(info[1]), int(info[2]), int(info[4]), int(info[6])
-        q, off = edgpu.split(dimdw, nranks, rank)
-        coloffs = [edgpu.split(dimdw, nranks, r)[1] for r in range(nranks)] + [dimdw]
-        # Lin table: first column of every group = rank of its smallest word; owner / cut flags from the split
-        lowmask = (1 << LR) - 1
-        gcut = {}
-        for h in range(1 << nhigh):
-            e = int(jhi[h])
-            nlow = ndw - bin(h).count("1")
-            if nlow < 0 or nlow > LR:
-                assert e == -1
-                continue
-            words = md[(md >> LR) == h]
-            base = int(np.searchsorted(md, words[0]))
-            assert (e & 0xFFFFF) == base and len(words) == math.comb(LR, nlow)
-            own = max(r for r in range(nranks) if coloffs[r] <= base)
-            cut = base + len(words) > coloffs[own + 1]
-            assert ((e >> 20) & 63) == own and bool(e & 0x40000000) == cut
-            gcut[h] = cut
-        colcut = np.array([gcut[int(w) >> LR] for w in md])
-        # chunks: whole, uncut local groups, contiguous, within the size limit
-        ch = chunks[:4 * nchunks].reshape(-1, 4)
-        for k in range(nchunks):
-            assert off <= ch[k, 2] < ch[k, 3] <= off + q and ch[k, 3] - ch[k, 2] <= info[5]
-            assert not colcut[ch[k, 2]:ch[k, 3]].any()
-            colcov[ch[k, 2]:ch[k, 3]] += 1
-            if k:
-                assert ch[k, 2] == ch[k - 1, 3] and ch[k, 0] == ch[k - 1, 1]
-        inchunk = np.zeros(dimdw, bool)
-        for k in range(nchunks):
-            inchunk[ch[k, 2]:ch[k, 3]] = True
-        # the kernel's rule: a hop is applied by k_srow iff its target is in a chunk and its source group is not cut
-        for t in range(off, off + q):
-            for e in range(rp[t], rp[t + 1]):
-                if inchunk[t] and not colcut[cc[e]]:
-                    handled[e] += 1
-        # fix-up list: targets in cut groups are initialised there, every listed edge is a real matrix element
-        for k in range(nfix):
-            t = off + int(tcol[k])
-            assert bool(tinit[k]) == bool(colcut[t])
-            if tinit[k]:
-                colcov[t] += 1
-            for e in range(tptr[k], tptr[k + 1]):
-                src = coloffs[int(eown[e])] + int(esrc[e])
-                hit = [x for x in range(rp[t], rp[t + 1]) if cc[x] == src]
-                assert len(hit) == 1 and vv[hit[0]] == ev[e]
-                handled[hit[0]] += 1
-    assert (colcov == 1).all()                                # every column written by exactly one kernel
-    assert (handled == 1).all()                               # every hop applied exactly once
-
-
-@pytest.mark.parametrize("name,ndw,lr", [("C1", 4, 5), ("C1", 5, 4), ("NS10", 5, 5), ("NS10V", 4, 4), ("NS12V", 6, 5), ("NS14", 7, 5)])
-def test_structured_hop_enumeration_reproduces_spH0dws(name, ndw, lr):
-    """The algebra k_srow relies on (hxv_fast.cu: srow_group / srow_prepare), restated in Python on top of the
-    engine's own Lin table: low group = (high word h, LR low bits), hop = impurity bit 0 <-> bath bit k, partner
-    column = jhi[h'] + rank of the partner's low pattern in its class, sign = parity of the occupied bits strictly
-    between the two.  Enumerated that way, the (target, source, value) triples must be EXACTLY spH0dws(1) of the
-    oracle (stored/H_dw.f90:8-80) -- structure bit-exact, values bit-exact."""
-    L = edgpu.lib()
-    cfg, o = make_oracle(name)
-    keep = _params(cfg)
-    i32p = C.POINTER(C.c_int32)
-    with o.sector(cfg["nup"], ndw) as s:
-        rp, cc, vv = s.hdw()
     info = np.zeros(8, np.int32)
-    jhi = np.zeros(1 << 15, np.int32)
-    rc = L.edgpu_selftest_srow_plan(C.byref(keep[0]), ndw, 1, 0, C.c_int64(lr), C.c_int64(0), info.ctypes.data_as(i32p),
-                                    jhi.ctypes.data_as(i32p), len(jhi), None, 0, None, None, None, 0, None, None, None, 0)
-    assert rc == 0 and info[0] == 1
-    LR, nhigh = int(info[1]), int(info[2])
-    ns = LR + nhigh
-    vk = [0.0] + [float(cfg["bath_v"].reshape(-1)[k]) for k in range(ns - 1)]      # V_k of the dw spin (Nspin = 1)
+    cap_j, cap_c, cap_r, cap_cols, cap_e, cap_s = 1 << 16, 1 << 14, 1 << 15, dimdw + 8, nnz + 8, dimdw + 8
+    jhi = np.zeros(cap_j, np.int32); chunks = np.zeros(4 * cap_c, np.int32); recs = np.zeros(20 * cap_r, np.int32)
+    lptr = np.zeros(cap_cols + 1, np.int32); linit = np.zeros(cap_cols, np.int32)
+    lloc = np.zeros(cap_e, np.int32); lamp = np.zeros(cap_e)
+    hown = np.zeros(cap_s, np.int32); hcol = np.zeros(cap_s, np.int32)
+    rc = L.edgpu_selftest_srow_plan(C.byref(p), ndw, nranks, rank, C.c_int64(lr), C.c_int64(st), info.ctypes.data_as(i32p),
+                                    jhi.ctypes.data_as(i32p), cap_j, chunks.ctypes.data_as(i32p), cap_c,
+                                    recs.ctypes.data_as(i32p), cap_r, lptr.ctypes.data_as(i32p), linit.ctypes.data_as(i32p), cap_cols,
+                                    lloc.ctypes.data_as(i32p), lamp.ctypes.data_as(dp), cap_e,
+                                    hown.ctypes.data_as(i32p), hcol.ctypes.data_as(i32p), cap_s)
+    assert rc == 0 and info[0] == 1, (rc, info)
+    return dict(LR=int(info[1]), T=int(info[2]), nhigh=int(info[3]), jhi=jhi[:1 << int(info[3])],
+                chunks=chunks[:4 * info[4]].reshape(-1, 4), recs=recs[:20 * info[5]].reshape(-1, 20).view(np.uint32),
+                lptr=lptr, linit=linit, lloc=lloc[:info[6]], lamp=lamp[:info[6]], hown=hown[:info[7]], hcol=hcol[:info[7]])
+
+
+def _kernel_hops(plan, ndw, vk):
+    """What k_srow does with the plan (hxv_fast.cu: srow_group / srow_hops), restated: {(target, source): value} in
+    shard-local column indices, and the set of columns it writes."""
+    LR, T, nhigh = plan["LR"], plan["T"], plan["nhigh"]
     popc = lambda x: bin(x).count("1")
     pats = {n: [q for q in range(1 << LR) if popc(q) == n] for n in range(LR + 1)}
     rank = lambda lo: pats[popc(lo)].index(lo)
-    trip = {}
-    for h in range(1 << nhigh):
-        n = ndw - popc(h)
-        if n < 0 or n > LR:
-            continue
-        base = int(jhi[h]) & 0xFFFFF
-        for i, lo in enumerate(pats[n]):
-            t = base + i
-            for kb in range(1, LR):                                   # hops among the low bits (register to register)
-                if ((lo >> kb) & 1) != (lo & 1):
-                    lo2 = lo ^ (1 | (1 << kb))
-                    sgn = -1.0 if popc(lo & ((1 << kb) - 2)) & 1 else 1.0
-                    trip[(t, base + rank(lo2))] = sgn * vk[kb]
-            for kk in range(nhigh):                                   # hops on the high bits (whole group -> one group)
-                bit = 1 << kk
-                if bool(h & bit) == bool(lo & 1):
-                    continue                                          # bath bit and impurity bit must differ
-                lo2 = lo ^ 1
-                base2 = int(jhi[h ^ bit]) & 0xFFFFF
-                sgn = -1.0 if (popc(lo >> 1) + popc(h & (bit - 1))) & 1 else 1.0
-                trip[(t, base2 + rank(lo2))] = sgn * vk[LR + kk]
-    ref = {(t, int(cc[e])): float(vv[e]) for t in range(len(rp) - 1) for e in range(rp[t], rp[t + 1])}
-    trip = {k: v for k, v in trip.items() if v != 0.0}                # the reference stores no entry for V_k = 0
-    assert trip.keys() == ref.keys()
-    assert all(trip[k] == ref[k] for k in ref)
+    hops, written = {}, []
+    for rb, ng, cb, ce in plan["chunks"]:
+        for rec in plan["recs"][rb:rb + ng]:
+            lb, N, hx, par = int(rec[0]), int(rec[1]), int(rec[2]), int(rec[3])
+            pc = rec[4:].view(np.int32)
+            h, ex = hx & 0xFFFF, hx >> 16
+            assert N == ndw - popc(h) and 0 <= lb and cb + lb + len(pats[N]) <= ce
+            for i, lo in enumerate(pats[N]):
+                t = cb + lb + i
+                written.append(t)
+                for kb in range(1, LR):                               # low bits: register to register
+                    if ((lo >> kb) & 1) != (lo & 1):
+                        sgn = -1.0 if popc(lo & ((1 << kb) - 2)) & 1 else 1.0
+                        hops[(t, cb + lb + rank(lo ^ (1 | (1 << kb))))] = sgn * vk[kb]
+                for kk in range(nhigh):                               # high bits: whole group -> one partner group
+                    if not (ex >> kk) & 1 or bool(h & (1 << kk)) == bool(lo & 1):
+                        continue
+                    base2 = (cb if kk < T else 0) + int(pc[kk])
+                    sgn = -1.0 if (popc(lo >> 1) + ((par >> kk) & 1)) & 1 else 1.0
+                    hops[(t, base2 + rank(lo ^ 1))] = sgn * vk[LR + kk]
+    return hops, written
+
+
+@pytest.mark.parametrize("name,ndw,nranks,lr,st", ROWPLAN_CASES)
+def test_row_kernel_plan_covers_every_hop_exactly_once(name, ndw, nranks, lr, st):
+    """Host arithmetic behind the structured row kernel and its sharded form (hxv_fast.cu: srow_plan_host /
+    srow_lists_host), checked without a GPU for every rank of a split: the records, evaluated the way the kernel
+    evaluates them, plus the column pass's source lists reproduce spH0dws(1) of the oracle (stored/H_dw.f90:8-80)
+    restricted to the rank's target columns EXACTLY once per entry, values bit-exact; every local column is written
+    by exactly one of the two kernels; halo slots name the right owner columns."""
+    cfg, o = make_oracle(name)
+    keep = _params(cfg)
+    ns = cfg["nbath"] + 1
+    dimdw = math.comb(ns, ndw)
+    big = dimdw > 20000                                           # Ns = 18: check against the closed-form structure
+    if not big:
+        with o.sector(cfg["nup"], ndw) as s:
+            rp, cc, vv = s.hdw()
+            md = s.map_dw()
+        ref_all = {(t, int(cc[e])): float(vv[e]) for t in range(dimdw) for e in range(rp[t], rp[t + 1])}
+        nnz = len(cc)
+    else:
+        nnz = dimdw * ns
+    vkall = [0.0] + [float(cfg["bath_v"].reshape(-1)[k]) for k in range(ns - 1)]
+    total = 0
+    for rank in range(nranks):
+        plan = _row_plan(keep[0], ndw, nranks, rank, lr, st, dimdw, nnz)
+        q, off = edgpu.split(dimdw, nranks, rank)
+        coloffs = [edgpu.split(dimdw, nranks, r)[1] for r in range(nranks)] + [dimdw]
+        hops, written = _kernel_hops(plan, ndw, vkall)
+        assert len(written) == len(set(written))
+        got = {}
+        for (t, s_), v in hops.items():
+            assert 0 <= t < q and 0 <= s_ < q                      # the row kernel never leaves the shard
+            got[(off + t, off + s_)] = v
+        cover = np.zeros(q, np.int32)
+        cover[written] += 1
+        if nranks == 1:
+            assert len(plan["lloc"]) == 0 and len(plan["hown"]) == 0
+        else:
+            lptr, linit = plan["lptr"], plan["linit"]
+            cover += linit[:q]
+            for t in range(q):
+                for e in range(lptr[t], lptr[t + 1]):
+                    loc = int(plan["lloc"][e])
+                    if loc >= 0:
+                        src = off + loc
+                    else:
+                        slot = -1 - loc
+                        own = int(plan["hown"][slot])
+                        assert own != rank
+                        src = coloffs[own] + int(plan["hcol"][slot])
+                        assert coloffs[own] <= src < coloffs[own + 1]
+                    assert (off + t, src) not in got
+                    got[(off + t, src)] = float(plan["lamp"][e])
+            slots = list(zip(plan["hown"].tolist(), plan["hcol"].tolist()))
+            assert len(slots) == len(set(slots))                   # one halo column per remote source
+        assert (cover == 1).all()                                  # every local column written by exactly one kernel
+        got = {k: v for k, v in got.items() if v != 0.0}           # the reference stores no entry for V_k = 0
+        if not big:
+            ref = {k: v for k, v in ref_all.items() if off <= k[0] < off + q}
+            assert got.keys() == ref.keys()
+            assert all(got[k] == ref[k] for k in ref)
+        else:
+            assert all(off <= k[0] < off + q for k in got)
+        total += len(got)
+    if big:                                                        # star geometry at half filling: exactly Ns/2 hops per column
+        assert total == dimdw * ns // 2 or ndw * 2 != ns
+    # chunk geometry: tiles fit the box grid and the group count the kernel assumes
+    assert plan["T"] <= 5 and all(ng <= 64 for _, ng, _, _ in plan["chunks"])

@@ -344,12 +344,13 @@ def test_tiled_hxv_matches_oracle(name, sec, opts, sparse):
         s.close()
 
 
-FAST_CASES = [("C1", (4, 4), {}), ("C1", (5, 3), {"srow_cmax": 20}), ("C1", (3, 6), {"srow_lr": 4, "srow_cmax": 12}),
-              ("NS10", (5, 5), {"srow_lr": 4, "srow_cmax": 40}), ("NS10", (5, 5), {"srow_lr": 5, "srow_cmax": 30}),
-              ("NS12", (6, 6), {"srow_cmax": 100}), ("NS12", (7, 4), {}), ("NS12", (6, 6), {"no_uniform": 1, "srow_lr": 4}), ("NS12", (6, 6), {"no_uniform": 2}),
-              ("NS6", (3, 3), {}), ("NS6", (3, 3), {"srow_lr": 4, "srow_cmax": 6}), ("NS10V", (5, 5), {"srow_cmax": 50}),
-              ("NS12V", (6, 5), {"srow_lr": 4, "srow_cmax": 64}), ("NS10V", (7, 2), {}), ("NS10", (9, 1), {}),
-              ("NS12", (6, 0), {}), ("NS12", (6, 12), {}),
+# srow_t = t + 1 forces chunks of 2^t low groups (t = 0: every high-bit hop reads L2, none the tile)
+FAST_CASES = [("C1", (4, 4), {}), ("C1", (5, 3), {"srow_t": 1}), ("C1", (3, 6), {"srow_lr": 4, "srow_t": 2}),
+              ("NS10", (5, 5), {"srow_lr": 4, "srow_t": 3}), ("NS10", (5, 5), {"srow_lr": 5, "srow_t": 2}),
+              ("NS12", (6, 6), {"srow_t": 4}), ("NS12", (7, 4), {}), ("NS12", (6, 6), {"no_uniform": 1, "srow_lr": 4}), ("NS12", (6, 6), {"no_uniform": 2}),
+              ("NS6", (3, 3), {}), ("NS6", (3, 3), {"srow_lr": 4, "srow_t": 1}), ("NS10V", (5, 5), {"srow_t": 3}),
+              ("NS12V", (6, 5), {"srow_lr": 4, "srow_t": 4}), ("NS10V", (7, 2), {}), ("NS10", (9, 1), {}),
+              ("NS12", (6, 0), {}), ("NS12", (6, 12), {}), ("NS14", (7, 7), {}), ("NS14V", (6, 8), {"srow_t": 3}),
               # two-CTA cluster column kernel (columns too long for one SM; forced here on small ones)
               ("C1", (4, 4), {"col_cluster": 1}), ("NS12", (6, 6), {"col_cluster": 1}), ("NS12", (7, 4), {"col_cluster": 1, "no_uniform": 1}),
               ("NS10V", (5, 5), {"col_cluster": 1}), ("NS12", (5, 6), {"col_cluster": 1, "srow_lr": 4})]
@@ -372,7 +373,7 @@ def test_fast_hxv_matches_oracle(name, sec, opts, sparse):
             s.build_Hv_sector(s.get_sector(*sec))
             hv = s.spHtimesV(v)
             assert np.abs(hv - ref).max() < 1e-13 * max(np.abs(ref).max(), 1e-300)
-            if os_.dim > 1:
+            if 1 < os_.dim < 2000000:
                 e_ref, _, a_ref, b_ref = os_.lanc_eigh(v0=np.ones(os_.dim) / np.sqrt(os_.dim))
                 e0, _, a, b = s.sp_lanc_eigh(np.ones(os_.dim) / np.sqrt(os_.dim))
                 assert abs(e0 - e_ref) < 1e-12 * abs(e_ref)
@@ -381,18 +382,20 @@ def test_fast_hxv_matches_oracle(name, sec, opts, sparse):
         s.close()
 
 
-SHARD_CASES = [("C1", (4, 4), 2, 0, 0), ("C1", (4, 4), 3, 0, 0), ("C1", (4, 4), 4, 0, 0), ("C1", (5, 3), 4, 0, 12),
-               ("NS10", (5, 5), 3, 4, 24), ("NS10", (5, 5), 8, 0, 0), ("NS10", (6, 4), 5, 0, 0), ("NS12", (6, 6), 7, 0, 64),
-               ("NS12", (7, 5), 4, 4, 0), ("NS10V", (5, 5), 6, 0, 0), ("NS12V", (6, 5), 8, 4, 48), ("C1", (3, 6), 8, 4, 12)]
+# (config, sector, ranks, srow_lr, srow_t, col_cluster)
+SHARD_CASES = [("C1", (4, 4), 2, 0, 0, 0), ("C1", (4, 4), 3, 0, 0, 0), ("C1", (4, 4), 4, 0, 1, 0), ("C1", (5, 3), 4, 0, 2, 0),
+               ("NS10", (5, 5), 3, 4, 3, 0), ("NS10", (5, 5), 8, 0, 0, 0), ("NS10", (6, 4), 5, 0, 0, 1), ("NS12", (6, 6), 7, 0, 4, 0),
+               ("NS12", (7, 5), 4, 4, 0, 0), ("NS10V", (5, 5), 6, 0, 0, 0), ("NS12V", (6, 5), 8, 4, 3, 1), ("C1", (3, 6), 8, 4, 1, 0),
+               ("NS14", (7, 7), 8, 0, 0, 0), ("NS14V", (7, 6), 5, 0, 4, 0)]
 
 
-@pytest.mark.parametrize("name,sec,nranks,lr,cmax", SHARD_CASES)
+@pytest.mark.parametrize("name,sec,nranks,lr,st,cluster", SHARD_CASES)
 @pytest.mark.parametrize("sparse", [True, False])
-def test_sharded_fast_path_emulated_on_one_gpu(name, sec, nranks, lr, cmax, sparse):
-    """The kernels and plans of the multi-GPU fast path (rank-aware Lin table, low groups cut by a rank boundary,
-    fix-up kernel, per-owner source pointers) with the ranks emulated by contexts on ONE device
-    (edgpu_selftest_sharded_hxv): any rank count 1..8, including splits where DimDw is not a multiple of P and
-    ranks that own no whole low group."""
+def test_sharded_fast_path_emulated_on_one_gpu(name, sec, nranks, lr, st, cluster, sparse):
+    """The kernels and plans of the multi-GPU fast path (whole / cut low groups, group records, the halo copy
+    kernel, the column pass's source lists for remote and boundary hops) with the ranks emulated by contexts on ONE
+    device (edgpu_selftest_sharded_hxv): any rank count 1..8, including splits where DimDw is not a multiple of P
+    and ranks that own no whole low group."""
     import ctypes as C
     cfg, o = make_oracle(name)
     s = _solver(cfg, sparse)
@@ -402,12 +405,12 @@ def test_sharded_fast_path_emulated_on_one_gpu(name, sec, nranks, lr, cmax, spar
             v /= np.linalg.norm(v)
             ref = os_.spmatvec(v)
             out = np.zeros(os_.dim)
-            L = edgpu.lib()
-            L.edgpu_selftest_sharded_hxv.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64,
+            L = edgpu.selftest_lib()
+            L.edgpu_selftest_sharded_hxv.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64,
                                                      C.c_void_p, C.c_void_p]
-            rc = L.edgpu_selftest_sharded_hxv(C.byref(s._keep[0]), sec[0], sec[1], nranks, lr, cmax,
+            rc = L.edgpu_selftest_sharded_hxv(C.byref(s._keep[0]), sec[0], sec[1], nranks, lr, st, cluster,
                                               v.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
-            assert rc == 0, L.edgpu_last_error().decode()
+            assert rc == 0, edgpu.lib().edgpu_last_error().decode()
             assert np.abs(out - ref).max() < 1e-13 * np.abs(ref).max()
     finally:
         s.close()

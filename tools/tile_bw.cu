@@ -69,7 +69,7 @@ int main() {
   CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q)); PFN enc = (PFN)p;
   CK(cudaFuncSetAttribute(k_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1); float ms;
-  struct Cfg { int R, BC, C; } cfgs[] = {{32, 32, 352}, {64, 32, 160}, {128, 16, 80}, {16, 64, 704}, {32, 32, 160}, {256, 8, 40}};
+  struct Cfg { int R, BC, C; } cfgs[] = {{32, 32, 352}, {64, 32, 160}, {128, 16, 80}, {16, 64, 704}, {32, 32, 160}, {256, 8, 40}, {32, 32, 256}, {16, 32, 640}, {16, 32, 320}, {8, 32, 1280}, {8, 64, 1280}, {64, 32, 96}, {64, 16, 128}};
   for (auto cf : cfgs) for (int mode = 0; mode < 2; mode++) {
     CUtensorMap tm; cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)nf}, str[1] = {(cuuint64_t)n * 8}; cuuint32_t box[2] = {(cuuint32_t)cf.R, (cuuint32_t)cf.BC}, es[2] = {1, 1};
     CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, x, dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

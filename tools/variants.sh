@@ -1,6 +1,6 @@
 #!/bin/bash
 # Build alternative libedgpu variants (compile-time kernel parameters) next to the product library:
-#   tools/variants.sh name "-DSROW_NB_FAR=4 -DSROW_NB_IN=2" ...
+#   tools/variants.sh name "-DSROW_NB_FAR=3 -DSROW_NB_IN=2" ...
 # and time them on the GPU box with EDGPU_LIB=dmft-lanc-ed_b200/variants/libedgpu_<name>.so python bench.py ...
 set -e
 cd "$(dirname "$0")/../dmft-lanc-ed_b200/csrc"
@@ -10,6 +10,6 @@ FLAGS="-O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompil
 while [ $# -ge 2 ]; do
   name=$1; defs=$2; shift 2
   $NVCC $FLAGS $defs -c hxv_fast.cu -o build_var/hxv_fast_$name.o
-  $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o ../variants/libedgpu_$name.so build/capi.o build/hxv.o build/hxv_tiled.o build_var/hxv_fast_$name.o build/lanczos.o build/comm.o build/selftest.o -ldl
+  $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o ../variants/libedgpu_$name.so build/capi.o build/hxv.o build/hxv_tiled.o build_var/hxv_fast_$name.o build/lanczos.o build/comm.o -ldl
   echo built $name
 done
