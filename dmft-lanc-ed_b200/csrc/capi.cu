@@ -367,7 +367,7 @@ extern "C" int edgpu_build_hv_sector(edgpu_ctx *c, int isector) {
     // room for the engine's Lanczos vectors, the staging pair and a few user vectors, identical on every rank
     int64_t qmax = (c->dimdw + c->nranks - 1) / c->nranks;
     size_t per = (((size_t)(c->dimup * qmax) + 2) * sizeof(double) + 255) & ~(size_t)255;
-    int rc2 = comm_symm_setup(c, per, 10);
+    int rc2 = comm_symm_setup(c, per, 12);
     if (rc2) { edgpu_delete_hv_sector(c); return rc2; }
   }
   g_current = c;
@@ -546,9 +546,14 @@ extern "C" int edgpu_dev_free(edgpu_ctx *c, void *dptr) {
   CK(cudaSetDevice(c->device));
   // buffers carved from the symmetric slab (edgpu_dev_alloc while a sharded sector is live) belong to that sector:
   // they are released by delete_Hv_sector, and freeing one -- before or after -- is a no-op
-  if (sym_offset(c, dptr) >= 0) return EDGPU_OK;
   for (size_t i = 0; i < c->slab_ptrs.size(); i++)
-    if (c->slab_ptrs[i] == dptr) { c->slab_ptrs.erase(c->slab_ptrs.begin() + (long)i); return EDGPU_OK; }
+    if (c->slab_ptrs[i] == dptr) {
+      c->slab_ptrs.erase(c->slab_ptrs.begin() + (long)i);
+      double *p = reinterpret_cast<double *>(dptr);
+      if (sym_offset(c, dptr) >= 0) vec_free(c, &p);             // back to the live slab; after teardown: nothing to do
+      return EDGPU_OK;
+    }
+  if (sym_offset(c, dptr) >= 0) return EDGPU_OK;
   CK(cudaFree(dptr));
   return EDGPU_OK;
 }

@@ -115,11 +115,14 @@ int vec_alloc(edgpu_ctx *c, double **p, int64_t n) {
   const size_t bytes = (((size_t)(n > 0 ? n : 1) + 2) * sizeof(double) + 255) & ~(size_t)255;
   if (c->sym_ok && c->sym_unit) {
     // nloc differs by one column between ranks: carve in rank-independent units so that the same vector
-    // sits at the same offset on every rank
-    const size_t need = (bytes + c->sym_unit - 1) / c->sym_unit * c->sym_unit;
-    if (c->sym_used + need <= c->sym_bytes) {
-      *p = reinterpret_cast<double *>(c->sym_slab + c->sym_used);
-      c->sym_used += need;
+    // sits at the same offset on every rank (every rank performs the same sequence of allocations and frees)
+    const int need = (int)((bytes + c->sym_unit - 1) / c->sym_unit), total = (int)(c->sym_bytes / c->sym_unit);
+    for (int u = 0; u + need <= total && u + need <= 64; u++) {
+      bool free_run = true;
+      for (int k = 0; k < need; k++) if (c->sym_units[u + k]) { free_run = false; break; }
+      if (!free_run) continue;
+      for (int k = 0; k < need; k++) c->sym_units[u + k] = (k == 0) ? need : -1;
+      *p = reinterpret_cast<double *>(c->sym_slab + (size_t)u * c->sym_unit);
       return EDGPU_OK;
     }
   }
@@ -127,7 +130,14 @@ int vec_alloc(edgpu_ctx *c, double **p, int64_t n) {
   return EDGPU_OK;
 }
 void vec_free(edgpu_ctx *c, double **p) {
-  if (*p && sym_offset(c, *p) < 0) cudaFree(*p);
+  if (!*p) return;
+  const int64_t off = sym_offset(c, *p);
+  if (off < 0) cudaFree(*p);
+  else if (c->sym_unit) {
+    const int u = (int)((size_t)off / c->sym_unit);
+    const int need = u < 64 ? c->sym_units[u] : 0;
+    for (int k = 0; k < need && u + k < 64; k++) c->sym_units[u + k] = 0;
+  }
   *p = nullptr;
 }
 int comm_barrier(edgpu_ctx *c) {
@@ -188,6 +198,7 @@ int comm_symm_setup(edgpu_ctx *c, size_t unit, int nunits) {
   }
   CK(cudaMemsetAsync(c->sym_slab, 0, bytes, c->stream));
   c->sym_bytes = bytes; c->sym_used = 0; c->sym_ok = true;
+  memset(c->sym_units, 0, sizeof(c->sym_units));
   TRY(comm_barrier(c));
   CK(cudaStreamSynchronize(c->stream));
   return EDGPU_OK;
@@ -245,8 +256,8 @@ static int ensure(double **p, int64_t n) {
   return EDGPU_OK;
 }
 
-static int exchange(edgpu_ctx *c, const double *send, const int64_t *soff, const int64_t *scnt, double *recv,
-                    const int64_t *roff, const int64_t *rcnt) {
+int comm_exchange(edgpu_ctx *c, const double *send, const int64_t *soff, const int64_t *scnt, double *recv,
+                  const int64_t *roff, const int64_t *rcnt) {
   const int P = c->nranks, me = c->rank;
   NK(g_nccl.GroupStart());
   for (int p = 0; p < P; p++) {
@@ -302,7 +313,7 @@ int comm_transpose_fwd(edgpu_ctx *c, const double *d_x, double *d_vt) {
       CKL(c);
     }
   }
-  TRY(exchange(c, c->d_send, soff, scnt, c->d_recv, roff, rcnt));
+  TRY(comm_exchange(c, c->d_send, soff, scnt, c->d_recv, roff, rcnt));
   for (int p = 0; p < P; p++) {
     int64_t qc, co;
     edgpu_split(c->dimdw, P, p, &qc, &co);
@@ -329,7 +340,7 @@ int comm_transpose_bwd_add(edgpu_ctx *c, const double *d_hvt, double *d_y) {
       CKL(c);
     }
   }
-  TRY(exchange(c, c->d_send, soff, scnt, c->d_recv, roff, rcnt));
+  TRY(comm_exchange(c, c->d_send, soff, scnt, c->d_recv, roff, rcnt));
   for (int p = 0; p < P; p++) {
     int64_t qr, ro;
     edgpu_split(c->dimup, P, p, &qr, &ro);

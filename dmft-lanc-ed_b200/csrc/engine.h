@@ -86,6 +86,7 @@ struct edgpu_ctx {
   int gs_nup = -1, gs_ndw = -1;
   int64_t gs_nloc = 0;
   double gs_e0 = 0.0;
+  bool lv_valid = false;                      // d_lv holds the normalised eigenvector of the last sp_lanc_eigh (live sector)
   // options
   int algo = EDGPU_ALGO_AUTO;
   int64_t opt_tile_rows = 0, opt_tile_h = -1, opt_col_h = -1;
@@ -99,6 +100,7 @@ struct edgpu_ctx {
   // through CUDA IPC, so that kernels can read a peer's copy of a vector over NVLink
   char *sym_slab = nullptr;
   size_t sym_bytes = 0, sym_used = 0, sym_unit = 0;
+  int sym_units[64] = {0};                    // per unit: length of the allocation that starts here, -1 = continuation, 0 = free
   char *sym_peer[64] = {nullptr};
   bool sym_ok = false;
   std::vector<void *> slab_ptrs;              // edgpu_dev_alloc buffers carved from the slab (die with the sector)
@@ -193,3 +195,7 @@ int comm_allreduce_scalar(edgpu_ctx *c, double *d_scalar);
 int comm_transpose_fwd(edgpu_ctx *c, const double *d_x, double *d_vt);          // V(DimUp,qdw) -> Vt(DimDw,qup)
 int comm_transpose_bwd_add(edgpu_ctx *c, const double *d_hvt, double *d_y);     // Hv += (Hvt)^T
 int comm_allgather(edgpu_ctx *c, const double *d_x, double *d_full);
+// grouped point-to-point exchange of doubles: segment p of send (soff[p], scnt[p]) goes to rank p, segment p of recv
+// comes from rank p; the own segment is a device copy
+int comm_exchange(edgpu_ctx *c, const double *send, const int64_t *soff, const int64_t *scnt, double *recv,
+                  const int64_t *roff, const int64_t *rcnt);

@@ -54,7 +54,7 @@
 #define SROW_NB_FAR 4             // far (L2) hops of one kind whose loads are in flight together
 #endif
 #ifndef SROW_NB_IN
-#define SROW_NB_IN 2              // ... for sources inside the shared-memory tile
+#define SROW_NB_IN 1              // ... for sources inside the shared-memory tile (measured: 1 beats 2)
 #endif
 #define SROW_MAXG 64              // groups per chunk: 2^T, T <= 6
 #define SMEM_LIMIT 232448        // 227 KB per CTA on sm_100
@@ -526,26 +526,14 @@ __device__ __forceinline__ double *col_at(double *p, uint32_t n8, uint32_t j) {
   return reinterpret_cast<double *>(reinterpret_cast<char *>(p) + (uint64_t)n8 * (uint64_t)j);
 }
 
-// predicated loads (no control flow around the loads of a hop slot that is switched off)
-__device__ __forceinline__ double ldg_if(const double *p, int on) {
-  double v;
-  asm("{\n.reg .pred q;\nsetp.ne.s32 q, %2, 0;\nmov.f64 %0, 0d0000000000000000;\n@q ld.global.f64 %0, [%1];\n}" : "=d"(v) : "l"(p), "r"(on));
-  return v;
-}
-template <int OFF>
-__device__ __forceinline__ double lds_if(uint32_t saddr, int on) {
-  double v;
-  asm("{\n.reg .pred q;\nsetp.ne.s32 q, %2, 0;\nmov.f64 %0, 0d0000000000000000;\n@q ld.shared.f64 %0, [%1+%3];\n}" : "=d"(v) : "r"(saddr), "r"(on), "n"(OFF));
-  return v;
-}
-
 // All hops of ONE kind of a low group, NB at a time so that their loads are in flight together.  m: the hopped
 // high bits.  BK = the bath bit is occupied in the target group: targets are the columns with the impurity
 // empty, sources lo|1 in class N+1 of the partner group; otherwise targets have the impurity occupied, sources
 // lo&~1 in class N-1.  SM = the partner group is in the shared-memory tile (column stride 32 doubles, immediate
 // offsets), else in global memory (column stride n8 bytes).  pc[kk] = first column of the partner group (tile-local
-// resp. shard-local), par bit kk = parity of the occupied high bits below kk.  Slots beyond the last hop are
-// switched off by predicated loads and a zero amplitude (no divergent control flow, no wasted traffic).
+// resp. shard-local), par bit kk = parity of the occupied high bits below kk.  A slot beyond the last hop gets a
+// zero amplitude and re-reads one line of x that is in L1 anyway (zero column stride): no divergent control flow,
+// no predicate set-up per load, no extra L2 traffic.
 template <int LR, int N, bool BK, bool SM, int NB>
 __device__ __forceinline__ void srow_hops(uint32_t m, const int32_t *pc, const double *vhigh, uint32_t par, const double *src0,
                                           uint32_t n8, double (&acc)[lowtab::binom(LR, N)]) {
@@ -556,19 +544,18 @@ __device__ __forceinline__ void srow_hops(uint32_t m, const int32_t *pc, const d
     constexpr int HB = BK ? lowtab::binom(LR - 1, N) : lowtab::binom(LR - 1, N - 1);
     while (m) {
       const double *p[NB];
-      uint32_t sp[NB];
       double amp[NB];
-      int on[NB];
+      uint32_t st[NB];
 #pragma unroll
       for (int q = 0; q < NB; q++) {
-        on[q] = m != 0;
-        const int kk = on[q] ? __ffs((int)m) - 1 : 0;
+        const bool on = m != 0;
+        const int kk = on ? __ffs((int)m) - 1 : 0;
         m &= m - 1;
-        const uint32_t col = (uint32_t)pc[kk];
-        if (SM) { sp[q] = smem_u32(src0) + col * (SROW_R * 8); p[q] = nullptr; }
-        else { p[q] = col_at(src0, n8, col); sp[q] = 0; }
+        const uint32_t col = on ? (uint32_t)pc[kk] : 0u;
+        st[q] = on ? n8 : 0u;
+        p[q] = SM ? src0 + col * SROW_R : col_at(src0, n8, col);
         const double v = vhigh[kk];
-        amp[q] = on[q] ? (((par >> kk) & 1u) ? -v : v) : 0.0;
+        amp[q] = on ? (((par >> kk) & 1u) ? -v : v) : 0.0;
       }
       double v[NB][HB];
       static_for<NB>([&](auto bc) {
@@ -579,8 +566,8 @@ __device__ __forceinline__ void srow_hops(uint32_t m, const int32_t *pc, const d
           if constexpr (((lo & 1) == 0) == BK) {
             constexpr int j = lowtab::rank(BK ? (lo | 1) : (lo & ~1));
             constexpr int hi = lowtab::half_index(LR, N, i, BK ? 0 : 1);
-            if constexpr (SM) v[q][hi] = lds_if<j * SROW_R * 8>(sp[q], on[q]);
-            else v[q][hi] = ldg_if(col_at(p[q], n8, j), on[q]);
+            if constexpr (SM) v[q][hi] = p[q][j * SROW_R];
+            else v[q][hi] = *col_at(p[q], st[q], j);
           }
         });
       });

@@ -41,6 +41,12 @@ __global__ void __launch_bounds__(RED_THREADS) k_norm2(const double *__restrict_
   s = block_sum(s);
   if (threadIdx.x == 0) partials[blockIdx.x] = s;
 }
+__global__ void __launch_bounds__(RED_THREADS) k_dot(const double *__restrict__ x, const double *__restrict__ y, int64_t n, double *__restrict__ partials) {
+  double s = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) s += x[i] * y[i];
+  s = block_sum(s);
+  if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
 // deterministic fixed-order sum of the per-block partials -> st->red
 __global__ void __launch_bounds__(RED_THREADS) k_finalize(const double *__restrict__ partials, int nb, LancState *st) {
   double s = 0.0;
@@ -75,14 +81,28 @@ __global__ void __launch_bounds__(RED_THREADS) k_lanc_b(double *__restrict__ w, 
   s = block_sum(s);
   if (threadIdx.x == 0) partials[blockIdx.x] = s;
 }
-__global__ void k_post_norm(LancState *st) { st->norm2 = st->red; st->sx = 1.0 / sqrt(st->red); st->cprev = 0.0; }
-__global__ void k_post_alpha(LancState *st, double *alanc, int k) { st->alpha = st->red; alanc[k] = st->red; }
-__global__ void k_post_beta(LancState *st, double *blanc, int k) {
-  double b = sqrt(st->red);
-  st->beta = b;
-  blanc[k + 1] = b;               // blanc(k+1) = b_k ; blanc(1) = 0
-  st->cprev = b * st->sx;         // next step: w = H v_{k+1} - b_k v_k , v_k = sx_old * X_old
-  st->sx = 1.0 / b;               // v_{k+1} = w / b_k
+// what a reduction result means for the recurrence: KIND 0 = |x|^2 of the start vector, 1 = a_k, 2 = b_k^2
+template <int KIND>
+__device__ __forceinline__ void post_scalar(LancState *st, double *coef, int k) {
+  if (KIND == 0) { st->norm2 = st->red; st->sx = 1.0 / sqrt(st->red); st->cprev = 0.0; }
+  if (KIND == 1) { st->alpha = st->red; coef[k] = st->red; }
+  if (KIND == 2) {
+    const double b = sqrt(st->red);
+    st->beta = b;
+    coef[k + 1] = b;              // blanc(k+1) = b_k ; blanc(1) = 0
+    st->cprev = b * st->sx;       // next step: w = H v_{k+1} - b_k v_k , v_k = sx_old * X_old
+    st->sx = 1.0 / b;             // v_{k+1} = w / b_k
+  }
+}
+template <int KIND>
+__global__ void k_post(LancState *st, double *coef, int k) { post_scalar<KIND>(st, coef, k); }
+// single rank: the final reduction and its interpretation in one launch
+template <int KIND>
+__global__ void __launch_bounds__(RED_THREADS) k_finalize_post(const double *__restrict__ partials, int nb, LancState *st, double *coef, int k) {
+  double s = 0.0;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) s += partials[i];
+  s = block_sum(s);
+  if (threadIdx.x == 0) { st->red = s; post_scalar<KIND>(st, coef, k); }
 }
 // second sweep of sp_lanc_eigh (all scalars known): w = sx*t - cprev*xp - (a*sx)*x over xp,
 // vect += (zk*sx)*x
@@ -124,6 +144,19 @@ static int reduce_to_state(edgpu_ctx *c, int nb = RED_BLOCKS) {   // partials ->
   CKL(c);
   return comm_allreduce_scalar(c, &c->d_st->red);
 }
+// partials -> st->red (all ranks) -> Lanczos scalar of kind KIND; one launch on a single rank
+template <int KIND>
+static int reduce_and_post(edgpu_ctx *c, int nb, double *coef, int k) {
+  if (c->nranks == 1) {
+    k_finalize_post<KIND><<<1, RED_THREADS, 0, c->stream>>>(c->d_partials, nb, c->d_st, coef, k);
+    CKL(c);
+    return EDGPU_OK;
+  }
+  TRY(reduce_to_state(c, nb));
+  k_post<KIND><<<1, 1, 0, c->stream>>>(c->d_st, coef, k);
+  CKL(c);
+  return EDGPU_OK;
+}
 
 // one Lanczos step on device; on entry X = c->d_lx (scale st->sx), Xp = c->d_lp; on exit rotated
 static int lanczos_step(edgpu_ctx *c, int k /*0-based*/) {
@@ -131,20 +164,16 @@ static int lanczos_step(edgpu_ctx *c, int k /*0-based*/) {
     // w = sx*(H x) - cprev*xp and the alpha partials come out of the column kernel's epilogue
     int nb = 0;
     TRY(fast_apply_local(c, c->d_lx, c->d_lt, c->d_lp, &nb));
-    TRY(reduce_to_state(c, nb));
+    TRY(reduce_and_post<1>(c, nb, c->d_alanc, k));
   } else {
     TRY(hxv_apply(c, c->d_lx, c->d_lt));
     k_lanc_a<<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(c->d_lt, c->d_lx, c->d_lp, c->nloc, c->d_st, c->d_partials);
     CKL(c);
-    TRY(reduce_to_state(c));
+    TRY(reduce_and_post<1>(c, RED_BLOCKS, c->d_alanc, k));
   }
-  k_post_alpha<<<1, 1, 0, c->stream>>>(c->d_st, c->d_alanc, k);
-  CKL(c);
   k_lanc_b<<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(c->d_lp, c->d_lx, c->nloc, c->d_st, c->d_partials);
   CKL(c);
-  TRY(reduce_to_state(c));
-  k_post_beta<<<1, 1, 0, c->stream>>>(c->d_st, c->d_blanc, k);
-  CKL(c);
+  TRY(reduce_and_post<2>(c, RED_BLOCKS, c->d_blanc, k));
   std::swap(c->d_lx, c->d_lp);    // X <- w (scale 1/b), Xp <- old X
   return EDGPU_OK;
 }
@@ -161,10 +190,7 @@ static int lanczos_begin(edgpu_ctx *c, int ncoef) {
 static int lanczos_norm_start(edgpu_ctx *c) {   // st->sx = 1/|X|, st->norm2 = |X|^2
   k_norm2<<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(c->d_lx, c->nloc, c->d_partials);
   CKL(c);
-  TRY(reduce_to_state(c));
-  k_post_norm<<<1, 1, 0, c->stream>>>(c->d_st);
-  CKL(c);
-  return EDGPU_OK;
+  return reduce_and_post<0>(c, RED_BLOCKS, nullptr, 0);
 }
 
 // ---- host-side tridiagonal QL (implicit shifts, EISPACK tql2 algorithm) -----------------------
@@ -245,6 +271,37 @@ static int tridiag_eig(int n, const double *alanc, const double *blanc, std::vec
   return EDGPU_OK;
 }
 
+// Lowest eigenvalue of the n x n tridiagonal (diagonal a[0..n), sub-diagonal b[1..n)) by Sturm-sequence bisection:
+// O(n) per probe, no eigenvectors.  Used for the running convergence test of sp_lanc_eigh (the reference re-runs a
+// full tql2 with eigenvectors at every step, O(n^3) each); an algorithm independent of tql2 above.
+static double tridiag_lowest(int n, const double *a, const double *b) {
+  double lo = a[0], hi = a[0];
+  for (int i = 0; i < n; i++) {                                    // Gershgorin interval
+    const double r = (i > 0 ? fabs(b[i]) : 0.0) + (i + 1 < n ? fabs(b[i + 1]) : 0.0);
+    lo = std::min(lo, a[i] - r);
+    hi = std::max(hi, a[i] + r);
+  }
+  if (n == 1) return a[0];
+  const double tiny = 1e-300;
+  auto below = [&](double x) {                                     // number of eigenvalues < x
+    int cnt = 0;
+    double q = a[0] - x;
+    if (q < 0.0) cnt++;
+    for (int i = 1; i < n; i++) {
+      if (fabs(q) < tiny) q = (q < 0.0) ? -tiny : tiny;
+      q = a[i] - x - b[i] * b[i] / q;
+      if (q < 0.0) cnt++;
+    }
+    return cnt;
+  };
+  for (int it = 0; it < 200; it++) {
+    const double mid = 0.5 * (lo + hi);
+    if (mid <= lo || mid >= hi) break;                             // interval is one ulp wide
+    if (below(mid) >= 1) hi = mid; else lo = mid;
+  }
+  return 0.5 * (lo + hi);
+}
+
 // ---- sp_lanc_eigh -----------------------------------------------------------------------------
 extern "C" int edgpu_sp_lanc_eigh(edgpu_ctx *c, double *egs, double *vect, int64_t nloc, int nitermax,
                                   int iverbose, double threshold, int ncheck,
@@ -254,6 +311,7 @@ extern "C" int edgpu_sp_lanc_eigh(edgpu_ctx *c, double *egs, double *vect, int64
   if (nitermax < 1) return edgpu_set_err(EDGPU_ERR_INVALID, "sp_lanc_eigh: Nitermax < 1");
   if (ncheck <= 0) ncheck = 10;
   CK(cudaSetDevice(c->device));
+  c->lv_valid = false;
   TRY(lanczos_begin(c, nitermax));
   TRY(vec_alloc(c, &c->d_l0, c->nloc));
   TRY(vec_alloc(c, &c->d_lv, c->nloc));
@@ -276,24 +334,61 @@ extern "C" int edgpu_sp_lanc_eigh(edgpu_ctx *c, double *egs, double *vect, int64
   int nlanc = 0;
   double e_prev = 0.0, a_last = 0.0;
   *egs = 0.0;
-  for (int iter = 1; iter <= nitermax; iter++) {
-    TRY(lanczos_step(c, iter - 1));
-    CK(cudaMemcpyAsync(c->h_pinned, &c->d_st->alpha, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    const double a_ = c->h_pinned[0], b_ = c->h_pinned[1];
-    a_last = a_;
-    if (fabs(b_) < threshold) break;
-    nlanc++;
-    alanc[iter - 1] = a_;
-    blanc[iter] = b_;
-    if (nlanc >= ncheck) {
-      TRY(tridiag_eig(nlanc, alanc.data(), blanc.data(), diag, z));
-      double diff = e_prev - diag[0];
-      e_prev = diag[0];
-      if (iverbose) fprintf(stderr, "edgpu lanczos iter %d E0 %.15g dE %.3e\n", iter, diag[0], diff);
-      if (nlanc > ncheck && fabs(diff) <= threshold) break;
+  // The recurrence runs on the device in blocks of `ncheck` steps; the host looks at a block's coefficients while
+  // the NEXT block is already running (one event wait per block, never per step), and applies the reference's
+  // per-step tests to them: exit on |b_k| < threshold, or on |E0(k) - E0(k-1)| <= threshold once ncheck steps are in.
+  // Steps the device ran past the stopping point are simply not used (the second sweep replays the accepted ones).
+  const size_t cap = (size_t)nitermax + 2;
+  double *h_coef = nullptr;                                        // [2 blocks in flight][alanc | blanc]
+  CK(cudaMallocHost(&h_coef, 4 * cap * sizeof(double)));
+  cudaEvent_t evb[2] = {nullptr, nullptr};
+  int rc = EDGPU_OK;
+  for (int q = 0; q < 2 && !rc; q++) if (cudaEventCreateWithFlags(&evb[q], cudaEventDisableTiming) != cudaSuccess) rc = edgpu_set_err(EDGPU_ERR_CUDA, "event");
+  int enq = 0, seen = 0, nblocks = 0;
+  bool stop = false;
+  auto enqueue_block = [&]() -> int {
+    const int bs = std::min(ncheck, nitermax - enq);
+    for (int k = 0; k < bs; k++) TRY(lanczos_step(c, enq + k));
+    enq += bs;
+    double *h = h_coef + (size_t)(nblocks & 1) * 2 * cap;
+    CK(cudaMemcpyAsync(h, c->d_alanc, (size_t)enq * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(h + cap, c->d_blanc, (size_t)(enq + 1) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaEventRecord(evb[nblocks & 1], c->stream));
+    nblocks++;
+    return EDGPU_OK;
+  };
+  auto examine_block = [&](int blk, int upto) -> int {            // steps [seen, upto) of block blk have landed
+    CK(cudaEventSynchronize(evb[blk & 1]));
+    const double *h = h_coef + (size_t)(blk & 1) * 2 * cap;
+    for (int k = seen; k < upto && !stop; k++) {
+      const double a_ = h[k], b_ = h[cap + k + 1];
+      a_last = a_;
+      if (!(fabs(b_) >= threshold)) { stop = true; break; }        // also stops on NaN
+      nlanc++;
+      alanc[(size_t)k] = a_;
+      blanc[(size_t)k + 1] = b_;
+      if (nlanc >= ncheck) {
+        const double e0 = tridiag_lowest(nlanc, alanc.data(), blanc.data());
+        const double diff = e_prev - e0;
+        e_prev = e0;
+        if (iverbose) fprintf(stderr, "edgpu lanczos iter %d E0 %.15g dE %.3e\n", k + 1, e0, diff);
+        if (nlanc > ncheck && fabs(diff) <= threshold) stop = true;
+      }
     }
+    seen = upto;
+    return EDGPU_OK;
+  };
+  if (!rc) rc = enqueue_block();
+  while (!rc && !stop) {
+    const int prev_blk = nblocks - 1, prev_upto = enq;
+    if (enq < nitermax) rc = enqueue_block();                      // the device keeps working ...
+    if (!rc) rc = examine_block(prev_blk, prev_upto);              // ... while the host tests the block before
+    if (!rc && !stop && seen == nitermax) break;
   }
+  cudaStreamSynchronize(c->stream);
+  for (int q = 0; q < 2; q++) if (evb[q]) cudaEventDestroy(evb[q]);
+  cudaFreeHost(h_coef);
+  if (rc) return rc;
   if (nlanc == 0) { nlanc = 1; alanc[0] = a_last; }
   TRY(tridiag_eig(nlanc, alanc.data(), blanc.data(), diag, z));
   *egs = diag[0];
@@ -321,6 +416,8 @@ extern "C" int edgpu_sp_lanc_eigh(edgpu_ctx *c, double *egs, double *vect, int64
   CKL(c);
   CK(cudaMemcpyAsync(vect, c->d_lv, (size_t)nloc * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  c->lv_valid = true;
+  c->gs_e0 = *egs;
   if (nlanc_out) *nlanc_out = nlanc;
   if (alanc_out) memcpy(alanc_out, alanc.data(), (size_t)nlanc * sizeof(double));
   if (blanc_out) memcpy(blanc_out, blanc.data(), (size_t)nlanc * sizeof(double));
@@ -374,6 +471,21 @@ extern "C" int edgpu_time_lanczos_device(edgpu_ctx *c, int64_t nloc, double *d_v
   return EDGPU_OK;
 }
 
+// <a, b> over the whole sector vector (local shards, all-reduced over the ranks): the reference's
+// dot_product + MPI_Allreduce of its MPI Lanczos, exposed for hosts that keep vectors in HBM.  Collective.
+extern "C" int edgpu_dev_dot(edgpu_ctx *c, int64_t nloc, const double *d_a, const double *d_b, double *out) {
+  if (!c || !c->hstatus) return edgpu_set_err(EDGPU_ERR_INVALID, "dev_dot: Hsector NOT set");
+  if (nloc != c->nloc) return edgpu_set_err(EDGPU_ERR_INVALID, "dev_dot: nloc != vecDim");
+  CK(cudaSetDevice(c->device));
+  k_dot<<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(d_a, d_b, nloc, c->d_partials);
+  CKL(c);
+  TRY(reduce_to_state(c));
+  CK(cudaMemcpyAsync(c->h_pinned, &c->d_st->red, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  *out = c->h_pinned[0];
+  return EDGPU_OK;
+}
+
 // ---- Green's function chains ------------------------------------------------------------------------
 extern "C" int edgpu_gf_set_state(edgpu_ctx *c, int isector, const double *gs, int64_t nloc, double e0) {
   if (!c) return edgpu_set_err(EDGPU_ERR_INVALID, "ctx == NULL");
@@ -391,41 +503,151 @@ extern "C" int edgpu_gf_set_state(edgpu_ctx *c, int isector, const double *gs, i
   return EDGPU_OK;
 }
 
+// The same hand-off without the host: the eigenvector the last edgpu_sp_lanc_eigh left on the device (sector still
+// live) becomes the state of the chains.  Replaces es_return_cvector's gather to the master rank
+// (ED_EIGENSPACE.f90:502-572): every rank keeps its own shard.
+extern "C" int edgpu_gf_set_state_from_eigh(edgpu_ctx *c) {
+  if (!c || !c->hstatus) return edgpu_set_err(EDGPU_ERR_INVALID, "gf_set_state_from_eigh: Hsector NOT set");
+  if (!c->lv_valid || !c->d_lv) return edgpu_set_err(EDGPU_ERR_INVALID, "gf_set_state_from_eigh: no eigenvector of this sector on the device (call edgpu_sp_lanc_eigh first)");
+  CK(cudaSetDevice(c->device));
+  cudaFree(c->d_gs); c->d_gs = nullptr;
+  CK(cudaMalloc(&c->d_gs, (size_t)std::max<int64_t>(c->nloc, 1) * sizeof(double)));
+  CK(cudaMemcpyAsync(c->d_gs, c->d_lv, (size_t)c->nloc * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  c->gs_nup = c->nup; c->gs_ndw = c->ndw; c->gs_nloc = c->nloc;
+  return EDGPU_OK;
+}
+
 // vvinit(j) = sgn * gs(i), |j> = c^+_{iorb,ispin}|i> or c_{iorb,ispin}|i>  (ED_GF_NORMAL.f90:190-209,
 // 264-283), evaluated from the TARGET element: the source word is the target with the orbital's
 // bit flipped back, its position the closed-form rank (no gathered vector, no master-only loop).
 __global__ void k_gf_start(const int32_t *__restrict__ tmap_up, const int32_t *__restrict__ tmap_dw, int64_t tdimup,
-                           int64_t tqdw, int64_t tcoloff, int64_t sdimup, int64_t scoloff,
-                           const double *__restrict__ gs, int iorb, int ispin, int add,
+                           int64_t tqdw, int64_t tcoloff, int64_t sdimup,
+                           const double *__restrict__ gs, int iorb, int add,
                            const uint32_t *__restrict__ binom, double *__restrict__ out) {
+  // spin-up operator: acts inside a column (the local dw columns of the target and of the state coincide)
   const uint32_t bit = 1u << (iorb - 1);
+  (void)tmap_dw; (void)tcoloff;
   for (int64_t jl = blockIdx.y; jl < tqdw; jl += gridDim.y) {
-    int64_t scol = jl;                                    // ispin==1: same local column
-    double csgn = 1.0;
-    bool col_ok = true;
-    if (ispin == 2) {
-      uint32_t r = (uint32_t)tmap_dw[tcoloff + jl];
-      bool has = (r & bit) != 0;
-      col_ok = add ? has : !has;
-      uint32_t m = add ? (r & ~bit) : (r | bit);
-      csgn = hd_sign_below(m, iorb);
-      scol = hd_rank(m, binom) - scoloff;                 // nranks==1 only: scoloff = 0
-    }
     for (int64_t ju = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; ju < tdimup; ju += (int64_t)gridDim.x * blockDim.x) {
       double v = 0.0;
-      if (ispin == 1) {
-        uint32_t r = (uint32_t)tmap_up[ju];
-        bool has = (r & bit) != 0;
-        if (add ? has : !has) {
-          uint32_t m = add ? (r & ~bit) : (r | bit);
-          v = hd_sign_below(m, iorb) * gs[hd_rank(m, binom) + scol * sdimup];
-        }
-      } else if (col_ok) {
-        v = csgn * gs[ju + scol * sdimup];
+      const uint32_t r = (uint32_t)tmap_up[ju];
+      const bool has = (r & bit) != 0;
+      if (add ? has : !has) {
+        const uint32_t m = add ? (r & ~bit) : (r | bit);
+        v = hd_sign_below(m, iorb) * gs[hd_rank(m, binom) + jl * sdimup];
       }
       out[ju + jl * tdimup] = v;
     }
   }
+}
+
+// spin-down operator: target column jl is sgn[jl] times column src[jl] of S (src < 0: zero column)
+__global__ void k_gf_start_dw(const double *__restrict__ S, const int *__restrict__ src, const double *__restrict__ sgn,
+                              int64_t dimup, int64_t tqdw, double *__restrict__ out) {
+  for (int64_t jl = blockIdx.y; jl < tqdw; jl += gridDim.y) {
+    const int sc = src[jl];
+    const double sg = sgn[jl];
+    for (int64_t ju = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; ju < dimup; ju += (int64_t)gridDim.x * blockDim.x)
+      out[ju + jl * dimup] = sc >= 0 ? sg * S[ju + (int64_t)sc * dimup] : 0.0;
+  }
+}
+// gathers whole columns: out(:, i) = in(:, idx[i])
+__global__ void k_gather_cols(const double *__restrict__ in, const int *__restrict__ idx, int64_t dimup, int64_t ncols, double *__restrict__ out) {
+  for (int64_t i = blockIdx.y; i < ncols; i += gridDim.y) {
+    const int64_t sc = idx[i];
+    for (int64_t ju = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; ju < dimup; ju += (int64_t)gridDim.x * blockDim.x)
+      out[ju + i * dimup] = in[ju + sc * dimup];
+  }
+}
+
+// Start vector of a spin-DOWN channel into c->d_lx: c / c^+ on the dw word maps every target column onto ONE column
+// of the state with a sign (the up word is a spectator), so it is a signed column permutation.  On one rank the
+// columns are read in place; on a sharded state each rank receives the columns it needs from their owners in one
+// grouped exchange (the reference gathers the whole state on the master and scatters the result,
+// ED_GF_NORMAL.f90:184-216, ED_EIGENSPACE.f90:540-549).
+static int gf_start_dw(edgpu_ctx *c, int iorb, int add) {
+  const int P = c->nranks, me = c->rank;
+  const uint32_t bit = 1u << (iorb - 1);
+  const int64_t sdimdw = c->h_binom[c->ns * EDGPU_BINOM_LD + c->gs_ndw];
+  const int64_t dimup = c->dimup;                                  // the up basis is the state's
+  std::vector<int32_t> tmap((size_t)c->dimdw);
+  CK(cudaMemcpy(tmap.data(), c->dw.d_map, tmap.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  std::vector<int64_t> gq((size_t)P), goff((size_t)P), tq((size_t)P), toff((size_t)P);
+  for (int p = 0; p < P; p++) { edgpu_split(sdimdw, P, p, &gq[p], &goff[p]); edgpu_split(c->dimdw, P, p, &tq[p], &toff[p]); }
+  auto gs_owner = [&](int64_t sc) { int p = 0; while (p + 1 < P && sc >= goff[(size_t)p + 1]) p++; return p; };
+  // source column (in the state's dw basis) and sign of target column t, -1 if the operator annihilates it
+  auto source_of = [&](int64_t t, double &sg) -> int64_t {
+    const uint32_t r = (uint32_t)tmap[(size_t)t];
+    const bool has = (r & bit) != 0;
+    if (add ? !has : has) return -1;
+    const uint32_t m = add ? (r & ~bit) : (r | bit);
+    sg = hd_sign_below(m, iorb);
+    return hd_rank(m, c->h_binom);
+  };
+  // what I receive, target column by target column (segments ordered by owner), and what every peer receives from me
+  std::vector<int> src((size_t)c->qdw, -1);
+  std::vector<double> sgn((size_t)c->qdw, 0.0);
+  std::vector<int64_t> rcnt((size_t)P, 0), roff((size_t)P, 0), scnt((size_t)P, 0), soff((size_t)P, 0);
+  std::vector<int> sendcols;
+  if (P == 1) {
+    for (int64_t jl = 0; jl < c->qdw; jl++) { double sg = 0.0; const int64_t sc = source_of(jl, sg); src[(size_t)jl] = (int)sc; sgn[(size_t)jl] = sg; }
+  } else {
+    std::vector<int> own((size_t)c->qdw, -1);
+    for (int64_t jl = 0; jl < c->qdw; jl++) {
+      double sg = 0.0;
+      const int64_t sc = source_of(toff[(size_t)me] + jl, sg);
+      if (sc < 0) continue;
+      own[(size_t)jl] = gs_owner(sc); sgn[(size_t)jl] = sg;
+      rcnt[(size_t)own[(size_t)jl]]++;
+    }
+    for (int p = 1; p < P; p++) roff[(size_t)p] = roff[(size_t)p - 1] + rcnt[(size_t)p - 1];
+    std::vector<int64_t> fill(roff);
+    for (int64_t jl = 0; jl < c->qdw; jl++) if (own[(size_t)jl] >= 0) src[(size_t)jl] = (int)fill[(size_t)own[(size_t)jl]]++;
+    for (int q = 0; q < P; q++) {                                  // rank q's requests to me, in q's target order
+      soff[(size_t)q] = (int64_t)sendcols.size();
+      for (int64_t jl = 0; jl < tq[(size_t)q]; jl++) {
+        double sg;
+        const int64_t sc = source_of(toff[(size_t)q] + jl, sg);
+        if (sc >= 0 && gs_owner(sc) == me) sendcols.push_back((int)(sc - goff[(size_t)me]));
+      }
+      scnt[(size_t)q] = (int64_t)sendcols.size() - soff[(size_t)q];
+    }
+  }
+  int *d_src = nullptr, *d_idx = nullptr;
+  double *d_sgn = nullptr, *d_sbuf = nullptr, *d_rbuf = nullptr;
+  int rc = EDGPU_OK;
+  auto fail = [&](const char *what) { rc = edgpu_set_err(EDGPU_ERR_CUDA, "gf_start_dw: %s", what); };
+  const size_t nq = (size_t)std::max<int64_t>(c->qdw, 1);
+  if (cudaMalloc(&d_src, nq * sizeof(int)) != cudaSuccess || cudaMalloc(&d_sgn, nq * sizeof(double)) != cudaSuccess) fail("cudaMalloc");
+  if (!rc && (cudaMemcpy(d_src, src.data(), (size_t)c->qdw * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
+              cudaMemcpy(d_sgn, sgn.data(), (size_t)c->qdw * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess)) fail("upload");
+  const double *S = c->d_gs;
+  if (!rc && P > 1) {
+    const int64_t nsend = (int64_t)sendcols.size(), nrecv = roff[(size_t)P - 1] + rcnt[(size_t)P - 1];
+    if (cudaMalloc(&d_idx, (size_t)std::max<int64_t>(nsend, 1) * sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&d_sbuf, (size_t)std::max<int64_t>(nsend * dimup, 1) * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&d_rbuf, (size_t)std::max<int64_t>(nrecv * dimup, 1) * sizeof(double)) != cudaSuccess) fail("cudaMalloc (exchange)");
+    if (!rc && nsend) {
+      if (cudaMemcpy(d_idx, sendcols.data(), (size_t)nsend * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) fail("upload (exchange)");
+      dim3 grid((unsigned)((dimup + 255) / 256), (unsigned)std::min<int64_t>(nsend, 32768));
+      if (!rc) { k_gather_cols<<<grid, 256, 0, c->stream>>>(c->d_gs, d_idx, dimup, nsend, d_sbuf); c->launches++; }
+    }
+    if (!rc) {
+      for (int p = 0; p < P; p++) { soff[(size_t)p] *= dimup; scnt[(size_t)p] *= dimup; roff[(size_t)p] *= dimup; rcnt[(size_t)p] *= dimup; }
+      rc = comm_exchange(c, d_sbuf, soff.data(), scnt.data(), d_rbuf, roff.data(), rcnt.data());
+    }
+    S = d_rbuf;
+  }
+  if (!rc && c->qdw > 0) {
+    dim3 grid((unsigned)((dimup + 255) / 256), (unsigned)std::min<int64_t>(c->qdw, 32768));
+    k_gf_start_dw<<<grid, 256, 0, c->stream>>>(S, d_src, d_sgn, dimup, c->qdw, c->d_lx);
+    c->launches++;
+    if (cudaGetLastError() != cudaSuccess) fail("k_gf_start_dw launch");
+  }
+  if (cudaStreamSynchronize(c->stream) != cudaSuccess && !rc) fail("sync");
+  cudaFree(d_src); cudaFree(d_sgn); cudaFree(d_idx); cudaFree(d_sbuf); cudaFree(d_rbuf);
+  return rc;
 }
 
 extern "C" int edgpu_gf_chains(edgpu_ctx *c, int nchains, const int *iorb, const int *ispin,
@@ -440,8 +662,6 @@ extern "C" int edgpu_gf_chains(edgpu_ctx *c, int nchains, const int *iorb, const
     for (int k = 0; k < nlanc_max; k++) { alanc[(size_t)ch * nlanc_max + k] = 0.0; blanc[(size_t)ch * nlanc_max + k] = 0.0; }
     if (iorb[ch] < 1 || iorb[ch] > c->dp.norb || ispin[ch] < 1 || ispin[ch] > 2 || (addrem[ch] != 1 && addrem[ch] != -1))
       return edgpu_set_err(EDGPU_ERR_INVALID, "gf_chains: bad channel %d", ch);
-    if (ispin[ch] == 2 && c->nranks > 1)
-      return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "gf_chains: spin-down operators on a sharded state need a column exchange (next row of SURVEY 8f)");
   }
   for (int ch = 0; ch < nchains; ch++) {
     if (done[ch]) continue;
@@ -462,12 +682,17 @@ extern "C" int edgpu_gf_chains(edgpu_ctx *c, int nchains, const int *iorb, const
       const int nl = (int)std::min<int64_t>(jdim, nlanc_max);   // nlanc=min(jdim,lanc_nGFiter), :219
       rc = lanczos_begin(c, nl);
       if (rc) break;
-      const int64_t sdimup = c->h_binom[c->ns * EDGPU_BINOM_LD + c->gs_nup];
-      dim3 grid((unsigned)((c->dimup + 255) / 256), (unsigned)(c->qdw < 32768 ? c->qdw : 32768));
-      k_gf_start<<<grid, 256, 0, c->stream>>>(c->up.d_map, c->dw.d_map, c->dimup, c->qdw, c->coloff, sdimup, 0,
-                                              c->d_gs, iorb[ch2], ispin[ch2], addrem[ch2] == 1 ? 1 : 0, c->d_binom, c->d_lx);
-      c->launches++;
-      if (cudaGetLastError() != cudaSuccess) { rc = edgpu_set_err(EDGPU_ERR_CUDA, "k_gf_start launch failed"); break; }
+      if (ispin[ch2] == 2) {
+        rc = gf_start_dw(c, iorb[ch2], addrem[ch2] == 1 ? 1 : 0);
+        if (rc) break;
+      } else {
+        const int64_t sdimup = c->h_binom[c->ns * EDGPU_BINOM_LD + c->gs_nup];
+        dim3 grid((unsigned)((c->dimup + 255) / 256), (unsigned)(c->qdw < 32768 ? c->qdw : 32768));
+        k_gf_start<<<grid, 256, 0, c->stream>>>(c->up.d_map, c->dw.d_map, c->dimup, c->qdw, c->coloff, sdimup,
+                                                c->d_gs, iorb[ch2], addrem[ch2] == 1 ? 1 : 0, c->d_binom, c->d_lx);
+        c->launches++;
+        if (cudaGetLastError() != cudaSuccess) { rc = edgpu_set_err(EDGPU_ERR_CUDA, "k_gf_start launch failed"); break; }
+      }
       rc = tridiag_device(c, nl, threshold, alanc + (size_t)ch2 * nlanc_max, blanc + (size_t)ch2 * nlanc_max);
       if (rc) break;
       if (cudaMemcpy(&norm2[ch2], &c->d_st->norm2, sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) {

@@ -83,6 +83,32 @@ extern "C" int edgpu_selftest_nonlocal_row(const edgpu_params *p, uint32_t mup, 
   return hd_nonlocal_row(d, mup, mdw, cup, cdw, val);
 }
 
+// max |a - b| and max |a| of two device vectors (full-size comparisons without a host round trip)
+__global__ void k_maxabsdiff(const double *__restrict__ a, const double *__restrict__ b, int64_t n, unsigned long long *out) {
+  double md = 0.0, ma = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    md = fmax(md, fabs(a[i] - b[i]));
+    ma = fmax(ma, fabs(a[i]));
+  }
+  if (md != md) md = 1e300;                                        // NaN counts as a mismatch
+  for (int o = 16; o > 0; o >>= 1) { md = fmax(md, __shfl_xor_sync(0xffffffffu, md, o)); ma = fmax(ma, __shfl_xor_sync(0xffffffffu, ma, o)); }
+  if ((threadIdx.x & 31) == 0) {                                   // non-negative doubles order like their bit patterns
+    atomicMax(&out[0], (unsigned long long)__double_as_longlong(md));
+    atomicMax(&out[1], (unsigned long long)__double_as_longlong(ma));
+  }
+}
+extern "C" int edgpu_selftest_dev_maxabsdiff(const double *d_a, const double *d_b, int64_t n, double *maxdiff, double *maxabs) {
+  unsigned long long *d_out = nullptr, h[2] = {0, 0};
+  if (cudaMalloc(&d_out, 16) != cudaSuccess) return 1;
+  cudaMemset(d_out, 0, 16);
+  k_maxabsdiff<<<1184, 256>>>(d_a, d_b, n, d_out);
+  if (cudaMemcpy(h, d_out, 16, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaFree(d_out); return 1; }
+  cudaFree(d_out);
+  memcpy(maxdiff, &h[0], 8);
+  memcpy(maxabs, &h[1], 8);
+  return 0;
+}
+
 // Sharded fast path on ONE device: `nranks` contexts stand in for the ranks (no NCCL; each "rank" pulls its halo
 // from the others' shards through ordinary device pointers).  Exercises exactly the kernels and plans of the
 // multi-GPU path -- whole / cut low groups, group records, the halo copy kernel, the source lists of the column

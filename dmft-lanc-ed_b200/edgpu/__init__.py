@@ -32,10 +32,10 @@ ABI_SYMBOLS = [
     "edgpu_device_count", "edgpu_comm_unique_id", "edgpu_comm_init", "edgpu_comm_finalize",
     "edgpu_get_sector", "edgpu_get_nup_ndw", "edgpu_split", "edgpu_transpose_plan", "edgpu_build_hv_sector",
     "edgpu_delete_hv_sector", "edgpu_vecdim_hv_sector", "edgpu_hxv", "edgpu_sphtimesv",
-    "edgpu_hxv_device", "edgpu_sp_lanc_eigh", "edgpu_sp_lanc_tridiag", "edgpu_gf_set_state",
+    "edgpu_hxv_device", "edgpu_sp_lanc_eigh", "edgpu_sp_lanc_tridiag", "edgpu_gf_set_state", "edgpu_gf_set_state_from_eigh",
     "edgpu_gf_chains", "edgpu_add_to_lanczos_gf", "edgpu_get_dims", "edgpu_get_sector_map",
     "edgpu_get_csr", "edgpu_get_diag", "edgpu_dev_alloc", "edgpu_dev_free", "edgpu_dev_upload",
-    "edgpu_dev_download", "edgpu_dev_fill_bench_vector", "edgpu_sync", "edgpu_time_hxv_device",
+    "edgpu_dev_download", "edgpu_dev_fill_bench_vector", "edgpu_sync", "edgpu_dev_dot", "edgpu_time_hxv_device",
     "edgpu_time_lanczos_device", "edgpu_launch_count", "edgpu_time_hxv_passes",
 ]
 
@@ -88,6 +88,7 @@ def lib():
                                          c_ip, c_dp, c_dp]
         L.edgpu_sp_lanc_tridiag.argtypes = [C.c_void_p, c_dp, C.c_int64, c_dp, c_dp, C.c_int, C.c_double]
         L.edgpu_gf_set_state.argtypes = [C.c_void_p, C.c_int, c_dp, C.c_int64, C.c_double]
+        L.edgpu_gf_set_state_from_eigh.argtypes = [C.c_void_p]
         L.edgpu_gf_chains.argtypes = [C.c_void_p, C.c_int, c_ip, c_ip, c_ip, C.c_int, C.c_double, c_dp, c_ip, c_dp, c_dp]
         L.edgpu_add_to_lanczos_gf.argtypes = [C.c_double, C.c_double, C.c_double, c_dp, c_dp, C.c_int, C.c_int,
                                               c_dp, C.c_int, c_dp]
@@ -101,6 +102,7 @@ def lib():
         L.edgpu_dev_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
         L.edgpu_dev_fill_bench_vector.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]
         L.edgpu_sync.argtypes = [C.c_void_p]
+        L.edgpu_dev_dot.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, c_dp]
         L.edgpu_time_hxv_device.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, c_dp]
         L.edgpu_time_lanczos_device.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, c_dp]
         L.edgpu_launch_count.argtypes = [C.c_void_p, c_i64p]
@@ -283,6 +285,10 @@ class Solver:
         gs = np.ascontiguousarray(gs, dtype=np.float64)
         _ck(lib().edgpu_gf_set_state(self.h, isector, _dp(gs), gs.size, e0))
 
+    def gf_set_state_from_eigh(self):
+        """Keep the eigenvector of the last sp_lanc_eigh (sector still live) on the device as the chains' state."""
+        _ck(lib().edgpu_gf_set_state_from_eigh(self.h))
+
     def gf_chains(self, channels, nlanc_max=200, threshold=1e-12):
         """channels: list of (iorb, ispin, +1|-1).  Returns list of dicts(norm2, nlanc, alanc, blanc)."""
         n = len(channels)
@@ -341,6 +347,17 @@ class Solver:
 
     def sync(self):
         _ck(lib().edgpu_sync(self.h))
+
+    def dev_dot(self, d_a, d_b):
+        """<a, b> over the whole sector vector (all ranks): collective."""
+        out = C.c_double(0.0)
+        _ck(lib().edgpu_dev_dot(self.h, self.nloc, d_a, d_b, C.byref(out)))
+        return out.value
+
+    def dev_download_slice(self, p, offset_elems, arr):
+        """arr <- device doubles [offset, offset + arr.size) of buffer p."""
+        q = C.c_void_p(p.value + 8 * int(offset_elems))
+        _ck(lib().edgpu_dev_download(self.h, arr.ctypes.data, q, arr.nbytes))
 
     def time_hxv_device(self, d_v, d_hv, reps):
         ms = C.c_double(0.0)

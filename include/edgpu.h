@@ -133,10 +133,16 @@ int  edgpu_sp_lanc_tridiag(edgpu_ctx *c, const double *vin, int64_t nloc, double
 /* Keeps the ground state of sector (nup,ndw) on device for the chains; gs is the local shard.
  * Replaces es_return_cvector + the master-only c/cdg loops (:184-216, :259-290). */
 int  edgpu_gf_set_state(edgpu_ctx *c, int isector, const double *gs, int64_t nloc, double e0);
+/* The same hand-off without the host round trip: the eigenvector that the last edgpu_sp_lanc_eigh left on the
+ * device (its sector must still be live) becomes the state of the chains; every rank keeps its own shard.
+ * Replaces es_return_cvector's gather to the master rank (ED_EIGENSPACE.f90:502-572). */
+int  edgpu_gf_set_state_from_eigh(edgpu_ctx *c);
 /* Batched chains: for ch < nchains applies c^+ (addrem[ch]=+1) or c (addrem[ch]=-1) of orbital
  * iorb[ch] (1-based) and spin ispin[ch] (1=up,2=dw) to the stored state on device, normalises,
  * and runs nlanc_max Lanczos steps in the target sector (chains with the same target sector
- * share one build_Hv_sector).  Outputs per chain: norm2[ch], nlanc[ch] (=min(jdim,nlanc_max), 0 if
+ * share one build_Hv_sector).  On a sharded state a spin-up operator acts inside the local columns;
+ * a spin-down operator is a signed permutation of i_dw columns and is applied through one grouped
+ * column exchange between the ranks (no gather on a master rank).  Outputs per chain: norm2[ch], nlanc[ch] (=min(jdim,nlanc_max), 0 if
  * the target sector does not exist), alanc/blanc rows of length nlanc_max. */
 int  edgpu_gf_chains(edgpu_ctx *c, int nchains, const int *iorb, const int *ispin,
                      const int *addrem, int nlanc_max, double threshold,
@@ -167,6 +173,9 @@ int  edgpu_dev_upload(edgpu_ctx *c, void *dptr, const void *host, int64_t nbytes
 int  edgpu_dev_download(edgpu_ctx *c, void *host, const void *dptr, int64_t nbytes);
 int  edgpu_dev_fill_bench_vector(edgpu_ctx *c, double *d_v, int64_t nloc, int64_t global_offset);
 int  edgpu_sync(edgpu_ctx *c);
+/* <a, b> of two device-resident sector vectors (local shards of length nloc; the partial sums are all-reduced over
+ * the ranks, so the call is collective): dot_product + MPI_Allreduce of the reference's MPI Lanczos. */
+int  edgpu_dev_dot(edgpu_ctx *c, int64_t nloc, const double *d_a, const double *d_b, double *out);
 /* Times `reps` back-to-back device-resident H*v with CUDA events on the engine's stream;
  * ms_total = elapsed over all reps.  ms_kernel[k] (k < 8, may be NULL) = per-kernel-class totals. */
 int  edgpu_time_hxv_device(edgpu_ctx *c, int64_t nloc, const double *d_v, double *d_hv,

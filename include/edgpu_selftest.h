@@ -37,6 +37,8 @@ int edgpu_selftest_srow_plan(const edgpu_params *p, int ndw, int nranks, int ran
  * device pointers instead of NVLink mappings); x, y are full host vectors.  Test instrumentation only. */
 int edgpu_selftest_sharded_hxv(const edgpu_params *p, int nup, int ndw, int nranks, int64_t srow_lr, int64_t srow_t,
                                int64_t col_cluster, const double *x, double *y);
+/* GPU: max |a - b| and max |a| of two device vectors of n doubles (full-size comparisons on the device) */
+int edgpu_selftest_dev_maxabsdiff(const double *d_a, const double *d_b, int64_t n, double *maxdiff, double *maxabs);
 #ifdef __cplusplus
 }
 #endif

@@ -524,6 +524,52 @@ void orc_spmatvec_block(const orc_sector *s, const double *v_full, double *hv_bl
       for (int64_t jj = s->hnd.rowptr[i]; jj < s->hnd.rowptr[i + 1]; jj++)
         hv_block[i] = hv_block[i] + s->hnd.vals[jj] * v_full[s->hnd.cols[jj]];
 }
+/* The same loops as orc_spmatvec_block (same summation order, same results) for a caller that holds only the
+ * columns of v the block touches: colidx[0..ncolidx) = ascending global i_dw indices, xcols = those columns, DimUp
+ * values each, in that order.  Used for spot checks of sectors whose full vector does not fit the host
+ * (Ns = 18: 19 GB).  Returns 0, or 1 if a needed column is missing. */
+static int64_t col_slot(const int64_t *colidx, int64_t n, int64_t col) {
+  int64_t lo = 0, hi = n - 1;
+  while (lo <= hi) {
+    int64_t mid = (lo + hi) / 2;
+    if (colidx[mid] == col) return mid;
+    if (colidx[mid] < col) lo = mid + 1; else hi = mid - 1;
+  }
+  return -1;
+}
+int orc_spmatvec_block_cols(const orc_sector *s, const int64_t *colidx, int64_t ncolidx, const double *xcols,
+                            double *hv_block) {
+  const int64_t du = s->dimup, c0 = s->istart / du, c1 = s->iend / du;
+  const int64_t nloc = s->iend - s->istart, sh = s->ishift;
+  if (s->ctx->jhflag) return 1;                       /* spH0nd needs the whole vector */
+  for (int64_t i = 0; i < nloc; i++) hv_block[i] = 0.0;
+  for (int64_t idw = c0; idw < c1; idw++) {
+    int64_t p = col_slot(colidx, ncolidx, idw);
+    if (p < 0) return 1;
+    for (int64_t iup = 0; iup < du; iup++) {
+      int64_t i = iup + idw * du - sh;
+      hv_block[i] = hv_block[i] + s->h0d[i] * xcols[iup + p * du];
+    }
+  }
+  for (int64_t iup = 0; iup < du; iup++)
+    for (int64_t idw = c0; idw < c1; idw++) {
+      int64_t i = iup + idw * du - sh;
+      for (int64_t jj = s->hdw.rowptr[idw]; jj < s->hdw.rowptr[idw + 1]; jj++) {
+        int64_t p = col_slot(colidx, ncolidx, s->hdw.cols[jj]);
+        if (p < 0) return 1;
+        hv_block[i] = hv_block[i] + s->hdw.vals[jj] * xcols[iup + p * du];
+      }
+    }
+  for (int64_t idw = c0; idw < c1; idw++) {
+    int64_t p = col_slot(colidx, ncolidx, idw);
+    for (int64_t iup = 0; iup < du; iup++) {
+      int64_t i = iup + idw * du - sh;
+      for (int64_t jj = s->hup.rowptr[iup]; jj < s->hup.rowptr[iup + 1]; jj++)
+        hv_block[i] = hv_block[i] + s->hup.vals[jj] * xcols[s->hup.cols[jj] + p * du];
+    }
+  }
+  return 0;
+}
 typedef struct { orc_sector **secs; const double *v; double **out; } blk_job;
 static void blk_rank(int r, void *arg) {
   blk_job *b = (blk_job *)arg;

@@ -89,6 +89,9 @@ void orc_directmatvec_main(const orc_sector *s, int64_t nloc, const double *v, d
 void orc_spmatvec_block(const orc_sector *s, const double *v_full, double *hv_block);
 int64_t orc_spmatvec_blocks_mt(orc_sector **secs, int nblk, int nthreads, const double *v_full,
                                double **hv_blocks);
+/* same loops, for a caller that holds only the columns of v the block touches (ascending colidx) */
+int orc_spmatvec_block_cols(const orc_sector *s, const int64_t *colidx, int64_t ncolidx, const double *xcols,
+                            double *hv_block);
 /* Emulation of nranks MPI ranks in one process; v/hv are the concatenated shards (= the
  * serial vector, because the split is by contiguous i_dw column blocks). */
 void orc_spmatvec_mpi_main_all(const orc_ctx *c, int nup, int ndw, int nranks, int nthreads,

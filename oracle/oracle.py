@@ -71,6 +71,7 @@ def lib():
         L.orc_spmatvec_main.argtypes = [C.POINTER(_Sector), C.c_int64, c_dp, c_dp]
         L.orc_directmatvec_main.argtypes = [C.POINTER(_Sector), C.c_int64, c_dp, c_dp]
         L.orc_spmatvec_block.argtypes = [C.POINTER(_Sector), c_dp, c_dp]
+        L.orc_spmatvec_block_cols.argtypes = [C.POINTER(_Sector), C.POINTER(C.c_int64), C.c_int64, c_dp, c_dp]
         L.orc_spmatvec_blocks_mt.restype = C.c_int64
         L.orc_spmatvec_blocks_mt.argtypes = [C.POINTER(C.POINTER(_Sector)), C.c_int, C.c_int, c_dp, C.POINTER(c_dp)]
         L.orc_spmatvec_mpi_main_all.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_dp, c_dp]
@@ -188,6 +189,25 @@ class Sector:
         v = _f64(v_full)
         hv = np.empty(self.nloc)
         lib().orc_spmatvec_block(self.p, _dp(v), _dp(hv))
+        return hv
+
+    def block_columns(self):
+        """Ascending global i_dw indices of the columns of v that spmatvec_block reads for this block."""
+        rp, cols, _ = self.hdw()
+        c0, c1 = self.istart // self.dimup, self.iend // self.dimup
+        need = set(range(c0, c1))
+        for j in range(c0, c1):
+            need.update(int(x) for x in cols[rp[j]:rp[j + 1]])
+        return np.array(sorted(need), dtype=np.int64)
+
+    def spmatvec_block_cols(self, colidx, xcols):
+        """spmatvec_block for a caller that holds only the needed columns (xcols[k] = column colidx[k])."""
+        colidx = np.ascontiguousarray(colidx, dtype=np.int64)
+        x = _f64(np.ascontiguousarray(xcols).reshape(-1))
+        assert x.size == colidx.size * self.dimup
+        hv = np.empty(self.nloc)
+        rc = lib().orc_spmatvec_block_cols(self.p, colidx.ctypes.data_as(C.POINTER(C.c_int64)), colidx.size, _dp(x), _dp(hv))
+        assert rc == 0
         return hv
 
     def directmatvec(self, v):
@@ -336,6 +356,14 @@ def tql2(d, e):
     rc = lib().orc_tql2(n, _dp(dd), _dp(ee), _dp(z))
     assert rc == 0
     return dd, z.reshape((n, n), order="F")
+
+
+def spmatvec_mpi_prebuilt(sectors, v, hv, nthreads):
+    """spMatVec_MPI_main (ED_HAMILTONIAN_SPARSE_HxV.f90:568-694) for all ranks of a split at once, INCLUDING the two
+    vector_transpose_MPI exchanges, on pre-built per-rank sectors; rank r runs on thread r % nthreads."""
+    n = len(sectors)
+    arr = (C.POINTER(_Sector) * n)(*[s.p for s in sectors])
+    lib().orc_spmatvec_mpi_main_prebuilt(arr, n, nthreads, _dp(v), _dp(hv))
 
 
 def spmatvec_blocks_mt(sectors, v_full, outs, nthreads):

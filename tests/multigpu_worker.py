@@ -82,22 +82,24 @@ def main():
             dist.all_reduce(ov)
             check("vec", abs(abs(ov[0].item()) - 1) < 1e-10 and abs(ov[1].item() - 1) < 1e-12, "overlap %.3e" % (abs(ov[0].item()) - 1))
             s.delete_Hv_sector()
-            # GF chains from the sharded ground state
+            # GF chains from the sharded ground state: spin-up channels act inside the local columns, spin-down
+            # channels are a signed column permutation (one grouped exchange between the ranks)
             s.gf_set_state(isec, vec_ref[sl], e_ref)
-            chans = [(io, 1, sg) for io in range(1, cfg["norb"] + 1) for sg in (1, -1)]
+            chans = [(io, sp, sg) for io in range(1, cfg["norb"] + 1) for sp in (1, 2) for sg in (1, -1)]
             res = s.gf_chains(chans, nlanc_max=60)
             k = 0
             for io in range(1, cfg["norb"] + 1):
-                rr = o.build_gf_normal(sec[0], sec[1], vec_ref, e_ref, io, ngfiter=60, lmats=8, lreal=8)
-                for p in range(2):
-                    r, rc = res[k], rr["chains"][p]
-                    k += 1
-                    check("gf nlanc", r["nlanc"] == rc["nlanc"])
-                    if rc["nlanc"]:
-                        m = min(20, rc["nlanc"])
-                        check("gf norm2", abs(r["norm2"] - rc["norm2"]) < 1e-12)
-                        check("gf a", np.abs(r["alanc"][:m] - rc["alanc"][:m]).max() < 1e-8)
-                        check("gf b", np.abs(r["blanc"][:m] - rc["blanc"][:m]).max() < 1e-8)
+                for sp in (1, 2):
+                    rr = o.build_gf_normal(sec[0], sec[1], vec_ref, e_ref, io, ispin=sp, ngfiter=60, lmats=8, lreal=8)
+                    for p in range(2):
+                        r, rc = res[k], rr["chains"][p]
+                        k += 1
+                        check("gf nlanc", r["nlanc"] == rc["nlanc"], "%d vs %d" % (r["nlanc"], rc["nlanc"]))
+                        if rc["nlanc"]:
+                            m = min(20, rc["nlanc"])
+                            check("gf norm2 spin %d" % sp, abs(r["norm2"] - rc["norm2"]) < 1e-12)
+                            check("gf a spin %d" % sp, np.abs(r["alanc"][:m] - rc["alanc"][:m]).max() < 1e-8)
+                            check("gf b spin %d" % sp, np.abs(r["blanc"][:m] - rc["blanc"][:m]).max() < 1e-8)
         s.close()
     t = torch.tensor([len(fails)], device="cuda")
     dist.all_reduce(t)

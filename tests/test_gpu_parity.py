@@ -233,6 +233,42 @@ def test_gf_chains_g_and_sigma(name):
         s.close()
 
 
+@pytest.mark.parametrize("name", ["C1", "C4"])
+def test_gf_chains_spin_down_and_device_state(name):
+    """Spin-down channels (c / c^+ on the dw word = signed column permutation of the state) and the device-resident
+    hand-off of the ground state from sp_lanc_eigh to the chains (no host round trip): norm2, a_n, b_n against the
+    oracle's lanc_build_gf_normal_main with ispin = 2 (Nspin = 1 parameters, so G_dw = G_up is an extra check)."""
+    cfg, o = make_oracle(name)
+    nup, ndw = cfg["nup"], cfg["ndw"]
+    s = _solver(cfg)
+    try:
+        with o.sector(nup, ndw) as os_:
+            v0 = np.ones(os_.dim) / np.sqrt(os_.dim)
+            e_ref, gs_ref, _, _ = os_.lanc_eigh(v0=v0)
+        isec = s.get_sector(nup, ndw)
+        s.build_Hv_sector(isec)
+        e0, vec, _, _ = s.sp_lanc_eigh(v0)
+        s.gf_set_state_from_eigh()                              # eigenvector stays on the device
+        s.delete_Hv_sector()
+        sign = 1.0 if vec @ gs_ref > 0 else -1.0                 # the chains are invariant under gs -> -gs
+        chans = [(io, sp, ar) for io in range(1, cfg["norb"] + 1) for sp in (1, 2) for ar in (1, -1)]
+        res = s.gf_chains(chans, nlanc_max=120)
+        k = 0
+        for io in range(1, cfg["norb"] + 1):
+            for sp in (1, 2):
+                ref = o.build_gf_normal(nup, ndw, sign * vec, e0, io, ispin=sp, ngfiter=120, lmats=16, lreal=8)
+                for p_ in range(2):
+                    r, rc = res[k], ref["chains"][p_]
+                    k += 1
+                    assert r["nlanc"] == rc["nlanc"]
+                    assert abs(r["norm2"] - rc["norm2"]) < 1e-12
+                    assert np.abs(r["alanc"][:25] - rc["alanc"][:25]).max() < 1e-8
+                    assert np.abs(r["blanc"][:25] - rc["blanc"][:25]).max() < 1e-8
+        assert abs(e0 - e_ref) < 1e-12 * abs(e_ref)
+    finally:
+        s.close()
+
+
 def test_golden_fixtures_on_gpu():
     gold = np.load(os.path.join(ROOT, "tests", "golden", "c1_golden.npz"))
     cfg = configs.config("C1")
@@ -307,11 +343,13 @@ def test_full_size_properties(name):
             s.close()
     scale = np.abs(outs[True]).max()
     assert np.abs(outs[True] - outs[False]).max() < 1e-12 * scale
-    # spot check one column block against the oracle (rank 0 of 256 = ~13-50 columns)
+    # spot checks against the oracle's spMatVec_main loops: column blocks spread over the whole i_dw range
+    # (ranks 0, 85, 170, 255 of 256 = ~13-50 columns each, both ends included)
     _, o = make_oracle(name)
-    with o.sector(nup, ndw, 0, 256) as blk:
-        ref = blk.spmatvec_block(x)
-        assert np.abs(outs[True][:blk.nloc] - ref).max() < 1e-13 * scale
+    for r in (0, 85, 170, 255):
+        with o.sector(nup, ndw, r, 256) as blk:
+            ref = blk.spmatvec_block(x)
+            assert np.abs(outs[True][blk.ishift:blk.ishift + blk.nloc] - ref).max() < 1e-13 * scale
 
 
 TILED_CASES = [("C1", (4, 4), {}), ("C1", (5, 3), {}), ("C1", (3, 6), {"col_h": 2, "tile_h": 3}),
@@ -350,7 +388,7 @@ FAST_CASES = [("C1", (4, 4), {}), ("C1", (5, 3), {"srow_t": 1}), ("C1", (3, 6), 
               ("NS12", (6, 6), {"srow_t": 4}), ("NS12", (7, 4), {}), ("NS12", (6, 6), {"no_uniform": 1, "srow_lr": 4}), ("NS12", (6, 6), {"no_uniform": 2}),
               ("NS6", (3, 3), {}), ("NS6", (3, 3), {"srow_lr": 4, "srow_t": 1}), ("NS10V", (5, 5), {"srow_t": 3}),
               ("NS12V", (6, 5), {"srow_lr": 4, "srow_t": 4}), ("NS10V", (7, 2), {}), ("NS10", (9, 1), {}),
-              ("NS12", (6, 0), {}), ("NS12", (6, 12), {}), ("NS14", (7, 7), {}), ("NS14V", (6, 8), {"srow_t": 3}),
+              ("NS12", (6, 0), {}), ("NS12", (6, 12), {}), ("NS14", (7, 7), {}), ("NS14V", (7, 6), {"srow_t": 3}),
               # two-CTA cluster column kernel (columns too long for one SM; forced here on small ones)
               ("C1", (4, 4), {"col_cluster": 1}), ("NS12", (6, 6), {"col_cluster": 1}), ("NS12", (7, 4), {"col_cluster": 1, "no_uniform": 1}),
               ("NS10V", (5, 5), {"col_cluster": 1}), ("NS12", (5, 6), {"col_cluster": 1, "srow_lr": 4})]
@@ -459,6 +497,45 @@ def test_fast_equals_gather_full_size(name):
     scale = np.abs(ref).max()
     assert np.abs(ref - out[(edgpu.ALGO_FAST, False)]).max() < 1e-12 * scale
     assert np.abs(ref - out[(edgpu.ALGO_FAST, True)]).max() < 1e-12 * scale
+
+
+def test_c5_ns18_on_one_gpu():
+    """BASELINE configs[4]: Ns=18, sector 9:9, dim 2 363 904 400 (19 GB per vector) on ONE B200.  The fast path
+    (aligned-chunk row kernel + 2-CTA cluster column kernel) equals the one-pass gather kernel on the whole vector
+    (compared on the device), and both ends plus the middle of the i_dw range agree with the oracle's spMatVec_main
+    loops (oracle/, sparse-column form: the full vector does not have to exist on the host)."""
+    import ctypes as C
+    cfg = configs.config("C5")
+    _, o = make_oracle("C5")
+    s = _solver(cfg, False, edgpu.ALGO_FAST)
+    try:
+        s.build_Hv_sector(s.get_sector(cfg["nup"], cfg["ndw"]))
+        n = s.nloc
+        assert n == 2363904400
+        dx, dyf, dyg = s.dev_alloc(8 * n), s.dev_alloc(8 * n), s.dev_alloc(8 * n)
+        s.dev_fill_bench_vector(dx, n, 0)
+        s.hxv_device(dx, dyf)
+        s.set_option("hxv_algo", edgpu.ALGO_GATHER)
+        s.hxv_device(dx, dyg)
+        s.sync()
+        T = edgpu.selftest_lib()
+        T.edgpu_selftest_dev_maxabsdiff.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        md, ma = C.c_double(0), C.c_double(0)
+        assert T.edgpu_selftest_dev_maxabsdiff(dyf, dyg, n, C.byref(md), C.byref(ma)) == 0
+        assert ma.value > 1.0 and md.value < 1e-12 * ma.value, (md.value, ma.value)
+        for j in (0, 1, s.dimdw // 3, s.dimdw // 2, s.dimdw - 2, s.dimdw - 1):
+            with o.sector(cfg["nup"], cfg["ndw"], j, s.dimdw) as blk:
+                ci = blk.block_columns()
+                xc = np.stack([configs.bench_vector(s.dimup, int(q) * s.dimup) for q in ci])
+                ref = blk.spmatvec_block_cols(ci, xc)
+            got = np.empty(s.dimup)
+            s.dev_download_slice(dyf, j * s.dimup, got)
+            assert np.abs(got - ref).max() < 1e-13 * ma.value, j
+        for d in (dx, dyf, dyg):
+            s.dev_free(d)
+        s.delete_Hv_sector()
+    finally:
+        s.close()
 
 
 @pytest.mark.parametrize("name", ["C2", "C3"])
