@@ -427,7 +427,7 @@ def measure(H, workload, steps, full):
 def kernel_table(res, stored, peak):
     bytes_per_el = 24 if stored else 16
     alg = {"k_srow": 16 + (8 if stored else 0), "k_fcol": 24, "k_tile_col": 16 + (8 if stored else 0),
-           "k_tile_row": 24, "k_hxv_gather": bytes_per_el, "k_halo_pull": 16}
+           "k_tile_row": 24, "k_hxv_gather": bytes_per_el, "k_halo_axpy": 16}
     kernels = []
     passes = res.get("passes") or []
     tot = sum(m for _, m in passes)
@@ -463,7 +463,7 @@ def run_b200(args):
     ms_step = res["ms_per_step"]
     step_gbs = bytes_per_el * nloc / (ms_step * 1e-3) / 1e9      # per GPU: algorithmic bytes of the local shard
     kernels = kernel_table(res, args.stored, peak)
-    dom = max([k for k in kernels if k["name"] != "k_halo_pull"], key=lambda k: k["ms"]) if kernels else None
+    dom = max([k for k in kernels if k["name"] != "k_halo_axpy"], key=lambda k: k["ms"]) if kernels else None
     if dom:
         traffic, tsrc = dram_traffic(args.workload, args.stored, dom["name"]) if world == 1 else (None, None)
         roof = {"bound": "hbm", "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dom["frac"], "traffic": traffic,

@@ -87,6 +87,7 @@ static int create_device_state(edgpu_ctx *c) {
   CK(cudaEventCreate(&c->ev1));
   CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  for (int w = 0; w < EDGPU_MAX_WINDOWS; w++) CK(cudaEventCreateWithFlags(&c->ev_win[w], cudaEventDisableTiming));
   // exact binomials by Pascal's rule (== binomial(), ED_SETUP.f90:1017-1035, for these sizes)
   memset(c->h_binom, 0, sizeof(c->h_binom));
   for (int n = 0; n < EDGPU_BINOM_LD; n++) {
@@ -142,6 +143,7 @@ extern "C" int edgpu_set_option(edgpu_ctx *c, const char *key, int64_t value) {
   if (!strcmp(key, "no_fuse")) { c->opt_no_fuse = value; return EDGPU_OK; }    // Lanczos update as a separate pass
   if (!strcmp(key, "halo_ctas")) { c->opt_halo_ctas = value; return EDGPU_OK; }
   if (!strcmp(key, "no_overlap")) { c->opt_no_overlap = value; return EDGPU_OK; }
+  if (!strcmp(key, "halo_chunks")) { c->opt_halo_chunks = value; return EDGPU_OK; }
   if (!strcmp(key, "no_peer")) { c->opt_no_peer = value; return EDGPU_OK; }
   if (!strcmp(key, "col_cluster")) { c->opt_col_cluster = value; return EDGPU_OK; }
   if (!strcmp(key, "no_uniform")) { c->opt_no_uniform = value; return EDGPU_OK; }
@@ -250,6 +252,18 @@ __global__ void k_nd_fill(DevParams P, const int32_t *__restrict__ map_up, const
     ocols[p + k] = ju + jd * dimup;
     ovals[p + k] = v[k];
   }
+}
+
+// Hs%map of one spin species on the device (build_sector, ED_SETUP.f90:764-777) without the factors
+int build_sector_map_device(edgpu_ctx *c, int npart, int32_t **d_map) {
+  const int64_t n = binom64(c, c->ns, npart);
+  CK(cudaMalloc(d_map, (size_t)std::max<int64_t>(n, 1) * sizeof(int32_t)));
+  uint64_t top = 1ull << c->ns;
+  int blocks = (int)((top + 255) / 256);
+  if (blocks > 65535 * 4) blocks = 65535 * 4;
+  k_build_map<<<blocks, 256, 0, c->stream>>>(c->ns, npart, c->d_binom, *d_map);
+  CKL(c);
+  return EDGPU_OK;
 }
 
 static int build_factor(edgpu_ctx *c, Factor &f, int spin, int npart, bool stored) {
@@ -408,6 +422,7 @@ extern "C" int edgpu_destroy(edgpu_ctx *c) {
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
+  for (int w = 0; w < EDGPU_MAX_WINDOWS; w++) if (c->ev_win[w]) cudaEventDestroy(c->ev_win[w]);
   if (c->stream2) cudaStreamDestroy(c->stream2);
   for (int i = 0; i < 6; i++) if (c->pev[i]) cudaEventDestroy(c->pev[i]);
   if (c->stream) cudaStreamDestroy(c->stream);

@@ -219,6 +219,12 @@ int comm_allreduce_scalar(edgpu_ctx *c, double *d_scalar) {
   return EDGPU_OK;
 }
 
+int comm_allreduce_array(edgpu_ctx *c, double *d_a, int n) {
+  if (c->nranks == 1) return EDGPU_OK;
+  NK(g_nccl.AllReduce(d_a, d_a, (size_t)n, ncclDouble, ncclSum, (ncclComm_t)c->comm, c->stream));
+  return EDGPU_OK;
+}
+
 // out[b + nb*a] = A[(a0 + a) + lda*b],  a < na, b < nb   (32x32 tiles through shared memory)
 __global__ void k_pack_transpose(const double *__restrict__ A, int64_t lda, int64_t a0, int64_t na, int64_t nb,
                                  double *__restrict__ out) {

@@ -27,6 +27,7 @@ struct LancState {              // device-resident Lanczos scalars (no host sync
 };
 
 #define EDGPU_MAXP 8            // ranks of one NVLink domain (peer-mapped symmetric slab)
+#define EDGPU_MAX_WINDOWS 8     // column windows of the sharded H*v pipeline (halo of window w+1 under the column pass of w)
 
 // One low group of the structured row kernel (hxv_fast.cu), precomputed per sector: 80 bytes, bulk-copied next
 // to the tile.  hx = high word h | (mask of the high-bit hops the kernel applies) << 16; par bit kk = parity of
@@ -46,7 +47,7 @@ struct edgpu_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;             // halo copy next to the row kernel (sharded fast path)
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr, ev_win[EDGPU_MAX_WINDOWS] = {nullptr};
   bool fast_attrs_set = false, tiled_attrs_set = false;   // per-device function attributes (this context's device)
   int sm_count = 148;
   // inputs
@@ -93,7 +94,7 @@ struct edgpu_ctx {
   TiledPlan *plan = nullptr;
   FastPlan *fplan = nullptr;
   int64_t opt_srow_lr = 0, opt_srow_t = 0, opt_no_uniform = 0, opt_no_fuse = 0, opt_no_peer = 0, opt_col_cluster = 0;
-  int64_t opt_halo_ctas = 0, opt_no_overlap = 0;
+  int64_t opt_halo_ctas = 0, opt_no_overlap = 0, opt_halo_chunks = 0;
   const double *const *peer_override = nullptr;   // selftest only: the ranks emulated on one device
   int64_t launches = 0;
   // symmetric slab (nranks > 1): one allocation per rank at identical offsets, opened by every peer
@@ -164,10 +165,10 @@ struct SRowHostPlan {
   std::vector<char> gwhole;            // [2^nhigh] every column of the group is on this rank
   std::vector<int4> chunks;            // (first record, groups, local column begin, local column end)
   std::vector<SRowRec> recs;
-  std::vector<int> lptr, lloc;         // column-pass source lists (srow_lists_host)
+  std::vector<int> lptr, lown, lcol;   // source lists of the hops the row kernel leaves out (srow_lists_host)
   std::vector<double> lamp;
-  std::vector<unsigned char> linit;
-  std::vector<int> hown, hcol;         // halo slots
+  std::vector<unsigned char> lflag;    // per local column: 1 = not written by the row kernel, 2 = has entries
+  std::vector<int> zcols;              // local columns that have entries
 };
 // returns 1 = plan built, 0 = the structured kernel does not apply, -1 = internal inconsistency
 int srow_plan_host(int ns, int ndw, int64_t dimdw, int nranks, int rank, int lr, int tbits_opt, SRowHostPlan &hp);
@@ -179,9 +180,9 @@ bool fast_supported_local(edgpu_ctx *c);          // full operator on the local 
 bool fast_supported_col(edgpu_ctx *c, int k);     // whole-column kernel for factor k
 int fast_apply_local(edgpu_ctx *c, const double *d_x, double *d_y, double *d_xp = nullptr, int *npartials = nullptr);
 int fast_apply_col(edgpu_ctx *c, int k, bool with_diag, bool acc, const double *d_x, double *d_y, int64_t ncols, int64_t coloff,
-                   double *d_xp = nullptr, int *npartials = nullptr, bool dw_lists = false);
+                   double *d_xp = nullptr, int *npartials = nullptr, bool dw_lists = false, int64_t list_col0 = 0, int grid_limit = 0);
 int fast_apply_row(edgpu_ctx *c, const double *d_x, double *d_y, int grid_limit = 0);
-int fast_halo_pull(edgpu_ctx *c, const double *const *xpeer, cudaStream_t st, int ctas);
+int fast_halo_axpy(edgpu_ctx *c, const double *const *xpeer, const double *d_x, cudaStream_t st, int ctas, int z0, int z1);
 bool fast_peer_ready(edgpu_ctx *c, const double *d_x);   // sharded: x lives in the symmetric slab, peers are mapped
 // comm.cu
 int comm_symm_setup(edgpu_ctx *c, size_t unit, int nunits);   // collective: nunits vectors of `unit` bytes
@@ -192,6 +193,9 @@ int vec_alloc(edgpu_ctx *c, double **p, int64_t n);
 void vec_free(edgpu_ctx *c, double **p);
 int64_t sym_offset(const edgpu_ctx *c, const void *p);  // byte offset inside the slab, -1 if not in it
 int comm_allreduce_scalar(edgpu_ctx *c, double *d_scalar);
+int comm_allreduce_array(edgpu_ctx *c, double *d_a, int n);
+// capi.cu
+int build_sector_map_device(edgpu_ctx *c, int npart, int32_t **d_map);
 int comm_transpose_fwd(edgpu_ctx *c, const double *d_x, double *d_vt);          // V(DimUp,qdw) -> Vt(DimDw,qup)
 int comm_transpose_bwd_add(edgpu_ctx *c, const double *d_hvt, double *d_y);     // Hv += (Hvt)^T
 int comm_allgather(edgpu_ctx *c, const double *d_x, double *d_full);

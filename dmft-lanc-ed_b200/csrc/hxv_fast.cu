@@ -23,9 +23,9 @@
 //
 // Sharded vector (i_dw columns split over the GPUs of one NVLink domain, ED_HAMILTONIAN.f90:96-110): k_srow only
 // touches local memory.  The dw hops whose source column lives on another rank -- and the few that touch a low
-// group cut by a rank boundary -- are applied by pass 2 from per-column source lists; their sources are copied
-// once per H*v from the owners' copies of x (peer-mapped symmetric slab, comm.cu) into a local halo buffer by
-// k_halo_pull, which runs on a second stream and on its own SMs while k_srow works.
+// group cut by a rank boundary -- come from per-column source lists: k_halo_axpy reads the sources straight from
+// the owners' copies of x over NVLink (peer-mapped symmetric slab, comm.cu) and leaves z = sum of those hops in a
+// local vector, on a second stream and on its own SMs while k_srow works; pass 2 then adds z like it adds y.
 //
 // The factor values are exactly the reference's V_k * sg1 * sg2 (stored/H_up.f90:55-81); only the
 // order of the floating-point sums differs.
@@ -58,7 +58,6 @@
 #endif
 #define SROW_MAXG 64              // groups per chunk: 2^T, T <= 6
 #define SMEM_LIMIT 232448        // 227 KB per CTA on sm_100
-#define HALO_CHUNK 8192           // doubles per work item of the halo copy kernel
 
 struct FastFactor {
   int W = 0, WT = 0, nvals = 0;
@@ -80,17 +79,20 @@ struct SRowPlan {
   double vk[EDGPU_MAX_SITES];    // V_k of the dw spin, k = bath bit (1-based site k+1)
   double *d_vk = nullptr;
   size_t smem = 0;
-  // sharded vector: dw hops left to the column pass (source on another rank, or a low group cut by a boundary)
+  // sharded vector: dw hops the row kernel leaves out (source on another rank, or a low group cut by a boundary)
   bool lists = false;
-  int *d_lptr = nullptr, *d_lloc = nullptr;    // per local column: entry range; entry: local column (>= 0) or -1 - halo slot
+  int nlist = 0, nzcols = 0;                   // entries; local columns that have entries
+  int *d_lptr = nullptr;                       // [qdw+1] entry range of every local column
+  int *d_lown = nullptr, *d_lcol = nullptr;    // entry: owner rank, column inside the owner's shard
   double *d_lamp = nullptr;
-  unsigned char *d_linit = nullptr;            // column is not written by k_srow at all (cut group): diagonal added here
-  int nslots = 0;                              // halo columns
-  int *d_hown = nullptr, *d_hcol = nullptr;    // owner rank, column inside the owner's shard
-  double *d_halo = nullptr;                    // [nslots][DimUp]
+  int *d_zcols = nullptr;                      // the local columns that have entries (work list of k_halo_axpy)
+  unsigned char *d_lflag = nullptr;            // per local column: 1 = not written by k_srow (cut group: starts from the
+                                               // diagonal in pass 2), 2 = has entries (z(:, j) is valid)
+  double *d_z = nullptr;                       // [qdw][DimUp] sum of the listed hops
 };
 
 struct FastPlan {
+  std::vector<int> h_zcols;          // host copy of sr.d_zcols (column windows of the sharded pipeline)
   FastFactor ff[2];
   bool col_ok[2] = {false, false};
   size_t col_smem[2] = {0, 0};
@@ -167,14 +169,11 @@ struct FColArgs {
   double *xp;
   const LancState *st;
   double *partials;
-  // LISTS (sharded vector): dw hops that the row pass leaves to this one (source on another rank, or a low group
-  // cut by a rank boundary).  Entry e of local column j, lptr[j] <= e < lptr[j+1]: y(:, j) += lamp[e] * src(:),
-  // src = local column lloc[e] of x when lloc[e] >= 0, else halo column -1 - lloc[e].  linit[j]: the row pass did
-  // not write column j at all, so y(:, j) starts from the diagonal term here (diagmode 1 stored, 2 recomputed).
-  const int *lptr, *lloc;
-  const double *lamp;
-  const unsigned char *linit;
-  const double *halo;
+  // LISTS (sharded vector): z(:, j) = the dw hops the row pass left out (k_halo_axpy), lflag[j] & 2 when column j has
+  // any; lflag[j] & 1: the row pass did not write column j at all, so y(:, j) starts from the diagonal term here
+  // (diagmode 1 stored, 2 recomputed).
+  const double *z;
+  const unsigned char *lflag;
   int diagmode;
 };
 
@@ -189,16 +188,6 @@ __device__ __forceinline__ double fcol_init_diag(const FColArgs &a, int64_t j, i
         if ((ms >> q) & 1u) d += (o == q) ? a.uloc[o] : a.ust;
   return d;
 }
-// the listed hops of one element
-__device__ __forceinline__ double fcol_lists(const FColArgs &a, int l0, int l1, int r, double acc) {
-  for (int e = l0; e < l1; e++) {
-    const int loc = __ldg(a.lloc + e);
-    const double *sp = loc >= 0 ? a.x + (size_t)loc * a.n : a.halo + (size_t)(-1 - loc) * a.n;
-    acc = fma(__ldg(a.lamp + e), __ldcs(sp + r), acc);
-  }
-  return acc;
-}
-
 // MODE: 0 = y = F x, 1 = y += F x, 2 = y += F x fused with the first Lanczos vector update (y is only read)
 // UNI: 0 = general (value table), 1 = uniform magnitude with 4-byte entries, 2 = uniform with 2-byte entries
 template <int WT, int DIAG, int UNI, int MODE, bool LISTS>
@@ -257,9 +246,9 @@ __global__ void __launch_bounds__(FCOL_THREADS, 1) k_fcol(FColArgs a) {
       uint32_t ms = 0;
       if (DIAG == 2) { dcol = a.dfac_s[a.coloff + j]; ms = (uint32_t)a.map_s[a.coloff + j]; }
       double *yc = a.y + j * (int64_t)n;
-      int l0 = 0, l1 = 0;
-      bool init = false;
-      if (LISTS) { l0 = __ldg(a.lptr + j); l1 = __ldg(a.lptr + j + 1); init = __ldg(a.linit + j) != 0; }
+      bool init = false, hasz = false;
+      if (LISTS) { const unsigned char f = __ldg(a.lflag + j); init = (f & 1) != 0; hasz = (f & 2) != 0; }
+      const double *zc = a.z + j * (int64_t)n;
       uint32_t en[WT];
       auto load_ell = [&](int row) {
         if (UNI == 2 && WT == 8) {                                 // 8 two-byte entries = one LDG.128
@@ -272,17 +261,19 @@ __global__ void __launch_bounds__(FCOL_THREADS, 1) k_fcol(FColArgs a) {
         }
       };
       if (tid < n) load_ell(tid);                                  // independent of the column: issued before the wait
-      double ynext = 0.0;
+      double ynext = 0.0, znext = 0.0;
       if (ACC && tid < n) ynext = __ldcs(yc + tid);
+      if (LISTS && hasz && tid < n) znext = __ldcs(zc + tid);
       mbar_wait(&bar[b], (uint32_t)((it >> 1) & 1));
       for (int r = tid; r < n; r += NCT) {
         uint32_t e[WT];
 #pragma unroll
         for (int s = 0; s < WT; s++) e[s] = en[s];
-        const double yold = ynext;
+        const double yold = ynext, zold = znext;
         if (r + NCT < n) {                                         // software prefetch of the next row's inputs
           load_ell(r + NCT);
           if (ACC) ynext = __ldcs(yc + r + NCT);
+          if (LISTS && hasz) znext = __ldcs(zc + r + NCT);
         }
         double acc0 = 0.0;
         if (DIAG == 1) acc0 = __ldcs(a.diag + j * (int64_t)n + r) * xs[r];
@@ -306,7 +297,7 @@ __global__ void __launch_bounds__(FCOL_THREADS, 1) k_fcol(FColArgs a) {
         if (UNI) acc0 = fma(a.vuni, acc, acc0); else acc0 += acc;
         if (LISTS) {
           acc0 += init ? fcol_init_diag(a, j, r) * xs[r] : yold;
-          acc0 = fcol_lists(a, l0, l1, r, acc0);
+          acc0 += zold;
         } else if (ACC) {
           acc0 += yold;
         }
@@ -394,15 +385,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FCOL_THREADS, 1) k_f
     mbar_wait(&bar[0], (uint32_t)(it & 1));
     cluster_sync_all();                                            // both halves of column j are in place
     double *yc = a.y + j * (int64_t)n + r0;
-    int l0 = 0, l1 = 0;
-    bool init = false;
-    if (LISTS) { l0 = __ldg(a.lptr + j); l1 = __ldg(a.lptr + j + 1); init = __ldg(a.linit + j) != 0; }
+    bool init = false, hasz = false;
+    if (LISTS) { const unsigned char f = __ldg(a.lflag + j); init = (f & 1) != 0; hasz = (f & 2) != 0; }
+    const double *zc = a.z + j * (int64_t)n + r0;
     for (int r = tid; r < nr; r += FCOL_THREADS) {
       uint32_t e[WT];
 #pragma unroll
       for (int s = 0; s < WT; s++) e[s] = __ldg(a.ell + (size_t)s * n + r0 + r);
-      double yold = 0.0;
+      double yold = 0.0, zold = 0.0;
       if (ACC) yold = __ldcs(yc + r);
+      if (LISTS && hasz) zold = __ldcs(zc + r);
       double acc = 0.0;
 #pragma unroll
       for (int s = 0; s < WT; s++) {
@@ -417,7 +409,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FCOL_THREADS, 1) k_f
       double acc0 = UNI ? a.vuni * acc : acc;
       if (LISTS) {
         acc0 += init ? fcol_init_diag(a, j, r0 + r) * buf[r] : yold;
-        acc0 = fcol_lists(a, l0, l1, r0 + r, acc0);
+        acc0 += zold;
       } else if (ACC) {
         acc0 += yold;
       }
@@ -754,39 +746,53 @@ __global__ void __launch_bounds__(SROW_THREADS, 1) k_srow(const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------------
-// halo: copies of the remote source columns, pulled from the owners' shards over NVLink
+// halo: z(:, t) = sum over the listed hops (t <- s) of amp * x_owner(:, s), the sources read from the owners'
+// shards over NVLink (or from the local shard).  Work item = (listed column, chunk of rows); every thread keeps the
+// loads of up to HALO_UNROLL rows x all sources of its column in flight.
 // ---------------------------------------------------------------------------------------------
 struct HaloArgs {
-  double *halo;                  // [nslots][n]
-  int n, nslots;
-  const int *hown, *hcol;
-  const double *xb[EDGPU_MAXP];  // every rank's copy of x (peer-mapped)
+  double *z;                     // [qdw][n]
+  int n, nzcols;
+  const int *zcols, *lptr, *lown, *lcol;
+  const double *lamp;
+  const double *xb[EDGPU_MAXP];  // every rank's copy of x (peer-mapped); xb[me] = local x
 };
-__global__ void __launch_bounds__(512) k_halo_pull(HaloArgs a) {
+#define HALO_THREADS 512
+#define HALO_UNROLL 8
+__global__ void __launch_bounds__(HALO_THREADS) k_halo_axpy(HaloArgs a) {
   __shared__ const double *xb[EDGPU_MAXP];
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int p = 0; p < EDGPU_MAXP; p++) xb[p] = a.xb[p];
   }
   __syncthreads();
-  const int nrc = (a.n + HALO_CHUNK - 1) / HALO_CHUNK;
-  const int64_t nitems = (int64_t)a.nslots * nrc;
+  constexpr int ROWS = HALO_THREADS * HALO_UNROLL * 2;             // rows per item (double2 per thread and unroll step)
+  const int nrc = (a.n + ROWS - 1) / ROWS;
+  const int64_t nitems = (int64_t)a.nzcols * nrc;
   for (int64_t it = blockIdx.x; it < nitems; it += gridDim.x) {
-    const int slot = (int)(it / nrc), rc = (int)(it % nrc);
-    const int r0 = rc * HALO_CHUNK;
-    const int cnt2 = (min(HALO_CHUNK, a.n - r0)) >> 1;             // n is even: whole double2
-    const double2 *src = reinterpret_cast<const double2 *>(xb[__ldg(a.hown + slot)] + (size_t)__ldg(a.hcol + slot) * a.n + r0);
-    double2 *dst = reinterpret_cast<double2 *>(a.halo + (size_t)slot * a.n + r0);
-    double2 v[HALO_CHUNK / 2 / 512];
+    const int t = __ldg(a.zcols + (int)(it / nrc)), rc = (int)(it % nrc);
+    const int e0 = __ldg(a.lptr + t), e1 = __ldg(a.lptr + t + 1);
+    const int r0 = rc * ROWS;
+    double2 acc[HALO_UNROLL];
 #pragma unroll
-    for (int q = 0; q < HALO_CHUNK / 2 / 512; q++) {
-      const int i = threadIdx.x + q * 512;
-      if (i < cnt2) v[q] = src[i];
+    for (int q = 0; q < HALO_UNROLL; q++) acc[q] = make_double2(0.0, 0.0);
+    for (int e = e0; e < e1; e++) {
+      const double am = __ldg(a.lamp + e);
+      const double2 *src = reinterpret_cast<const double2 *>(xb[__ldg(a.lown + e)] + (size_t)__ldg(a.lcol + e) * a.n + r0);
+      double2 v[HALO_UNROLL];
+#pragma unroll
+      for (int q = 0; q < HALO_UNROLL; q++) {
+        const int i = threadIdx.x + q * HALO_THREADS;
+        v[q] = (r0 + 2 * i < a.n) ? src[i] : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int q = 0; q < HALO_UNROLL; q++) { acc[q].x = fma(am, v[q].x, acc[q].x); acc[q].y = fma(am, v[q].y, acc[q].y); }
     }
+    double2 *dst = reinterpret_cast<double2 *>(a.z + (size_t)t * a.n + r0);
 #pragma unroll
-    for (int q = 0; q < HALO_CHUNK / 2 / 512; q++) {
-      const int i = threadIdx.x + q * 512;
-      if (i < cnt2) dst[i] = v[q];
+    for (int q = 0; q < HALO_UNROLL; q++) {
+      const int i = threadIdx.x + q * HALO_THREADS;
+      if (r0 + 2 * i < a.n) dst[i] = acc[q];
     }
   }
 }
@@ -934,38 +940,30 @@ int srow_plan_host(int ns, int ndw, int64_t dimdw, int nranks, int rank, int lr,
   return 1;
 }
 
-// Source lists of the column pass: every dw hop (target <- source) of a LOCAL target column that the row kernel does
-// not apply, i.e. the target's or the source's low group is not whole on this rank, from the reference-order CSR of
-// spH0dws (stored/H_dw.f90).  Columns of groups that are not whole are computed entirely here (linit).  Remote
-// sources get a halo slot each.  map: Hs(2)%map.
+// Source lists: every dw hop (target <- source) of a LOCAL target column that the row kernel does not apply, i.e. the
+// target's or the source's low group is not whole on this rank, from the reference-order CSR of spH0dws
+// (stored/H_dw.f90).  Columns of groups that are not whole are not written by the row kernel at all (lflag & 1).
+// map: Hs(2)%map.
 void srow_lists_host(SRowHostPlan &hp, int rank, int64_t dimdw, const int32_t *map, const int32_t *rp, const int32_t *cc, const double *vv) {
   const int P = (int)hp.coloffs.size() - 1;
   const int c0 = hp.coloffs[(size_t)rank], c1 = hp.coloffs[(size_t)rank + 1];
-  hp.lptr.assign(1, 0); hp.lloc.clear(); hp.lamp.clear(); hp.linit.clear(); hp.hown.clear(); hp.hcol.clear();
+  hp.lptr.assign(1, 0); hp.lown.clear(); hp.lcol.clear(); hp.lamp.clear(); hp.lflag.clear(); hp.zcols.clear();
   if (P <= 1) return;
   (void)dimdw;
   auto owner_of = [&](int col) { int p = 0; while (p + 1 < P && col >= hp.coloffs[(size_t)p + 1]) p++; return p; };
-  std::map<int, int> slot;                                         // global source column -> halo slot
   for (int t = c0; t < c1; t++) {
     const bool tw = hp.gwhole[(size_t)((uint32_t)map[t] >> hp.LR)] != 0;
+    const size_t before = hp.lown.size();
     for (int32_t q = rp[(size_t)t]; q < rp[(size_t)t + 1]; q++) {
       const int s = cc[(size_t)q];
       if (tw && hp.gwhole[(size_t)((uint32_t)map[s] >> hp.LR)]) continue;      // k_srow applies it
-      int loc;
-      if (s >= c0 && s < c1) loc = s - c0;
-      else {
-        auto it = slot.find(s);
-        if (it == slot.end()) {
-          const int own = owner_of(s);
-          it = slot.emplace(s, (int)hp.hown.size()).first;
-          hp.hown.push_back(own); hp.hcol.push_back(s - hp.coloffs[(size_t)own]);
-        }
-        loc = -1 - it->second;
-      }
-      hp.lloc.push_back(loc); hp.lamp.push_back(vv[(size_t)q]);
+      const int own = owner_of(s);
+      hp.lown.push_back(own); hp.lcol.push_back(s - hp.coloffs[(size_t)own]); hp.lamp.push_back(vv[(size_t)q]);
     }
-    hp.lptr.push_back((int)hp.lloc.size());
-    hp.linit.push_back(tw ? 0 : 1);
+    hp.lptr.push_back((int)hp.lown.size());
+    const bool has = hp.lown.size() > before;
+    hp.lflag.push_back((unsigned char)((tw ? 0 : 1) | (has ? 2 : 0)));
+    if (has) hp.zcols.push_back(t - c0);
   }
 }
 
@@ -1001,7 +999,7 @@ static int build_srow(edgpu_ctx *c, SRowPlan &sr) {
     TRY(to_device(&sr.d_dr0, d0));
     TRY(to_device(&sr.d_dr1, d1));
   }
-  sr.lists = false; sr.nslots = 0;
+  sr.lists = false; sr.nlist = 0; sr.nzcols = 0;
   if (c->nranks > 1) {
     std::vector<int32_t> map((size_t)c->dw.n), rp((size_t)c->dw.n + 1), cc((size_t)std::max<int64_t>(c->dw.nnz, 1));
     std::vector<double> vv((size_t)std::max<int64_t>(c->dw.nnz, 1));
@@ -1013,14 +1011,16 @@ static int build_srow(edgpu_ctx *c, SRowPlan &sr) {
     }
     srow_lists_host(hp, c->rank, c->dimdw, map.data(), rp.data(), cc.data(), vv.data());
     sr.lists = true;
-    sr.nslots = (int)hp.hown.size();
+    sr.nlist = (int)hp.lown.size();
+    sr.nzcols = (int)hp.zcols.size();
     TRY(to_device(&sr.d_lptr, hp.lptr));
-    TRY(to_device(&sr.d_lloc, hp.lloc));
+    TRY(to_device(&sr.d_lown, hp.lown));
+    TRY(to_device(&sr.d_lcol, hp.lcol));
     TRY(to_device(&sr.d_lamp, hp.lamp));
-    TRY(to_device(&sr.d_linit, hp.linit));
-    TRY(to_device(&sr.d_hown, hp.hown));
-    TRY(to_device(&sr.d_hcol, hp.hcol));
-    if (sr.nslots) CK(cudaMalloc(&sr.d_halo, (size_t)sr.nslots * (size_t)c->dimup * sizeof(double)));
+    TRY(to_device(&sr.d_lflag, hp.lflag));
+    TRY(to_device(&sr.d_zcols, hp.zcols));
+    c->fplan->h_zcols = hp.zcols;
+    if (sr.nzcols) CK(cudaMalloc(&sr.d_z, (size_t)std::max<int64_t>(c->nloc, 1) * sizeof(double)));
   }
   sr.ok = true;
   return EDGPU_OK;
@@ -1031,7 +1031,7 @@ int fast_plan_free(edgpu_ctx *c) {
   for (int k = 0; k < 2; k++) { cudaFree(c->fplan->ff[k].d_ell); cudaFree(c->fplan->ff[k].d_ell16); cudaFree(c->fplan->ff[k].d_vtab); }
   SRowPlan &r = c->fplan->sr;
   cudaFree(r.d_recs); cudaFree(r.d_chunks); cudaFree(r.d_vk); cudaFree(r.d_dr0); cudaFree(r.d_dr1);
-  cudaFree(r.d_lptr); cudaFree(r.d_lloc); cudaFree(r.d_lamp); cudaFree(r.d_linit); cudaFree(r.d_hown); cudaFree(r.d_hcol); cudaFree(r.d_halo);
+  cudaFree(r.d_lptr); cudaFree(r.d_lown); cudaFree(r.d_lcol); cudaFree(r.d_lamp); cudaFree(r.d_lflag); cudaFree(r.d_zcols); cudaFree(r.d_z);
   delete c->fplan;
   c->fplan = nullptr;
   return EDGPU_OK;
@@ -1153,7 +1153,7 @@ static void launch_fcol2(int WT, int uni, int mode, bool lists, int grid, size_t
 // y (+)= [Hd o x +] F_k x on a matrix whose contiguous dimension is factor k's index.  dw_lists: also apply the dw
 // hops the row pass left to this one (sharded vector, k == 0, accumulate form).
 int fast_apply_col(edgpu_ctx *c, int k, bool with_diag, bool acc, const double *d_x, double *d_y, int64_t ncols, int64_t coloff,
-                   double *d_xp, int *npartials, bool dw_lists) {
+                   double *d_xp, int *npartials, bool dw_lists, int64_t list_col0, int grid_limit) {
   TRY(fast_plan_build(c));
   FastPlan *p = c->fplan;
   const bool use2 = p->col2_ok[k] && (!p->col_ok[k] || c->opt_col_cluster);
@@ -1168,7 +1168,8 @@ int fast_apply_col(edgpu_ctx *c, int k, bool with_diag, bool acc, const double *
   a.dfac_c = fc.d_dfac; a.dfac_s = fs.d_dfac; a.map_c = fc.d_map; a.map_s = fs.d_map;
   a.norb = c->dp.norb; a.ust = c->dp.ust;
   for (int i = 0; i < EDGPU_MAX_ORB; i++) a.uloc[i] = c->dp.uloc[i];
-  const int grid = (int)std::min<int64_t>(ncols, c->sm_count);
+  int grid = (int)std::min<int64_t>(ncols, c->sm_count);
+  if (grid_limit > 0 && grid > grid_limit) grid = grid_limit;
   if (grid < 1) return EDGPU_OK;
   const int diag = !with_diag ? 0 : (c->d_diag ? 1 : 2);
   const int mode = d_xp ? 2 : (acc ? 1 : 0);
@@ -1176,16 +1177,20 @@ int fast_apply_col(edgpu_ctx *c, int k, bool with_diag, bool acc, const double *
   const bool lists = dw_lists && p->sr.lists;
   if (lists) {
     if (k != 0 || diag != 0 || !acc) return edgpu_set_err(EDGPU_ERR_INVALID, "dw source lists belong to the accumulating up pass");
-    a.lptr = p->sr.d_lptr; a.lloc = p->sr.d_lloc; a.lamp = p->sr.d_lamp; a.linit = p->sr.d_linit; a.halo = p->sr.d_halo;
+    a.z = p->sr.d_z + list_col0 * c->dimup; a.lflag = p->sr.d_lflag + list_col0;
     a.diagmode = c->d_diag ? 1 : 2;
+    if (c->d_diag) a.diag = c->d_diag + list_col0 * c->dimup;      // the skipped columns' stored diagonal, same column window
   }
-  a.xp = d_xp; a.st = c->d_st; a.partials = c->d_partials;
-  if (npartials) *npartials = grid;
+  // *npartials on entry = partial sums already in c->d_partials (earlier column windows of the same H*v)
+  const int pbase = (npartials && d_xp) ? *npartials : 0;
+  a.xp = d_xp; a.st = c->d_st; a.partials = c->d_partials + pbase;
+  if (npartials) *npartials = pbase + grid;
   if (use2) {
     if (diag != 0) return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "cluster column kernel has no fused diagonal");
-    const int pairs = (int)std::min<int64_t>(ncols, c->sm_count / 2);
+    int pairs = (int)std::min<int64_t>(ncols, c->sm_count / 2);
+    if (grid_limit > 0 && 2 * pairs > grid_limit) pairs = std::max(1, grid_limit / 2);
     const int uni2 = (ff.uniform && c->opt_no_uniform != 1) ? 1 : 0;
-    if (npartials) *npartials = 2 * pairs;
+    if (npartials) *npartials = pbase + 2 * pairs;
     launch_fcol2(ff.WT, uni2, mode, lists, 2 * pairs, p->col2_smem[k], c->stream, a);
     CKL(c);
     return EDGPU_OK;
@@ -1257,16 +1262,18 @@ int fast_apply_row(edgpu_ctx *c, const double *d_x, double *d_y, int grid_limit)
   return EDGPU_OK;
 }
 
-// copies the remote source columns of this H*v into the halo buffer (stream st); xpeer[p] = rank p's pointer of x
-int fast_halo_pull(edgpu_ctx *c, const double *const *xpeer, cudaStream_t st, int ctas) {
+// z = the listed dw hops of this H*v (stream st); xpeer[p] = rank p's pointer of x
+int fast_halo_axpy(edgpu_ctx *c, const double *const *xpeer, const double *d_x, cudaStream_t st, int ctas, int z0, int z1) {
   const SRowPlan &sr = c->fplan->sr;
-  if (!sr.lists || sr.nslots == 0) return EDGPU_OK;
+  if (!sr.lists || z1 <= z0) return EDGPU_OK;
   HaloArgs h{};
-  h.halo = sr.d_halo; h.n = (int)c->dimup; h.nslots = sr.nslots; h.hown = sr.d_hown; h.hcol = sr.d_hcol;
+  h.z = sr.d_z; h.n = (int)c->dimup; h.nzcols = z1 - z0;
+  h.zcols = sr.d_zcols + z0; h.lptr = sr.d_lptr; h.lown = sr.d_lown; h.lcol = sr.d_lcol; h.lamp = sr.d_lamp;
   for (int p = 0; p < EDGPU_MAXP; p++) h.xb[p] = xpeer[p < c->nranks ? p : 0];
-  const int64_t nitems = (int64_t)sr.nslots * ((c->dimup + HALO_CHUNK - 1) / HALO_CHUNK);
+  h.xb[c->rank] = d_x;
+  const int64_t nitems = (int64_t)(z1 - z0) * ((c->dimup + HALO_THREADS * HALO_UNROLL * 2 - 1) / (HALO_THREADS * HALO_UNROLL * 2));
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(nitems, ctas));
-  k_halo_pull<<<grid, 512, 0, st>>>(h);
+  k_halo_axpy<<<grid, HALO_THREADS, 0, st>>>(h);
   CKL(c);
   return EDGPU_OK;
 }
@@ -1287,40 +1294,62 @@ bool fast_peer_ready(edgpu_ctx *c, const double *d_x) {
 
 // d_xp != nullptr: Lanczos form -- d_y only holds the row-pass partial result, w = sx*(H x) - cprev*xp goes to
 // d_xp and the per-CTA partial sums of (sx*x).w to c->d_partials (*npartials of them)
+//
+// Sharded pipeline (one stream-ordered barrier, then everything asynchronous):
+//   stream2 : k_halo_axpy on window 1 | window 2 | ... | window K of the local columns   (NVLink bound, few SMs)
+//   stream  : k_srow (all local columns, the other SMs) | k_fcol window 1 after its halo | ... | k_fcol window K
+// so the column pass of a window runs while the halo of the next ones is still in flight.
 int fast_apply_local(edgpu_ctx *c, const double *d_x, double *d_y, double *d_xp, int *npartials) {
   TRY(fast_plan_build(c));
   const SRowPlan &sr = c->fplan->sr;
   const double *pb[64];
   const double *const *xpeer = peer_ptrs(c, d_x, pb);
   if (c->nranks > 1 && !xpeer) return edgpu_set_err(EDGPU_ERR_INVALID, "sharded fast H*v: the vector is not in the symmetric slab");
-  int grid_limit = 0;
-  bool forked = false;
-  if (c->nranks > 1) {
-    // Peers read x while this rank reads theirs.  One stream-ordered barrier per application orders every rank's
-    // earlier writes of x before the reads (RAW) and, because each rank enqueues it after its previous H*v, every
-    // rank's previous remote reads before anybody's later overwrite of those buffers (WAR).
-    TRY(comm_barrier(c));
-    if (sr.nslots > 0) {
-      const int hctas = (int)std::max<int64_t>(1, std::min<int64_t>(c->opt_halo_ctas > 0 ? c->opt_halo_ctas : 32, c->sm_count / 2));
-      if (c->stream2 && !c->opt_no_overlap) {
-        // the copy runs on its own stream and SMs, next to the row kernel (both only read x)
-        CK(cudaEventRecord(c->ev_fork, c->stream));
-        CK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
-        TRY(fast_halo_pull(c, xpeer, c->stream2, hctas));
-        CK(cudaEventRecord(c->ev_join, c->stream2));
-        grid_limit = c->sm_count - hctas;
-        forked = true;
-      } else {
-        prof_mark(c, "k_halo_pull");
-        TRY(fast_halo_pull(c, xpeer, c->stream, c->sm_count * 2));
-      }
-    }
+  if (npartials) *npartials = 0;
+  if (c->nranks == 1 || sr.nzcols == 0) {
+    if (c->nranks > 1) TRY(comm_barrier(c));
+    // row tiles first (y = Hd o x + x Hdw^T, write only), then whole columns (y += Hup x, contiguous RMW)
+    prof_mark(c, "k_srow");
+    TRY(fast_apply_row(c, d_x, d_y, 0));
+    prof_mark(c, "k_fcol");
+    return fast_apply_col(c, 0, false, true, d_x, d_y, c->qdw, c->coloff, d_xp, npartials, true, 0, 0);
   }
-  // row tiles first (y = Hd o x + x Hdw^T, write only), then whole columns (y += Hup x, contiguous RMW)
+  // Peers read x while this rank reads theirs.  One stream-ordered barrier per application orders every rank's
+  // earlier writes of x before the reads (RAW) and, because each rank enqueues it after its previous H*v, every
+  // rank's previous remote reads before anybody's later overwrite of those buffers (WAR).
+  TRY(comm_barrier(c));
+  const int hctas = (int)std::max<int64_t>(1, std::min<int64_t>(c->opt_halo_ctas > 0 ? c->opt_halo_ctas : 32, c->sm_count / 2));
+  if (!c->stream2 || c->opt_no_overlap) {
+    prof_mark(c, "k_halo_axpy");
+    TRY(fast_halo_axpy(c, xpeer, d_x, c->stream, c->sm_count * 2, 0, sr.nzcols));
+    prof_mark(c, "k_srow");
+    TRY(fast_apply_row(c, d_x, d_y, 0));
+    prof_mark(c, "k_fcol");
+    return fast_apply_col(c, 0, false, true, d_x, d_y, c->qdw, c->coloff, d_xp, npartials, true, 0, 0);
+  }
+  const int K = (int)std::max<int64_t>(1, std::min<int64_t>(c->opt_halo_chunks > 0 ? c->opt_halo_chunks : 4, EDGPU_MAX_WINDOWS));
+  CK(cudaEventRecord(c->ev_fork, c->stream));
+  CK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+  // windows of local columns with (about) the same number of listed columns each
+  int64_t wcol[EDGPU_MAX_WINDOWS + 1];
+  int wz[EDGPU_MAX_WINDOWS + 1];
+  for (int w = 0; w <= K; w++) {
+    wz[w] = (int)((int64_t)sr.nzcols * w / K);
+    wcol[w] = (w == 0) ? 0 : (w == K ? c->qdw : (int64_t)c->fplan->h_zcols[(size_t)wz[w]]);
+  }
+  for (int w = 0; w < K; w++) {
+    TRY(fast_halo_axpy(c, xpeer, d_x, c->stream2, hctas, wz[w], wz[w + 1]));
+    CK(cudaEventRecord(c->ev_win[w], c->stream2));
+  }
   prof_mark(c, "k_srow");
-  TRY(fast_apply_row(c, d_x, d_y, grid_limit));
-  if (forked) CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+  TRY(fast_apply_row(c, d_x, d_y, c->sm_count - hctas));
   prof_mark(c, "k_fcol");
-  TRY(fast_apply_col(c, 0, false, true, d_x, d_y, c->qdw, c->coloff, d_xp, npartials, true));
+  for (int w = 0; w < K; w++) {
+    const int64_t j0 = wcol[w], j1 = wcol[w + 1];
+    CK(cudaStreamWaitEvent(c->stream, c->ev_win[w], 0));
+    if (j1 <= j0) continue;
+    TRY(fast_apply_col(c, 0, false, true, d_x + j0 * c->dimup, d_y + j0 * c->dimup, j1 - j0, c->coloff + j0,
+                       d_xp ? d_xp + j0 * c->dimup : nullptr, npartials, true, j0, w + 1 < K ? c->sm_count - hctas : 0));
+  }
   return EDGPU_OK;
 }

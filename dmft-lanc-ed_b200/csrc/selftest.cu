@@ -163,14 +163,14 @@ extern "C" int edgpu_selftest_sharded_hxv(const edgpu_params *p, int nup, int nd
 }
 
 // HOST ONLY (no device): the plan of the structured row kernel for `rank` of `nranks` -- Lin table, chunk table,
-// group records, column-pass source lists and halo slots -- exactly as build_Hv_sector computes it, so that the
-// CPU-only tests can check the chunking / sharding logic.  info[8] = {ok, LR, T, nhigh, nchunks, nrecs, list
-// entries, halo slots}; arrays may be NULL; capacities in entries.  recs: 20 int32 per record (lb, N, hx, par,
-// pc[16]).  lptr has qdw+1 entries, linit qdw.  Returns 0, or 1 when a capacity was too small.
+// group records and the source lists of the hops the row kernel leaves out -- exactly as build_Hv_sector computes it,
+// so that the CPU-only tests can check the chunking / sharding logic.  info[8] = {ok, LR, T, nhigh, nchunks, nrecs,
+// list entries, listed columns}; arrays may be NULL; capacities in entries.  recs: 20 int32 per record (lb, N, hx,
+// par, pc[16]).  lptr has qdw+1 entries, lflag qdw.  Returns 0, or 1 when a capacity was too small.
 extern "C" int edgpu_selftest_srow_plan(const edgpu_params *p, int ndw, int nranks, int rank, int64_t lr, int64_t tbits_opt,
                                         int32_t *info, int32_t *jhi, int cap_jhi, int32_t *chunks, int cap_chunks,
-                                        int32_t *recs, int cap_recs, int32_t *lptr, int32_t *linit, int cap_cols,
-                                        int32_t *lloc, double *lamp, int cap_e, int32_t *hown, int32_t *hcol, int cap_slots) {
+                                        int32_t *recs, int cap_recs, int32_t *lptr, int32_t *lflag, int cap_cols,
+                                        int32_t *lown, int32_t *lcol, double *lamp, int cap_e) {
   DevParams d = make_dp(p);
   const int64_t n = edgpu_selftest_map(d.ns, ndw, nullptr);
   SRowHostPlan hp;
@@ -189,7 +189,7 @@ extern "C" int edgpu_selftest_srow_plan(const edgpu_params *p, int ndw, int nran
   rp[(size_t)n] = (int32_t)cc.size();
   srow_lists_host(hp, rank, n, map.data(), rp.data(), cc.data(), vv.data());
   info[0] = 1; info[1] = hp.LR; info[2] = hp.T; info[3] = hp.nhigh; info[4] = (int32_t)hp.chunks.size();
-  info[5] = (int32_t)hp.recs.size(); info[6] = (int32_t)hp.lloc.size(); info[7] = (int32_t)hp.hown.size();
+  info[5] = (int32_t)hp.recs.size(); info[6] = (int32_t)hp.lown.size(); info[7] = (int32_t)hp.zcols.size();
   int small = 0;
   if (jhi) { if ((int)hp.jhi.size() > cap_jhi) small = 1; else memcpy(jhi, hp.jhi.data(), hp.jhi.size() * sizeof(int32_t)); }
   if (chunks) {
@@ -198,16 +198,12 @@ extern "C" int edgpu_selftest_srow_plan(const edgpu_params *p, int ndw, int nran
   }
   if (recs) { if ((int)hp.recs.size() > cap_recs) small = 1; else if (!hp.recs.empty()) memcpy(recs, hp.recs.data(), hp.recs.size() * sizeof(SRowRec)); }
   if (lptr) {
-    if ((int)hp.linit.size() > cap_cols) small = 1;
-    else { for (size_t k = 0; k < hp.lptr.size(); k++) lptr[k] = hp.lptr[k]; for (size_t k = 0; k < hp.linit.size(); k++) linit[k] = hp.linit[k]; }
+    if ((int)hp.lflag.size() > cap_cols) small = 1;
+    else { for (size_t k = 0; k < hp.lptr.size(); k++) lptr[k] = hp.lptr[k]; for (size_t k = 0; k < hp.lflag.size(); k++) lflag[k] = hp.lflag[k]; }
   }
-  if (lloc) {
-    if ((int)hp.lloc.size() > cap_e) small = 1;
-    else for (size_t k = 0; k < hp.lloc.size(); k++) { lloc[k] = hp.lloc[k]; lamp[k] = hp.lamp[k]; }
-  }
-  if (hown) {
-    if ((int)hp.hown.size() > cap_slots) small = 1;
-    else for (size_t k = 0; k < hp.hown.size(); k++) { hown[k] = hp.hown[k]; hcol[k] = hp.hcol[k]; }
+  if (lown) {
+    if ((int)hp.lown.size() > cap_e) small = 1;
+    else for (size_t k = 0; k < hp.lown.size(); k++) { lown[k] = hp.lown[k]; lcol[k] = hp.lcol[k]; lamp[k] = hp.lamp[k]; }
   }
   return small;
 }

@@ -33,7 +33,7 @@ ABI_SYMBOLS = [
     "edgpu_get_sector", "edgpu_get_nup_ndw", "edgpu_split", "edgpu_transpose_plan", "edgpu_build_hv_sector",
     "edgpu_delete_hv_sector", "edgpu_vecdim_hv_sector", "edgpu_hxv", "edgpu_sphtimesv",
     "edgpu_hxv_device", "edgpu_sp_lanc_eigh", "edgpu_sp_lanc_tridiag", "edgpu_gf_set_state", "edgpu_gf_set_state_from_eigh",
-    "edgpu_gf_chains", "edgpu_add_to_lanczos_gf", "edgpu_get_dims", "edgpu_get_sector_map",
+    "edgpu_gf_chains", "edgpu_add_to_lanczos_gf", "edgpu_observables_normal", "edgpu_get_dims", "edgpu_get_sector_map",
     "edgpu_get_csr", "edgpu_get_diag", "edgpu_dev_alloc", "edgpu_dev_free", "edgpu_dev_upload",
     "edgpu_dev_download", "edgpu_dev_fill_bench_vector", "edgpu_sync", "edgpu_dev_dot", "edgpu_time_hxv_device",
     "edgpu_time_lanczos_device", "edgpu_launch_count", "edgpu_time_hxv_passes",
@@ -44,6 +44,22 @@ class EdgpuError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("edgpu error %d: %s" % (code, msg))
         self.code = code
+
+
+class Observables(C.Structure):
+    """edgpu_observables (include/edgpu.h): ED_OBSERVABLES.f90 outputs of one state."""
+    _fields_ = [("dens", C.c_double * 5), ("dens_up", C.c_double * 5), ("dens_dw", C.c_double * 5), ("docc", C.c_double * 5),
+                ("magz", C.c_double * 5), ("sz2", C.c_double * 25), ("n2", C.c_double * 25), ("s2tot", C.c_double),
+                ("prob", C.c_double * 243), ("dm", (C.c_double * 25) * 2),
+                ("eknot", C.c_double), ("epot", C.c_double), ("ehartree", C.c_double), ("dust", C.c_double),
+                ("dund", C.c_double), ("dse", C.c_double), ("dph", C.c_double)]
+
+    def as_dict(self):
+        out = {}
+        for name, _ in self._fields_:
+            v = getattr(self, name)
+            out[name] = float(v) if isinstance(v, float) else np.array(v, dtype=np.float64)
+        return out
 
 
 class Params(C.Structure):
@@ -92,6 +108,7 @@ def lib():
         L.edgpu_gf_chains.argtypes = [C.c_void_p, C.c_int, c_ip, c_ip, c_ip, C.c_int, C.c_double, c_dp, c_ip, c_dp, c_dp]
         L.edgpu_add_to_lanczos_gf.argtypes = [C.c_double, C.c_double, C.c_double, c_dp, c_dp, C.c_int, C.c_int,
                                               c_dp, C.c_int, c_dp]
+        L.edgpu_observables_normal.argtypes = [C.c_void_p, C.c_double, C.POINTER(Observables)]
         L.edgpu_get_dims.argtypes = [C.c_void_p, c_i64p, c_i64p, c_i64p, c_i64p, c_i64p]
         L.edgpu_get_sector_map.argtypes = [C.c_void_p, C.c_int, c_i32p]
         L.edgpu_get_csr.argtypes = [C.c_void_p, C.c_int, c_i64p, c_i64p, c_i64p, c_i64p, c_dp]
@@ -302,6 +319,12 @@ class Solver:
         _ck(lib().edgpu_gf_chains(self.h, n, io, sp, ar, nlanc_max, threshold, _dp(norm2), nl, _dp(a), _dp(b)))
         return [dict(norm2=norm2[k], nlanc=nl[k], alanc=a[k, :nl[k]].copy(), blanc=b[k, :nl[k]].copy())
                 for k in range(n)]
+
+    def observables(self, zeta=1.0):
+        """lanc_observables + lanc_local_energy of the state kept for the chains (collective when sharded)."""
+        o = Observables()
+        _ck(lib().edgpu_observables_normal(self.h, zeta, C.byref(o)))
+        return o.as_dict()
 
     # ---- introspection ---------------------------------------------------------------------------------------
     def sector_map(self, which):

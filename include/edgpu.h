@@ -154,6 +154,24 @@ int  edgpu_add_to_lanczos_gf(double norm2, double zeta, double ei, const double 
                              const double *blanc, int nlanc, int isign,
                              const double *z, int nz, double *g);
 
+/* ---- observables (lanc_observables, ED_OBSERVABLES.f90:95-363; lanc_local_energy, :372-600) ------------------- */
+/* Local observables and energies of the state kept on the device for the chains (edgpu_gf_set_state /
+ * edgpu_gf_set_state_from_eigh), T = 0, one state, zeta = zeta_function (number of degenerate ground states).
+ * The state is not gathered: every rank reduces its own shard and the 4^Norb weights are all-reduced, so the
+ * call is collective and every rank gets the same numbers (the reference broadcasts them from the master).
+ * Arrays are indexed like the reference's with leading dimension EDGPU_MAX_ORB: sz2[iorb + 5*jorb] = sz2(iorb,jorb),
+ * dm[ispin][iorb + 5*jorb] = imp_density_matrix(ispin,ispin,iorb,jorb) for ispin <= Nspin, prob[i] = Prob(i+1);
+ * epot includes ehartree (ED_OBSERVABLES.f90:587). */
+typedef struct edgpu_observables {
+  double dens[EDGPU_MAX_ORB], dens_up[EDGPU_MAX_ORB], dens_dw[EDGPU_MAX_ORB], docc[EDGPU_MAX_ORB], magz[EDGPU_MAX_ORB];
+  double sz2[EDGPU_MAX_ORB * EDGPU_MAX_ORB], n2[EDGPU_MAX_ORB * EDGPU_MAX_ORB];
+  double s2tot;
+  double prob[243];
+  double dm[2][EDGPU_MAX_ORB * EDGPU_MAX_ORB];
+  double eknot, epot, ehartree, dust, dund, dse, dph;
+} edgpu_observables;
+int  edgpu_observables_normal(edgpu_ctx *c, double zeta, edgpu_observables *out);
+
 /* ---- introspection for bit-exact checks (Appendix C of SURVEY.md) ---------------------------------- */
 int  edgpu_get_dims(const edgpu_ctx *c, int64_t *dimup, int64_t *dimdw, int64_t *qdw,
                     int64_t *ishift, int64_t *nloc);

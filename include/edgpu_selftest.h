@@ -24,15 +24,16 @@ double edgpu_selftest_diag(const edgpu_params *p, uint32_t mup, uint32_t mdw, in
 /* one row of spH0nd: returns the entry count, outputs column words and values */
 int edgpu_selftest_nonlocal_row(const edgpu_params *p, uint32_t mup, uint32_t mdw, uint32_t *cup, uint32_t *cdw,
                                 double *val);
-/* HOST: plan of the structured row kernel for `rank` of `nranks` (Lin table, chunk table, group records, the
- * column-pass source lists of the hops the row kernel leaves out on a sharded vector, halo slots), as
- * build_Hv_sector computes it.  tbits_opt = t + 1 forces chunks of 2^t low groups (0 = automatic).
- * info[8] = {ok, LR, T, nhigh, nchunks, nrecs, list entries, halo slots}; arrays may be NULL; recs: 20 int32 per
- * record (lb, N, hx, par, pc[16]); lptr: qdw+1 entries, linit: qdw. */
+/* HOST: plan of the structured row kernel for `rank` of `nranks` (Lin table, chunk table, group records, the source
+ * lists of the hops the row kernel leaves out on a sharded vector), as build_Hv_sector computes it.  tbits_opt = t + 1
+ * forces chunks of 2^t low groups (0 = automatic).  info[8] = {ok, LR, T, nhigh, nchunks, nrecs, list entries, listed
+ * columns}; arrays may be NULL; recs: 20 int32 per record (lb, N, hx, par, pc[16]); lptr: qdw+1 entries; lflag: qdw
+ * (bit 0: column not written by the row kernel, bit 1: column has entries); entry = (owner rank, column inside the
+ * owner's shard, amplitude). */
 int edgpu_selftest_srow_plan(const edgpu_params *p, int ndw, int nranks, int rank, int64_t lr, int64_t tbits_opt,
                              int32_t *info, int32_t *jhi, int cap_jhi, int32_t *chunks, int cap_chunks,
-                             int32_t *recs, int cap_recs, int32_t *lptr, int32_t *linit, int cap_cols,
-                             int32_t *lloc, double *lamp, int cap_e, int32_t *hown, int32_t *hcol, int cap_slots);
+                             int32_t *recs, int cap_recs, int32_t *lptr, int32_t *lflag, int cap_cols,
+                             int32_t *lown, int32_t *lcol, double *lamp, int cap_e);
 /* GPU: the sharded fast H*v path with `nranks` ranks emulated by `nranks` contexts on ONE device (peers are plain
  * device pointers instead of NVLink mappings); x, y are full host vectors.  Test instrumentation only. */
 int edgpu_selftest_sharded_hxv(const edgpu_params *p, int nup, int ndw, int nranks, int64_t srow_lr, int64_t srow_t,

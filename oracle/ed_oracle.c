@@ -1063,6 +1063,157 @@ int orc_lanc_tridiag_sector(const orc_sector *s, int mode, double *vin,
 }
 
 /* ===================================================================================== */
+/* ED_OBSERVABLES: lanc_observables (:95-363) + lanc_local_energy (:372-600), one state   */
+/* ===================================================================================== */
+void orc_observables_normal(const orc_ctx *c, int nup_, int ndw_, const double *gs, double zeta, orc_observables *o) {
+  const int norb = c->norb, ns = c->ns, LD = ORC_MAX_ORB;
+  const int64_t du = orc_binomial(ns, nup_), dd = orc_binomial(ns, ndw_), dim = du * dd;
+  int32_t *hu = (int32_t *)xmalloc((size_t)du * 4), *hd = (int32_t *)xmalloc((size_t)dd * 4);
+  orc_build_sector_map(ns, nup_, hu);
+  orc_build_sector_map(ns, ndw_, hd);
+  memset(o, 0, sizeof(*o));
+  const double peso = 1.0 / zeta;                            /* T = 0: peso = 1/zeta_function (:144-145) */
+  int ibup[64], ibdw[64];
+  double nup[ORC_MAX_ORB], ndw[ORC_MAX_ORB], sz[ORC_MAX_ORB], nt[ORC_MAX_ORB];
+  /* ---- first loop of lanc_observables (:153-212) ---- */
+  for (int64_t i = 0; i < dim; i++) {
+    int64_t iup = i % du, idw = i / du;
+    int32_t mup = hu[iup], mdw = hd[idw];
+    bdecomp(mup, ns, ibup);
+    bdecomp(mdw, ns, ibdw);
+    double gs_weight = peso * fabs(gs[i]) * fabs(gs[i]);
+    for (int io = 0; io < norb; io++) {
+      nup[io] = ibup[io]; ndw[io] = ibdw[io];
+      sz[io] = (nup[io] - ndw[io]) / 2.0;
+      nt[io] = nup[io] + ndw[io];
+    }
+    int iprob = 1, p3 = 1;
+    for (int io = 0; io < norb; io++) { iprob += (int)lround(nt[io]) * p3; p3 *= 3; }
+    o->prob[iprob - 1] += gs_weight;
+    double ssum = 0.0;
+    for (int io = 0; io < norb; io++) {
+      o->dens[io] += nt[io] * gs_weight;
+      o->dens_up[io] += nup[io] * gs_weight;
+      o->dens_dw[io] += ndw[io] * gs_weight;
+      o->docc[io] += nup[io] * ndw[io] * gs_weight;
+      o->magz[io] += (nup[io] - ndw[io]) * gs_weight;
+      o->sz2[io + LD * io] += (sz[io] * sz[io]) * gs_weight;
+      o->n2[io + LD * io] += (nt[io] * nt[io]) * gs_weight;
+      for (int jo = io + 1; jo < norb; jo++) {
+        o->sz2[io + LD * jo] += (sz[io] * sz[jo]) * gs_weight;
+        o->sz2[jo + LD * io] += (sz[jo] * sz[io]) * gs_weight;
+        o->n2[io + LD * jo] += (nt[io] * nt[jo]) * gs_weight;
+        o->n2[jo + LD * io] += (nt[jo] * nt[io]) * gs_weight;
+      }
+      ssum += sz[io];
+    }
+    o->s2tot += ssum * ssum * gs_weight;
+  }
+  /* ---- impurity density matrix (:240-305) ---- */
+  for (int64_t i = 0; i < dim; i++) {
+    int64_t iup = i % du, idw = i / du;
+    int32_t iud[2] = { hu[iup], hd[idw] };
+    bdecomp(iud[0], ns, ibup);
+    bdecomp(iud[1], ns, ibdw);
+    const int *nud[2] = { ibup, ibdw };
+    for (int is = 0; is < c->nspin; is++)
+      for (int io = 0; io < norb; io++)
+        o->dm[is][io + LD * io] += peso * nud[is][io] * gs[i] * gs[i];
+    for (int is = 0; is < c->nspin; is++)
+      for (int io = 0; io < norb; io++)
+        for (int jo = 0; jo < norb; jo++)
+          if (nud[is][jo] == 1 && nud[is][io] == 0) {
+            int32_t r, k; double sgn1, sgn2;
+            orc_c(jo + 1, iud[is], &r, &sgn1);
+            orc_cdg(io + 1, r, &k, &sgn2);
+            int64_t ju = iup, jd = idw;
+            if (is == 0) ju = orc_binary_search(hu, du, k) - 1;
+            else         jd = orc_binary_search(hd, dd, k) - 1;
+            int64_t j = ju + jd * du;
+            o->dm[is][io + LD * jo] += peso * sgn1 * gs[i] * sgn2 * gs[j];
+          }
+  }
+  /* ---- lanc_local_energy (:419-560) ---- */
+  const int sl = c->nspin - 1;
+  for (int64_t i = 0; i < dim; i++) {
+    int64_t iup = i % du, idw = i / du;
+    int32_t mup = hu[iup], mdw = hd[idw];
+    bdecomp(mup, ns, ibup);
+    bdecomp(mdw, ns, ibdw);
+    for (int io = 0; io < norb; io++) { nup[io] = ibup[io]; ndw[io] = ibdw[io]; }
+    double gs_weight = peso * fabs(gs[i]) * fabs(gs[i]);
+    for (int io = 0; io < norb; io++) {
+      o->eknot += HLOC(c, 0, 0, io, io) * nup[io] * gs_weight;
+      o->eknot += HLOC(c, sl, sl, io, io) * ndw[io] * gs_weight;
+    }
+    for (int io = 0; io < norb; io++)
+      for (int jo = 0; jo < norb; jo++) {
+        if (HLOC(c, 0, 0, io, jo) != 0.0 && nup[jo] == 1 && nup[io] == 0) {
+          int32_t k1, k2; double sg1, sg2;
+          orc_c(jo + 1, mup, &k1, &sg1);
+          orc_cdg(io + 1, k1, &k2, &sg2);
+          int64_t j = (orc_binary_search(hu, du, k2) - 1) + idw * du;
+          o->eknot += HLOC(c, 0, 0, io, jo) * sg1 * sg2 * gs[i] * gs[j] * peso;
+        }
+        if (HLOC(c, sl, sl, io, jo) != 0.0 && ndw[jo] == 1 && ndw[io] == 0) {
+          int32_t k1, k2; double sg1, sg2;
+          orc_c(jo + 1, mdw, &k1, &sg1);
+          orc_cdg(io + 1, k1, &k2, &sg2);
+          int64_t j = iup + (orc_binary_search(hd, dd, k2) - 1) * du;
+          o->eknot += HLOC(c, sl, sl, io, jo) * sg1 * sg2 * gs[i] * gs[j] * peso;
+        }
+      }
+    if (c->jhflag && c->jx != 0.0)
+      for (int io = 0; io < norb; io++)
+        for (int jo = 0; jo < norb; jo++)
+          if (io != jo && nup[jo] == 1 && ndw[io] == 1 && ndw[jo] == 0 && nup[io] == 0) {
+            int32_t k1, k2, k3, k4; double sg1, sg2, sg3, sg4;
+            orc_c(io + 1, mdw, &k1, &sg1); orc_cdg(jo + 1, k1, &k2, &sg2);
+            orc_c(jo + 1, mup, &k3, &sg3); orc_cdg(io + 1, k3, &k4, &sg4);
+            int64_t j = (orc_binary_search(hu, du, k4) - 1) + (orc_binary_search(hd, dd, k2) - 1) * du;
+            o->epot += c->jx * sg1 * sg2 * sg3 * sg4 * gs[i] * gs[j] * peso;
+            o->dse += sg1 * sg2 * sg3 * sg4 * gs[i] * gs[j] * peso;
+          }
+    if (c->jhflag && c->jp != 0.0)
+      for (int io = 0; io < norb; io++)
+        for (int jo = 0; jo < norb; jo++)
+          if (nup[jo] == 1 && ndw[jo] == 1 && ndw[io] == 0 && nup[io] == 0) {
+            int32_t k1, k2, k3, k4; double sg1, sg2, sg3, sg4;
+            orc_c(jo + 1, mdw, &k1, &sg1); orc_cdg(io + 1, k1, &k2, &sg2);
+            orc_c(jo + 1, mup, &k3, &sg3); orc_cdg(io + 1, k3, &k4, &sg4);
+            int64_t j = (orc_binary_search(hu, du, k4) - 1) + (orc_binary_search(hd, dd, k2) - 1) * du;
+            o->epot += c->jp * sg1 * sg2 * sg3 * sg4 * gs[i] * gs[j] * peso;
+            o->dph += sg1 * sg2 * sg3 * sg4 * gs[i] * gs[j] * peso;
+          }
+    for (int io = 0; io < norb; io++) o->epot += c->uloc[io] * nup[io] * ndw[io] * gs_weight;
+    if (norb > 1) {
+      for (int io = 0; io < norb; io++)
+        for (int jo = io + 1; jo < norb; jo++) {
+          o->epot += c->ust * (nup[io] * ndw[jo] + nup[jo] * ndw[io]) * gs_weight;
+          o->dust += (nup[io] * ndw[jo] + nup[jo] * ndw[io]) * gs_weight;
+        }
+      for (int io = 0; io < norb; io++)
+        for (int jo = io + 1; jo < norb; jo++) {
+          o->epot += (c->ust - c->jh) * (nup[io] * nup[jo] + ndw[io] * ndw[jo]) * gs_weight;
+          o->dund += (nup[io] * nup[jo] + ndw[io] * ndw[jo]) * gs_weight;
+        }
+    }
+    if (c->hfmode) {
+      for (int io = 0; io < norb; io++)
+        o->ehartree += -0.5 * c->uloc[io] * (nup[io] + ndw[io]) * gs_weight + 0.25 * c->uloc[io] * gs_weight;
+      if (norb > 1)
+        for (int io = 0; io < norb; io++)
+          for (int jo = io + 1; jo < norb; jo++) {
+            o->ehartree += -0.5 * c->ust * (nup[io] + ndw[io] + nup[jo] + ndw[jo]) * gs_weight + 0.25 * c->ust * gs_weight;
+            o->ehartree += -0.5 * (c->ust - c->jh) * (nup[io] + ndw[io] + nup[jo] + ndw[jo]) * gs_weight + 0.25 * (c->ust - c->jh) * gs_weight;
+          }
+    }
+  }
+  o->epot = o->epot + o->ehartree;                           /* :587 */
+  free(hu); free(hd);
+}
+
+/* ===================================================================================== */
 /* ED_GF_NORMAL                                                                          */
 /* ===================================================================================== */
 int64_t orc_gf_start_vector(const orc_ctx *c, int nup, int ndw, const double *gs,

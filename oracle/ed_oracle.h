@@ -101,6 +101,20 @@ void orc_directmatvec_mpi_main_all(const orc_ctx *c, int nup, int ndw, int nrank
 /* same, with pre-built per-rank sectors (for timing without the build) */
 void orc_spmatvec_mpi_main_prebuilt(orc_sector **secs, int nranks, int nthreads,
                                     const double *v, double *hv);
+/* ---- observables of one state at T = 0 (lanc_observables, ED_OBSERVABLES.f90:95-363, and lanc_local_energy,
+ * :372-600; bath_type normal, ed_total_ud = T, DimPh = 1).  Arrays use the Fortran index order of the reference
+ * with leading dimension ORC_MAX_ORB: sz2[iorb + 5*jorb], dm[ispin][iorb + 5*jorb] =
+ * imp_density_matrix(ispin,ispin,iorb,jorb) for ispin <= Nspin. */
+typedef struct orc_observables {
+  double dens[ORC_MAX_ORB], dens_up[ORC_MAX_ORB], dens_dw[ORC_MAX_ORB], docc[ORC_MAX_ORB], magz[ORC_MAX_ORB];
+  double sz2[ORC_MAX_ORB * ORC_MAX_ORB], n2[ORC_MAX_ORB * ORC_MAX_ORB];
+  double s2tot;
+  double prob[243];
+  double dm[2][ORC_MAX_ORB * ORC_MAX_ORB];
+  double eknot, epot, ehartree, dust, dund, dse, dph;
+} orc_observables;
+void orc_observables_normal(const orc_ctx *c, int nup, int ndw, const double *gs, double zeta, orc_observables *out);
+
 /* vector_transpose_MPI restated for all ranks at once (ED_HAMILTONIAN_COMMON.f90:53-118). */
 void orc_vector_transpose_all(int nranks, int64_t nrow, int64_t ncol,
                               double *const *a_shards, double *const *b_shards);

@@ -32,6 +32,22 @@ class _Csr(C.Structure):
                 ("cols", c_i64p), ("vals", c_dp)]
 
 
+class Observables(C.Structure):
+    """orc_observables / edgpu_observables (same layout): ED_OBSERVABLES.f90 outputs of one state."""
+    _fields_ = [("dens", C.c_double * 5), ("dens_up", C.c_double * 5), ("dens_dw", C.c_double * 5), ("docc", C.c_double * 5),
+                ("magz", C.c_double * 5), ("sz2", C.c_double * 25), ("n2", C.c_double * 25), ("s2tot", C.c_double),
+                ("prob", C.c_double * 243), ("dm", (C.c_double * 25) * 2),
+                ("eknot", C.c_double), ("epot", C.c_double), ("ehartree", C.c_double), ("dust", C.c_double),
+                ("dund", C.c_double), ("dse", C.c_double), ("dph", C.c_double)]
+
+    def as_dict(self):
+        out = {}
+        for name, _ in self._fields_:
+            v = getattr(self, name)
+            out[name] = float(v) if isinstance(v, float) else np.array(v, dtype=np.float64)
+        return out
+
+
 class _Sector(C.Structure):
     _fields_ = [("ctx", C.c_void_p), ("nup", C.c_int), ("ndw", C.c_int),
                 ("dimup", C.c_int64), ("dimdw", C.c_int64), ("dim", C.c_int64),
@@ -90,6 +106,7 @@ def lib():
         L.orc_lanc_build_gf_normal_main.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dp, C.c_double, C.c_double,
                                                     C.c_int, C.c_int, C.c_int, C.c_int, c_dp, C.c_int, c_dp,
                                                     c_dp, C.c_int, C.c_double, c_dp, c_dp, c_ip]
+        L.orc_observables_normal.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dp, C.c_double, C.POINTER(Observables)]
         L.orc_sigma_normal.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dp, C.c_int, c_dp, c_dp, c_dp]
         L.orc_allocate_grids.argtypes = [C.c_double, C.c_int, C.c_double, C.c_double, C.c_int, c_dp, c_dp]
         _LIB = L
@@ -318,6 +335,13 @@ class Oracle:
             out["chains"].append({"norm2": chain[p, 0], "alanc": chain[p, 1:1 + n].copy(),
                                   "blanc": chain[p, 1 + ngfiter:1 + ngfiter + n].copy(), "nlanc": n})
         return out
+
+    def observables(self, nup, ndw, gs, zeta=1.0):
+        """lanc_observables + lanc_local_energy of one state at T = 0 (ED_OBSERVABLES.f90:95-363, 372-600)."""
+        gs = _f64(gs)
+        o = Observables()
+        lib().orc_observables_normal(self.h, nup, ndw, _dp(gs), zeta, C.byref(o))
+        return o.as_dict()
 
     def sigma_normal(self, iorb, ispin, z, g):
         z = np.ascontiguousarray(z, dtype=np.complex128)

@@ -139,20 +139,18 @@ def _row_plan(p, ndw, nranks, rank, lr, st, dimdw, nnz):
     L = edgpu.selftest_lib()
     i32p, dp = C.POINTER(C.c_int32), C.POINTER(C.c_double)
     info = np.zeros(8, np.int32)
-    cap_j, cap_c, cap_r, cap_cols, cap_e, cap_s = 1 << 16, 1 << 14, 1 << 15, dimdw + 8, nnz + 8, dimdw + 8
+    cap_j, cap_c, cap_r, cap_cols, cap_e = 1 << 16, 1 << 14, 1 << 15, dimdw + 8, nnz + 8
     jhi = np.zeros(cap_j, np.int32); chunks = np.zeros(4 * cap_c, np.int32); recs = np.zeros(20 * cap_r, np.int32)
-    lptr = np.zeros(cap_cols + 1, np.int32); linit = np.zeros(cap_cols, np.int32)
-    lloc = np.zeros(cap_e, np.int32); lamp = np.zeros(cap_e)
-    hown = np.zeros(cap_s, np.int32); hcol = np.zeros(cap_s, np.int32)
+    lptr = np.zeros(cap_cols + 1, np.int32); lflag = np.zeros(cap_cols, np.int32)
+    lown = np.zeros(cap_e, np.int32); lcol = np.zeros(cap_e, np.int32); lamp = np.zeros(cap_e)
     rc = L.edgpu_selftest_srow_plan(C.byref(p), ndw, nranks, rank, C.c_int64(lr), C.c_int64(st), info.ctypes.data_as(i32p),
                                     jhi.ctypes.data_as(i32p), cap_j, chunks.ctypes.data_as(i32p), cap_c,
-                                    recs.ctypes.data_as(i32p), cap_r, lptr.ctypes.data_as(i32p), linit.ctypes.data_as(i32p), cap_cols,
-                                    lloc.ctypes.data_as(i32p), lamp.ctypes.data_as(dp), cap_e,
-                                    hown.ctypes.data_as(i32p), hcol.ctypes.data_as(i32p), cap_s)
+                                    recs.ctypes.data_as(i32p), cap_r, lptr.ctypes.data_as(i32p), lflag.ctypes.data_as(i32p), cap_cols,
+                                    lown.ctypes.data_as(i32p), lcol.ctypes.data_as(i32p), lamp.ctypes.data_as(dp), cap_e)
     assert rc == 0 and info[0] == 1, (rc, info)
     return dict(LR=int(info[1]), T=int(info[2]), nhigh=int(info[3]), jhi=jhi[:1 << int(info[3])],
                 chunks=chunks[:4 * info[4]].reshape(-1, 4), recs=recs[:20 * info[5]].reshape(-1, 20).view(np.uint32),
-                lptr=lptr, linit=linit, lloc=lloc[:info[6]], lamp=lamp[:info[6]], hown=hown[:info[7]], hcol=hcol[:info[7]])
+                lptr=lptr, lflag=lflag, lown=lown[:info[6]], lcol=lcol[:info[6]], lamp=lamp[:info[6]], nzcols=int(info[7]))
 
 
 def _kernel_hops(plan, ndw, vk):
@@ -189,9 +187,9 @@ def _kernel_hops(plan, ndw, vk):
 def test_row_kernel_plan_covers_every_hop_exactly_once(name, ndw, nranks, lr, st):
     """Host arithmetic behind the structured row kernel and its sharded form (hxv_fast.cu: srow_plan_host /
     srow_lists_host), checked without a GPU for every rank of a split: the records, evaluated the way the kernel
-    evaluates them, plus the column pass's source lists reproduce spH0dws(1) of the oracle (stored/H_dw.f90:8-80)
+    evaluates them, plus the source lists of the halo kernel reproduce spH0dws(1) of the oracle (stored/H_dw.f90:8-80)
     restricted to the rank's target columns EXACTLY once per entry, values bit-exact; every local column is written
-    by exactly one of the two kernels; halo slots name the right owner columns."""
+    by exactly one of the two passes; list entries name valid owner columns."""
     cfg, o = make_oracle(name)
     keep = _params(cfg)
     ns = cfg["nbath"] + 1
@@ -220,25 +218,21 @@ def test_row_kernel_plan_covers_every_hop_exactly_once(name, ndw, nranks, lr, st
         cover = np.zeros(q, np.int32)
         cover[written] += 1
         if nranks == 1:
-            assert len(plan["lloc"]) == 0 and len(plan["hown"]) == 0
+            assert len(plan["lown"]) == 0 and plan["nzcols"] == 0
         else:
-            lptr, linit = plan["lptr"], plan["linit"]
-            cover += linit[:q]
+            lptr, lflag = plan["lptr"], plan["lflag"]
+            cover += lflag[:q] & 1
+            nz = 0
             for t in range(q):
+                assert bool(lflag[t] & 2) == (lptr[t + 1] > lptr[t])
+                nz += int(lptr[t + 1] > lptr[t])
                 for e in range(lptr[t], lptr[t + 1]):
-                    loc = int(plan["lloc"][e])
-                    if loc >= 0:
-                        src = off + loc
-                    else:
-                        slot = -1 - loc
-                        own = int(plan["hown"][slot])
-                        assert own != rank
-                        src = coloffs[own] + int(plan["hcol"][slot])
-                        assert coloffs[own] <= src < coloffs[own + 1]
+                    own = int(plan["lown"][e])
+                    src = coloffs[own] + int(plan["lcol"][e])
+                    assert 0 <= own < nranks and coloffs[own] <= src < coloffs[own + 1]
                     assert (off + t, src) not in got
                     got[(off + t, src)] = float(plan["lamp"][e])
-            slots = list(zip(plan["hown"].tolist(), plan["hcol"].tolist()))
-            assert len(slots) == len(set(slots))                   # one halo column per remote source
+            assert nz == plan["nzcols"]
         assert (cover == 1).all()                                  # every local column written by exactly one kernel
         got = {k: v for k, v in got.items() if v != 0.0}           # the reference stores no entry for V_k = 0
         if not big:

@@ -269,6 +269,35 @@ def test_gf_chains_spin_down_and_device_state(name):
         s.close()
 
 
+def _c4_offdiag_hloc():
+    h = np.zeros((1, 1, 2, 2))
+    h[0, 0, 0, 1] = h[0, 0, 1, 0] = 0.3
+    h[0, 0, 0, 0], h[0, 0, 1, 1] = 0.1, -0.2
+    return h
+
+
+@pytest.mark.parametrize("name,over", [("C1", {}), ("NS10V", {}), ("C4", {}), ("C4", {"imphloc": _c4_offdiag_hloc()})])
+def test_observables_match_oracle(name, over):
+    """One fused device reduction over the resident ground state (observables.cu) against the oracle's restatement
+    of lanc_observables / lanc_local_energy (ED_OBSERVABLES.f90:95-363, 372-600): every output to 1e-12."""
+    cfg, o = make_oracle(name, **over)
+    nup, ndw = cfg["nup"], cfg["ndw"]
+    with o.sector(nup, ndw) as os_:
+        e0, gs, _, _ = os_.lanc_eigh(v0=np.ones(os_.dim) / np.sqrt(os_.dim))
+    ref = o.observables(nup, ndw, gs, zeta=1.0)
+    s = _solver(cfg)
+    try:
+        s.gf_set_state(s.get_sector(nup, ndw), gs, e0)
+        got = s.observables(zeta=1.0)
+        for key, val in ref.items():
+            assert np.abs(np.asarray(got[key]) - np.asarray(val)).max() < 1e-12, key
+        if cfg["xmu"] == 0.0 and not over:                     # half filling with HFMODE: <n> = 1 per orbital
+            assert np.abs(got["dens"][:cfg["norb"]] - 1.0).max() < 1e-8
+        assert abs(got["prob"].sum() - 1.0) < 1e-10
+    finally:
+        s.close()
+
+
 def test_golden_fixtures_on_gpu():
     gold = np.load(os.path.join(ROOT, "tests", "golden", "c1_golden.npz"))
     cfg = configs.config("C1")
