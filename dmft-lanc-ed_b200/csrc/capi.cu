@@ -144,8 +144,7 @@ extern "C" int edgpu_set_option(edgpu_ctx *c, const char *key, int64_t value) {
   if (!strcmp(key, "halo_ctas")) { c->opt_halo_ctas = value; return EDGPU_OK; }
   if (!strcmp(key, "no_overlap")) { c->opt_no_overlap = value; return EDGPU_OK; }
   if (!strcmp(key, "halo_chunks")) { c->opt_halo_chunks = value; return EDGPU_OK; }
-  if (!strcmp(key, "ccol_cs")) { c->opt_ccol_cs = value; return EDGPU_OK; }          // force the cluster size of the column pass
-  if (!strcmp(key, "no_ccol")) { c->opt_no_ccol = value; return EDGPU_OK; }          // 1: column pass with entries streamed from L2
+  if (!strcmp(key, "no_batch")) { c->opt_no_batch = value; return EDGPU_OK; }        // GF chains of a sector one after another
   if (!strcmp(key, "no_peer")) { c->opt_no_peer = value; return EDGPU_OK; }
   if (!strcmp(key, "col_cluster")) { c->opt_col_cluster = value; return EDGPU_OK; }
   if (!strcmp(key, "no_uniform")) { c->opt_no_uniform = value; return EDGPU_OK; }

@@ -94,7 +94,7 @@ struct edgpu_ctx {
   TiledPlan *plan = nullptr;
   FastPlan *fplan = nullptr;
   int64_t opt_srow_lr = 0, opt_srow_t = 0, opt_no_uniform = 0, opt_no_fuse = 0, opt_no_peer = 0, opt_col_cluster = 0;
-  int64_t opt_halo_ctas = 0, opt_no_overlap = 0, opt_halo_chunks = 0, opt_no_ccol = 0, opt_ccol_cs = 0;
+  int64_t opt_halo_ctas = 0, opt_no_overlap = 0, opt_halo_chunks = 0, opt_no_batch = 0;
   const double *const *peer_override = nullptr;   // selftest only: the ranks emulated on one device
   int64_t launches = 0;
   // symmetric slab (nranks > 1): one allocation per rank at identical offsets, opened by every peer

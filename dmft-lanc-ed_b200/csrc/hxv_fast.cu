@@ -68,19 +68,8 @@ struct FastFactor {
                                  // [n][8] row-major when WT == 8 (one 16-byte load per row), else [WT][n]
   bool uniform = false;          // every stored magnitude identical -> y = v * sum(+-x)
   double vuni = 0.0;
-};
-
-// cluster column kernel (k_ccol): rows split over CS CTAs by the top bits of the word, entries resident in shared memory
-struct CColPlan {
-  bool ok = false;
-  int cs = 0, WT = 0, rmax = 0, maxclusters = 0;
-  int r0[9] = {0};
-  uint32_t ctop[8] = {0};
-  uint16_t *d_cell = nullptr, *d_cmlow = nullptr;
-  bool uniform = false;
-  double vuni = 0.0;
-  double vk[EDGPU_MAX_SITES];
-  size_t smem = 0;
+  bool korder = false;           // single band: slots in the order of the row's eligible bath bits (UNI = 3 of k_fcol)
+  double vk[EDGPU_MAX_SITES];    // V_k of this spin (korder)
 };
 
 struct SRowPlan {
@@ -111,7 +100,6 @@ struct FastPlan {
   size_t col_smem[2] = {0, 0};
   bool col2_ok[2] = {false, false};   // two-CTA cluster variant (half a column per SM)
   size_t col2_smem[2] = {0, 0};
-  CColPlan cc[2];
   SRowPlan sr;
 };
 
@@ -189,6 +177,9 @@ struct FColArgs {
   const double *z;
   const unsigned char *lflag;
   int diagmode;
+  // UNI == 3 (single band, level-dependent V_k): slot s of a row is its s-th eligible bath bit, amplitude V_k from the word
+  int ns;
+  double vk[EDGPU_MAX_SITES];
 };
 
 // diagonal of element (r, local column j) for the columns the row pass skipped (runtime form of DIAG 1 / 2)
@@ -203,7 +194,10 @@ __device__ __forceinline__ double fcol_init_diag(const FColArgs &a, int64_t j, i
   return d;
 }
 // MODE: 0 = y = F x, 1 = y += F x, 2 = y += F x fused with the first Lanczos vector update (y is only read)
-// UNI: 0 = general (value table), 1 = uniform magnitude with 4-byte entries, 2 = uniform with 2-byte entries
+// UNI: 0 = general (value table, 4-byte entries), 1 = uniform magnitude with 4-byte entries, 2 = uniform with 2-byte
+// entries, 3 = single-band star geometry with level-dependent V_k: 2-byte entries in the order of the row's eligible
+// bath bits (the ones whose occupation differs from the impurity's), so the amplitude of slot s is V_k of the s-th
+// such bit of the row's word -- 20 bytes of index data per row instead of 32
 template <int WT, int DIAG, int UNI, int MODE, bool LISTS>
 __global__ void __launch_bounds__(FCOL_THREADS, 1) k_fcol(FColArgs a) {
   constexpr bool ACC = MODE >= 1;
@@ -230,8 +224,10 @@ __global__ void __launch_bounds__(FCOL_THREADS, 1) k_fcol(FColArgs a) {
   }
   if (UNI == 0)
     for (int i = tid; i < a.nvals; i += FCOL_THREADS) vtab[i] = a.vtab[i];
+  if (UNI == 3 && tid < 34) vtab[tid] = (tid >= 2 && tid - 1 < a.ns) ? a.vk[tid - 1] : 0.0;   // vtab[j] = V_{j-1}; 0 = padding slot
   __syncthreads();
   const uint32_t colbytes = (uint32_t)n * 8u;
+  const uint32_t bathmask = UNI == 3 ? (((1u << a.ns) - 1u) & ~1u) : 0u;
   const int64_t G = gridDim.x;
   if (warp == NCW) {
     // ---- producer warp: one whole column per stage; a stage is refilled as soon as every consumer warp
@@ -264,14 +260,16 @@ __global__ void __launch_bounds__(FCOL_THREADS, 1) k_fcol(FColArgs a) {
       if (LISTS) { const unsigned char f = __ldg(a.lflag + j); init = (f & 1) != 0; hasz = (f & 2) != 0; }
       const double *zc = a.z + j * (int64_t)n;
       uint32_t en[WT];
+      uint32_t mnext = 0;
       auto load_ell = [&](int row) {
-        if (UNI == 2 && WT == 8) {                                 // 8 two-byte entries = one LDG.128
+        if (UNI == 3) mnext = (uint32_t)__ldg(a.map_c + row);
+        if ((UNI == 2 || UNI == 3) && WT == 8) {                   // 8 two-byte entries = one LDG.128
           const uint4 q = __ldg(reinterpret_cast<const uint4 *>(a.ell16) + row);
           en[0] = q.x & 0xFFFFu; en[1] = q.x >> 16; en[2] = q.y & 0xFFFFu; en[3] = q.y >> 16;
           en[4 % WT] = q.z & 0xFFFFu; en[5 % WT] = q.z >> 16; en[6 % WT] = q.w & 0xFFFFu; en[7 % WT] = q.w >> 16;
         } else {
 #pragma unroll
-          for (int s = 0; s < WT; s++) en[s] = (UNI == 2) ? (uint32_t)__ldg(a.ell16 + (size_t)s * n + row) : __ldg(a.ell + (size_t)s * n + row);
+          for (int s = 0; s < WT; s++) en[s] = (UNI >= 2) ? (uint32_t)__ldg(a.ell16 + (size_t)s * n + row) : __ldg(a.ell + (size_t)s * n + row);
         }
       };
       if (tid < n) load_ell(tid);                                  // independent of the column: issued before the wait
@@ -284,6 +282,8 @@ __global__ void __launch_bounds__(FCOL_THREADS, 1) k_fcol(FColArgs a) {
 #pragma unroll
         for (int s = 0; s < WT; s++) e[s] = en[s];
         const double yold = ynext, zold = znext;
+        uint32_t E = 0;
+        if (UNI == 3) E = (mnext & 1u) ? (~mnext & bathmask) : (mnext & bathmask);
         if (r + NCT < n) {                                         // software prefetch of the next row's inputs
           load_ell(r + NCT);
           if (ACC) ynext = __ldcs(yc + r + NCT);
@@ -304,11 +304,17 @@ __global__ void __launch_bounds__(FCOL_THREADS, 1) k_fcol(FColArgs a) {
 #pragma unroll
         for (int s = 0; s < WT; s++) {
           if (UNI == 2) { acc += flip_sign(xs[e[s] & 0x7FFFu], (e[s] & 0x8000u) << 16); continue; }
+          if (UNI == 3) {
+            const int kk = __ffs((int)E);                          // 1-based bath bit of this slot, 0 once the row has run out
+            E &= E - 1;
+            acc = fma(flip_sign(vtab[kk], (e[s] & 0x8000u) << 16), xs[e[s] & 0x7FFFu], acc);
+            continue;
+          }
           const double xv = xs[e[s] & F_COL_MASK];
           if (UNI) acc += flip_sign(xv, e[s] & 0x80000000u);
           else acc = fma(flip_sign(vtab[(e[s] >> F_COL_BITS) & F_VID_MASK], e[s] & 0x80000000u), xv, acc);
         }
-        if (UNI) acc0 = fma(a.vuni, acc, acc0); else acc0 += acc;
+        if (UNI == 1 || UNI == 2) acc0 = fma(a.vuni, acc, acc0); else acc0 += acc;
         if (LISTS) {
           acc0 += init ? fcol_init_diag(a, j, r) * xs[r] : yold;
           acc0 += zold;
@@ -451,224 +457,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FCOL_THREADS, 1) k_f
   }
 }
 
-
-// ---------------------------------------------------------------------------------------------
-// pass 2, cluster form: the column is split over a CLUSTER of CS CTAs by the top log2(CS) bits of the up word (in
-// the sorted basis those are contiguous row ranges), and every CTA keeps the packed ELL entries of ITS rows resident
-// in shared memory for the whole kernel, next to two stages of its part of the column.  Nothing but x, y (and w) is
-// streamed any more: no index traffic through L2 at all.  A hop on one of the top bits reads the partner CTA's part
-// through distributed shared memory (1/15 of the gathers at Ns = 16 with CS = 2, 3/17 at Ns = 18 with CS = 8).
-// Single band only (every hop is impurity bit 0 <-> bath bit k): the slots of a row are its eligible bath bits in
-// ascending order, so an entry needs no value id -- level-dependent V_k come from the row's word (16 low bits kept
-// per row) -- and fits 16 bits: sign << 15 | where << 13 | index inside the source part.
-//   full[b]   TMA copy of my part of the column of stage b has landed                       (local, tx count)
-//   ready[b]  ... and so have the parts of the CTAs I read from (remote arrivals, cluster scope release/acquire)
-//   empty[b]  every consumer warp of every CTA that reads my part is done with stage b     (remote arrivals)
-// ---------------------------------------------------------------------------------------------
-#define CCOL_MAXCS 8
-struct CColArgs {
-  FColArgs f;
-  const uint16_t *cell;          // [CS][rmax][WT] entries of every part
-  const uint16_t *cmlow;         // [CS][rmax] low 16 bits of the rows' words
-  int rmax;                      // rows reserved per part
-  int r0[CCOL_MAXCS + 1];        // first row of every part (r0[CS] = n)
-  uint32_t ctop[CCOL_MAXCS];     // bits >= 16 of the words of a part (constant inside a part)
-  int ns;
-  double vk[EDGPU_MAX_SITES];    // V_k of this spin, k = 1 .. Ns-1
-};
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAITC_%=:\n"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONEC_%=;\n"
-      "bra WAITC_%=;\n"
-      "DONEC_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void cluster_sync_relaxed() {
-  asm volatile("barrier.cluster.arrive.release;\n" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire;\n" ::: "memory");
-}
-
-template <int CS, int WT, bool UNI, int MODE, bool LISTS>
-__global__ void __launch_bounds__(FCOL_THREADS, 1) k_ccol(const __grid_constant__ CColArgs a) {
-  static_assert(WT == 8 || WT == 16, "entries are read as 16-byte groups");
-  constexpr bool ACC = MODE >= 1;
-  constexpr int NCW = FCOL_THREADS / 32 - 1;                      // 31 consumer warps + 1 producer warp
-  constexpr int NCT = NCW * 32;
-  constexpr int NN = CS == 1 ? 1 : (CS == 2 ? 2 : (CS == 4 ? 3 : 4));   // CTAs that read a part: its owner and the hop partners
-  extern __shared__ __align__(128) unsigned char smraw[];
-  const int n = a.f.n;
-  const uint32_t me = CS > 1 ? cluster_ctarank() : 0u;
-  const int r0 = a.r0[me], nr = a.r0[me + 1] - r0;
-  const int r0a = r0 & ~1;                                         // bulk copies start on a 16-byte boundary
-  const int len = ((r0 + nr + 1) & ~1) - r0a;                      // rows copied per stage (even)
-  const int ldb = ((a.rmax + 3) & ~1) + 2;                         // doubles per stage buffer (zero slot at [len])
-  uint16_t *ell_s = reinterpret_cast<uint16_t *>(smraw);           // [rmax][WT]
-  uint16_t *mlow_s = ell_s + (size_t)a.rmax * WT;                  // [rmax + pad]
-  double *buf0 = reinterpret_cast<double *>(mlow_s + ((a.rmax + 7) & ~7));
-  double *vt = buf0 + 2 * ldb;                                     // [34] vt[j] = V_{j-1}, vt[0] = vt[1] = 0
-  uint64_t *bar = reinterpret_cast<uint64_t *>(vt + 34);           // full[2], ready[2], empty[2]
-  double *red = reinterpret_cast<double *>(bar + 6);               // [32]
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  double lsx = 0.0, lcp = 0.0, lsum = 0.0;
-  if (MODE == 2) { lsx = a.f.st->sx; lcp = a.f.st->cprev; }
-  if (tid == 0) {
-    mbar_init(&bar[0], 1); mbar_init(&bar[1], 1);
-    mbar_init(&bar[2], NN); mbar_init(&bar[3], NN);
-    mbar_init(&bar[4], NCW * NN); mbar_init(&bar[5], NCW * NN);
-    fence_barrier_init();
-  }
-  // resident tables of this part
-  {
-    const uint4 *src = reinterpret_cast<const uint4 *>(a.cell + (size_t)me * a.rmax * WT);
-    uint4 *dst = reinterpret_cast<uint4 *>(ell_s);
-    const int nq = nr * WT / 8;
-    for (int i = tid; i < nq; i += FCOL_THREADS) dst[i] = __ldg(src + i);
-    if (!UNI) for (int i = tid; i < nr; i += FCOL_THREADS) mlow_s[i] = __ldg(a.cmlow + (size_t)me * a.rmax + i);
-    if (tid < 34) vt[tid] = (tid >= 2 && tid - 1 < a.ns) ? a.vk[tid - 1] : 0.0;
-    if (tid < 2) { buf0[tid * ldb + len] = 0.0; buf0[tid * ldb + len + 1] = 0.0; }   // zero slot of the padding entries
-  }
-  __syncthreads();
-  if (CS > 1) cluster_sync_relaxed();                              // every CTA's barriers exist before anybody arrives remotely
-  // cluster addresses of the partners' stage buffers and barriers: partner w = me ^ (1 << (w - 1)), w = 1 .. NN-1
-  uint32_t pbuf[4] = {0, 0, 0, 0}, pbar[4] = {0, 0, 0, 0};
-  pbuf[0] = smem_u32(buf0); pbar[0] = smem_u32(bar);
-  if (CS > 1) {
-#pragma unroll
-    for (int w = 1; w < NN; w++) {
-      pbuf[w] = mapa_u32(smem_u32(buf0), me ^ (1u << (w - 1)));
-      pbar[w] = mapa_u32(smem_u32(bar), me ^ (1u << (w - 1)));
-    }
-    pbar[0] = mapa_u32(smem_u32(bar), me);
-  }
-  const int64_t nclus = gridDim.x / CS, cid = blockIdx.x / CS;
-  const uint32_t bathmask = ((1u << a.ns) - 1u) & ~1u;
-  const uint32_t ctop = a.ctop[me] << 16;
-  if (warp == NCW) {
-    // ---- producer warp: my part of one column per stage
-    if (lane == 0) {
-      for (int64_t it = 0;; it++) {
-        const int64_t j = cid + it * nclus;
-        if (j >= a.f.ncols) break;
-        const int b = (int)(it & 1);
-        if (it >= 2) mbar_wait_cluster(&bar[4 + b], (uint32_t)(((it >> 1) - 1) & 1));
-        fence_proxy_async();
-        const uint32_t bytes = (uint32_t)len * 8u;
-        mbar_expect_tx(&bar[b], bytes);
-        const char *src = reinterpret_cast<const char *>(a.f.x + j * (int64_t)n + r0a);
-        char *dst = reinterpret_cast<char *>(buf0 + b * ldb);
-        for (uint32_t off = 0; off < bytes; off += 32768u) bulk_g2s(dst + off, src + off, min(32768u, bytes - off), &bar[b]);
-      }
-    }
-  } else {
-    for (int64_t it = 0;; it++) {
-      const int64_t j = cid + it * nclus;
-      if (j >= a.f.ncols) break;
-      const int b = (int)(it & 1);
-      const uint32_t ph = (uint32_t)((it >> 1) & 1);
-      const double *xs = buf0 + b * ldb;
-      double *yc = a.f.y + j * (int64_t)n + r0;
-      bool init = false, hasz = false;
-      if (LISTS) { const unsigned char f = __ldg(a.f.lflag + j); init = (f & 1) != 0; hasz = (f & 2) != 0; }
-      const double *zc = a.f.z + j * (int64_t)n + r0;
-      double ynext = 0.0, znext = 0.0;
-      if (ACC && tid < nr) ynext = __ldcs(yc + tid);
-      if (LISTS && hasz && tid < nr) znext = __ldcs(zc + tid);
-      if (CS == 1) {
-        mbar_wait(&bar[b], ph);
-      } else {
-        if (warp == 0 && lane == 0) {                               // my part has landed: tell everybody who reads it
-          mbar_wait(&bar[b], ph);
-#pragma unroll
-          for (int w = 0; w < NN; w++) mbar_arrive_cluster(pbar[w] + (2 + b) * 8);
-        }
-        mbar_wait_cluster(&bar[2 + b], ph);                         // all the parts I read are in place
-      }
-      const uint32_t boff = (uint32_t)(b * ldb * 8);
-      for (int rl = tid; rl < nr; rl += NCT) {
-        uint32_t e[WT];
-        {
-          const uint4 q = *reinterpret_cast<const uint4 *>(ell_s + (size_t)rl * WT);
-          e[0] = q.x & 0xFFFFu; e[1] = q.x >> 16; e[2] = q.y & 0xFFFFu; e[3] = q.y >> 16;
-          e[4] = q.z & 0xFFFFu; e[5] = q.z >> 16; e[6] = q.w & 0xFFFFu; e[7] = q.w >> 16;
-          if (WT == 16) {
-            const uint4 q2 = *reinterpret_cast<const uint4 *>(ell_s + (size_t)rl * WT + 8);
-            e[8 % WT] = q2.x & 0xFFFFu; e[9 % WT] = q2.x >> 16; e[10 % WT] = q2.y & 0xFFFFu; e[11 % WT] = q2.y >> 16;
-            e[12 % WT] = q2.z & 0xFFFFu; e[13 % WT] = q2.z >> 16; e[14 % WT] = q2.w & 0xFFFFu; e[15 % WT] = q2.w >> 16;
-          }
-        }
-        const double yold = ynext, zold = znext;
-        if (rl + NCT < nr) {                                       // software prefetch of the next row's streamed inputs
-          if (ACC) ynext = __ldcs(yc + rl + NCT);
-          if (LISTS && hasz) znext = __ldcs(zc + rl + NCT);
-        }
-        uint32_t E = 0;
-        if (!UNI) {
-          const uint32_t m = (uint32_t)mlow_s[rl] | ctop;
-          E = (m & 1u) ? (~m & bathmask) : (m & bathmask);         // bath bits whose occupation differs from the impurity's
-        }
-        double acc = 0.0;
-#pragma unroll
-        for (int s = 0; s < WT; s++) {
-          const uint32_t idx = e[s] & 0x1FFFu, w = (e[s] >> 13) & 3u;
-          double xv;
-          if (CS == 1 || w == 0) xv = xs[idx];
-          else xv = ld_dsmem((w == 1 ? pbuf[1] : (w == 2 ? pbuf[2] : pbuf[3])) + boff + idx * 8u);
-          if (UNI) {
-            acc += flip_sign(xv, (e[s] & 0x8000u) << 16);
-          } else {
-            const int kk = __ffs((int)E);                          // 1-based bit of this slot's bath level, 0 = padding slot
-            E &= E - 1;
-            acc = fma(flip_sign(vt[kk], (e[s] & 0x8000u) << 16), xv, acc);
-          }
-        }
-        double acc0 = UNI ? a.f.vuni * acc : acc;
-        const double xr = xs[rl + (r0 - r0a)];
-        if (LISTS) {
-          acc0 += init ? fcol_init_diag(a.f, j, r0 + rl) * xr : yold;
-          acc0 += zold;
-        } else if (ACC) {
-          acc0 += yold;
-        }
-        if (MODE == 2) {
-          double *wp = a.f.xp + j * (int64_t)n + r0 + rl;
-          const double w2 = lsx * acc0 - lcp * __ldcs(wp);
-          __stcs(wp, w2);
-          lsum = fma(lsx * xr, w2, lsum);
-        } else {
-          __stcs(yc + rl, acc0);
-        }
-      }
-      __syncwarp();
-      if (lane == 0) {                                             // this warp is done with stage b of every part it read
-        if (CS == 1) mbar_arrive(&bar[4 + b]);
-        else {
-#pragma unroll
-          for (int w = 0; w < NN; w++) mbar_arrive_cluster(pbar[w] + (4 + b) * 8);
-        }
-      }
-    }
-  }
-  if (MODE == 2) {                                               // deterministic: fixed order inside the CTA, one partial per CTA
-    for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
-    if (lane == 0) red[warp] = lsum;
-    __syncthreads();
-    if (tid < 32) {
-      double r2 = red[tid];
-      for (int o = 16; o > 0; o >>= 1) r2 += __shfl_xor_sync(0xffffffffu, r2, o);
-      if (tid == 0) a.f.partials[blockIdx.x] = r2;
-    }
-  }
-  if (CS > 1) cluster_sync_relaxed();                              // nobody leaves while a partner may still read or signal it
-}
 
 // ---------------------------------------------------------------------------------------------
 // pass 1: structured row-tile kernel for the single-band star geometry
@@ -1033,30 +821,65 @@ __global__ void __launch_bounds__(HALO_THREADS) k_halo_axpy(HaloArgs a) {
 // plan
 // ---------------------------------------------------------------------------------------------
 static int pack_fast(edgpu_ctx *c, const Factor &f, FastFactor &ff) {
-  std::vector<int32_t> rp((size_t)f.n + 1), cols((size_t)std::max<int64_t>(f.nnz, 1));
+  std::vector<int32_t> rp((size_t)f.n + 1), cols((size_t)std::max<int64_t>(f.nnz, 1)), map((size_t)f.n);
   std::vector<double> vals((size_t)std::max<int64_t>(f.nnz, 1));
   CK(cudaMemcpy(rp.data(), f.d_rowptr, rp.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(map.data(), f.d_map, map.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
   if (f.nnz) {
     CK(cudaMemcpy(cols.data(), f.d_cols, (size_t)f.nnz * sizeof(int32_t), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(vals.data(), f.d_vals, (size_t)f.nnz * sizeof(double), cudaMemcpyDeviceToHost));
   }
   ff.n = f.n;
-  ff.W = std::max(f.maxrow, 1);
+  // Single band: every entry (row <- col) differs from the row's word in the impurity bit and ONE bath bit k and
+  // carries +-V_k.  Then the slots of a row can follow its eligible bath bits (those whose occupation differs from
+  // the impurity's) in ascending order, and no value id has to be stored: slot s <-> s-th eligible bit.
+  const int ns = c->ns, spin = (&f == &c->dw) ? 1 : 0;
+  for (int k = 0; k < EDGPU_MAX_SITES; k++) ff.vk[k] = 0.0;
+  for (int k = 1; k < ns; k++) ff.vk[k] = spin ? c->dp.bv_dw[k - 1] : c->dp.bv_up[k - 1];
+  const uint32_t bath = ((1u << ns) - 1u) & ~1u;
+  bool star = c->dp.norb == 1;
+  int wstar = 1;
+  for (int64_t i = 0; i < f.n && star; i++) {
+    const uint32_t m = (uint32_t)map[(size_t)i];
+    wstar = std::max(wstar, __builtin_popcount((m & 1u) ? (~m & bath) : (m & bath)));
+    for (int32_t p = rp[(size_t)i]; p < rp[(size_t)i + 1]; p++) {
+      const uint32_t x = m ^ (uint32_t)map[(size_t)cols[(size_t)p]];
+      if (!(x & 1u) || __builtin_popcount(x) != 2) { star = false; break; }
+      const int k = __builtin_ctz(x & ~1u);
+      if (fabs(vals[(size_t)p]) != fabs(ff.vk[k])) { star = false; break; }
+    }
+  }
+  ff.korder = star && wstar <= 16;
+  ff.W = ff.korder ? wstar : std::max(f.maxrow, 1);
   ff.WT = ff.W <= 8 ? 8 : (ff.W <= 12 ? 12 : 16);
   if (ff.W > 16) return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "factor row too long for the fast column kernel");
   std::map<double, int> ids;
   std::vector<double> vtab(1, 0.0);
   std::vector<uint32_t> ell((size_t)ff.WT * f.n, (uint32_t)f.n);       // padding: zero slot, value id 0
   for (int64_t i = 0; i < f.n; i++) {
+    const uint32_t m = (uint32_t)map[(size_t)i];
+    uint32_t E = (m & 1u) ? (~m & bath) : (m & bath);
     int k = 0;
-    for (int32_t p = rp[i]; p < rp[i + 1]; p++, k++) {
-      const double av = vals[p] < 0 ? -vals[p] : vals[p];
+    auto put = [&](int slot, int32_t p) {
+      const double av = vals[(size_t)p] < 0 ? -vals[(size_t)p] : vals[(size_t)p];
       auto it = ids.find(av);
       int id;
       if (it == ids.end()) { id = (int)vtab.size(); ids[av] = id; vtab.push_back(av); }
       else id = it->second;
-      if (id >= F_MAXVALS) return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "too many distinct matrix elements for the fast column kernel");
-      ell[(size_t)k * f.n + i] = (uint32_t)cols[p] | ((uint32_t)id << F_COL_BITS) | (vals[p] < 0 ? 0x80000000u : 0u);
+      if (id >= F_MAXVALS) return false;
+      ell[(size_t)slot * f.n + i] = (uint32_t)cols[(size_t)p] | ((uint32_t)id << F_COL_BITS) | (vals[(size_t)p] < 0 ? 0x80000000u : 0u);
+      return true;
+    };
+    if (ff.korder) {
+      for (; E; E &= E - 1, k++) {                                  // slot k = k-th eligible bath bit; V_k = 0: padding entry
+        const uint32_t m2 = m ^ 1u ^ (1u << __builtin_ctz(E));
+        for (int32_t p = rp[(size_t)i]; p < rp[(size_t)i + 1]; p++)
+          if ((uint32_t)map[(size_t)cols[(size_t)p]] == m2 && !put(k, p))
+            return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "too many distinct matrix elements for the fast column kernel");
+      }
+    } else {
+      for (int32_t p = rp[(size_t)i]; p < rp[(size_t)i + 1]; p++, k++)
+        if (!put(k, p)) return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "too many distinct matrix elements for the fast column kernel");
     }
   }
   ff.nvals = (int)vtab.size();
@@ -1066,7 +889,7 @@ static int pack_fast(edgpu_ctx *c, const Factor &f, FastFactor &ff) {
   CK(cudaMalloc(&ff.d_vtab, vtab.size() * sizeof(double)));
   CK(cudaMemcpy(ff.d_ell, ell.data(), ell.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(ff.d_vtab, vtab.data(), vtab.size() * sizeof(double), cudaMemcpyHostToDevice));
-  if (ff.uniform && f.n < 32768) {
+  if ((ff.uniform || ff.korder) && f.n < 32768) {
     std::vector<uint16_t> e16(ell.size());
     for (int k = 0; k < ff.WT; k++)
       for (int64_t i = 0; i < f.n; i++) {
@@ -1258,201 +1081,9 @@ static int build_srow(edgpu_ctx *c, SRowPlan &sr) {
   return EDGPU_OK;
 }
 
-// ---- cluster column kernel: plan -------------------------------------------------------------------------
-static size_t ccol_smem(int rmax, int WT) {
-  const size_t ldb = (size_t)((rmax + 3) & ~1) + 2;
-  return (size_t)rmax * WT * 2 + (size_t)((rmax + 7) & ~7) * 2 + 2 * ldb * 8 + 34 * 8 + 6 * 8 + 32 * 8;
-}
-template <int CS, int WT, bool UNI>
-static cudaError_t set_ccol_attr_m() {
-  cudaError_t e = cudaSuccess;
-#define SETC(M, L) if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ccol<CS, WT, UNI, M, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT)
-  SETC(0, false); SETC(1, false); SETC(2, false); SETC(1, true); SETC(2, true);
-#undef SETC
-  return e;
-}
-template <int CS>
-static cudaError_t set_ccol_attr() {
-  cudaError_t e = set_ccol_attr_m<CS, 8, true>();
-  if (e == cudaSuccess) e = set_ccol_attr_m<CS, 8, false>();
-  if (e == cudaSuccess) e = set_ccol_attr_m<CS, 16, true>();
-  if (e == cudaSuccess) e = set_ccol_attr_m<CS, 16, false>();
-  return e;
-}
-template <int CS, int WT, bool UNI>
-static const void *ccol_fn(int mode, bool lists) {
-  if (lists) return mode == 2 ? (const void *)k_ccol<CS, WT, UNI, 2, true> : (const void *)k_ccol<CS, WT, UNI, 1, true>;
-  if (mode == 2) return (const void *)k_ccol<CS, WT, UNI, 2, false>;
-  if (mode == 1) return (const void *)k_ccol<CS, WT, UNI, 1, false>;
-  return (const void *)k_ccol<CS, WT, UNI, 0, false>;
-}
-template <int CS>
-static const void *ccol_fn_cs(int WT, bool uni, int mode, bool lists) {
-  if (WT == 8) return uni ? ccol_fn<CS, 8, true>(mode, lists) : ccol_fn<CS, 8, false>(mode, lists);
-  return uni ? ccol_fn<CS, 16, true>(mode, lists) : ccol_fn<CS, 16, false>(mode, lists);
-}
-static const void *ccol_fn_any(int cs, int WT, bool uni, int mode, bool lists) {
-  switch (cs) {
-    case 1: return ccol_fn_cs<1>(WT, uni, mode, lists);
-    case 2: return ccol_fn_cs<2>(WT, uni, mode, lists);
-    case 4: return ccol_fn_cs<4>(WT, uni, mode, lists);
-    default: return ccol_fn_cs<8>(WT, uni, mode, lists);
-  }
-}
-
-// Single band only.  Rows split by the top log2(CS) bits of the word; slot s of a row = its s-th eligible bath bit
-// (ascending), entry = sign << 15 | where << 13 | (source row - first copied row of the source part).
-static int build_ccol(edgpu_ctx *c, const Factor &f, int spin, CColPlan &cp) {
-  cp.ok = false;
-  if (c->dp.norb != 1 || c->opt_no_ccol || f.n < 2 || (f.n & 1) || f.maxrow > 16) return EDGPU_OK;
-  const int ns = c->ns;
-  std::vector<int32_t> map((size_t)f.n), rp((size_t)f.n + 1), cols((size_t)std::max<int64_t>(f.nnz, 1));
-  std::vector<double> vals((size_t)std::max<int64_t>(f.nnz, 1));
-  CK(cudaMemcpy(map.data(), f.d_map, map.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(rp.data(), f.d_rowptr, rp.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
-  if (f.nnz) {
-    CK(cudaMemcpy(cols.data(), f.d_cols, (size_t)f.nnz * sizeof(int32_t), cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(vals.data(), f.d_vals, (size_t)f.nnz * sizeof(double), cudaMemcpyDeviceToHost));
-  }
-  for (int k = 0; k < EDGPU_MAX_SITES; k++) cp.vk[k] = 0.0;
-  for (int k = 1; k < ns; k++) cp.vk[k] = spin ? c->dp.bv_dw[k - 1] : c->dp.bv_up[k - 1];
-  cp.uniform = true; cp.vuni = 0.0;
-  for (int k = 1; k < ns; k++) {
-    const double av = fabs(cp.vk[k]);
-    if (av == 0.0) continue;
-    if (cp.vuni == 0.0) cp.vuni = av;
-    else if (av != cp.vuni) cp.uniform = false;
-  }
-  // widest row (eligible bath bits: the occupied ones when the impurity is empty, else the empty ones)
-  const int npart = __builtin_popcount((unsigned)map[0]);
-  const int wmax = std::max(npart, ns - npart);
-  if (wmax > 16) return EDGPU_OK;
-  cp.WT = wmax <= 8 ? 8 : 16;
-  int cs = 0, lb = 0;
-  for (int tcs = 1, tlb = 0; tcs <= CCOL_MAXCS; tcs *= 2, tlb++) {
-    if (ns - 16 > tlb || tlb >= ns) continue;                      // bits >= 16 must be constant inside a part
-    if (c->opt_ccol_cs > 0 && tcs != c->opt_ccol_cs) continue;     // tests: force a cluster size
-    int r0[9]; r0[0] = 0;
-    bool okp = true;
-    int rmax = 0;
-    for (int p = 0; p < tcs; p++) {
-      const int32_t lim = (int32_t)(((int64_t)p + 1) << (ns - tlb));    // first word of the next part
-      r0[p + 1] = (int)(std::lower_bound(map.begin(), map.end(), lim) - map.begin());
-      rmax = std::max(rmax, r0[p + 1] - r0[p]);
-      if (r0[p + 1] == r0[p]) okp = false;                         // an empty part would leave a CTA without a role
-    }
-    if (!okp || rmax + 2 >= 8192) continue;
-    if (ccol_smem(rmax, cp.WT) > SMEM_LIMIT) continue;
-    if (tcs > 1 && c->sm_count < tcs) continue;
-    cs = tcs; lb = tlb;
-    for (int p = 0; p <= tcs; p++) cp.r0[p] = r0[p];
-    cp.rmax = rmax;
-    break;
-  }
-  if (cs == 0) return EDGPU_OK;
-  cp.cs = cs;
-  cp.smem = ccol_smem(cp.rmax, cp.WT);
-  std::vector<uint16_t> cell((size_t)cs * cp.rmax * cp.WT, 0), cmlow((size_t)cs * cp.rmax, 0);
-  for (int p = 0; p < cs; p++) {
-    const int r0 = cp.r0[p], nr = cp.r0[p + 1] - r0, r0a = r0 & ~1;
-    const int len = ((r0 + nr + 1) & ~1) - r0a;
-    cp.ctop[p] = (uint32_t)map[(size_t)r0] >> 16;
-    for (int rl = 0; rl < nr; rl++) {
-      const int r = r0 + rl;
-      const uint32_t m = (uint32_t)map[(size_t)r];
-      if ((m >> 16) != cp.ctop[p]) return EDGPU_OK;                 // cannot happen for aligned parts
-      cmlow[(size_t)p * cp.rmax + rl] = (uint16_t)(m & 0xFFFFu);
-      const uint32_t bath = ((1u << ns) - 1u) & ~1u;
-      uint32_t E = (m & 1u) ? (~m & bath) : (m & bath);
-      uint16_t *row = &cell[((size_t)p * cp.rmax + rl) * cp.WT];
-      int s = 0;
-      for (; E; E &= E - 1, s++) {
-        const int k = __builtin_ctz(E);
-        const uint32_t m2 = m ^ 1u ^ (1u << k);
-        const int r2 = (int)(std::lower_bound(map.begin(), map.end(), (int32_t)m2) - map.begin());
-        if (r2 >= f.n || (uint32_t)map[(size_t)r2] != m2) return EDGPU_OK;
-        int sign = 0; bool found = false;
-        for (int32_t q = rp[(size_t)r]; q < rp[(size_t)r + 1]; q++)
-          if (cols[(size_t)q] == r2) {
-            found = true;
-            sign = vals[(size_t)q] < 0.0;
-            if (fabs(vals[(size_t)q]) != fabs(cp.vk[k])) return EDGPU_OK;   // not the star geometry this kernel assumes
-          }
-        if (!found) {                                              // V_k = 0: the reference stores no entry
-          if (cp.vk[k] != 0.0) return EDGPU_OK;
-          row[s] = (uint16_t)len;
-          continue;
-        }
-        const int p2 = lb ? (int)(m2 >> (ns - lb)) : 0;
-        int w = 0;
-        if (p2 != p) {
-          const int d = p2 ^ p;
-          if (d & (d - 1)) return EDGPU_OK;                         // more than one top bit differs: impossible for one hop
-          w = __builtin_ctz((unsigned)d) + 1;
-        }
-        const int idx = r2 - (cp.r0[p2] & ~1);
-        row[s] = (uint16_t)((sign << 15) | (w << 13) | idx);
-      }
-      for (; s < cp.WT; s++) row[s] = (uint16_t)len;                // padding: the zero slot of my own stage buffer
-    }
-  }
-  // every CSR entry must have been placed (rows with inter-orbital terms etc. would show up here)
-  for (int64_t r = 0; r < f.n; r++) {
-    const uint32_t m = (uint32_t)map[(size_t)r];
-    const uint32_t bath = ((1u << ns) - 1u) & ~1u;
-    const uint32_t E = (m & 1u) ? (~m & bath) : (m & bath);
-    int nz = 0;
-    for (uint32_t e2 = E; e2; e2 &= e2 - 1) if (cp.vk[__builtin_ctz(e2)] != 0.0) nz++;
-    if (rp[(size_t)r + 1] - rp[(size_t)r] != nz) return EDGPU_OK;
-  }
-  TRY(to_device(&cp.d_cell, cell));
-  TRY(to_device(&cp.d_cmlow, cmlow));
-  // clusters that can be resident at once
-  cp.maxclusters = cs == 1 ? c->sm_count : 0;
-  if (cs > 1) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(c->sm_count / cs * cs)); cfg.blockDim = dim3(FCOL_THREADS); cfg.dynamicSmemBytes = cp.smem;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    int nc = 0;
-    if (cudaOccupancyMaxActiveClusters(&nc, ccol_fn_any(cs, cp.WT, cp.uniform, 1, false), &cfg) != cudaSuccess || nc < 1) { cudaGetLastError(); return EDGPU_OK; }
-    cp.maxclusters = nc;
-  }
-  cp.ok = true;
-  return EDGPU_OK;
-}
-
-// launch for `ncols` columns; *nctas = CTAs launched (one partial sum per CTA in MODE 2)
-static int launch_ccol(edgpu_ctx *c, const CColPlan &cp, const FColArgs &fa, int mode, bool lists, int64_t ncols, int grid_limit, int *nctas) {
-  CColArgs a{};
-  a.f = fa;
-  a.cell = cp.d_cell; a.cmlow = cp.d_cmlow; a.rmax = cp.rmax; a.ns = c->ns;
-  for (int p = 0; p <= cp.cs; p++) a.r0[p] = cp.r0[p];
-  for (int p = 0; p < cp.cs; p++) a.ctop[p] = cp.ctop[p];
-  for (int k = 0; k < EDGPU_MAX_SITES; k++) a.vk[k] = cp.vk[k];
-  a.f.vuni = cp.vuni;
-  int64_t nclus = std::min<int64_t>(ncols, cp.maxclusters);
-  if (grid_limit > 0) nclus = std::min<int64_t>(nclus, std::max(1, grid_limit / cp.cs));
-  if (nclus < 1) { *nctas = 0; return EDGPU_OK; }
-  const bool uni = cp.uniform && c->opt_no_uniform != 1;
-  const void *fn = ccol_fn_any(cp.cs, cp.WT, uni, mode, lists);
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(nclus * cp.cs)); cfg.blockDim = dim3(FCOL_THREADS); cfg.dynamicSmemBytes = cp.smem; cfg.stream = c->stream;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)cp.cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = cp.cs > 1 ? 1 : 0;
-  void *args[1] = {(void *)&a};
-  CK(cudaLaunchKernelExC(&cfg, fn, args));
-  c->launches++;
-  *nctas = (int)(nclus * cp.cs);
-  return EDGPU_OK;
-}
-
 int fast_plan_free(edgpu_ctx *c) {
   if (!c->fplan) return EDGPU_OK;
   for (int k = 0; k < 2; k++) { cudaFree(c->fplan->ff[k].d_ell); cudaFree(c->fplan->ff[k].d_ell16); cudaFree(c->fplan->ff[k].d_vtab); }
-  for (int k = 0; k < 2; k++) { cudaFree(c->fplan->cc[k].d_cell); cudaFree(c->fplan->cc[k].d_cmlow); }
   SRowPlan &r = c->fplan->sr;
   cudaFree(r.d_recs); cudaFree(r.d_chunks); cudaFree(r.d_vk); cudaFree(r.d_dr0); cudaFree(r.d_dr1);
   cudaFree(r.d_lptr); cudaFree(r.d_lown); cudaFree(r.d_lcol); cudaFree(r.d_lamp); cudaFree(r.d_lflag); cudaFree(r.d_zcols); cudaFree(r.d_z);
@@ -1466,10 +1097,12 @@ template <int WT, int DIAG>
 static cudaError_t set_fcol_attr() {
   cudaError_t e = cudaSuccess;
 #define SETF(U, A, L) if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fcol<WT, DIAG, U, A, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT)
-  SETF(0, 0, false); SETF(1, 0, false); SETF(2, 0, false); SETF(0, 1, false); SETF(1, 1, false); SETF(2, 1, false);
+  SETF(0, 0, false); SETF(1, 0, false); SETF(2, 0, false); SETF(3, 0, false);
+  SETF(0, 1, false); SETF(1, 1, false); SETF(2, 1, false); SETF(3, 1, false);
   if (DIAG == 0) {
-    SETF(0, 2, false); SETF(1, 2, false); SETF(2, 2, false);
-    SETF(0, 1, true); SETF(1, 1, true); SETF(2, 1, true); SETF(0, 2, true); SETF(1, 2, true); SETF(2, 2, true);
+    SETF(0, 2, false); SETF(1, 2, false); SETF(2, 2, false); SETF(3, 2, false);
+    SETF(0, 1, true); SETF(1, 1, true); SETF(2, 1, true); SETF(3, 1, true);
+    SETF(0, 2, true); SETF(1, 2, true); SETF(2, 2, true); SETF(3, 2, true);
   }
 #undef SETF
   return e;
@@ -1490,7 +1123,6 @@ static int set_kernel_attrs(edgpu_ctx *c) {
   CK((set_fcol_attr<12, 0>())); CK((set_fcol_attr<12, 1>())); CK((set_fcol_attr<12, 2>()));
   CK((set_fcol_attr<16, 0>())); CK((set_fcol_attr<16, 1>())); CK((set_fcol_attr<16, 2>()));
   CK(set_fcol2_attr<8>()); CK(set_fcol2_attr<12>()); CK(set_fcol2_attr<16>());
-  CK(set_ccol_attr<1>()); CK(set_ccol_attr<2>()); CK(set_ccol_attr<4>()); CK(set_ccol_attr<8>());
   CK(cudaFuncSetAttribute(k_srow<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
   CK(cudaFuncSetAttribute(k_srow<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
   CK(cudaFuncSetAttribute(k_srow<5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
@@ -1515,7 +1147,6 @@ int fast_plan_build(edgpu_ctx *c) {
       if (rc == EDGPU_ERR_UNSUPPORTED) { p->col_ok[k] = false; p->col2_ok[k] = false; }
       else if (rc) { fast_plan_free(c); return rc; }
     }
-    { int rc = build_ccol(c, f, k, p->cc[k]); if (rc) { fast_plan_free(c); return rc; } }
   }
   int rc = build_srow(c, p->sr);
   if (rc) { fast_plan_free(c); return rc; }
@@ -1525,17 +1156,18 @@ int fast_plan_build(edgpu_ctx *c) {
 bool fast_supported_local(edgpu_ctx *c) {
   if (!c->hstatus || c->dp.jhflag) return false;
   if (fast_plan_build(c)) return false;
-  return (c->fplan->col_ok[0] || c->fplan->col2_ok[0] || c->fplan->cc[0].ok) && c->fplan->sr.ok;
+  return (c->fplan->col_ok[0] || c->fplan->col2_ok[0]) && c->fplan->sr.ok;
 }
 bool fast_supported_col(edgpu_ctx *c, int k) {
   if (!c->hstatus || c->dp.jhflag) return false;
   if (fast_plan_build(c)) return false;
-  return c->fplan->col_ok[k] || c->fplan->col2_ok[k] || c->fplan->cc[k].ok;
+  return c->fplan->col_ok[k] || c->fplan->col2_ok[k];
 }
 
 template <int WT, int DIAG, int MODE, bool LISTS>
 static void launch_fcol_m(int uni, int grid, size_t smem, cudaStream_t st, const FColArgs &a) {
-  if (uni == 2) k_fcol<WT, DIAG, 2, MODE, LISTS><<<grid, FCOL_THREADS, smem, st>>>(a);
+  if (uni == 3) k_fcol<WT, DIAG, 3, MODE, LISTS><<<grid, FCOL_THREADS, smem, st>>>(a);
+  else if (uni == 2) k_fcol<WT, DIAG, 2, MODE, LISTS><<<grid, FCOL_THREADS, smem, st>>>(a);
   else if (uni == 1) k_fcol<WT, DIAG, 1, MODE, LISTS><<<grid, FCOL_THREADS, smem, st>>>(a);
   else k_fcol<WT, DIAG, 0, MODE, LISTS><<<grid, FCOL_THREADS, smem, st>>>(a);
 }
@@ -1582,9 +1214,8 @@ int fast_apply_col(edgpu_ctx *c, int k, bool with_diag, bool acc, const double *
                    double *d_xp, int *npartials, bool dw_lists, int64_t list_col0, int grid_limit) {
   TRY(fast_plan_build(c));
   FastPlan *p = c->fplan;
-  const bool usec = p->cc[k].ok && !with_diag && c->opt_col_cluster != 1;   // col_cluster = 1 forces the older 2-CTA kernel
-  const bool use2 = !usec && p->col2_ok[k] && (!p->col_ok[k] || c->opt_col_cluster);
-  if (!usec && !p->col_ok[k] && !use2) return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "fast column kernel does not cover this factor");
+  const bool use2 = p->col2_ok[k] && (!p->col_ok[k] || c->opt_col_cluster);
+  if (!p->col_ok[k] && !use2) return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "fast column kernel does not cover this factor");
   if ((reinterpret_cast<uintptr_t>(d_x) & 15) != 0) return edgpu_set_err(EDGPU_ERR_INVALID, "fast H*v needs 16-byte aligned vectors");
   const FastFactor &ff = p->ff[k];
   FColArgs a{};
@@ -1612,12 +1243,6 @@ int fast_apply_col(edgpu_ctx *c, int k, bool with_diag, bool acc, const double *
   const int pbase = (npartials && d_xp) ? *npartials : 0;
   a.xp = d_xp; a.st = c->d_st; a.partials = c->d_partials + pbase;
   if (npartials) *npartials = pbase + grid;
-  if (usec) {
-    int nctas = 0;
-    TRY(launch_ccol(c, p->cc[k], a, mode, lists, ncols, grid_limit, &nctas));
-    if (npartials) *npartials = pbase + nctas;
-    return EDGPU_OK;
-  }
   if (use2) {
     if (diag != 0) return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "cluster column kernel has no fused diagonal");
     int pairs = (int)std::min<int64_t>(ncols, c->sm_count / 2);
@@ -1628,9 +1253,12 @@ int fast_apply_col(edgpu_ctx *c, int k, bool with_diag, bool acc, const double *
     CKL(c);
     return EDGPU_OK;
   }
-  // no_uniform: 0 = best available, 1 = force the value-table kernel, 2 = uniform kernel with 4-byte entries
+  // no_uniform: 0 = best available, 1 = force the value-table kernel, 2 = 4-byte entries (uniform kernel when it applies)
   int uni = 0;
   if (ff.uniform && c->opt_no_uniform != 1) uni = (ff.d_ell16 && c->opt_no_uniform != 2) ? 2 : 1;
+  else if (ff.korder && ff.d_ell16 && c->opt_no_uniform == 0) uni = 3;
+  a.ns = c->ns;
+  for (int q = 0; q < EDGPU_MAX_SITES; q++) a.vk[q] = ff.vk[q];
   if (diag == 0) launch_fcol_w<0>(ff.WT, uni, mode, lists, grid, p->col_smem[k], c->stream, a);
   else if (diag == 1) launch_fcol_w<1>(ff.WT, uni, mode, false, grid, p->col_smem[k], c->stream, a);
   else launch_fcol_w<2>(ff.WT, uni, mode, false, grid, p->col_smem[k], c->stream, a);

@@ -650,6 +650,111 @@ static int gf_start_dw(edgpu_ctx *c, int iorb, int add) {
   return rc;
 }
 
+// One chain of a batch: its own Lanczos vectors, scalars, coefficient arrays and stream.  The recurrences of all the
+// channels that share a target sector advance in lock step, one stream each, so kernels of different chains overlap on
+// the device while the sector's factors, group records and packed entries are built and read once.
+struct ChainWork {
+  cudaStream_t stream = nullptr;
+  double *lx = nullptr, *lp = nullptr, *lt = nullptr, *partials = nullptr, *alanc = nullptr, *blanc = nullptr;
+  LancState *st = nullptr;
+};
+struct ChainBind {                                                 // the context's single-chain state, swapped while a chain is bound
+  cudaStream_t stream; double *lx, *lp, *lt, *partials, *alanc, *blanc; LancState *st; int cap;
+};
+static void chain_bind(edgpu_ctx *c, ChainWork &w, ChainBind &keep, int cap) {
+  keep = {c->stream, c->d_lx, c->d_lp, c->d_lt, c->d_partials, c->d_alanc, c->d_blanc, c->d_st, c->lanc_cap};
+  c->stream = w.stream; c->d_lx = w.lx; c->d_lp = w.lp; c->d_lt = w.lt; c->d_partials = w.partials;
+  c->d_alanc = w.alanc; c->d_blanc = w.blanc; c->d_st = w.st; c->lanc_cap = cap;
+}
+static void chain_unbind(edgpu_ctx *c, ChainWork &w, const ChainBind &keep) {
+  w.lx = c->d_lx; w.lp = c->d_lp;                                   // the step rotates the two
+  c->stream = keep.stream; c->d_lx = keep.lx; c->d_lp = keep.lp; c->d_lt = keep.lt; c->d_partials = keep.partials;
+  c->d_alanc = keep.alanc; c->d_blanc = keep.blanc; c->d_st = keep.st; c->lanc_cap = keep.cap;
+}
+static void chain_free(ChainWork &w) {
+  cudaFree(w.lx); cudaFree(w.lp); cudaFree(w.lt); cudaFree(w.partials); cudaFree(w.alanc); cudaFree(w.blanc); cudaFree(w.st);
+  if (w.stream) cudaStreamDestroy(w.stream);
+  w = ChainWork();
+}
+static int chain_alloc(edgpu_ctx *c, ChainWork &w, int nl) {
+  const size_t nb = ((size_t)std::max<int64_t>(c->nloc, 1) + 2) * sizeof(double);
+  CK(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
+  CK(cudaMalloc(&w.lx, nb)); CK(cudaMalloc(&w.lp, nb)); CK(cudaMalloc(&w.lt, nb));
+  CK(cudaMalloc(&w.partials, 4096 * sizeof(double)));
+  CK(cudaMalloc(&w.alanc, (size_t)(nl + 2) * sizeof(double))); CK(cudaMalloc(&w.blanc, (size_t)(nl + 2) * sizeof(double)));
+  CK(cudaMalloc(&w.st, sizeof(LancState)));
+  CK(cudaMemsetAsync(w.alanc, 0, (size_t)(nl + 2) * sizeof(double), w.stream));
+  CK(cudaMemsetAsync(w.blanc, 0, (size_t)(nl + 2) * sizeof(double), w.stream));
+  CK(cudaMemsetAsync(w.lp, 0, nb, w.stream));
+  CK(cudaMemsetAsync(w.st, 0, sizeof(LancState), w.stream));
+  return EDGPU_OK;
+}
+
+// start vector of one channel into c->d_lx (on c->stream)
+static int gf_start_vector(edgpu_ctx *c, int iorb, int ispin, int add) {
+  if (ispin == 2) return gf_start_dw(c, iorb, add);
+  const int64_t sdimup = c->h_binom[c->ns * EDGPU_BINOM_LD + c->gs_nup];
+  dim3 grid((unsigned)((c->dimup + 255) / 256), (unsigned)(c->qdw < 32768 ? c->qdw : 32768));
+  k_gf_start<<<grid, 256, 0, c->stream>>>(c->up.d_map, c->dw.d_map, c->dimup, c->qdw, c->coloff, sdimup,
+                                          c->d_gs, iorb, add, c->d_binom, c->d_lx);
+  CKL(c);
+  return EDGPU_OK;
+}
+
+// reference bookkeeping of sp_lanc_tridiag on raw device coefficients: alanc(k)=a_k ; if |b_k|<threshold exit ; blanc(k+1)=b_k
+static void tridiag_bookkeeping(int nlanc, double threshold, const double *a, const double *b, double *alanc, double *blanc) {
+  for (int k = 0; k < nlanc; k++) { alanc[k] = 0.0; blanc[k] = 0.0; }
+  for (int k = 0; k < nlanc; k++) {
+    alanc[k] = a[k];
+    const double bk = b[k + 1];
+    if (!(fabs(bk) >= threshold)) break;          // also stops on NaN
+    if (k + 1 < nlanc) blanc[k + 1] = bk;
+  }
+}
+
+// all the chains of one target sector (live in c), batched: lock-step recurrences on one stream per chain
+static int gf_chains_batched(edgpu_ctx *c, const std::vector<int> &grp, const int *iorb, const int *ispin, const int *addrem,
+                             int nl, int nlanc_max, double threshold, double *norm2, int *nlanc, double *alanc, double *blanc) {
+  const int nb = (int)grp.size();
+  std::vector<ChainWork> work((size_t)nb);
+  std::vector<double> ha((size_t)nb * (nl + 2)), hb((size_t)nb * (nl + 2)), hn((size_t)nb);
+  ChainBind keep;
+  int rc = EDGPU_OK;
+  CK(cudaStreamSynchronize(c->stream));                            // the sector build is complete before the chains' streams start
+  for (int q = 0; q < nb && !rc; q++) {
+    rc = chain_alloc(c, work[(size_t)q], nl);
+    if (rc) break;
+    chain_bind(c, work[(size_t)q], keep, nl + 2);
+    rc = gf_start_vector(c, iorb[grp[(size_t)q]], ispin[grp[(size_t)q]], addrem[grp[(size_t)q]] == 1 ? 1 : 0);
+    if (!rc) rc = lanczos_norm_start(c);
+    chain_unbind(c, work[(size_t)q], keep);
+  }
+  for (int k = 0; k < nl && !rc; k++)
+    for (int q = 0; q < nb && !rc; q++) {
+      chain_bind(c, work[(size_t)q], keep, nl + 2);
+      rc = lanczos_step(c, k);
+      chain_unbind(c, work[(size_t)q], keep);
+    }
+  for (int q = 0; q < nb && !rc; q++) {
+    ChainWork &w = work[(size_t)q];
+    if (cudaMemcpyAsync(&ha[(size_t)q * (nl + 2)], w.alanc, (size_t)(nl + 1) * sizeof(double), cudaMemcpyDeviceToHost, w.stream) != cudaSuccess ||
+        cudaMemcpyAsync(&hb[(size_t)q * (nl + 2)], w.blanc, (size_t)(nl + 2) * sizeof(double), cudaMemcpyDeviceToHost, w.stream) != cudaSuccess ||
+        cudaMemcpyAsync(&hn[(size_t)q], &w.st->norm2, sizeof(double), cudaMemcpyDeviceToHost, w.stream) != cudaSuccess)
+      rc = edgpu_set_err(EDGPU_ERR_CUDA, "gf_chains: coefficient read-back failed");
+  }
+  for (int q = 0; q < nb; q++)
+    if (work[(size_t)q].stream && cudaStreamSynchronize(work[(size_t)q].stream) != cudaSuccess && !rc)
+      rc = edgpu_set_err(EDGPU_ERR_CUDA, "gf_chains: %s", cudaGetErrorString(cudaGetLastError()));
+  for (int q = 0; q < nb && !rc; q++) {
+    const int ch = grp[(size_t)q];
+    tridiag_bookkeeping(nl, threshold, &ha[(size_t)q * (nl + 2)], &hb[(size_t)q * (nl + 2)], alanc + (size_t)ch * nlanc_max, blanc + (size_t)ch * nlanc_max);
+    norm2[ch] = hn[(size_t)q];
+    nlanc[ch] = nl;
+  }
+  for (int q = 0; q < nb; q++) chain_free(work[(size_t)q]);
+  return rc;
+}
+
 extern "C" int edgpu_gf_chains(edgpu_ctx *c, int nchains, const int *iorb, const int *ispin,
                                const int *addrem, int nlanc_max, double threshold,
                                double *norm2, int *nlanc, double *alanc, double *blanc) {
@@ -672,34 +777,32 @@ extern "C" int edgpu_gf_chains(edgpu_ctx *c, int nchains, const int *iorb, const
     int jsector;
     TRY(edgpu_get_sector(c, jnup, jndw, &jsector));
     TRY(edgpu_build_hv_sector(c, jsector));
-    int rc = EDGPU_OK;
-    for (int ch2 = ch; ch2 < nchains && !rc; ch2++) {       // every channel sharing this target sector
+    std::vector<int> grp;                                   // every channel sharing this target sector
+    for (int ch2 = ch; ch2 < nchains; ch2++) {
       if (done[ch2]) continue;
       int n2 = c->gs_nup + (ispin[ch2] == 1 ? addrem[ch2] : 0), d2 = c->gs_ndw + (ispin[ch2] == 2 ? addrem[ch2] : 0);
       if (n2 != jnup || d2 != jndw) continue;
       done[ch2] = 1;
-      const int64_t jdim = c->dimup * c->dimdw;
-      const int nl = (int)std::min<int64_t>(jdim, nlanc_max);   // nlanc=min(jdim,lanc_nGFiter), :219
-      rc = lanczos_begin(c, nl);
-      if (rc) break;
-      if (ispin[ch2] == 2) {
-        rc = gf_start_dw(c, iorb[ch2], addrem[ch2] == 1 ? 1 : 0);
-        if (rc) break;
-      } else {
-        const int64_t sdimup = c->h_binom[c->ns * EDGPU_BINOM_LD + c->gs_nup];
-        dim3 grid((unsigned)((c->dimup + 255) / 256), (unsigned)(c->qdw < 32768 ? c->qdw : 32768));
-        k_gf_start<<<grid, 256, 0, c->stream>>>(c->up.d_map, c->dw.d_map, c->dimup, c->qdw, c->coloff, sdimup,
-                                                c->d_gs, iorb[ch2], addrem[ch2] == 1 ? 1 : 0, c->d_binom, c->d_lx);
-        c->launches++;
-        if (cudaGetLastError() != cudaSuccess) { rc = edgpu_set_err(EDGPU_ERR_CUDA, "k_gf_start launch failed"); break; }
+      grp.push_back(ch2);
+    }
+    const int64_t jdim = c->dimup * c->dimdw;
+    const int nl = (int)std::min<int64_t>(jdim, nlanc_max);   // nlanc=min(jdim,lanc_nGFiter), :219
+    int rc = EDGPU_OK;
+    // the batch needs 3 vectors per chain; sharded runs share one halo buffer per context, so their chains go one by one
+    const bool batch = c->nranks == 1 && grp.size() > 1 && !c->opt_no_batch &&
+                       (double)grp.size() * 3.0 * 8.0 * (double)c->nloc < 60e9;
+    if (batch) {
+      rc = gf_chains_batched(c, grp, iorb, ispin, addrem, nl, nlanc_max, threshold, norm2, nlanc, alanc, blanc);
+    } else {
+      for (size_t q = 0; q < grp.size() && !rc; q++) {
+        const int ch2 = grp[q];
+        rc = lanczos_begin(c, nl);
+        if (!rc) rc = gf_start_vector(c, iorb[ch2], ispin[ch2], addrem[ch2] == 1 ? 1 : 0);
+        if (!rc) rc = tridiag_device(c, nl, threshold, alanc + (size_t)ch2 * nlanc_max, blanc + (size_t)ch2 * nlanc_max);
+        if (!rc && cudaMemcpy(&norm2[ch2], &c->d_st->norm2, sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess)
+          rc = edgpu_set_err(EDGPU_ERR_CUDA, "norm2 read-back failed");
+        if (!rc) nlanc[ch2] = nl;
       }
-      rc = tridiag_device(c, nl, threshold, alanc + (size_t)ch2 * nlanc_max, blanc + (size_t)ch2 * nlanc_max);
-      if (rc) break;
-      if (cudaMemcpy(&norm2[ch2], &c->d_st->norm2, sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) {
-        rc = edgpu_set_err(EDGPU_ERR_CUDA, "norm2 read-back failed");
-        break;
-      }
-      nlanc[ch2] = nl;
     }
     edgpu_delete_hv_sector(c);
     if (rc) return rc;

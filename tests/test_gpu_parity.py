@@ -418,12 +418,6 @@ FAST_CASES = [("C1", (4, 4), {}), ("C1", (5, 3), {"srow_t": 1}), ("C1", (3, 6), 
               ("NS6", (3, 3), {}), ("NS6", (3, 3), {"srow_lr": 4, "srow_t": 1}), ("NS10V", (5, 5), {"srow_t": 3}),
               ("NS12V", (6, 5), {"srow_lr": 4, "srow_t": 4}), ("NS10V", (7, 2), {}), ("NS10", (9, 1), {}),
               ("NS12", (6, 0), {}), ("NS12", (6, 12), {}), ("NS14", (7, 7), {}), ("NS14V", (7, 6), {"srow_t": 3}),
-              # cluster column kernel with forced cluster sizes (rows split by the top 1 / 2 / 3 bits of the up word) and the
-              # variant that streams the entries from L2
-              ("C1", (4, 4), {"ccol_cs": 2}), ("NS10", (5, 5), {"ccol_cs": 4}), ("NS12", (6, 6), {"ccol_cs": 8}), ("NS12", (7, 4), {"ccol_cs": 2}),
-              ("NS10V", (5, 5), {"ccol_cs": 2}), ("NS12V", (6, 5), {"ccol_cs": 8, "srow_t": 3}), ("NS14V", (7, 6), {"ccol_cs": 4}),
-              ("NS12", (9, 6), {"ccol_cs": 4}), ("NS12V", (3, 6), {"ccol_cs": 2}), ("NS14", (7, 7), {"ccol_cs": 8}),
-              ("NS12", (6, 6), {"no_ccol": 1}), ("NS12V", (6, 5), {"no_ccol": 1}),
               # two-CTA cluster column kernel (columns too long for one SM; forced here on small ones)
               ("C1", (4, 4), {"col_cluster": 1}), ("NS12", (6, 6), {"col_cluster": 1}), ("NS12", (7, 4), {"col_cluster": 1, "no_uniform": 1}),
               ("NS10V", (5, 5), {"col_cluster": 1}), ("NS12", (5, 6), {"col_cluster": 1, "srow_lr": 4})]
