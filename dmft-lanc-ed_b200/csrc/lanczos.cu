@@ -303,20 +303,11 @@ static double tridiag_lowest(int n, const double *a, const double *b) {
 }
 
 // ---- sp_lanc_eigh -----------------------------------------------------------------------------
-extern "C" int edgpu_sp_lanc_eigh(edgpu_ctx *c, double *egs, double *vect, int64_t nloc, int nitermax,
-                                  int iverbose, double threshold, int ncheck,
-                                  int *nlanc_out, double *alanc_out, double *blanc_out) {
-  if (!c || !c->hstatus) return edgpu_set_err(EDGPU_ERR_INVALID, "sp_lanc_eigh: Hsector NOT set");
-  if (nloc != c->nloc) return edgpu_set_err(EDGPU_ERR_INVALID, "sp_lanc_eigh: size(vect) != vecDim");
-  if (nitermax < 1) return edgpu_set_err(EDGPU_ERR_INVALID, "sp_lanc_eigh: Nitermax < 1");
-  if (ncheck <= 0) ncheck = 10;
-  CK(cudaSetDevice(c->device));
-  c->lv_valid = false;
-  TRY(lanczos_begin(c, nitermax));
-  TRY(vec_alloc(c, &c->d_l0, c->nloc));
-  TRY(vec_alloc(c, &c->d_lv, c->nloc));
-  // start vector
-  CK(cudaMemcpyAsync(c->d_lx, vect, (size_t)nloc * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+// Core of sp_lanc_eigh on device vectors: on entry c->d_lx holds the start vector (all zero => pseudo-random),
+// on exit c->d_lv the normalised eigenvector; nothing but scalars crosses the host boundary.
+static int lanc_eigh_core(edgpu_ctx *c, int nitermax, int iverbose, double threshold, int ncheck, double *egs,
+                          int *nlanc_out, std::vector<double> &alanc, std::vector<double> &blanc) {
+  const int64_t nloc = c->nloc;
   TRY(lanczos_norm_start(c));
   CK(cudaMemcpyAsync(c->h_pinned, &c->d_st->norm2, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
@@ -330,7 +321,8 @@ extern "C" int edgpu_sp_lanc_eigh(edgpu_ctx *c, double *egs, double *vect, int64
   CK(cudaStreamSynchronize(c->stream));
   const double norm0 = sqrt(c->h_pinned[0]);
 
-  std::vector<double> alanc((size_t)nitermax + 2, 0.0), blanc((size_t)nitermax + 2, 0.0), diag, z;
+  alanc.assign((size_t)nitermax + 2, 0.0); blanc.assign((size_t)nitermax + 2, 0.0);
+  std::vector<double> diag, z;
   int nlanc = 0;
   double e_prev = 0.0, a_last = 0.0;
   *egs = 0.0;
@@ -414,13 +406,83 @@ extern "C" int edgpu_sp_lanc_eigh(edgpu_ctx *c, double *egs, double *vect, int64
   CK(cudaStreamSynchronize(c->stream));
   k_scale<<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(c->d_lv, c->nloc, 1.0 / sqrt(c->h_pinned[0]));
   CKL(c);
-  CK(cudaMemcpyAsync(vect, c->d_lv, (size_t)nloc * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
   c->lv_valid = true;
   c->gs_e0 = *egs;
   if (nlanc_out) *nlanc_out = nlanc;
+  return EDGPU_OK;
+}
+
+extern "C" int edgpu_sp_lanc_eigh(edgpu_ctx *c, double *egs, double *vect, int64_t nloc, int nitermax,
+                                  int iverbose, double threshold, int ncheck,
+                                  int *nlanc_out, double *alanc_out, double *blanc_out) {
+  if (!c || !c->hstatus) return edgpu_set_err(EDGPU_ERR_INVALID, "sp_lanc_eigh: Hsector NOT set");
+  if (nloc != c->nloc) return edgpu_set_err(EDGPU_ERR_INVALID, "sp_lanc_eigh: size(vect) != vecDim");
+  if (nitermax < 1) return edgpu_set_err(EDGPU_ERR_INVALID, "sp_lanc_eigh: Nitermax < 1");
+  if (ncheck <= 0) ncheck = 10;
+  CK(cudaSetDevice(c->device));
+  c->lv_valid = false;
+  TRY(lanczos_begin(c, nitermax));
+  TRY(vec_alloc(c, &c->d_l0, c->nloc));
+  TRY(vec_alloc(c, &c->d_lv, c->nloc));
+  CK(cudaMemcpyAsync(c->d_lx, vect, (size_t)nloc * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  std::vector<double> alanc, blanc;
+  int nlanc = 0;
+  TRY(lanc_eigh_core(c, nitermax, iverbose, threshold, ncheck, egs, &nlanc, alanc, blanc));
+  CK(cudaMemcpyAsync(vect, c->d_lv, (size_t)nloc * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (nlanc_out) *nlanc_out = nlanc;
   if (alanc_out) memcpy(alanc_out, alanc.data(), (size_t)nlanc * sizeof(double));
   if (blanc_out) memcpy(blanc_out, blanc.data(), (size_t)nlanc * sizeof(double));
+  return EDGPU_OK;
+}
+
+// ---- sector scan (ed_diag_d, ED_DIAG.f90:83-276) ---------------------------------------------------------------
+// For every listed sector: build_Hv_sector, lowest eigenpair by Lanczos from the pseudo-random start vector (the
+// reference: dense eigh below lanc_dim_threshold, sp_lanc_eigh above; Nitermax = min(dim, nitermax)), delete.  Twin
+// sectors (Nup <-> Ndw, ed_twin: same spectrum when the two spins have the same parameters) are diagonalised once.
+// The eigenvector of the lowest sector stays on the device as the state of the GF chains / observables
+// (edgpu_gf_set_state_from_eigh semantics), so nothing but the energies returns to the host.
+extern "C" int edgpu_diag_sectors(edgpu_ctx *c, int nsectors, const int *isector, int nitermax, double threshold,
+                                  int ncheck, int twin, double *e0, int *nlanc, int *best) {
+  if (!c || !isector || !e0 || nsectors < 1) return edgpu_set_err(EDGPU_ERR_INVALID, "diag_sectors: bad arguments");
+  if (c->hstatus) return edgpu_set_err(EDGPU_ERR_INVALID, "diag_sectors: a sector is live; call delete_Hv_sector first");
+  if (ncheck <= 0) ncheck = 10;
+  CK(cudaSetDevice(c->device));
+  int ibest = -1;
+  std::vector<int> src((size_t)nsectors, -1);                      // twin: index of the sector whose result is copied
+  for (int s = 0; s < nsectors; s++) {
+    int nup, ndw;
+    TRY(edgpu_get_nup_ndw(c, isector[s], &nup, &ndw));
+    if (twin && nup < ndw)
+      for (int t = 0; t < nsectors; t++) {
+        int nu2, nd2;
+        TRY(edgpu_get_nup_ndw(c, isector[t], &nu2, &nd2));
+        if (nu2 == ndw && nd2 == nup) { src[(size_t)s] = t; break; }
+      }
+  }
+  for (int s = 0; s < nsectors; s++) {
+    if (src[(size_t)s] >= 0) continue;
+    TRY(edgpu_build_hv_sector(c, isector[s]));
+    const int64_t dim = c->dimup * c->dimdw;
+    const int nit = (int)std::min<int64_t>(dim, nitermax);
+    int rc = lanczos_begin(c, nit);
+    if (!rc) rc = vec_alloc(c, &c->d_l0, c->nloc);
+    if (!rc) rc = vec_alloc(c, &c->d_lv, c->nloc);
+    if (!rc && cudaMemsetAsync(c->d_lx, 0, (size_t)std::max<int64_t>(c->nloc, 1) * sizeof(double), c->stream) != cudaSuccess) rc = edgpu_set_err(EDGPU_ERR_CUDA, "diag_sectors: memset");
+    std::vector<double> al, bl;
+    int nl = 0;
+    if (!rc) rc = lanc_eigh_core(c, nit, 0, threshold, ncheck, &e0[s], &nl, al, bl);
+    if (nlanc) nlanc[s] = nl;
+    if (!rc && (ibest < 0 || e0[s] < e0[ibest])) {
+      ibest = s;
+      rc = edgpu_gf_set_state_from_eigh(c);
+    }
+    edgpu_delete_hv_sector(c);
+    if (rc) return rc;
+  }
+  for (int s = 0; s < nsectors; s++)
+    if (src[(size_t)s] >= 0) { e0[s] = e0[src[(size_t)s]]; if (nlanc) nlanc[s] = nlanc[src[(size_t)s]]; }
+  if (best) *best = ibest;
   return EDGPU_OK;
 }
 

@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "edgpu_device_count", "edgpu_comm_unique_id", "edgpu_comm_init", "edgpu_comm_finalize",
     "edgpu_get_sector", "edgpu_get_nup_ndw", "edgpu_split", "edgpu_transpose_plan", "edgpu_build_hv_sector",
     "edgpu_delete_hv_sector", "edgpu_vecdim_hv_sector", "edgpu_hxv", "edgpu_sphtimesv",
-    "edgpu_hxv_device", "edgpu_sp_lanc_eigh", "edgpu_sp_lanc_tridiag", "edgpu_gf_set_state", "edgpu_gf_set_state_from_eigh",
+    "edgpu_hxv_device", "edgpu_sp_lanc_eigh", "edgpu_sp_lanc_tridiag", "edgpu_diag_sectors", "edgpu_gf_set_state", "edgpu_gf_set_state_from_eigh",
     "edgpu_gf_chains", "edgpu_add_to_lanczos_gf", "edgpu_observables_normal", "edgpu_get_dims", "edgpu_get_sector_map",
     "edgpu_get_csr", "edgpu_get_diag", "edgpu_dev_alloc", "edgpu_dev_free", "edgpu_dev_upload",
     "edgpu_dev_download", "edgpu_dev_fill_bench_vector", "edgpu_sync", "edgpu_dev_dot", "edgpu_time_hxv_device",
@@ -103,6 +103,7 @@ def lib():
         L.edgpu_sp_lanc_eigh.argtypes = [C.c_void_p, c_dp, c_dp, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_int,
                                          c_ip, c_dp, c_dp]
         L.edgpu_sp_lanc_tridiag.argtypes = [C.c_void_p, c_dp, C.c_int64, c_dp, c_dp, C.c_int, C.c_double]
+        L.edgpu_diag_sectors.argtypes = [C.c_void_p, C.c_int, c_ip, C.c_int, C.c_double, C.c_int, C.c_int, c_dp, c_ip, c_ip]
         L.edgpu_gf_set_state.argtypes = [C.c_void_p, C.c_int, c_dp, C.c_int64, C.c_double]
         L.edgpu_gf_set_state_from_eigh.argtypes = [C.c_void_p]
         L.edgpu_gf_chains.argtypes = [C.c_void_p, C.c_int, c_ip, c_ip, c_ip, C.c_int, C.c_double, c_dp, c_ip, c_dp, c_dp]
@@ -296,6 +297,17 @@ class Solver:
         b = np.zeros(nlanc)
         _ck(lib().edgpu_sp_lanc_tridiag(self.h, _dp(v), v.size, _dp(a), _dp(b), nlanc, threshold))
         return a, b
+
+    def diag_sectors(self, sectors, nitermax=512, threshold=1e-18, ncheck=10, twin=False):
+        """ed_diag_d's sector loop (ED_DIAG.f90:83-276): (e0[], nlanc[], best) -- the lowest sector's eigenvector stays
+        on the device as the state of the chains / observables."""
+        n = len(sectors)
+        sec = (C.c_int * n)(*sectors)
+        e0 = np.zeros(n)
+        nl = (C.c_int * n)()
+        best = C.c_int(-1)
+        _ck(lib().edgpu_diag_sectors(self.h, n, sec, nitermax, threshold, ncheck, int(bool(twin)), _dp(e0), nl, C.byref(best)))
+        return e0, np.array(nl[:]), best.value
 
     # ---- Green's function chains -----------------------------------------------------------------------
     def gf_set_state(self, isector, gs, e0):

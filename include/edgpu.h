@@ -129,6 +129,16 @@ int  edgpu_sp_lanc_eigh(edgpu_ctx *c, double *egs, double *vect, int64_t nloc, i
 int  edgpu_sp_lanc_tridiag(edgpu_ctx *c, const double *vin, int64_t nloc, double *alanc,
                            double *blanc, int nlanc, double threshold);
 
+/* ---- sector scan (ed_diag_d, ED_DIAG.f90:83-276) -------------------------------------------------------------------- */
+/* Lowest eigenvalue of every listed sector: build_Hv_sector, Lanczos from the pseudo-random start vector with
+ * Nitermax = min(dim, nitermax) (the reference diagonalises sectors below lanc_dim_threshold densely and the others
+ * with sp_lanc_eigh), delete_Hv_sector.  twin != 0: a sector (Nup < Ndw) whose mirror (Ndw, Nup) is in the list is
+ * not diagonalised again (ed_twin: same spectrum when both spins have the same parameters).  The eigenvector of the
+ * lowest sector stays on the device as the state of the chains / observables (no host round trip); *best = its
+ * position in the list.  e0[nsectors]; nlanc[nsectors] may be NULL. */
+int  edgpu_diag_sectors(edgpu_ctx *c, int nsectors, const int *isector, int nitermax, double threshold,
+                        int ncheck, int twin, double *e0, int *nlanc, int *best);
+
 /* ---- Green's function chains (lanc_build_gf_normal_main, ED_GF_NORMAL.f90:124-334) --------------- */
 /* Keeps the ground state of sector (nup,ndw) on device for the chains; gs is the local shard.
  * Replaces es_return_cvector + the master-only c/cdg loops (:184-216, :259-290). */

@@ -269,6 +269,41 @@ def test_gf_chains_spin_down_and_device_state(name):
         s.close()
 
 
+@pytest.mark.parametrize("name", ["C1", "NS6V"])
+def test_sector_scan_matches_oracle(name):
+    """ed_diag_d's loop over all (Nup, Ndw) sectors on the device (edgpu_diag_sectors): E0 of every sector against dense
+    eigh of the oracle's Hmat (small sectors) or the oracle's Lanczos, twin sectors reused, and the global ground state
+    left on the device drives the observables without a host round trip."""
+    cfg, o = make_oracle(name)
+    ns = cfg["nbath"] + 1
+    s = _solver(cfg)
+    try:
+        pairs = [(nu, nd) for nu in range(ns + 1) for nd in range(ns + 1)]
+        secs = [s.get_sector(nu, nd) for nu, nd in pairs]
+        e0, nl, best = s.diag_sectors(secs, twin=True)
+        ref = np.zeros(len(pairs))
+        for k, (nu, nd) in enumerate(pairs):
+            if nu < nd:
+                continue
+            with o.sector(nu, nd) as os_:
+                if os_.dim <= 800:
+                    ref[k] = np.linalg.eigvalsh(os_.hmat())[0]
+                else:
+                    ref[k] = os_.lanc_eigh(v0=None)[0]
+        for k, (nu, nd) in enumerate(pairs):
+            if nu < nd:
+                ref[k] = ref[pairs.index((nd, nu))]
+        assert np.abs(e0 - ref).max() < 1e-9 * max(1.0, np.abs(ref).max())
+        assert best == int(np.argmin(e0)) or abs(e0[best] - e0.min()) < 1e-12
+        nu, nd = pairs[best]
+        with o.sector(nu, nd) as os_:
+            _, gs, _, _ = os_.lanc_eigh()                     # pseudo-random start: no symmetry constraint
+        obs, oref = s.observables(), o.observables(nu, nd, gs)
+        assert np.abs(obs["dens"] - oref["dens"]).max() < 1e-7 and np.abs(obs["docc"] - oref["docc"]).max() < 1e-7
+    finally:
+        s.close()
+
+
 def _c4_offdiag_hloc():
     h = np.zeros((1, 1, 2, 2))
     h[0, 0, 0, 1] = h[0, 0, 1, 0] = 0.3
