@@ -142,8 +142,8 @@ extern "C" int edgpu_set_option(edgpu_ctx *c, const char *key, int64_t value) {
   if (!strcmp(key, "srow_t")) { c->opt_srow_t = value; return EDGPU_OK; }      // t + 1 forces chunks of 2^t low groups
   if (!strcmp(key, "no_fuse")) { c->opt_no_fuse = value; return EDGPU_OK; }    // Lanczos update as a separate pass
   if (!strcmp(key, "halo_ctas")) { c->opt_halo_ctas = value; return EDGPU_OK; }
+  if (!strcmp(key, "halo_windows")) { c->opt_halo_windows = value; return EDGPU_OK; }   // before build_Hv_sector
   if (!strcmp(key, "no_overlap")) { c->opt_no_overlap = value; return EDGPU_OK; }
-  if (!strcmp(key, "halo_chunks")) { c->opt_halo_chunks = value; return EDGPU_OK; }
   if (!strcmp(key, "no_batch")) { c->opt_no_batch = value; return EDGPU_OK; }        // GF chains of a sector one after another
   if (!strcmp(key, "no_peer")) { c->opt_no_peer = value; return EDGPU_OK; }
   if (!strcmp(key, "col_cluster")) { c->opt_col_cluster = value; return EDGPU_OK; }
@@ -378,11 +378,12 @@ extern "C" int edgpu_build_hv_sector(edgpu_ctx *c, int isector) {
     cudaFree(d_tmp);
   }
   CK(cudaStreamSynchronize(c->stream));
-  if (c->nranks > 1 && !c->opt_no_peer) {
-    // room for the engine's Lanczos vectors, the staging pair and a few user vectors, identical on every rank
-    int64_t qmax = (c->dimdw + c->nranks - 1) / c->nranks;
-    size_t per = (((size_t)(c->dimup * qmax) + 2) * sizeof(double) + 255) & ~(size_t)255;
-    int rc2 = comm_symm_setup(c, per, 12);
+  if (c->nranks > 1 && !c->opt_no_peer && !c->dp.jhflag && (c->algo == EDGPU_ALGO_AUTO || c->algo == EDGPU_ALGO_FAST)) {
+    // sharded fast path: the halo slab is allocated and mapped here, collectively (the plan is rank independent,
+    // so either every rank gets a slab of the same size or none does)
+    size_t hb = 0;
+    int rc2 = fast_halo_bytes(c, &hb);
+    if (!rc2) rc2 = comm_symm_setup(c, hb);
     if (rc2) { edgpu_delete_hv_sector(c); return rc2; }
   }
   g_current = c;
@@ -425,7 +426,7 @@ extern "C" int edgpu_destroy(edgpu_ctx *c) {
   if (c->ev_join) cudaEventDestroy(c->ev_join);
   for (int w = 0; w < EDGPU_MAX_WINDOWS; w++) if (c->ev_win[w]) cudaEventDestroy(c->ev_win[w]);
   if (c->stream2) cudaStreamDestroy(c->stream2);
-  for (int i = 0; i < 6; i++) if (c->pev[i]) cudaEventDestroy(c->pev[i]);
+  for (int i = 0; i < 8; i++) if (c->pev[i]) cudaEventDestroy(c->pev[i]);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return EDGPU_OK;
@@ -438,11 +439,7 @@ extern "C" int edgpu_hxv_device(edgpu_ctx *c, int64_t nloc, const double *d_v, d
   if (!c || !c->hstatus) return edgpu_set_err(EDGPU_ERR_INVALID, "HxV: Hsector NOT set");
   if (nloc != c->nloc) return edgpu_set_err(EDGPU_ERR_INVALID, "HxV: Nloc=%lld != vecDim=%lld", (long long)nloc, (long long)c->nloc);
   CK(cudaSetDevice(c->device));
-  TRY(hxv_apply(c, d_v, d_hv));
-  // sharded fast path: peers pull columns of d_v during the call.  The caller owns d_v and may overwrite it as soon
-  // as this returns, so every rank's reads are ordered before the return of anybody's next stream operation.
-  if (c->sym_ok && sym_offset(c, d_v) >= 0) TRY(comm_barrier(c));
-  return EDGPU_OK;
+  return hxv_apply(c, d_v, d_hv);                               // nobody but this rank ever reads d_v (halo is pushed)
 }
 
 extern "C" int edgpu_hxv(edgpu_ctx *c, int64_t nloc, const double *v, double *hv) {
@@ -453,7 +450,6 @@ extern "C" int edgpu_hxv(edgpu_ctx *c, int64_t nloc, const double *v, double *hv
   TRY(vec_alloc(c, &c->d_out, c->nloc));
   CK(cudaMemcpyAsync(c->d_in, v, (size_t)nloc * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   TRY(hxv_apply(c, c->d_in, c->d_out));
-  if (c->sym_ok) TRY(comm_barrier(c));                          // ... and nobody overwrites it while it is read
   CK(cudaMemcpyAsync(hv, c->d_out, (size_t)nloc * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return EDGPU_OK;
@@ -543,33 +539,15 @@ extern "C" int edgpu_get_diag(const edgpu_ctx *cc, double *out, int64_t nloc) {
 // device helpers
 // ------------------------------------------------------------------------------------------
 extern "C" int edgpu_dev_alloc(edgpu_ctx *c, int64_t nbytes, void **dptr) {
+  if (!c || !dptr) return edgpu_set_err(EDGPU_ERR_INVALID, "ctx/dptr == NULL");
   CK(cudaSetDevice(c->device));
-  if (c->sym_ok && c->hstatus) {                                // peer-readable when a sharded sector is live
-    double *p = nullptr;
-    TRY(vec_alloc(c, &p, (nbytes + 7) / 8));
-    if (sym_offset(c, p) >= 0) c->slab_ptrs.push_back(p);       // remembered: dies with the sector
-    *dptr = p;
-    return EDGPU_OK;
-  }
   CK(cudaMalloc(dptr, (size_t)nbytes + 16));
-  for (size_t i = 0; i < c->slab_ptrs.size(); i++)               // an address of a released slab may come back
-    if (c->slab_ptrs[i] == *dptr) { c->slab_ptrs.erase(c->slab_ptrs.begin() + (long)i); break; }
   return EDGPU_OK;
 }
 extern "C" int edgpu_dev_free(edgpu_ctx *c, void *dptr) {
   if (!c) return edgpu_set_err(EDGPU_ERR_INVALID, "ctx == NULL");
   if (!dptr) return EDGPU_OK;
   CK(cudaSetDevice(c->device));
-  // buffers carved from the symmetric slab (edgpu_dev_alloc while a sharded sector is live) belong to that sector:
-  // they are released by delete_Hv_sector, and freeing one -- before or after -- is a no-op
-  for (size_t i = 0; i < c->slab_ptrs.size(); i++)
-    if (c->slab_ptrs[i] == dptr) {
-      c->slab_ptrs.erase(c->slab_ptrs.begin() + (long)i);
-      double *p = reinterpret_cast<double *>(dptr);
-      if (sym_offset(c, dptr) >= 0) vec_free(c, &p);             // back to the live slab; after teardown: nothing to do
-      return EDGPU_OK;
-    }
-  if (sym_offset(c, dptr) >= 0) return EDGPU_OK;
   CK(cudaFree(dptr));
   return EDGPU_OK;
 }
@@ -605,14 +583,14 @@ extern "C" int edgpu_launch_count(const edgpu_ctx *c, int64_t *n) {
   return EDGPU_OK;
 }
 // Per-kernel split of a device-resident H*v (single rank): CUDA events between the passes, summed over
-// `reps` applications.  names receives up to 4 NUL-terminated kernel names of 32 bytes each.
+// `reps` applications.  ms_pass[6]; names receives up to 6 NUL-terminated kernel names of 32 bytes each.
 extern "C" int edgpu_time_hxv_passes(edgpu_ctx *c, int64_t nloc, const double *d_v, double *d_hv, int reps,
                                      int *npasses, double *ms_pass, char *names) {
   if (!c || !c->hstatus) return edgpu_set_err(EDGPU_ERR_INVALID, "HxV: Hsector NOT set");
   if (nloc != c->nloc) return edgpu_set_err(EDGPU_ERR_INVALID, "nloc mismatch");
   CK(cudaSetDevice(c->device));
-  for (int i = 0; i < 6; i++) if (!c->pev[i]) CK(cudaEventCreate(&c->pev[i]));
-  for (int i = 0; i < 4; i++) ms_pass[i] = 0.0;
+  for (int i = 0; i < 8; i++) if (!c->pev[i]) CK(cudaEventCreate(&c->pev[i]));
+  for (int i = 0; i < 6; i++) ms_pass[i] = 0.0;
   int np = 0;
   for (int r = 0; r < reps; r++) {
     c->prof = true; c->prof_n = 0;
@@ -622,14 +600,14 @@ extern "C" int edgpu_time_hxv_passes(edgpu_ctx *c, int64_t nloc, const double *d
     if (rc) return rc;
     CK(cudaStreamSynchronize(c->stream));
     np = c->prof_n - 1;
-    for (int i = 0; i < np && i < 4; i++) {
+    for (int i = 0; i < np && i < 6; i++) {
       float ms = 0.f;
       CK(cudaEventElapsedTime(&ms, c->pev[i], c->pev[i + 1]));
       ms_pass[i] += ms;
       if (names) { strncpy(names + 32 * i, c->prof_name[i], 31); names[32 * i + 31] = 0; }
     }
   }
-  if (npasses) *npasses = np < 4 ? np : 4;
+  if (npasses) *npasses = np < 6 ? np : 6;
   return EDGPU_OK;
 }
 extern "C" int edgpu_time_hxv_device(edgpu_ctx *c, int64_t nloc, const double *d_v, double *d_hv,

@@ -103,55 +103,32 @@ extern "C" int edgpu_comm_finalize(edgpu_ctx *c) {
   return EDGPU_OK;
 }
 
-// ---- symmetric slab ----------------------------------------------------------------------------------
-int64_t sym_offset(const edgpu_ctx *c, const void *p) {
-  if (!c->sym_ok || !c->sym_slab) return -1;
-  const char *q = reinterpret_cast<const char *>(p);
-  if (q < c->sym_slab || q >= c->sym_slab + c->sym_bytes) return -1;
-  return (int64_t)(q - c->sym_slab);
-}
+// ---- work vectors ------------------------------------------------------------------------------------
 int vec_alloc(edgpu_ctx *c, double **p, int64_t n) {
+  (void)c;
   if (*p) return EDGPU_OK;
   const size_t bytes = (((size_t)(n > 0 ? n : 1) + 2) * sizeof(double) + 255) & ~(size_t)255;
-  if (c->sym_ok && c->sym_unit) {
-    // nloc differs by one column between ranks: carve in rank-independent units so that the same vector
-    // sits at the same offset on every rank (every rank performs the same sequence of allocations and frees)
-    const int need = (int)((bytes + c->sym_unit - 1) / c->sym_unit), total = (int)(c->sym_bytes / c->sym_unit);
-    for (int u = 0; u + need <= total && u + need <= 64; u++) {
-      bool free_run = true;
-      for (int k = 0; k < need; k++) if (c->sym_units[u + k]) { free_run = false; break; }
-      if (!free_run) continue;
-      for (int k = 0; k < need; k++) c->sym_units[u + k] = (k == 0) ? need : -1;
-      *p = reinterpret_cast<double *>(c->sym_slab + (size_t)u * c->sym_unit);
-      return EDGPU_OK;
-    }
-  }
   CK(cudaMalloc(p, bytes));
   return EDGPU_OK;
 }
 void vec_free(edgpu_ctx *c, double **p) {
+  (void)c;
   if (!*p) return;
-  const int64_t off = sym_offset(c, *p);
-  if (off < 0) cudaFree(*p);
-  else if (c->sym_unit) {
-    const int u = (int)((size_t)off / c->sym_unit);
-    const int need = u < 64 ? c->sym_units[u] : 0;
-    for (int k = 0; k < need && u + k < 64; k++) c->sym_units[u + k] = 0;
-  }
+  cudaFree(*p);
   *p = nullptr;
 }
+// ---- symmetric slab ----------------------------------------------------------------------------------
 int comm_barrier(edgpu_ctx *c) {
   if (c->nranks == 1 || !c->comm) return EDGPU_OK;
   NK(g_nccl.AllReduce(c->d_partials + 4000, c->d_partials + 4000, 1, ncclDouble, ncclSum, (ncclComm_t)c->comm, c->stream));
   return EDGPU_OK;
 }
-// Collective.  On any failure (e.g. peers not visible to this process) every rank ends with sym_ok = false
-// and H*v uses the all-to-all transposes instead.
-int comm_symm_setup(edgpu_ctx *c, size_t unit, int nunits) {
+// Collective: every rank allocates `bytes`, the CUDA IPC handles travel with one ncclAllGather, every rank maps its
+// peers' slabs.  On any failure (e.g. peers not visible to this process) every rank ends with sym_ok = false and
+// H*v uses the all-to-all transposes instead.
+int comm_symm_setup(edgpu_ctx *c, size_t bytes) {
   c->sym_ok = false;
-  c->sym_unit = (unit + 255) & ~(size_t)255;
-  size_t bytes = c->sym_unit * (size_t)nunits;
-  if (c->nranks == 1 || !c->comm) return EDGPU_OK;
+  if (c->nranks == 1 || !c->comm || bytes == 0) return EDGPU_OK;
   const int P = c->nranks, me = c->rank;
   bytes = (bytes + 255) & ~(size_t)255;
   int good = 1;
@@ -162,7 +139,10 @@ int comm_symm_setup(edgpu_ctx *c, size_t unit, int nunits) {
   // exchange the handles (and the success flags) with NCCL: no host-side plumbing needed
   const size_t rec = sizeof(cudaIpcMemHandle_t) + 8;
   char *d_all = nullptr;
-  CK(cudaMalloc(&d_all, rec * (size_t)P));
+  if (cudaMalloc(&d_all, rec * (size_t)P) != cudaSuccess) {       // cannot even take part in the exchange: fatal for the job
+    if (c->sym_slab) { cudaFree(c->sym_slab); c->sym_slab = nullptr; }
+    return edgpu_set_err(EDGPU_ERR_CUDA, "comm_symm_setup: cudaMalloc of the handle table failed");
+  }
   std::vector<char> h_all(rec * (size_t)P, 0);
   memcpy(h_all.data() + rec * me, &mine, sizeof(mine));
   h_all[rec * me + sizeof(mine)] = (char)good;
@@ -197,8 +177,7 @@ int comm_symm_setup(edgpu_ctx *c, size_t unit, int nunits) {
     return EDGPU_OK;
   }
   CK(cudaMemsetAsync(c->sym_slab, 0, bytes, c->stream));
-  c->sym_bytes = bytes; c->sym_used = 0; c->sym_ok = true;
-  memset(c->sym_units, 0, sizeof(c->sym_units));
+  c->sym_bytes = bytes; c->sym_ok = true;
   TRY(comm_barrier(c));
   CK(cudaStreamSynchronize(c->stream));
   return EDGPU_OK;
@@ -209,7 +188,7 @@ int comm_symm_teardown(edgpu_ctx *c) {
   for (int p = 0; p < c->nranks; p++) { if (p != c->rank && c->sym_peer[p]) cudaIpcCloseMemHandle(c->sym_peer[p]); c->sym_peer[p] = nullptr; }
   if (c->comm) { comm_barrier(c); cudaStreamSynchronize(c->stream); }   // every peer has closed its mapping
   cudaFree(c->sym_slab);
-  c->sym_slab = nullptr; c->sym_bytes = c->sym_used = 0; c->sym_ok = false;
+  c->sym_slab = nullptr; c->sym_bytes = 0; c->sym_ok = false;
   return EDGPU_OK;
 }
 

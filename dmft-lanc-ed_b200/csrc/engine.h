@@ -27,7 +27,8 @@ struct LancState {              // device-resident Lanczos scalars (no host sync
 };
 
 #define EDGPU_MAXP 8            // ranks of one NVLink domain (peer-mapped symmetric slab)
-#define EDGPU_MAX_WINDOWS 8     // column windows of the sharded H*v pipeline (halo of window w+1 under the column pass of w)
+#define EDGPU_MAX_WINDOWS 8
+#define EDGPU_HALO_HDR 1024     // bytes of arrival flags in front of the halo buffers: [window][source rank] 64-bit epochs
 
 // One low group of the structured row kernel (hxv_fast.cu), precomputed per sector: 80 bytes, bulk-copied next
 // to the tile.  hx = high word h | (mask of the high-bit hops the kernel applies) << 16; par bit kk = parity of
@@ -94,27 +95,27 @@ struct edgpu_ctx {
   TiledPlan *plan = nullptr;
   FastPlan *fplan = nullptr;
   int64_t opt_srow_lr = 0, opt_srow_t = 0, opt_no_uniform = 0, opt_no_fuse = 0, opt_no_peer = 0, opt_col_cluster = 0;
-  int64_t opt_halo_ctas = 0, opt_no_overlap = 0, opt_halo_chunks = 0, opt_no_batch = 0;
-  const double *const *peer_override = nullptr;   // selftest only: the ranks emulated on one device
+  int64_t opt_halo_ctas = 0, opt_no_overlap = 0, opt_no_batch = 0, opt_halo_windows = 0;
   int64_t launches = 0;
-  // symmetric slab (nranks > 1): one allocation per rank at identical offsets, opened by every peer
-  // through CUDA IPC, so that kernels can read a peer's copy of a vector over NVLink
+  // symmetric slab (nranks > 1): one allocation per rank with the same layout, opened by every peer through CUDA
+  // IPC.  It holds the halo of the sharded fast path: a block of arrival flags and two buffers of source columns
+  // that the OWNERS store into over NVLink (k_halo_push); nobody ever reads a peer's memory.
   char *sym_slab = nullptr;
-  size_t sym_bytes = 0, sym_used = 0, sym_unit = 0;
-  int sym_units[64] = {0};                    // per unit: length of the allocation that starts here, -1 = continuation, 0 = free
+  size_t sym_bytes = 0;
   char *sym_peer[64] = {nullptr};
   bool sym_ok = false;
-  std::vector<void *> slab_ptrs;              // edgpu_dev_alloc buffers carved from the slab (die with the sector)
+  bool halo_emul = false;                     // selftest only: ranks emulated on one device (sym_peer set by hand, no flags)
+  unsigned long long halo_epoch = 0;          // H*v counter of the sharded fast path: buffer = epoch & 1, flag value = epoch
   // per-pass timing (edgpu_time_hxv_passes): events recorded between the kernels of one H*v
   bool prof = false;
   int prof_n = 0;
-  cudaEvent_t pev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  const char *prof_name[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t pev[8] = {nullptr};
+  const char *prof_name[7] = {nullptr};
 };
 
 // marks the start of pass `name` (and the end of the previous one) when per-pass timing is on
 static inline void prof_mark(edgpu_ctx *c, const char *name) {
-  if (!c->prof || c->prof_n >= 5) return;
+  if (!c->prof || c->prof_n >= 7) return;
   cudaEventRecord(c->pev[c->prof_n], c->stream);
   c->prof_name[c->prof_n] = name;
   c->prof_n++;
@@ -182,16 +183,16 @@ int fast_apply_local(edgpu_ctx *c, const double *d_x, double *d_y, double *d_xp 
 int fast_apply_col(edgpu_ctx *c, int k, bool with_diag, bool acc, const double *d_x, double *d_y, int64_t ncols, int64_t coloff,
                    double *d_xp = nullptr, int *npartials = nullptr, bool dw_lists = false, int64_t list_col0 = 0, int grid_limit = 0);
 int fast_apply_row(edgpu_ctx *c, const double *d_x, double *d_y, int grid_limit = 0);
-int fast_halo_axpy(edgpu_ctx *c, const double *const *xpeer, const double *d_x, cudaStream_t st, int ctas, int z0, int z1);
-bool fast_peer_ready(edgpu_ctx *c, const double *d_x);   // sharded: x lives in the symmetric slab, peers are mapped
+bool fast_peer_ready(edgpu_ctx *c);                // sharded: the halo slab exists and every peer's copy is mapped
+int fast_halo_bytes(edgpu_ctx *c, size_t *bytes);   // size of the halo slab of the live sector (0: no sharded fast path)
+// this rank's columns -> the peers' halo buffers, column window w of the targets (w < 0: every window)
+int fast_halo_push(edgpu_ctx *c, const double *d_x, cudaStream_t st, int ctas, int w);
 // comm.cu
-int comm_symm_setup(edgpu_ctx *c, size_t unit, int nunits);   // collective: nunits vectors of `unit` bytes
+int comm_symm_setup(edgpu_ctx *c, size_t bytes);        // collective: `bytes` per rank, mapped by every peer
 int comm_symm_teardown(edgpu_ctx *c);                   // collective
 int comm_barrier(edgpu_ctx *c);                         // stream-ordered cross-rank barrier (tiny all-reduce)
-// vectors that H*v may read on a peer: carved from the symmetric slab when there is one
-int vec_alloc(edgpu_ctx *c, double **p, int64_t n);
+int vec_alloc(edgpu_ctx *c, double **p, int64_t n);     // engine work vector of n doubles (+ padding for 16-byte copies)
 void vec_free(edgpu_ctx *c, double **p);
-int64_t sym_offset(const edgpu_ctx *c, const void *p);  // byte offset inside the slab, -1 if not in it
 int comm_allreduce_scalar(edgpu_ctx *c, double *d_scalar);
 int comm_allreduce_array(edgpu_ctx *c, double *d_a, int n);
 // capi.cu

@@ -164,7 +164,7 @@ static int pick_col(edgpu_ctx *c) {
 bool hxv_fast_path(edgpu_ctx *c, const double *d_x) {
   if (c->dp.jhflag || c->opt_no_fuse) return false;
   if (c->nranks == 1) return pick_local(c) == EDGPU_ALGO_FAST && fast_supported_local(c);
-  return (c->algo == EDGPU_ALGO_AUTO || c->algo == EDGPU_ALGO_FAST) && fast_peer_ready(c, d_x) && fast_supported_local(c);
+  return (c->algo == EDGPU_ALGO_AUTO || c->algo == EDGPU_ALGO_FAST) && fast_peer_ready(c) && fast_supported_local(c);
 }
 
 int hxv_apply(edgpu_ctx *c, const double *d_x, double *d_y) {
@@ -181,9 +181,9 @@ int hxv_apply(edgpu_ctx *c, const double *d_x, double *d_y) {
     prof_mark(c, "k_hxv_gather");
     return gather_local(c, d_x, d_y, true, d_x);
   }
-  // sharded, fast path: the same two kernels as on one GPU; i_dw sources that live on another rank are read
-  // from that rank's copy of x over NVLink (no transposes, no packing)
-  if ((c->algo == EDGPU_ALGO_AUTO || c->algo == EDGPU_ALGO_FAST) && !c->dp.jhflag && fast_peer_ready(c, d_x) &&
+  // sharded, fast path: the same two kernels as on one GPU; i_dw sources that live on another rank arrive in the
+  // local halo buffer, stored there by their owner over NVLink (no transposes, no packing)
+  if ((c->algo == EDGPU_ALGO_AUTO || c->algo == EDGPU_ALGO_FAST) && !c->dp.jhflag && fast_peer_ready(c) &&
       fast_supported_local(c))
     return fast_apply_local(c, d_x, d_y);
   // sharded: diag + up locally; dw through the all-to-all transpose (spMatVec_MPI_main order,

@@ -23,9 +23,11 @@
 //
 // Sharded vector (i_dw columns split over the GPUs of one NVLink domain, ED_HAMILTONIAN.f90:96-110): k_srow only
 // touches local memory.  The dw hops whose source column lives on another rank -- and the few that touch a low
-// group cut by a rank boundary -- come from per-column source lists: k_halo_axpy reads the sources straight from
-// the owners' copies of x over NVLink (peer-mapped symmetric slab, comm.cu) and leaves z = sum of those hops in a
-// local vector, on a second stream and on its own SMs while k_srow works; pass 2 then adds z like it adds y.
+// group cut by a rank boundary -- come from per-column source lists.  The OWNER of a source column stores it into
+// the halo buffer of every rank that lists it (k_halo_push: posted NVLink writes into the peer-mapped symmetric
+// slab of comm.cu, on a second stream and on its own SMs while k_srow works; nobody reads remote memory), raises
+// an arrival flag on each peer, and pass 2 adds the arrived columns (amplitude * column) while it adds y.  Two halo
+// buffers alternate, so no cross-rank barrier is needed at all.
 //
 // The factor values are exactly the reference's V_k * sg1 * sg2 (stored/H_up.f90:55-81); only the
 // order of the floating-point sums differs.
@@ -87,14 +89,19 @@ struct SRowPlan {
   int *d_lptr = nullptr;                       // [qdw+1] entry range of every local column
   int *d_lown = nullptr, *d_lcol = nullptr;    // entry: owner rank, column inside the owner's shard
   double *d_lamp = nullptr;
-  int *d_zcols = nullptr;                      // the local columns that have entries (work list of k_halo_axpy)
   unsigned char *d_lflag = nullptr;            // per local column: 1 = not written by k_srow (cut group: starts from the
-                                               // diagonal in pass 2), 2 = has entries (z(:, j) is valid)
-  double *d_z = nullptr;                       // [qdw][DimUp] sum of the listed hops
+                                               // diagonal in pass 2), 2 = has entries
+  // halo (push model): the remote entries of rank q are numbered in list order = slots of q's halo buffers
+  int nslot = 0, maxslot = 0;                  // slots of this rank; largest slot count of any rank (symmetric layout)
+  int *d_lcol2 = nullptr;                      // entry: halo slot (remote owner) or local column (own)
+  int npush = 0;                               // (peer, slot, local column) triples this rank stores every H*v
+  int *d_pdst = nullptr, *d_pslot = nullptr, *d_psrc = nullptr;
+  int nwin = 1;                                // column windows of the targets: triples sorted by (window, source column)
+  int pwin[EDGPU_MAX_WINDOWS + 1] = {0};       // triple range of every window
+  unsigned int *d_pushctr = nullptr;           // [window] CTAs of k_halo_push that are done (the last one raises the flags)
 };
 
 struct FastPlan {
-  std::vector<int> h_zcols;          // host copy of sr.d_zcols (column windows of the sharded pipeline)
   FastFactor ff[2];
   bool col_ok[2] = {false, false};
   size_t col_smem[2] = {0, 0};
@@ -171,10 +178,13 @@ struct FColArgs {
   double *xp;
   const LancState *st;
   double *partials;
-  // LISTS (sharded vector): z(:, j) = the dw hops the row pass left out (k_halo_axpy), lflag[j] & 2 when column j has
-  // any; lflag[j] & 1: the row pass did not write column j at all, so y(:, j) starts from the diagonal term here
-  // (diagmode 1 stored, 2 recomputed).
-  const double *z;
+  // LISTS (sharded vector): the dw hops the row pass left out, entries lptr[j] .. lptr[j+1] of local column j: amplitude
+  // lamp, source column lcol of xb[lown] (a slot of the halo buffer for a remote owner, the local shard for an own
+  // cut group).  lflag[j] & 1: the row pass did not write column j at all, so y(:, j) starts from the diagonal term
+  // here (diagmode 1 stored, 2 recomputed).
+  const int *lptr, *lown, *lcol;
+  const double *lamp;
+  const double *xb[EDGPU_MAXP];
   const unsigned char *lflag;
   int diagmode;
   // UNI == 3 (single band, level-dependent V_k): slot s of a row is its s-th eligible bath bit, amplitude V_k from the word
@@ -193,6 +203,35 @@ __device__ __forceinline__ double fcol_init_diag(const FColArgs &a, int64_t j, i
         if ((ms >> q) & 1u) d += (o == q) ? a.uloc[o] : a.ust;
   return d;
 }
+// the listed dw hops of one column (LISTS): a small table per pipeline stage in shared memory, written by the thread
+// that issues the column's bulk copy (so it is published by the same mbarrier).  Four entries inline (the usual
+// case: one per rank-crossing bath bit); the rest -- columns of a low group cut by a rank boundary list all their
+// hops -- through the global tables.
+struct ColEnt { const double *p; double a; };
+struct ColTab {
+  int ne, e0, flag, pad;
+  ColEnt ent[4];
+};
+static_assert(sizeof(ColTab) == 80, "ColTab layout");
+__device__ __forceinline__ void coltab_fill(ColTab &T, const FColArgs &a, int64_t j) {
+  const int f = (int)__ldg(a.lflag + j);
+  T.flag = f;
+  T.e0 = __ldg(a.lptr + j);
+  T.ne = (f & 2) ? __ldg(a.lptr + j + 1) - T.e0 : 0;
+  for (int q = 0; q < 4 && q < T.ne; q++) {
+    T.ent[q].p = a.xb[__ldg(a.lown + T.e0 + q)] + (size_t)__ldg(a.lcol + T.e0 + q) * a.n;
+    T.ent[q].a = __ldg(a.lamp + T.e0 + q);
+  }
+}
+__device__ __forceinline__ double coltab_at(const ColTab &T, const FColArgs &a, int ne, int r) {
+  double z = 0.0;
+#pragma unroll
+  for (int q = 0; q < 4; q++)
+    if (q < ne) { const ColEnt e = T.ent[q]; z = fma(e.a, __ldcs(e.p + r), z); }
+  for (int e = T.e0 + 4; e < T.e0 + ne; e++)
+    z = fma(__ldg(a.lamp + e), __ldcs(a.xb[__ldg(a.lown + e)] + (size_t)__ldg(a.lcol + e) * a.n + r), z);
+  return z;
+}
 // MODE: 0 = y = F x, 1 = y += F x, 2 = y += F x fused with the first Lanczos vector update (y is only read)
 // UNI: 0 = general (value table, 4-byte entries), 1 = uniform magnitude with 4-byte entries, 2 = uniform with 2-byte
 // entries, 3 = single-band star geometry with level-dependent V_k: 2-byte entries in the order of the row's eligible
@@ -210,6 +249,7 @@ __global__ void __launch_bounds__(FCOL_THREADS, 1) k_fcol(FColArgs a) {
   double *vtab = buf1 + ld;
   uint64_t *bar = reinterpret_cast<uint64_t *>(vtab + F_MAXVALS);  // full[2], empty[2]
   double *red = reinterpret_cast<double *>(bar + 4);             // [32] block reduction (MODE == 2)
+  ColTab *tab = reinterpret_cast<ColTab *>(red + 32);            // [2] listed hops of the column in each stage (LISTS)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   double lsx = 0.0, lcp = 0.0, lsum = 0.0;
   if (MODE == 2) { lsx = a.st->sx; lcp = a.st->cprev; }
@@ -238,6 +278,7 @@ __global__ void __launch_bounds__(FCOL_THREADS, 1) k_fcol(FColArgs a) {
         if (j >= a.ncols) break;
         const int b = (int)(it & 1);
         if (it >= 2) mbar_wait(&bar[2 + b], (uint32_t)(((it >> 1) - 1) & 1));
+        if (LISTS) coltab_fill(tab[b], a, j);
         fence_proxy_async();
         mbar_expect_tx(&bar[b], colbytes);
         const char *src = reinterpret_cast<const char *>(a.x + j * (int64_t)n);
@@ -256,9 +297,9 @@ __global__ void __launch_bounds__(FCOL_THREADS, 1) k_fcol(FColArgs a) {
       uint32_t ms = 0;
       if (DIAG == 2) { dcol = a.dfac_s[a.coloff + j]; ms = (uint32_t)a.map_s[a.coloff + j]; }
       double *yc = a.y + j * (int64_t)n;
-      bool init = false, hasz = false;
-      if (LISTS) { const unsigned char f = __ldg(a.lflag + j); init = (f & 1) != 0; hasz = (f & 2) != 0; }
-      const double *zc = a.z + j * (int64_t)n;
+      bool init = false;
+      int ne = 0;
+      const ColTab &T = tab[b];
       uint32_t en[WT];
       uint32_t mnext = 0;
       auto load_ell = [&](int row) {
@@ -275,8 +316,11 @@ __global__ void __launch_bounds__(FCOL_THREADS, 1) k_fcol(FColArgs a) {
       if (tid < n) load_ell(tid);                                  // independent of the column: issued before the wait
       double ynext = 0.0, znext = 0.0;
       if (ACC && tid < n) ynext = __ldcs(yc + tid);
-      if (LISTS && hasz && tid < n) znext = __ldcs(zc + tid);
       mbar_wait(&bar[b], (uint32_t)((it >> 1) & 1));
+      if (LISTS) {
+        init = (T.flag & 1) != 0; ne = T.ne;
+        if (ne && tid < n) znext = coltab_at(T, a, ne, tid);
+      }
       for (int r = tid; r < n; r += NCT) {
         uint32_t e[WT];
 #pragma unroll
@@ -287,7 +331,7 @@ __global__ void __launch_bounds__(FCOL_THREADS, 1) k_fcol(FColArgs a) {
         if (r + NCT < n) {                                         // software prefetch of the next row's inputs
           load_ell(r + NCT);
           if (ACC) ynext = __ldcs(yc + r + NCT);
-          if (LISTS && hasz) znext = __ldcs(zc + r + NCT);
+          if (LISTS && ne) znext = coltab_at(T, a, ne, r + NCT);
         }
         double acc0 = 0.0;
         if (DIAG == 1) acc0 = __ldcs(a.diag + j * (int64_t)n + r) * xs[r];
@@ -382,6 +426,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FCOL_THREADS, 1) k_f
   double *vtab = buf + hmax;
   uint64_t *bar = reinterpret_cast<uint64_t *>(vtab + F_MAXVALS);
   double *red = reinterpret_cast<double *>(bar + 2);
+  ColTab *tab = reinterpret_cast<ColTab *>(red + 32);            // listed hops of the current column (LISTS)
   const int tid = threadIdx.x;
   double lsx = 0.0, lcp = 0.0, lsum = 0.0;
   if (MODE == 2) { lsx = a.st->sx; lcp = a.st->cprev; }
@@ -396,6 +441,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FCOL_THREADS, 1) k_f
     const int64_t j = pair + it * G;
     if (j >= a.ncols) break;
     if (tid == 0) {
+      if (LISTS) coltab_fill(tab[0], a, j);
       fence_proxy_async();
       mbar_expect_tx(&bar[0], bytes);
       const char *src = reinterpret_cast<const char *>(a.x + j * (int64_t)n + r0);
@@ -405,16 +451,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FCOL_THREADS, 1) k_f
     mbar_wait(&bar[0], (uint32_t)(it & 1));
     cluster_sync_all();                                            // both halves of column j are in place
     double *yc = a.y + j * (int64_t)n + r0;
-    bool init = false, hasz = false;
-    if (LISTS) { const unsigned char f = __ldg(a.lflag + j); init = (f & 1) != 0; hasz = (f & 2) != 0; }
-    const double *zc = a.z + j * (int64_t)n + r0;
+    bool init = false;
+    int ne = 0;
+    const ColTab &T = tab[0];
+    if (LISTS) { init = (T.flag & 1) != 0; ne = T.ne; }
     for (int r = tid; r < nr; r += FCOL_THREADS) {
       uint32_t e[WT];
 #pragma unroll
       for (int s = 0; s < WT; s++) e[s] = __ldg(a.ell + (size_t)s * n + r0 + r);
       double yold = 0.0, zold = 0.0;
       if (ACC) yold = __ldcs(yc + r);
-      if (LISTS && hasz) zold = __ldcs(zc + r);
+      if (LISTS && ne) zold = coltab_at(T, a, ne, r0 + r);
       double acc = 0.0;
 #pragma unroll
       for (int s = 0; s < WT; s++) {
@@ -766,53 +813,86 @@ __global__ void __launch_bounds__(SROW_THREADS, 1) k_srow(const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------------
-// halo: z(:, t) = sum over the listed hops (t <- s) of amp * x_owner(:, s), the sources read from the owners'
-// shards over NVLink (or from the local shard).  Work item = (listed column, chunk of rows); every thread keeps the
-// loads of up to HALO_UNROLL rows x all sources of its column in flight.
+// halo, producer side: this rank's source columns go to the halo buffers of the ranks that list them, moved by the
+// TMA engine both ways -- cp.async.bulk global -> shared (local read) and shared -> global (posted writes to the
+// peer-mapped address over NVLink), a ring of 16 KB stages driven by ONE thread per CTA (measured against 16-byte
+// register stores: tools/nvlink_push.cu, 667 vs 523 GB/s with 32 CTAs).  Work item = (triple, 16 KB piece); triples
+// are sorted by source column, so a column that several peers need is read from HBM once.  The last CTA to finish raises this
+// rank's arrival flag (= the H*v epoch) on every peer: fence.sys by every CTA before it counts itself, fence.sys by
+// the last one before the flag stores (cumulativity makes all the data visible before the flag).
 // ---------------------------------------------------------------------------------------------
-struct HaloArgs {
-  double *z;                     // [qdw][n]
-  int n, nzcols;
-  const int *zcols, *lptr, *lown, *lcol;
-  const double *lamp;
-  const double *xb[EDGPU_MAXP];  // every rank's copy of x (peer-mapped); xb[me] = local x
+struct PushArgs {
+  const double *x;               // local shard
+  int n, npush;
+  const int *pdst, *pslot, *psrc;
+  double *hb[EDGPU_MAXP];        // rank p's halo buffer of this epoch
+  unsigned long long *flag[EDGPU_MAXP];   // rank p's arrival flag of THIS rank, nullptr = no flag (own rank, emulation)
+  unsigned long long epoch;
+  unsigned int *ctr;
 };
-#define HALO_THREADS 512
-#define HALO_UNROLL 8
-__global__ void __launch_bounds__(HALO_THREADS) k_halo_axpy(HaloArgs a) {
-  __shared__ const double *xb[EDGPU_MAXP];
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int p = 0; p < EDGPU_MAXP; p++) xb[p] = a.xb[p];
-  }
-  __syncthreads();
-  constexpr int ROWS = HALO_THREADS * HALO_UNROLL * 2;             // rows per item (double2 per thread and unroll step)
-  const int nrc = (a.n + ROWS - 1) / ROWS;
-  const int64_t nitems = (int64_t)a.nzcols * nrc;
-  for (int64_t it = blockIdx.x; it < nitems; it += gridDim.x) {
-    const int t = __ldg(a.zcols + (int)(it / nrc)), rc = (int)(it % nrc);
-    const int e0 = __ldg(a.lptr + t), e1 = __ldg(a.lptr + t + 1);
-    const int r0 = rc * ROWS;
-    double2 acc[HALO_UNROLL];
-#pragma unroll
-    for (int q = 0; q < HALO_UNROLL; q++) acc[q] = make_double2(0.0, 0.0);
-    for (int e = e0; e < e1; e++) {
-      const double am = __ldg(a.lamp + e);
-      const double2 *src = reinterpret_cast<const double2 *>(xb[__ldg(a.lown + e)] + (size_t)__ldg(a.lcol + e) * a.n + r0);
-      double2 v[HALO_UNROLL];
-#pragma unroll
-      for (int q = 0; q < HALO_UNROLL; q++) {
-        const int i = threadIdx.x + q * HALO_THREADS;
-        v[q] = (r0 + 2 * i < a.n) ? src[i] : make_double2(0.0, 0.0);
-      }
-#pragma unroll
-      for (int q = 0; q < HALO_UNROLL; q++) { acc[q].x = fma(am, v[q].x, acc[q].x); acc[q].y = fma(am, v[q].y, acc[q].y); }
+#define PUSH_SB 16384             // bytes per stage
+#define PUSH_STAGES 4
+#define PUSH_SMEM (PUSH_STAGES * PUSH_SB + 64)
+__global__ void __launch_bounds__(32) k_halo_push(PushArgs a) {
+  extern __shared__ __align__(128) unsigned char psm[];
+  uint64_t *bar = reinterpret_cast<uint64_t *>(psm + (size_t)PUSH_STAGES * PUSH_SB);
+  if (threadIdx.x != 0) return;                                    // the TMA engine does the work: one thread drives it
+  for (int s = 0; s < PUSH_STAGES; s++) mbar_init(&bar[s], 1);
+  fence_barrier_init();
+  const int64_t colbytes = (int64_t)a.n * 8;
+  const int npc = (int)((colbytes + PUSH_SB - 1) / PUSH_SB);
+  const int64_t nitems = (int64_t)a.npush * npc, G = gridDim.x;
+  const int64_t my = nitems > blockIdx.x ? (nitems - blockIdx.x + G - 1) / G : 0;
+  auto piece = [&](int64_t k, int *e, int64_t *off, uint32_t *bytes) {
+    const int64_t it = blockIdx.x + k * G;
+    *e = (int)(it / npc);
+    *off = (it % npc) * PUSH_SB;
+    *bytes = (uint32_t)min((int64_t)PUSH_SB, colbytes - *off);
+  };
+  auto load = [&](int64_t k) {
+    int e; int64_t off; uint32_t bytes;
+    piece(k, &e, &off, &bytes);
+    const int s = (int)(k % PUSH_STAGES);
+    mbar_expect_tx(&bar[s], bytes);
+    bulk_g2s(psm + (size_t)s * PUSH_SB, reinterpret_cast<const char *>(a.x + (size_t)__ldg(a.psrc + e) * a.n) + off, bytes, &bar[s]);
+  };
+  int64_t issued = 0;
+  for (; issued < my && issued < PUSH_STAGES; issued++) load(issued);
+  for (int64_t k = 0; k < my; k++) {
+    const int s = (int)(k % PUSH_STAGES);
+    mbar_wait(&bar[s], (uint32_t)((k / PUSH_STAGES) & 1));
+    int e; int64_t off; uint32_t bytes;
+    piece(k, &e, &off, &bytes);
+    char *dst = reinterpret_cast<char *>(a.hb[__ldg(a.pdst + e)] + (size_t)__ldg(a.pslot + e) * a.n) + off;
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(psm + (size_t)s * PUSH_SB)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    if (issued < my) {                                             // the next load reuses this stage: the store must have read it
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      load(issued);
+      issued++;
     }
-    double2 *dst = reinterpret_cast<double2 *>(a.z + (size_t)t * a.n + r0);
-#pragma unroll
-    for (int q = 0; q < HALO_UNROLL; q++) {
-      const int i = threadIdx.x + q * HALO_THREADS;
-      if (r0 + 2 * i < a.n) dst[i] = acc[q];
+  }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");       // every store of this CTA is complete ...
+  asm volatile("fence.proxy.async;" ::: "memory");                // ... and ordered before the generic-proxy flag protocol
+  __threadfence_system();
+  if (atomicAdd(a.ctr, 1u) == gridDim.x - 1) {
+    *a.ctr = 0u;                                                   // ready for the next launch (stream ordered)
+    __threadfence_system();
+    for (int p = 0; p < EDGPU_MAXP; p++)
+      if (a.flag[p]) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.flag[p]), "l"(a.epoch) : "memory");
+  }
+}
+// consumer side: wait until every peer's columns of this epoch have arrived (flags live in local memory)
+__global__ void k_halo_wait(const unsigned long long *flags, int nranks, int me, unsigned long long epoch) {
+  const int p = threadIdx.x;
+  if (p < nranks && p != me) {
+    const long long t0 = clock64();
+    for (;;) {
+      unsigned long long v;
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + p) : "memory");
+      if (v >= epoch) break;
+      if (clock64() - t0 > 60000000000LL) __trap();                // ~30 s: a peer died -- fail loudly instead of hanging
+      __nanosleep(200);
     }
   }
 }
@@ -903,8 +983,8 @@ static int pack_fast(edgpu_ctx *c, const Factor &f, FastFactor &ff) {
   return EDGPU_OK;
 }
 
-static size_t fcol_smem(int64_t n) { return (size_t)2 * (n + 2) * 8 + F_MAXVALS * 8 + 32 + 32 * 8; }
-static size_t fcol2_smem(int64_t n) { return (size_t)((((n >> 1) + 1) & ~(int64_t)1) + 2) * 8 + F_MAXVALS * 8 + 16 + 32 * 8; }
+static size_t fcol_smem(int64_t n) { return (size_t)2 * (n + 2) * 8 + F_MAXVALS * 8 + 32 + 32 * 8 + 2 * sizeof(ColTab); }
+static size_t fcol2_smem(int64_t n) { return (size_t)((((n >> 1) + 1) & ~(int64_t)1) + 2) * 8 + F_MAXVALS * 8 + 16 + 32 * 8 + sizeof(ColTab); }
 static size_t srow_smem(int cpad) {
   size_t b = (size_t)SROW_STAGES * ((size_t)cpad * SROW_R * 8 + (size_t)(cpad + 2) * 8 + 2 * SROW_R * 8 + SROW_MAXG * sizeof(SRowRec) + 16 + 4) +
              32 * 8 + 64;
@@ -1030,6 +1110,50 @@ static int to_device(T **d, const std::vector<T> &h) {
   return EDGPU_OK;
 }
 
+// Halo tables of the push model.  Rank q's remote entries (owner != q), in list order, are the slots of q's halo
+// buffers.  lcol2 (this rank's consumer view): slot for a remote entry, local column for an own one.  Triples (q, slot,
+// local column) for every entry of another rank q that this rank owns, sorted by (column window of the target on q,
+// source column): window w of rank q = its local columns [qdw*w/K, qdw*(w+1)/K), so that q's column pass of window w
+// can start when the triples of window w have arrived.  hp_me: this rank's plan with its lists built.
+static int halo_tables_host(edgpu_ctx *c, const SRowHostPlan &hp_me, const std::vector<int32_t> &map, const std::vector<int32_t> &rp,
+                            const std::vector<int32_t> &cc, const std::vector<double> &vv, int K, std::vector<int> &lcol2,
+                            std::vector<int> &pdst, std::vector<int> &pslot, std::vector<int> &psrc, int *pwin, int *nslot, int *maxslot) {
+  const int P = c->nranks, me = c->rank;
+  lcol2.clear(); pdst.clear(); pslot.clear(); psrc.clear();
+  *nslot = 0; *maxslot = 0;
+  struct Tr { int win, src, dst, slot; };
+  std::vector<Tr> tr;
+  for (int q = 0; q < P; q++) {
+    SRowHostPlan hq;
+    const SRowHostPlan *h = &hp_me;
+    if (q != me) {
+      if (srow_plan_host(c->ns, c->ndw, c->dimdw, P, q, (int)c->opt_srow_lr, (int)c->opt_srow_t, hq) != 1)
+        return edgpu_set_err(EDGPU_ERR_INVALID, "internal: row-kernel plan of rank %d differs from rank %d's", q, me);
+      srow_lists_host(hq, q, c->dimdw, map.data(), rp.data(), cc.data(), vv.data());
+      h = &hq;
+    }
+    const int64_t qq = (int64_t)h->lptr.size() - 1;                 // local columns of rank q
+    int slot = 0;
+    for (int64_t t = 0; t < qq; t++) {
+      int w = 0;
+      while (w + 1 < K && t >= qq * (w + 1) / K) w++;
+      for (int e = h->lptr[(size_t)t]; e < h->lptr[(size_t)t + 1]; e++) {
+        const bool remote = h->lown[(size_t)e] != q;
+        if (q == me) lcol2.push_back(remote ? slot : h->lcol[(size_t)e]);
+        else if (h->lown[(size_t)e] == me) tr.push_back(Tr{w, h->lcol[(size_t)e], q, slot});
+        if (remote) slot++;
+      }
+    }
+    if (q == me) *nslot = slot;
+    *maxslot = std::max(*maxslot, slot);
+  }
+  std::stable_sort(tr.begin(), tr.end(), [](const Tr &a, const Tr &b) { return a.win != b.win ? a.win < b.win : a.src < b.src; });
+  for (int w = 0; w <= K; w++) pwin[w] = 0;
+  for (const Tr &t : tr) { pdst.push_back(t.dst); pslot.push_back(t.slot); psrc.push_back(t.src); pwin[t.win + 1]++; }
+  for (int w = 0; w < K; w++) pwin[w + 1] += pwin[w];
+  return EDGPU_OK;
+}
+
 static int build_srow(edgpu_ctx *c, SRowPlan &sr) {
   // single band, star geometry, no inter-orbital terms: every dw hop is bit 0 <-> bit k
   sr.ok = false;
@@ -1068,14 +1192,24 @@ static int build_srow(edgpu_ctx *c, SRowPlan &sr) {
     sr.lists = true;
     sr.nlist = (int)hp.lown.size();
     sr.nzcols = (int)hp.zcols.size();
+    // halo slots and push triples: the plan and the lists are pure functions of (geometry, rank), so every rank
+    // derives every other rank's lists itself -- nothing is exchanged
+    std::vector<int> lcol2, pdst, pslot, psrc;
+    // windows pay when the halo outlasts the row pass: from 4 ranks on (measured)
+    sr.nwin = (int)std::max<int64_t>(1, std::min<int64_t>(c->opt_halo_windows > 0 ? c->opt_halo_windows : (c->nranks >= 4 ? 4 : 1), EDGPU_MAX_WINDOWS));
+    TRY(halo_tables_host(c, hp, map, rp, cc, vv, sr.nwin, lcol2, pdst, pslot, psrc, sr.pwin, &sr.nslot, &sr.maxslot));
+    sr.npush = (int)pdst.size();
     TRY(to_device(&sr.d_lptr, hp.lptr));
     TRY(to_device(&sr.d_lown, hp.lown));
     TRY(to_device(&sr.d_lcol, hp.lcol));
+    TRY(to_device(&sr.d_lcol2, lcol2));
     TRY(to_device(&sr.d_lamp, hp.lamp));
     TRY(to_device(&sr.d_lflag, hp.lflag));
-    TRY(to_device(&sr.d_zcols, hp.zcols));
-    c->fplan->h_zcols = hp.zcols;
-    if (sr.nzcols) CK(cudaMalloc(&sr.d_z, (size_t)std::max<int64_t>(c->nloc, 1) * sizeof(double)));
+    TRY(to_device(&sr.d_pdst, pdst));
+    TRY(to_device(&sr.d_pslot, pslot));
+    TRY(to_device(&sr.d_psrc, psrc));
+    CK(cudaMalloc(&sr.d_pushctr, EDGPU_MAX_WINDOWS * sizeof(unsigned int)));
+    CK(cudaMemset(sr.d_pushctr, 0, EDGPU_MAX_WINDOWS * sizeof(unsigned int)));
   }
   sr.ok = true;
   return EDGPU_OK;
@@ -1086,7 +1220,8 @@ int fast_plan_free(edgpu_ctx *c) {
   for (int k = 0; k < 2; k++) { cudaFree(c->fplan->ff[k].d_ell); cudaFree(c->fplan->ff[k].d_ell16); cudaFree(c->fplan->ff[k].d_vtab); }
   SRowPlan &r = c->fplan->sr;
   cudaFree(r.d_recs); cudaFree(r.d_chunks); cudaFree(r.d_vk); cudaFree(r.d_dr0); cudaFree(r.d_dr1);
-  cudaFree(r.d_lptr); cudaFree(r.d_lown); cudaFree(r.d_lcol); cudaFree(r.d_lamp); cudaFree(r.d_lflag); cudaFree(r.d_zcols); cudaFree(r.d_z);
+  cudaFree(r.d_lptr); cudaFree(r.d_lown); cudaFree(r.d_lcol); cudaFree(r.d_lamp); cudaFree(r.d_lflag);
+  cudaFree(r.d_lcol2); cudaFree(r.d_pdst); cudaFree(r.d_pslot); cudaFree(r.d_psrc); cudaFree(r.d_pushctr);
   delete c->fplan;
   c->fplan = nullptr;
   return EDGPU_OK;
@@ -1123,6 +1258,7 @@ static int set_kernel_attrs(edgpu_ctx *c) {
   CK((set_fcol_attr<12, 0>())); CK((set_fcol_attr<12, 1>())); CK((set_fcol_attr<12, 2>()));
   CK((set_fcol_attr<16, 0>())); CK((set_fcol_attr<16, 1>())); CK((set_fcol_attr<16, 2>()));
   CK(set_fcol2_attr<8>()); CK(set_fcol2_attr<12>()); CK(set_fcol2_attr<16>());
+  CK(cudaFuncSetAttribute(k_halo_push, cudaFuncAttributeMaxDynamicSharedMemorySize, PUSH_SMEM));
   CK(cudaFuncSetAttribute(k_srow<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
   CK(cudaFuncSetAttribute(k_srow<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
   CK(cudaFuncSetAttribute(k_srow<5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
@@ -1162,6 +1298,13 @@ bool fast_supported_col(edgpu_ctx *c, int k) {
   if (!c->hstatus || c->dp.jhflag) return false;
   if (fast_plan_build(c)) return false;
   return c->fplan->col_ok[k] || c->fplan->col2_ok[k];
+}
+
+static size_t halo_buf_bytes(const edgpu_ctx *c, const SRowPlan &sr) {
+  return (((size_t)sr.maxslot * (size_t)c->dimup + 2) * sizeof(double) + 255) & ~(size_t)255;
+}
+static double *halo_buf(const edgpu_ctx *c, const SRowPlan &sr, int p, unsigned long long epoch) {
+  return reinterpret_cast<double *>(c->sym_peer[p] + EDGPU_HALO_HDR + (size_t)(epoch & 1ull) * halo_buf_bytes(c, sr));
 }
 
 template <int WT, int DIAG, int MODE, bool LISTS>
@@ -1235,7 +1378,12 @@ int fast_apply_col(edgpu_ctx *c, int k, bool with_diag, bool acc, const double *
   const bool lists = dw_lists && p->sr.lists;
   if (lists) {
     if (k != 0 || diag != 0 || !acc) return edgpu_set_err(EDGPU_ERR_INVALID, "dw source lists belong to the accumulating up pass");
-    a.z = p->sr.d_z + list_col0 * c->dimup; a.lflag = p->sr.d_lflag + list_col0;
+    const SRowPlan &sr = p->sr;
+    a.lptr = sr.d_lptr + list_col0; a.lown = sr.d_lown; a.lcol = sr.d_lcol2; a.lamp = sr.d_lamp;
+    const double *hb = halo_buf(c, sr, c->rank, c->halo_epoch);
+    for (int q = 0; q < EDGPU_MAXP; q++) a.xb[q] = hb;
+    a.xb[c->rank] = d_x - list_col0 * c->dimup;                      // own cut groups: columns of the local shard
+    a.lflag = sr.d_lflag + list_col0;
     a.diagmode = c->d_diag ? 1 : 2;
     if (c->d_diag) a.diag = c->d_diag + list_col0 * c->dimup;      // the skipped columns' stored diagonal, same column window
   }
@@ -1323,91 +1471,103 @@ int fast_apply_row(edgpu_ctx *c, const double *d_x, double *d_y, int grid_limit)
   return EDGPU_OK;
 }
 
-// z = the listed dw hops of this H*v (stream st); xpeer[p] = rank p's pointer of x
-int fast_halo_axpy(edgpu_ctx *c, const double *const *xpeer, const double *d_x, cudaStream_t st, int ctas, int z0, int z1) {
+// ---- halo plumbing (sharded vector) ------------------------------------------------------------------------------
+// slab layout, identical on every rank: [EDGPU_HALO_HDR bytes of arrival flags][buffer 0][buffer 1], a buffer =
+// maxslot columns of DimUp doubles
+int fast_halo_bytes(edgpu_ctx *c, size_t *bytes) {
+  *bytes = 0;
+  if (c->nranks <= 1 || c->nranks > EDGPU_MAXP) return EDGPU_OK;
+  if (!fast_supported_local(c)) return EDGPU_OK;                 // builds the plan (and the tables) on first use
   const SRowPlan &sr = c->fplan->sr;
-  if (!sr.lists || z1 <= z0) return EDGPU_OK;
-  HaloArgs h{};
-  h.z = sr.d_z; h.n = (int)c->dimup; h.nzcols = z1 - z0;
-  h.zcols = sr.d_zcols + z0; h.lptr = sr.d_lptr; h.lown = sr.d_lown; h.lcol = sr.d_lcol; h.lamp = sr.d_lamp;
-  for (int p = 0; p < EDGPU_MAXP; p++) h.xb[p] = xpeer[p < c->nranks ? p : 0];
-  h.xb[c->rank] = d_x;
-  const int64_t nitems = (int64_t)(z1 - z0) * ((c->dimup + HALO_THREADS * HALO_UNROLL * 2 - 1) / (HALO_THREADS * HALO_UNROLL * 2));
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(nitems, ctas));
-  k_halo_axpy<<<grid, HALO_THREADS, 0, st>>>(h);
-  CKL(c);
+  if (!sr.lists) return EDGPU_OK;
+  *bytes = EDGPU_HALO_HDR + 2 * halo_buf_bytes(c, sr);
   return EDGPU_OK;
 }
-
-// peers' pointers of a vector that lives in the symmetric slab (nullptr if it does not)
-static const double *const *peer_ptrs(edgpu_ctx *c, const double *d_x, const double **buf) {
-  if (c->nranks == 1) return nullptr;
-  if (c->peer_override) return c->peer_override;                   // one-device emulation of the ranks (selftest)
-  const int64_t off = sym_offset(c, d_x);
-  if (off < 0) return nullptr;
-  for (int p = 0; p < c->nranks; p++) buf[p] = reinterpret_cast<const double *>(c->sym_peer[p] + off);
-  return buf;
+bool fast_peer_ready(edgpu_ctx *c) {
+  return c->nranks > 1 && c->nranks <= EDGPU_MAXP && c->sym_ok && c->sym_slab != nullptr;
 }
-bool fast_peer_ready(edgpu_ctx *c, const double *d_x) {
-  if (c->nranks > 1 && c->peer_override) return true;
-  return c->nranks > 1 && c->nranks <= EDGPU_MAXP && c->sym_ok && sym_offset(c, d_x) >= 0;
+// this rank's source columns -> the halo buffers (epoch c->halo_epoch) of the ranks that list them; w = column window
+// of the targets (its own launch, counter and arrival flags), w < 0: every window one after another
+int fast_halo_push(edgpu_ctx *c, const double *d_x, cudaStream_t st, int ctas, int w) {
+  const SRowPlan &sr = c->fplan->sr;
+  if (w < 0) {
+    for (int k = 0; k < sr.nwin; k++) TRY(fast_halo_push(c, d_x, st, ctas, k));
+    return EDGPU_OK;
+  }
+  PushArgs a{};
+  a.x = d_x; a.n = (int)c->dimup; a.npush = sr.pwin[w + 1] - sr.pwin[w];
+  a.pdst = sr.d_pdst + sr.pwin[w]; a.pslot = sr.d_pslot + sr.pwin[w]; a.psrc = sr.d_psrc + sr.pwin[w];
+  for (int p = 0; p < EDGPU_MAXP; p++) {
+    const int q = p < c->nranks ? p : c->rank;
+    a.hb[p] = halo_buf(c, sr, q, c->halo_epoch);
+    a.flag[p] = (p < c->nranks && p != c->rank && !c->halo_emul)
+                    ? reinterpret_cast<unsigned long long *>(c->sym_peer[p]) + w * EDGPU_MAXP + c->rank : nullptr;
+  }
+  a.epoch = c->halo_epoch; a.ctr = sr.d_pushctr + w;
+  const int64_t nitems = (int64_t)a.npush * ((c->dimup * 8 + PUSH_SB - 1) / PUSH_SB);
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(nitems, 1), ctas));   // runs even without work: flags
+  k_halo_push<<<grid, 32, PUSH_SMEM, st>>>(a);
+  CKL(c);
+  return EDGPU_OK;
 }
 
 // d_xp != nullptr: Lanczos form -- d_y only holds the row-pass partial result, w = sx*(H x) - cprev*xp goes to
 // d_xp and the per-CTA partial sums of (sx*x).w to c->d_partials (*npartials of them)
 //
-// Sharded pipeline (one stream-ordered barrier, then everything asynchronous):
-//   stream2 : k_halo_axpy on window 1 | window 2 | ... | window K of the local columns   (NVLink bound, few SMs)
-//   stream  : k_srow (all local columns, the other SMs) | k_fcol window 1 after its halo | ... | k_fcol window K
-// so the column pass of a window runs while the halo of the next ones is still in flight.
+// Sharded pipeline (no cross-rank barrier, no remote reads):
+//   stream2 : k_halo_push window 1 | window 2 | ... | window K   (this rank's columns -> the peers' halo buffers of
+//             this epoch, ordered by the column window of the TARGET, each followed by its arrival flags)
+//   stream  : k_srow (local groups, the other SMs) | k_halo_wait 1 | k_fcol window 1 (+ arrived columns) | ... | K
+// Ordering: a peer overwrites buffer b = epoch & 1 again at epoch + 2, which it starts only after it has seen this
+// rank's flag of epoch + 1, and this rank raises that flag in stream order after its k_fcol of this epoch.
 int fast_apply_local(edgpu_ctx *c, const double *d_x, double *d_y, double *d_xp, int *npartials) {
   TRY(fast_plan_build(c));
   const SRowPlan &sr = c->fplan->sr;
-  const double *pb[64];
-  const double *const *xpeer = peer_ptrs(c, d_x, pb);
-  if (c->nranks > 1 && !xpeer) return edgpu_set_err(EDGPU_ERR_INVALID, "sharded fast H*v: the vector is not in the symmetric slab");
   if (npartials) *npartials = 0;
-  if (c->nranks == 1 || sr.nzcols == 0) {
-    if (c->nranks > 1) TRY(comm_barrier(c));
+  if (c->nranks == 1) {
     // row tiles first (y = Hd o x + x Hdw^T, write only), then whole columns (y += Hup x, contiguous RMW)
     prof_mark(c, "k_srow");
     TRY(fast_apply_row(c, d_x, d_y, 0));
     prof_mark(c, "k_fcol");
     return fast_apply_col(c, 0, false, true, d_x, d_y, c->qdw, c->coloff, d_xp, npartials, true, 0, 0);
   }
-  // Peers read x while this rank reads theirs.  One stream-ordered barrier per application orders every rank's
-  // earlier writes of x before the reads (RAW) and, because each rank enqueues it after its previous H*v, every
-  // rank's previous remote reads before anybody's later overwrite of those buffers (WAR).
-  TRY(comm_barrier(c));
-  const int hctas = (int)std::max<int64_t>(1, std::min<int64_t>(c->opt_halo_ctas > 0 ? c->opt_halo_ctas : 32, c->sm_count / 2));
-  if (!c->stream2 || c->opt_no_overlap) {
-    prof_mark(c, "k_halo_axpy");
-    TRY(fast_halo_axpy(c, xpeer, d_x, c->stream, c->sm_count * 2, 0, sr.nzcols));
+  if (!fast_peer_ready(c)) return edgpu_set_err(EDGPU_ERR_INVALID, "sharded fast H*v: no halo slab (peers not mapped)");
+  const unsigned long long *flags = reinterpret_cast<const unsigned long long *>(c->sym_slab);
+  if (c->halo_emul) {                                              // emulation: the selftest has pushed for every rank
     prof_mark(c, "k_srow");
     TRY(fast_apply_row(c, d_x, d_y, 0));
     prof_mark(c, "k_fcol");
     return fast_apply_col(c, 0, false, true, d_x, d_y, c->qdw, c->coloff, d_xp, npartials, true, 0, 0);
   }
-  const int K = (int)std::max<int64_t>(1, std::min<int64_t>(c->opt_halo_chunks > 0 ? c->opt_halo_chunks : 4, EDGPU_MAX_WINDOWS));
+  c->halo_epoch++;
+  const int K = sr.nwin;
+  if (!c->stream2 || c->opt_no_overlap) {
+    prof_mark(c, "k_halo_push");
+    TRY(fast_halo_push(c, d_x, c->stream, c->sm_count, -1));
+    prof_mark(c, "k_srow");
+    TRY(fast_apply_row(c, d_x, d_y, 0));
+    prof_mark(c, "k_halo_wait");
+    for (int w = 0; w < K; w++) {
+      k_halo_wait<<<1, 32, 0, c->stream>>>(flags + w * EDGPU_MAXP, c->nranks, c->rank, c->halo_epoch);
+      CKL(c);
+    }
+    prof_mark(c, "k_fcol");
+    return fast_apply_col(c, 0, false, true, d_x, d_y, c->qdw, c->coloff, d_xp, npartials, true, 0, 0);
+  }
+  const int hctas = (int)std::max<int64_t>(1, std::min<int64_t>(c->opt_halo_ctas > 0 ? c->opt_halo_ctas : 32, c->sm_count / 2));
   CK(cudaEventRecord(c->ev_fork, c->stream));
   CK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
-  // windows of local columns with (about) the same number of listed columns each
-  int64_t wcol[EDGPU_MAX_WINDOWS + 1];
-  int wz[EDGPU_MAX_WINDOWS + 1];
-  for (int w = 0; w <= K; w++) {
-    wz[w] = (int)((int64_t)sr.nzcols * w / K);
-    wcol[w] = (w == 0) ? 0 : (w == K ? c->qdw : (int64_t)c->fplan->h_zcols[(size_t)wz[w]]);
-  }
-  for (int w = 0; w < K; w++) {
-    TRY(fast_halo_axpy(c, xpeer, d_x, c->stream2, hctas, wz[w], wz[w + 1]));
-    CK(cudaEventRecord(c->ev_win[w], c->stream2));
-  }
+  for (int w = 0; w < K; w++) TRY(fast_halo_push(c, d_x, c->stream2, hctas, w));
+  CK(cudaEventRecord(c->ev_join, c->stream2));
   prof_mark(c, "k_srow");
   TRY(fast_apply_row(c, d_x, d_y, c->sm_count - hctas));
-  prof_mark(c, "k_fcol");
+  prof_mark(c, "k_fcol");                                          // includes the waits for the arrivals
   for (int w = 0; w < K; w++) {
-    const int64_t j0 = wcol[w], j1 = wcol[w + 1];
-    CK(cudaStreamWaitEvent(c->stream, c->ev_win[w], 0));
+    const int64_t j0 = c->qdw * w / K, j1 = c->qdw * (w + 1) / K;
+    k_halo_wait<<<1, 32, 0, c->stream>>>(flags + w * EDGPU_MAXP, c->nranks, c->rank, c->halo_epoch);
+    CKL(c);
+    // the caller may overwrite d_x as soon as this stream is done: its own pushes (which read d_x) end before that
+    if (w == K - 1) CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     if (j1 <= j0) continue;
     TRY(fast_apply_col(c, 0, false, true, d_x + j0 * c->dimup, d_y + j0 * c->dimup, j1 - j0, c->coloff + j0,
                        d_xp ? d_xp + j0 * c->dimup : nullptr, npartials, true, j0, w + 1 < K ? c->sm_count - hctas : 0));

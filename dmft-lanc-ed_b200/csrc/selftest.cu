@@ -109,21 +109,29 @@ extern "C" int edgpu_selftest_dev_maxabsdiff(const double *d_a, const double *d_
   return 0;
 }
 
-// Sharded fast path on ONE device: `nranks` contexts stand in for the ranks (no NCCL; each "rank" pulls its halo
-// from the others' shards through ordinary device pointers).  Exercises exactly the kernels and plans of the
-// multi-GPU path -- whole / cut low groups, group records, the halo copy kernel, the source lists of the column
-// pass -- so that a single-GPU box can check them for any rank count.  x, y: full host vectors.
+// Sharded fast path on ONE device: `nranks` contexts stand in for the ranks (no NCCL, no IPC: every "rank" gets
+// a plain allocation as its halo slab and the others' addresses by hand; no arrival flags -- the pushes of all ranks
+// run first, then every rank's H*v).  Exercises exactly the kernels and plans of the multi-GPU path -- whole / cut
+// low groups, group records, halo push + sum kernels, the source lists of the column pass -- so that a single-GPU
+// box can check them for any rank count.  x, y: full host vectors.
 extern "C" int edgpu_selftest_sharded_hxv(const edgpu_params *p, int nup, int ndw, int nranks, int64_t srow_lr,
                                           int64_t srow_t, int64_t col_cluster, const double *x, double *y) {
   if (nranks < 1 || nranks > EDGPU_MAXP) return edgpu_set_err(EDGPU_ERR_INVALID, "selftest: 1 <= nranks <= 8");
   std::vector<edgpu_ctx *> cs((size_t)nranks, nullptr);
   std::vector<double *> dx((size_t)nranks, nullptr), dy((size_t)nranks, nullptr);
+  std::vector<char *> slab((size_t)nranks, nullptr);
   int rc = EDGPU_OK;
   auto cleanup = [&]() {
     for (int r = 0; r < nranks; r++) {
       if (dx[r]) cudaFree(dx[r]);
       if (dy[r]) cudaFree(dy[r]);
-      if (cs[r]) { cs[r]->peer_override = nullptr; cs[r]->rank = 0; cs[r]->nranks = 1; edgpu_destroy(cs[r]); }
+      if (slab[r]) cudaFree(slab[r]);
+      if (cs[r]) {
+        cs[r]->sym_slab = nullptr; cs[r]->sym_ok = false; cs[r]->halo_emul = false;
+        for (int q = 0; q < 64; q++) cs[r]->sym_peer[q] = nullptr;
+        cs[r]->rank = 0; cs[r]->nranks = 1;
+        edgpu_destroy(cs[r]);
+      }
     }
   };
   for (int r = 0; r < nranks && !rc; r++) {
@@ -133,7 +141,7 @@ extern "C" int edgpu_selftest_sharded_hxv(const edgpu_params *p, int nup, int nd
     edgpu_set_option(cs[r], "srow_lr", srow_lr);
     edgpu_set_option(cs[r], "srow_t", srow_t);
     edgpu_set_option(cs[r], "col_cluster", col_cluster);
-    edgpu_set_option(cs[r], "no_peer", 1);                         // no symmetric slab without a communicator
+    edgpu_set_option(cs[r], "no_peer", 1);                         // no collective slab setup without a communicator
     int isec = 0;
     rc = edgpu_get_sector(cs[r], nup, ndw, &isec);
     if (!rc) rc = edgpu_build_hv_sector(cs[r], isec);
@@ -147,11 +155,29 @@ extern "C" int edgpu_selftest_sharded_hxv(const edgpu_params *p, int nup, int nd
     }
   }
   if (!rc) cudaDeviceSynchronize();
-  const double *peers[EDGPU_MAXP];
-  for (int q = 0; q < EDGPU_MAXP; q++) peers[q] = dx[q < nranks ? q : 0];
+  if (nranks > 1) {
+    size_t hb0 = 0;
+    for (int r = 0; r < nranks && !rc; r++) {
+      size_t hb = 0;
+      if (!fast_supported_local(cs[r])) { rc = edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "selftest: fast path does not cover this sector"); break; }
+      rc = fast_halo_bytes(cs[r], &hb);
+      if (!rc && r > 0 && hb != hb0) rc = edgpu_set_err(EDGPU_ERR_INVALID, "selftest: halo slab size differs between ranks");
+      hb0 = hb;
+      if (!rc && hb && cudaMalloc(&slab[r], hb) != cudaSuccess) rc = edgpu_set_err(EDGPU_ERR_CUDA, "selftest: cudaMalloc of the halo slab");
+      if (!rc && hb) cudaMemset(slab[r], 0xff, hb);                // NaN pattern: a slot that nobody stores shows up
+    }
+    for (int r = 0; r < nranks && !rc && hb0; r++) {
+      cs[r]->sym_slab = slab[r]; cs[r]->sym_bytes = hb0; cs[r]->sym_ok = true; cs[r]->halo_emul = true;
+      for (int q = 0; q < nranks; q++) cs[r]->sym_peer[q] = slab[q];
+      cs[r]->halo_epoch = 1;
+    }
+    for (int r = 0; r < nranks && !rc && hb0; r++) {
+      rc = fast_halo_push(cs[r], dx[r], cs[r]->stream, 64, -1);
+      if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = edgpu_set_err(EDGPU_ERR_CUDA, "selftest: push: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+  }
   for (int r = 0; r < nranks && !rc; r++) {
     if (!fast_supported_local(cs[r])) { rc = edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "selftest: fast path does not cover this sector"); break; }
-    cs[r]->peer_override = peers;
     rc = fast_apply_local(cs[r], dx[r], dy[r], nullptr, nullptr);
     if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = edgpu_set_err(EDGPU_ERR_CUDA, "selftest: kernels: %s", cudaGetErrorString(cudaGetLastError()));
   }

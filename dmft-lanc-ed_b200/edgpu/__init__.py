@@ -402,8 +402,8 @@ class Solver:
     def time_hxv_passes(self, d_v, d_hv, reps):
         """[(kernel name, ms per launch)] of one device-resident H*v, CUDA events between the passes."""
         n = C.c_int(0)
-        ms = (C.c_double * 4)()
-        names = C.create_string_buffer(128)
+        ms = (C.c_double * 6)()
+        names = C.create_string_buffer(192)
         _ck(lib().edgpu_time_hxv_passes(self.h, self.nloc, d_v, d_hv, int(reps), C.byref(n), ms, names))
         return [(names.raw[32 * i:32 * i + 32].split(b"\0")[0].decode(), ms[i] / reps) for i in range(n.value)]
 

@@ -208,8 +208,8 @@ int  edgpu_dev_dot(edgpu_ctx *c, int64_t nloc, const double *d_a, const double *
  * ms_total = elapsed over all reps.  ms_kernel[k] (k < 8, may be NULL) = per-kernel-class totals. */
 int  edgpu_time_hxv_device(edgpu_ctx *c, int64_t nloc, const double *d_v, double *d_hv,
                            int reps, double *ms_total);
-/* Per-kernel split of the same loop (single rank): ms_pass[i] = total over reps of pass i (i < *npasses <= 4),
- * names = 4 x 32 bytes of NUL-terminated kernel names.  Used for bench.py's roofline of the dominant kernel. */
+/* Per-kernel split of the same loop (any rank count): ms_pass[i] = total over reps of pass i (i < *npasses <= 6),
+ * names = 6 x 32 bytes of NUL-terminated kernel names.  Used for bench.py's roofline of the dominant kernel. */
 int  edgpu_time_hxv_passes(edgpu_ctx *c, int64_t nloc, const double *d_v, double *d_hv, int reps,
                            int *npasses, double *ms_pass, char *names);
 /* One device-resident Lanczos iteration loop (reps steps, no host sync inside), for iter/s. */
