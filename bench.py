@@ -382,6 +382,28 @@ def measure(H, workload, steps, full):
     except Exception:
         res["passes"] = []
     H.barrier()
+    if H.world > 1:
+        # sharded: the halo push runs on its own stream next to the row pass, so the split above shows the waits, not
+        # the kernels.  Run the same H*v serialised once more (no_overlap) for the true per-kernel durations and the
+        # NVLink rate of the push (collective: every rank does it).
+        try:
+            bo, bi, nwin = s.halo_info()
+            s.set_option("no_overlap", 1)
+            s.hxv_device(d_v, d_hv)
+            s.sync()
+            H.barrier()
+            ser = s.time_hxv_passes(d_v, d_hv, max(3, min(steps, 10)))
+            s.set_option("no_overlap", 0)
+            push = [m for n_, m in ser if n_ == "k_halo_push"]
+            res["halo"] = {"bytes_out_per_gpu": H.maxr(float(bo)), "bytes_in_per_gpu": H.maxr(float(bi)), "windows": nwin,
+                           "serialised_passes": [(n_, H.maxr(m)) for n_, m in ser],
+                           "push_ms": H.maxr(push[0]) if push else None}
+            if push and push[0] > 0:
+                res["halo"]["nvlink_out_gbs_per_gpu"] = bo / (push[0] * 1e-3) / 1e9
+        except Exception as e:                                      # keep the line: the halo block is explanatory
+            res["halo"] = {"error": str(e)}
+            s.set_option("no_overlap", 0)
+        H.barrier()
 
     # ---- correctness of what was just timed -----------------------------------------------------------
     s.hxv_device(d_v, d_hv)
@@ -427,7 +449,7 @@ def measure(H, workload, steps, full):
 def kernel_table(res, stored, peak):
     bytes_per_el = 24 if stored else 16
     alg = {"k_srow": 16 + (8 if stored else 0), "k_fcol": 24, "k_tile_col": 16 + (8 if stored else 0),
-           "k_tile_row": 24, "k_hxv_gather": bytes_per_el, "k_halo_axpy": 16}
+           "k_tile_row": 24, "k_hxv_gather": bytes_per_el}
     kernels = []
     passes = res.get("passes") or []
     tot = sum(m for _, m in passes)
@@ -463,7 +485,7 @@ def run_b200(args):
     ms_step = res["ms_per_step"]
     step_gbs = bytes_per_el * nloc / (ms_step * 1e-3) / 1e9      # per GPU: algorithmic bytes of the local shard
     kernels = kernel_table(res, args.stored, peak)
-    dom = max([k for k in kernels if k["name"] != "k_halo_axpy"], key=lambda k: k["ms"]) if kernels else None
+    dom = max([k for k in kernels if not k["name"].startswith("k_halo")], key=lambda k: k["ms"]) if kernels else None
     if dom:
         traffic, tsrc = dram_traffic(args.workload, args.stored, dom["name"]) if world == 1 else (None, None)
         roof = {"bound": "hbm", "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dom["frac"], "traffic": traffic,
@@ -498,6 +520,8 @@ def run_b200(args):
         "gpu_launches": res["launches"],
         "clocks": clk,
     }
+    if res.get("halo"):
+        line["halo"] = res["halo"]
     ok = res["parity_check"]["ok"]
     # ---- the fitted-bath variant (level-dependent V_k: the value-table column kernel instead of the uniform one) ----
     if args.workload == "C3" and not args.no_fitted and not args.stored:
@@ -517,7 +541,7 @@ def run_b200(args):
             line["c5"] = {"workload": WORKLOADS["C5"], "ms_per_step": r5["ms_per_step"], "hxv_per_s": r5["value"],
                           "lanczos_iter_per_s": 1000.0 / r5["lanczos_ms_per_iter"], "elements_per_gpu": r5["nloc"],
                           "roofline_frac_16B": gbs5 / peak, "kernels": [[n, m] for n, m in (r5.get("passes") or [])],
-                          "build_s": r5["build_s"], "parity_check": r5["parity_check"]}
+                          "build_s": r5["build_s"], "parity_check": r5["parity_check"], "halo": r5.get("halo")}
             ok = ok and r5["parity_check"]["ok"]
         except Exception as e:
             line["c5"] = {"error": repr(e)}

@@ -174,6 +174,12 @@ struct SRowHostPlan {
 // returns 1 = plan built, 0 = the structured kernel does not apply, -1 = internal inconsistency
 int srow_plan_host(int ns, int ndw, int64_t dimdw, int nranks, int rank, int lr, int tbits_opt, SRowHostPlan &hp);
 void srow_lists_host(SRowHostPlan &hp, int rank, int64_t dimdw, const int32_t *map, const int32_t *rp, const int32_t *cc, const double *vv);
+// halo tables of the push model (pure host arithmetic): lcol2 = consumer column of every list entry of rank `me` (halo
+// slot for a remote owner, local column for an own one); triples (pdst, pslot, psrc) = what `me` stores into its
+// peers' halo buffers, sorted by (column window of the target, source column), pwin[K+1] = triple range per window
+int halo_tables_host(int ns, int ndw, int64_t dimdw, int P, int me, int lr, int tbits_opt, const SRowHostPlan &hp_me,
+                     const int32_t *map, const int32_t *rp, const int32_t *cc, const double *vv, int K, std::vector<int> &lcol2,
+                     std::vector<int> &pdst, std::vector<int> &pslot, std::vector<int> &psrc, int *pwin, int *nslot, int *maxslot);
 // hxv_fast.cu: TMA-staged whole-column kernel + structured single-band row kernel
 int fast_plan_build(edgpu_ctx *c);
 int fast_plan_free(edgpu_ctx *c);

@@ -1115,10 +1115,9 @@ static int to_device(T **d, const std::vector<T> &h) {
 // local column) for every entry of another rank q that this rank owns, sorted by (column window of the target on q,
 // source column): window w of rank q = its local columns [qdw*w/K, qdw*(w+1)/K), so that q's column pass of window w
 // can start when the triples of window w have arrived.  hp_me: this rank's plan with its lists built.
-static int halo_tables_host(edgpu_ctx *c, const SRowHostPlan &hp_me, const std::vector<int32_t> &map, const std::vector<int32_t> &rp,
-                            const std::vector<int32_t> &cc, const std::vector<double> &vv, int K, std::vector<int> &lcol2,
-                            std::vector<int> &pdst, std::vector<int> &pslot, std::vector<int> &psrc, int *pwin, int *nslot, int *maxslot) {
-  const int P = c->nranks, me = c->rank;
+int halo_tables_host(int ns, int ndw, int64_t dimdw, int P, int me, int lr, int tbits_opt, const SRowHostPlan &hp_me,
+                     const int32_t *map, const int32_t *rp, const int32_t *cc, const double *vv, int K, std::vector<int> &lcol2,
+                     std::vector<int> &pdst, std::vector<int> &pslot, std::vector<int> &psrc, int *pwin, int *nslot, int *maxslot) {
   lcol2.clear(); pdst.clear(); pslot.clear(); psrc.clear();
   *nslot = 0; *maxslot = 0;
   struct Tr { int win, src, dst, slot; };
@@ -1127,9 +1126,9 @@ static int halo_tables_host(edgpu_ctx *c, const SRowHostPlan &hp_me, const std::
     SRowHostPlan hq;
     const SRowHostPlan *h = &hp_me;
     if (q != me) {
-      if (srow_plan_host(c->ns, c->ndw, c->dimdw, P, q, (int)c->opt_srow_lr, (int)c->opt_srow_t, hq) != 1)
+      if (srow_plan_host(ns, ndw, dimdw, P, q, lr, tbits_opt, hq) != 1)
         return edgpu_set_err(EDGPU_ERR_INVALID, "internal: row-kernel plan of rank %d differs from rank %d's", q, me);
-      srow_lists_host(hq, q, c->dimdw, map.data(), rp.data(), cc.data(), vv.data());
+      srow_lists_host(hq, q, dimdw, map, rp, cc, vv);
       h = &hq;
     }
     const int64_t qq = (int64_t)h->lptr.size() - 1;                 // local columns of rank q
@@ -1197,7 +1196,8 @@ static int build_srow(edgpu_ctx *c, SRowPlan &sr) {
     std::vector<int> lcol2, pdst, pslot, psrc;
     // windows pay when the halo outlasts the row pass: from 4 ranks on (measured)
     sr.nwin = (int)std::max<int64_t>(1, std::min<int64_t>(c->opt_halo_windows > 0 ? c->opt_halo_windows : (c->nranks >= 4 ? 4 : 1), EDGPU_MAX_WINDOWS));
-    TRY(halo_tables_host(c, hp, map, rp, cc, vv, sr.nwin, lcol2, pdst, pslot, psrc, sr.pwin, &sr.nslot, &sr.maxslot));
+    TRY(halo_tables_host(c->ns, c->ndw, c->dimdw, c->nranks, c->rank, (int)c->opt_srow_lr, (int)c->opt_srow_t, hp, map.data(), rp.data(),
+                         cc.data(), vv.data(), sr.nwin, lcol2, pdst, pslot, psrc, sr.pwin, &sr.nslot, &sr.maxslot));
     sr.npush = (int)pdst.size();
     TRY(to_device(&sr.d_lptr, hp.lptr));
     TRY(to_device(&sr.d_lown, hp.lown));
@@ -1572,5 +1572,18 @@ int fast_apply_local(edgpu_ctx *c, const double *d_x, double *d_y, double *d_xp,
     TRY(fast_apply_col(c, 0, false, true, d_x + j0 * c->dimup, d_y + j0 * c->dimup, j1 - j0, c->coloff + j0,
                        d_xp ? d_xp + j0 * c->dimup : nullptr, npartials, true, j0, w + 1 < K ? c->sm_count - hctas : 0));
   }
+  return EDGPU_OK;
+}
+
+extern "C" int edgpu_halo_info(edgpu_ctx *c, int64_t *bytes_out, int64_t *bytes_in, int *windows) {
+  if (!c || !c->hstatus) return edgpu_set_err(EDGPU_ERR_INVALID, "halo_info: no live sector");
+  if (bytes_out) *bytes_out = 0;
+  if (bytes_in) *bytes_in = 0;
+  if (windows) *windows = 0;
+  if (c->nranks == 1 || !fast_peer_ready(c) || !c->fplan || !c->fplan->sr.lists) return EDGPU_OK;
+  const SRowPlan &sr = c->fplan->sr;
+  if (bytes_out) *bytes_out = (int64_t)sr.npush * c->dimup * 8;
+  if (bytes_in) *bytes_in = (int64_t)sr.nslot * c->dimup * 8;
+  if (windows) *windows = sr.nwin;
   return EDGPU_OK;
 }

@@ -233,3 +233,72 @@ extern "C" int edgpu_selftest_srow_plan(const edgpu_params *p, int ndw, int nran
   }
   return small;
 }
+
+// HOST ONLY: the halo tables of the push model for EVERY rank of `nranks`, cross-checked against each other: every
+// remote list entry (rank q, slot s, owner p, source column) must be stored by exactly one triple of rank p, in the
+// window of its target column, and no triple may exist without an entry.  info[6] = {ok, list entries, remote
+// entries, triples, largest slot count, windows used}.
+extern "C" int edgpu_selftest_halo_tables(const edgpu_params *p, int ndw, int nranks, int64_t lr, int64_t tbits_opt, int K, int32_t *info) {
+  for (int k = 0; k < 6; k++) info[k] = 0;
+  DevParams d = make_dp(p);
+  const int64_t n = edgpu_selftest_map(d.ns, ndw, nullptr);
+  std::vector<int32_t> map((size_t)n), rp((size_t)n + 1), cc;
+  std::vector<double> vv;
+  edgpu_selftest_map(d.ns, ndw, map.data());
+  int32_t cb[EDGPU_MAX_ROW_NNZ]; double vb[EDGPU_MAX_ROW_NNZ];
+  for (int64_t i = 0; i < n; i++) {
+    rp[(size_t)i] = (int32_t)cc.size();
+    const int m = hd_factor_row(d, 1, map.data(), n, (uint32_t)map[(size_t)i], cb, vb);
+    for (int k = 0; k < m; k++) { cc.push_back(cb[k]); vv.push_back(vb[k]); }
+  }
+  rp[(size_t)n] = (int32_t)cc.size();
+  struct Rank { SRowHostPlan hp; std::vector<int> lcol2, pdst, pslot, psrc; int pwin[EDGPU_MAX_WINDOWS + 1]; int nslot, maxslot; };
+  std::vector<Rank> R((size_t)nranks);
+  for (int r = 0; r < nranks; r++) {
+    if (srow_plan_host(d.ns, ndw, n, nranks, r, (int)lr, (int)tbits_opt, R[(size_t)r].hp) != 1) return 0;   // info[0] = 0
+    srow_lists_host(R[(size_t)r].hp, r, n, map.data(), rp.data(), cc.data(), vv.data());
+    if (halo_tables_host(d.ns, ndw, n, nranks, r, (int)lr, (int)tbits_opt, R[(size_t)r].hp, map.data(), rp.data(), cc.data(), vv.data(), K,
+                         R[(size_t)r].lcol2, R[(size_t)r].pdst, R[(size_t)r].pslot, R[(size_t)r].psrc, R[(size_t)r].pwin, &R[(size_t)r].nslot,
+                         &R[(size_t)r].maxslot)) return 0;
+  }
+  long entries = 0, remote = 0, triples = 0;
+  bool ok = true;
+  int maxslot = 0;
+  for (int q = 0; q < nranks && ok; q++) {
+    const Rank &Q = R[(size_t)q];
+    const int64_t qq = (int64_t)Q.hp.lptr.size() - 1;
+    if (Q.maxslot != R[0].maxslot) ok = false;                     // the slab layout must be the same everywhere
+    maxslot = std::max(maxslot, Q.nslot);
+    std::vector<char> hit((size_t)std::max(Q.nslot, 1), 0);
+    int slot = 0;
+    for (int64_t t = 0; t < qq && ok; t++) {
+      int w = 0;
+      while (w + 1 < K && t >= qq * (w + 1) / K) w++;
+      for (int e = Q.hp.lptr[(size_t)t]; e < Q.hp.lptr[(size_t)t + 1] && ok; e++) {
+        entries++;
+        const int own = Q.hp.lown[(size_t)e];
+        if (own == q) { if (Q.lcol2[(size_t)e] != Q.hp.lcol[(size_t)e]) ok = false; continue; }
+        remote++;
+        if (Q.lcol2[(size_t)e] != slot) ok = false;
+        // the owner's triple for (q, slot): in window w, with the entry's source column
+        const Rank &O = R[(size_t)own];
+        int found = 0;
+        for (int k = O.pwin[w]; k < O.pwin[w + 1]; k++)
+          if (O.pdst[(size_t)k] == q && O.pslot[(size_t)k] == slot) { found++; if (O.psrc[(size_t)k] != Q.hp.lcol[(size_t)e]) ok = false; }
+        if (found != 1) ok = false;
+        hit[(size_t)slot] = 1;
+        slot++;
+      }
+    }
+    if (slot != Q.nslot) ok = false;
+    triples += (long)Q.pdst.size();
+    if (Q.pwin[0] != 0 || Q.pwin[K] != (int)Q.pdst.size()) ok = false;
+    for (int w = 0; w < K; w++) {
+      if (Q.pwin[w] > Q.pwin[w + 1]) ok = false;
+      for (int k = Q.pwin[w] + 1; k < Q.pwin[w + 1]; k++) if (Q.psrc[(size_t)k] < Q.psrc[(size_t)k - 1]) ok = false;   // sorted by source column
+    }
+  }
+  if (triples != remote || maxslot != R[0].maxslot) ok = false;
+  info[0] = ok ? 1 : 0; info[1] = (int32_t)entries; info[2] = (int32_t)remote; info[3] = (int32_t)triples; info[4] = maxslot; info[5] = K;
+  return 0;
+}

@@ -36,7 +36,7 @@ ABI_SYMBOLS = [
     "edgpu_gf_chains", "edgpu_add_to_lanczos_gf", "edgpu_observables_normal", "edgpu_get_dims", "edgpu_get_sector_map",
     "edgpu_get_csr", "edgpu_get_diag", "edgpu_dev_alloc", "edgpu_dev_free", "edgpu_dev_upload",
     "edgpu_dev_download", "edgpu_dev_fill_bench_vector", "edgpu_sync", "edgpu_dev_dot", "edgpu_time_hxv_device",
-    "edgpu_time_lanczos_device", "edgpu_launch_count", "edgpu_time_hxv_passes",
+    "edgpu_time_lanczos_device", "edgpu_launch_count", "edgpu_time_hxv_passes", "edgpu_halo_info",
 ]
 
 
@@ -124,6 +124,7 @@ def lib():
         L.edgpu_time_hxv_device.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, c_dp]
         L.edgpu_time_lanczos_device.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, c_dp]
         L.edgpu_launch_count.argtypes = [C.c_void_p, c_i64p]
+        L.edgpu_halo_info.argtypes = [C.c_void_p, c_i64p, c_i64p, c_ip]
         L.edgpu_time_hxv_passes.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, c_ip, c_dp, C.c_char_p]
         _LIB = L
     return _LIB
@@ -411,6 +412,12 @@ class Solver:
         ms = C.c_double(0.0)
         _ck(lib().edgpu_time_lanczos_device(self.h, self.nloc, d_v0, reps, C.byref(ms)))
         return ms.value
+
+    def halo_info(self):
+        """(bytes stored into the peers' halo buffers per H*v, bytes received, column windows) of the live sector."""
+        bo, bi, w = C.c_int64(0), C.c_int64(0), C.c_int(0)
+        _ck(lib().edgpu_halo_info(self.h, C.byref(bo), C.byref(bi), C.byref(w)))
+        return bo.value, bi.value, w.value
 
     def launch_count(self):
         n = C.c_int64(0)

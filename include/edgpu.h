@@ -214,6 +214,10 @@ int  edgpu_time_hxv_passes(edgpu_ctx *c, int64_t nloc, const double *d_v, double
                            int *npasses, double *ms_pass, char *names);
 /* One device-resident Lanczos iteration loop (reps steps, no host sync inside), for iter/s. */
 int  edgpu_time_lanczos_device(edgpu_ctx *c, int64_t nloc, double *d_v0, int reps, double *ms_total);
+/* Halo of the sharded fast path of the live sector (ED_HAMILTONIAN_COMMON.f90:53-118 replaced): bytes this rank
+ * stores into its peers' halo buffers per H*v, bytes it receives, column windows of the pipeline.  All zero when the
+ * sector does not use the halo path (one rank, multi-orbital model, no_peer). */
+int  edgpu_halo_info(edgpu_ctx *c, int64_t *bytes_out, int64_t *bytes_in, int *windows);
 /* Kernel launches issued by this context since creation (bench.py's gpu_launches). */
 int  edgpu_launch_count(const edgpu_ctx *c, int64_t *n);
 

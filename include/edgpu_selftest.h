@@ -34,8 +34,14 @@ int edgpu_selftest_srow_plan(const edgpu_params *p, int ndw, int nranks, int ran
                              int32_t *info, int32_t *jhi, int cap_jhi, int32_t *chunks, int cap_chunks,
                              int32_t *recs, int cap_recs, int32_t *lptr, int32_t *lflag, int cap_cols,
                              int32_t *lown, int32_t *lcol, double *lamp, int cap_e);
-/* GPU: the sharded fast H*v path with `nranks` ranks emulated by `nranks` contexts on ONE device (peers are plain
- * device pointers instead of NVLink mappings); x, y are full host vectors.  Test instrumentation only. */
+/* HOST ONLY: the halo tables of the sharded fast path (push model) of EVERY rank, cross-checked: each remote list entry
+ * (rank q, slot s) is stored by exactly one (peer, slot, source column) triple of its owner, in the column window of
+ * its target; no stray triples; same slab layout on every rank.  info[6] = {ok, list entries, remote entries, triples,
+ * largest slot count, windows}. */
+int edgpu_selftest_halo_tables(const edgpu_params *p, int ndw, int nranks, int64_t lr, int64_t tbits_opt, int K, int32_t *info);
+/* GPU: the sharded fast H*v path with `nranks` ranks emulated by `nranks` contexts on ONE device (every rank's halo
+ * slab is a plain allocation, the pushes of all ranks run first, no arrival flags); x, y are full host vectors.  Test
+ * instrumentation only. */
 int edgpu_selftest_sharded_hxv(const edgpu_params *p, int nup, int ndw, int nranks, int64_t srow_lr, int64_t srow_t,
                                int64_t col_cluster, const double *x, double *y);
 /* GPU: max |a - b| and max |a| of two device vectors of n doubles (full-size comparisons on the device) */

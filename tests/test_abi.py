@@ -246,3 +246,28 @@ def test_row_kernel_plan_covers_every_hop_exactly_once(name, ndw, nranks, lr, st
         assert total == dimdw * ns // 2 or ndw * 2 != ns
     # chunk geometry: tiles fit the box grid and the group count the kernel assumes
     assert plan["T"] <= 5 and all(ng <= 64 for _, ng, _, _ in plan["chunks"])
+
+
+HALO_CASES = [("C1", 4, 2, 0, 0, 1), ("C1", 4, 3, 0, 1, 2), ("C1", 3, 4, 4, 1, 4), ("NS10", 5, 8, 0, 0, 4), ("NS12", 6, 7, 0, 4, 3),
+              ("NS12", 5, 8, 4, 2, 8), ("NS14", 7, 8, 0, 0, 4), ("NS16", 8, 2, 0, 0, 1), ("NS16", 8, 8, 0, 0, 4), ("NS16", 9, 5, 0, 0, 4),
+              ("NS18", 9, 8, 0, 0, 4)]
+
+
+@pytest.mark.parametrize("name,ndw,nranks,lr,st,nwin", HALO_CASES)
+def test_halo_push_tables_match_the_source_lists(name, ndw, nranks, lr, st, nwin):
+    """Host arithmetic of the sharded fast path's halo (hxv_fast.cu: halo_tables_host), without a GPU and for every rank
+    at once: what the owners store into their peers' halo buffers (k_halo_push) is exactly what the column pass of the
+    receivers reads -- one (peer, slot, source column) triple per remote list entry, filed under the column window of
+    its target, none left over, identical slab layout on every rank.  Replaces the per-column MPI_AllToAllV of
+    vector_transpose_MPI (ED_HAMILTONIAN_COMMON.f90:53-118) on this path."""
+    cfg, _ = make_oracle(name)
+    keep = _params(cfg)
+    L = edgpu.selftest_lib()
+    info = np.zeros(6, np.int32)
+    rc = L.edgpu_selftest_halo_tables(C.byref(keep[0]), ndw, nranks, C.c_int64(lr), C.c_int64(st), nwin,
+                                      info.ctypes.data_as(C.POINTER(C.c_int32)))
+    assert rc == 0
+    ok, entries, remote, triples, maxslot, k = (int(v) for v in info)
+    assert ok == 1, info
+    assert remote == triples and entries >= remote and k == nwin
+    assert remote > 0 and maxslot > 0                               # every split of these sectors crosses a rank boundary
