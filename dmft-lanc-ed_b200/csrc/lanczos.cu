@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <complex>
+#include <functional>
 #include <vector>
 
 #include "engine.h"
@@ -775,7 +776,8 @@ static void tridiag_bookkeeping(int nlanc, double threshold, const double *a, co
 }
 
 // all the chains of one target sector (live in c), batched: lock-step recurrences on one stream per chain
-static int gf_chains_batched(edgpu_ctx *c, const std::vector<int> &grp, const int *iorb, const int *ispin, const int *addrem,
+// start(ch): the start vector of channel ch into c->d_lx on c->stream
+static int gf_chains_batched(edgpu_ctx *c, const std::vector<int> &grp, const std::function<int(int)> &start,
                              int nl, int nlanc_max, double threshold, double *norm2, int *nlanc, double *alanc, double *blanc) {
   const int nb = (int)grp.size();
   std::vector<ChainWork> work((size_t)nb);
@@ -787,7 +789,7 @@ static int gf_chains_batched(edgpu_ctx *c, const std::vector<int> &grp, const in
     rc = chain_alloc(c, work[(size_t)q], nl);
     if (rc) break;
     chain_bind(c, work[(size_t)q], keep, nl + 2);
-    rc = gf_start_vector(c, iorb[grp[(size_t)q]], ispin[grp[(size_t)q]], addrem[grp[(size_t)q]] == 1 ? 1 : 0);
+    rc = start(grp[(size_t)q]);
     if (!rc) rc = lanczos_norm_start(c);
     chain_unbind(c, work[(size_t)q], keep);
   }
@@ -854,7 +856,8 @@ extern "C" int edgpu_gf_chains(edgpu_ctx *c, int nchains, const int *iorb, const
     const bool batch = c->nranks == 1 && grp.size() > 1 && !c->opt_no_batch &&
                        (double)grp.size() * 3.0 * 8.0 * (double)c->nloc < 60e9;
     if (batch) {
-      rc = gf_chains_batched(c, grp, iorb, ispin, addrem, nl, nlanc_max, threshold, norm2, nlanc, alanc, blanc);
+      rc = gf_chains_batched(c, grp, [&](int ch2) { return gf_start_vector(c, iorb[ch2], ispin[ch2], addrem[ch2] == 1 ? 1 : 0); },
+                             nl, nlanc_max, threshold, norm2, nlanc, alanc, blanc);
     } else {
       for (size_t q = 0; q < grp.size() && !rc; q++) {
         const int ch2 = grp[q];
@@ -868,6 +871,97 @@ extern "C" int edgpu_gf_chains(edgpu_ctx *c, int nchains, const int *iorb, const
     }
     edgpu_delete_hv_sector(c);
     if (rc) return rc;
+  }
+  return EDGPU_OK;
+}
+
+// ---- susceptibility chains (ED_GF_CHISPIN.f90:114-415, ED_GF_CHIDENS.f90:111-426) ---------------------------------------
+// vvinit = O|gs> with a DIAGONAL operator of the impurity occupations, in the state's own sector: spin
+// O = 1/2 sum_a (n_up,a - n_dw,a), density O = sum_a (n_up,a + n_dw,a), a over the orbitals of `mask` (one orbital: main;
+// two: mix, S_i + S_j; all: tot).  No gathered vector, no master-only loop: every rank scales its own shard.
+__global__ void k_chi_start(const int32_t *__restrict__ map_up, const int32_t *__restrict__ map_dw, int64_t dimup, int64_t qdw,
+                            int64_t coloff, const double *__restrict__ gs, uint32_t mask, int kind, double *__restrict__ out) {
+  for (int64_t jl = blockIdx.y; jl < qdw; jl += gridDim.y) {
+    const int ndw = __popc((uint32_t)map_dw[coloff + jl] & mask);
+    for (int64_t ju = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; ju < dimup; ju += (int64_t)gridDim.x * blockDim.x) {
+      const int nup = __popc((uint32_t)map_up[ju] & mask);
+      const double w = kind == 0 ? 0.5 * (double)(nup - ndw) : (double)(nup + ndw);
+      out[ju + jl * dimup] = w * gs[ju + jl * dimup];
+    }
+  }
+}
+
+extern "C" int edgpu_chi_chains(edgpu_ctx *c, int kind, int nchains, const int *iorb, const int *jorb, int nlanc_max,
+                                double threshold, double *norm2, int *nlanc, double *alanc, double *blanc) {
+  if (!c || !c->d_gs) return edgpu_set_err(EDGPU_ERR_INVALID, "chi_chains: no state set (edgpu_gf_set_state)");
+  if (c->hstatus) return edgpu_set_err(EDGPU_ERR_INVALID, "chi_chains: a sector is live; call delete_Hv_sector first");
+  if (kind != 0 && kind != 1) return edgpu_set_err(EDGPU_ERR_INVALID, "chi_chains: kind is 0 (spin) or 1 (density)");
+  CK(cudaSetDevice(c->device));
+  std::vector<uint32_t> mask((size_t)nchains);
+  for (int ch = 0; ch < nchains; ch++) {
+    norm2[ch] = 0.0; nlanc[ch] = 0;
+    for (int k = 0; k < nlanc_max; k++) { alanc[(size_t)ch * nlanc_max + k] = 0.0; blanc[(size_t)ch * nlanc_max + k] = 0.0; }
+    const int io = iorb[ch], jo = jorb[ch];
+    if (io == 0) mask[(size_t)ch] = (1u << c->dp.norb) - 1u;                                  // _tot_main
+    else if (io >= 1 && io <= c->dp.norb && jo >= 1 && jo <= c->dp.norb) mask[(size_t)ch] = (1u << (io - 1)) | (1u << (jo - 1));   // _main / _mix_main
+    else return edgpu_set_err(EDGPU_ERR_INVALID, "chi_chains: bad channel %d", ch);
+  }
+  int isector;
+  TRY(edgpu_get_sector(c, c->gs_nup, c->gs_ndw, &isector));
+  TRY(edgpu_build_hv_sector(c, isector));
+  int rc = EDGPU_OK;
+  if (c->nloc != c->gs_nloc) rc = edgpu_set_err(EDGPU_ERR_INVALID, "chi_chains: the state was set for another rank layout");
+  const int64_t dim = c->dimup * c->dimdw;
+  const int nl = (int)std::min<int64_t>(dim, nlanc_max);   // nlanc=min(idim,lanc_nGFiter), ED_GF_CHISPIN.f90:176
+  auto start = [&](int ch) -> int {
+    dim3 grid((unsigned)((c->dimup + 255) / 256), (unsigned)(c->qdw < 32768 ? std::max<int64_t>(c->qdw, 1) : 32768));
+    k_chi_start<<<grid, 256, 0, c->stream>>>(c->up.d_map, c->dw.d_map, c->dimup, c->qdw, c->coloff, c->d_gs, mask[(size_t)ch], kind, c->d_lx);
+    CKL(c);
+    return EDGPU_OK;
+  };
+  std::vector<int> grp((size_t)nchains);
+  for (int ch = 0; ch < nchains; ch++) grp[(size_t)ch] = ch;
+  const bool batch = !rc && c->nranks == 1 && nchains > 1 && !c->opt_no_batch && (double)nchains * 3.0 * 8.0 * (double)c->nloc < 60e9;
+  if (!rc && batch) {
+    rc = gf_chains_batched(c, grp, start, nl, nlanc_max, threshold, norm2, nlanc, alanc, blanc);
+  } else {
+    for (int ch = 0; ch < nchains && !rc; ch++) {
+      rc = lanczos_begin(c, nl);
+      if (!rc) rc = start(ch);
+      if (!rc) rc = tridiag_device(c, nl, threshold, alanc + (size_t)ch * nlanc_max, blanc + (size_t)ch * nlanc_max);
+      if (!rc && cudaMemcpy(&norm2[ch], &c->d_st->norm2, sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess)
+        rc = edgpu_set_err(EDGPU_ERR_CUDA, "norm2 read-back failed");
+      if (!rc) nlanc[ch] = nl;
+    }
+  }
+  edgpu_delete_hv_sector(c);
+  return rc;
+}
+
+// add_to_lanczos_spinChi (ED_GF_CHISPIN.f90:434-488) == add_to_lanczos_densChi (ED_GF_CHIDENS.f90:436-489), T = 0:
+// chi_iv[0..lmats] on the bosonic vm, chi_tau[0..ltau], chi_w[lreal] (interleaved complex); accumulates.
+extern "C" int edgpu_add_to_lanczos_chi(double norm2, double zeta, double ei, double beta, const double *alanc, const double *blanc,
+                                        int nlanc, const double *vm, int lmats, double *chi_iv, const double *tau, int ltau,
+                                        double *chi_tau, const double *vr, int lreal, double eps, double *chi_w) {
+  if (nlanc < 1) return edgpu_set_err(EDGPU_ERR_INVALID, "add_to_lanczos_chi: nlanc < 1");
+  std::vector<double> diag, z;
+  TRY(tridiag_eig(nlanc, alanc, blanc, diag, z));
+  std::complex<double> *cw = reinterpret_cast<std::complex<double> *>(chi_w);
+  const double pesof = norm2 / zeta;                              // pesoBZ = 1 at T = 0
+  for (int j = 0; j < nlanc; j++) {
+    const double de = diag[j] - ei;
+    const double z1 = z[0 + (size_t)nlanc * j];
+    const double peso = pesof * (z1 * z1);
+    const double bose = 1.0 - exp(-beta * de);
+    if (chi_iv) {
+      if (beta * de > 1e-3) chi_iv[0] += peso * 2 * bose / de;
+      for (int i = 1; i <= lmats; i++) chi_iv[i] += peso * bose * 2.0 * de / (vm[i] * vm[i] + de * de);
+    }
+    if (chi_tau) for (int i = 0; i <= ltau; i++) chi_tau[i] += exp(-tau[i] * de) * peso;
+    if (chi_w) for (int i = 0; i < lreal; i++) {
+      const std::complex<double> w(vr[i], eps);
+      cw[i] -= peso * bose * (1.0 / (w - de) - 1.0 / (w + de));
+    }
   }
   return EDGPU_OK;
 }

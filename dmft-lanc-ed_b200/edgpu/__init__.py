@@ -33,7 +33,7 @@ ABI_SYMBOLS = [
     "edgpu_get_sector", "edgpu_get_nup_ndw", "edgpu_split", "edgpu_transpose_plan", "edgpu_build_hv_sector",
     "edgpu_delete_hv_sector", "edgpu_vecdim_hv_sector", "edgpu_hxv", "edgpu_sphtimesv",
     "edgpu_hxv_device", "edgpu_sp_lanc_eigh", "edgpu_sp_lanc_tridiag", "edgpu_diag_sectors", "edgpu_gf_set_state", "edgpu_gf_set_state_from_eigh",
-    "edgpu_gf_chains", "edgpu_add_to_lanczos_gf", "edgpu_observables_normal", "edgpu_get_dims", "edgpu_get_sector_map",
+    "edgpu_gf_chains", "edgpu_add_to_lanczos_gf", "edgpu_chi_chains", "edgpu_add_to_lanczos_chi", "edgpu_observables_normal", "edgpu_get_dims", "edgpu_get_sector_map",
     "edgpu_get_csr", "edgpu_get_diag", "edgpu_dev_alloc", "edgpu_dev_free", "edgpu_dev_upload",
     "edgpu_dev_download", "edgpu_dev_fill_bench_vector", "edgpu_sync", "edgpu_dev_dot", "edgpu_time_hxv_device",
     "edgpu_time_lanczos_device", "edgpu_launch_count", "edgpu_time_hxv_passes", "edgpu_halo_info",
@@ -107,6 +107,9 @@ def lib():
         L.edgpu_gf_set_state.argtypes = [C.c_void_p, C.c_int, c_dp, C.c_int64, C.c_double]
         L.edgpu_gf_set_state_from_eigh.argtypes = [C.c_void_p]
         L.edgpu_gf_chains.argtypes = [C.c_void_p, C.c_int, c_ip, c_ip, c_ip, C.c_int, C.c_double, c_dp, c_ip, c_dp, c_dp]
+        L.edgpu_chi_chains.argtypes = [C.c_void_p, C.c_int, C.c_int, c_ip, c_ip, C.c_int, C.c_double, c_dp, c_ip, c_dp, c_dp]
+        L.edgpu_add_to_lanczos_chi.argtypes = [C.c_double, C.c_double, C.c_double, C.c_double, c_dp, c_dp, C.c_int,
+                                               c_dp, C.c_int, c_dp, c_dp, C.c_int, c_dp, c_dp, C.c_int, C.c_double, c_dp]
         L.edgpu_add_to_lanczos_gf.argtypes = [C.c_double, C.c_double, C.c_double, c_dp, c_dp, C.c_int, C.c_int,
                                               c_dp, C.c_int, c_dp]
         L.edgpu_observables_normal.argtypes = [C.c_void_p, C.c_double, C.POINTER(Observables)]
@@ -333,6 +336,20 @@ class Solver:
         return [dict(norm2=norm2[k], nlanc=nl[k], alanc=a[k, :nl[k]].copy(), blanc=b[k, :nl[k]].copy())
                 for k in range(n)]
 
+    def chi_chains(self, kind, channels, nlanc_max=200, threshold=1e-12):
+        """Susceptibility chains (lanc_ed_build_spinChi_* kind=0 / lanc_ed_build_densChi_* kind=1).  channels: list of
+        (iorb, jorb): iorb == jorb one orbital, iorb == 0 total, iorb != jorb mixed.  Same output as gf_chains."""
+        n = len(channels)
+        io = (C.c_int * n)(*[c[0] for c in channels])
+        jo = (C.c_int * n)(*[c[1] for c in channels])
+        norm2 = np.zeros(n)
+        nl = (C.c_int * n)()
+        a = np.zeros((n, nlanc_max))
+        b = np.zeros((n, nlanc_max))
+        _ck(lib().edgpu_chi_chains(self.h, int(kind), n, io, jo, nlanc_max, threshold, _dp(norm2), nl, _dp(a), _dp(b)))
+        return [dict(norm2=norm2[k], nlanc=nl[k], alanc=a[k, :nl[k]].copy(), blanc=b[k, :nl[k]].copy())
+                for k in range(n)]
+
     def observables(self, zeta=1.0):
         """lanc_observables + lanc_local_energy of the state kept for the chains (collective when sharded)."""
         o = Observables()
@@ -423,6 +440,19 @@ class Solver:
         n = C.c_int64(0)
         _ck(lib().edgpu_launch_count(self.h, C.byref(n)))
         return n.value
+
+
+def add_to_lanczos_chi(norm2, ei, beta, alanc, blanc, vm, tau, vr, eps, zeta=1.0):
+    """add_to_lanczos_spinChi / _densChi at T = 0: (chi_iv[0..Lmats], chi_tau[0..Ltau], chi_w[Lreal])."""
+    a = np.ascontiguousarray(alanc, dtype=np.float64)
+    b = np.ascontiguousarray(blanc, dtype=np.float64)
+    vm = np.ascontiguousarray(vm, dtype=np.float64)
+    tau = np.ascontiguousarray(tau, dtype=np.float64)
+    vr = np.ascontiguousarray(vr, dtype=np.float64)
+    civ, ctau, cw = np.zeros(len(vm)), np.zeros(len(tau)), np.zeros(len(vr), dtype=np.complex128)
+    _ck(lib().edgpu_add_to_lanczos_chi(norm2, zeta, ei, beta, _dp(a), _dp(b), a.size, _dp(vm), len(vm) - 1, _dp(civ),
+                                       _dp(tau), len(tau) - 1, _dp(ctau), _dp(vr), len(vr), eps, cw.ctypes.data_as(c_dp)))
+    return civ, ctau, cw
 
 
 def add_to_lanczos_gf(norm2, ei, alanc, blanc, isign, z, zeta=1.0):

@@ -163,6 +163,20 @@ int  edgpu_gf_chains(edgpu_ctx *c, int nchains, const int *iorb, const int *ispi
 int  edgpu_add_to_lanczos_gf(double norm2, double zeta, double ei, const double *alanc,
                              const double *blanc, int nlanc, int isign,
                              const double *z, int nz, double *g);
+/* Susceptibility chains: lanc_ed_build_spinChi_main / _tot_main / _mix_main (ED_GF_CHISPIN.f90:114-415) for kind = 0
+ * and lanc_ed_build_densChi_* (ED_GF_CHIDENS.f90:111-426) for kind = 1, ed_total_ud = T.  Start vector O|state> with
+ * the diagonal operator O = Sz resp. n of orbital iorb (iorb == jorb), of all impurity orbitals (iorb == 0) or the mixed
+ * combination O_iorb + O_jorb, applied on the device to the state of edgpu_gf_set_state* in its OWN sector (each rank
+ * scales its shard; the reference builds it on the master and scatters), then sp_lanc_tridiag; the channels run as a
+ * batch.  Outputs as edgpu_gf_chains. */
+int  edgpu_chi_chains(edgpu_ctx *c, int kind, int nchains, const int *iorb, const int *jorb, int nlanc_max,
+                      double threshold, double *norm2, int *nlanc, double *alanc, double *blanc);
+/* add_to_lanczos_spinChi (ED_GF_CHISPIN.f90:434-488) == add_to_lanczos_densChi (ED_GF_CHIDENS.f90:436-489), T = 0:
+ * accumulates chi_iv[0..lmats] on the bosonic frequencies vm[0..lmats], chi_tau[0..ltau] on tau[0..ltau] and
+ * chi_w[lreal] (interleaved complex) on vr[lreal] + i eps; any output may be NULL. */
+int  edgpu_add_to_lanczos_chi(double norm2, double zeta, double ei, double beta, const double *alanc, const double *blanc,
+                              int nlanc, const double *vm, int lmats, double *chi_iv, const double *tau, int ltau,
+                              double *chi_tau, const double *vr, int lreal, double eps, double *chi_w);
 
 /* ---- observables (lanc_observables, ED_OBSERVABLES.f90:95-363; lanc_local_energy, :372-600) ------------------- */
 /* Local observables and energies of the state kept on the device for the chains (edgpu_gf_set_state /

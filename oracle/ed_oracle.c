@@ -1312,6 +1312,85 @@ void orc_lanc_build_gf_normal_main(const orc_ctx *c, int nup, int ndw, const dou
   }
 }
 
+/* ===================================================================================== */
+/* ED_GF_CHISPIN / ED_GF_CHIDENS (ed_total_ud = T: ialfa = 1, iorb1 = iorb)              */
+/* ===================================================================================== */
+/* start vector O|gs> in the state's own sector, then norm2 and normalisation.
+ * kind 0 (spin): lanc_ed_build_spinChi_main ED_GF_CHISPIN.f90:150-170 (iorb == jorb >= 1), _tot_main :255-287 (iorb == 0),
+ *                _mix_main :370-400 (iorb != jorb);
+ * kind 1 (dens): lanc_ed_build_densChi_main ED_GF_CHIDENS.f90:150-175, _tot_main :255-285, _mix_main :370-395. */
+int64_t orc_chi_start_vector(const orc_ctx *c, int nup, int ndw, const double *gs, int kind, int iorb, int jorb,
+                             double *vvinit, double *norm2) {
+  int64_t idu = orc_binomial(c->ns, nup), idd = orc_binomial(c->ns, ndw), idim = idu * idd;
+  int32_t *hi_up = (int32_t *)xmalloc((size_t)idu * 4), *hi_dw = (int32_t *)xmalloc((size_t)idd * 4);
+  orc_build_sector_map(c->ns, nup, hi_up); orc_build_sector_map(c->ns, ndw, hi_dw);
+  int nu[64], nd[64];
+  for (int64_t i = 0; i < idim; i++) {
+    int64_t iu = i % idu, id = i / idu;
+    bdecomp(hi_up[iu], c->ns, nu);
+    bdecomp(hi_dw[id], c->ns, nd);
+    double sgn;
+    if (iorb == 0) {                                           /* total: sum over the impurity orbitals */
+      double sup = 0.0, sdw = 0.0;
+      for (int a = 0; a < c->norb; a++) { sup += nu[a]; sdw += nd[a]; }
+      sgn = kind == 0 ? 0.5 * (sup - sdw) : (sup + sdw);
+    } else if (iorb == jorb) {
+      sgn = kind == 0 ? 0.5 * ((double)nu[iorb - 1] - (double)nd[iorb - 1]) : (double)(nu[iorb - 1] + nd[iorb - 1]);
+    } else {
+      double si = kind == 0 ? (double)(nu[iorb - 1] - nd[iorb - 1]) : (double)(nu[iorb - 1] + nd[iorb - 1]);
+      double sj = kind == 0 ? (double)(nu[jorb - 1] - nd[jorb - 1]) : (double)(nu[jorb - 1] + nd[jorb - 1]);
+      sgn = kind == 0 ? 0.5 * si + 0.5 * sj : si + sj;
+    }
+    vvinit[i] = sgn * gs[i];
+  }
+  double n2 = ddot(idim, vvinit, vvinit);
+  double sq = sqrt(n2);
+  for (int64_t i = 0; i < idim; i++) vvinit[i] = vvinit[i] / sq;
+  *norm2 = n2;
+  free(hi_up); free(hi_dw);
+  return idim;
+}
+
+/* add_to_lanczos_spinChi ED_GF_CHISPIN.f90:434-488 == add_to_lanczos_densChi ED_GF_CHIDENS.f90:436-489, T = 0
+ * (pesoBZ = 1).  chi_iv[0..lmats], chi_tau[0..ltau], chi_w[lreal] complex; accumulates. */
+void orc_add_to_lanczos_chi(double norm2, double zeta, double ei, double beta, const double *alanc, const double *blanc, int nlanc,
+                            const double *vm, int lmats, double *chi_iv, const double *tau, int ltau, double *chi_tau,
+                            const double *vr, int lreal, double eps, double *chi_w) {
+  double pesof = norm2 / zeta, pesobz = 1.0;
+  double *diag = (double *)xmalloc((size_t)nlanc * sizeof(double));
+  double *z = (double *)xmalloc((size_t)nlanc * nlanc * sizeof(double));
+  tridiag_eig(nlanc, alanc, blanc, diag, z);
+  double complex *cw = (double complex *)chi_w;
+  for (int j = 0; j < nlanc; j++) {
+    double de = diag[j] - ei;
+    double z1 = z[0 + (size_t)nlanc * j];
+    double peso = pesof * (z1 * z1) * pesobz;
+    if (beta * de > 1e-3) chi_iv[0] += peso * 2 * (1.0 - exp(-beta * de)) / de;
+    for (int i = 1; i <= lmats; i++) chi_iv[i] += peso * (1.0 - exp(-beta * de)) * 2.0 * de / (vm[i] * vm[i] + de * de);
+    for (int i = 0; i <= ltau; i++) chi_tau[i] += exp(-tau[i] * de) * peso;
+    for (int i = 0; i < lreal; i++) {
+      double complex w = vr[i] + eps * I;
+      cw[i] -= peso * (1.0 - exp(-beta * de)) * (1.0 / (w - de) - 1.0 / (w + de));
+    }
+  }
+  free(diag); free(z);
+}
+
+/* one chain: start vector, sp_lanc_tridiag in the state's sector (nlanc = min(idim, lanc_nGFiter)) */
+int orc_chi_chain(const orc_ctx *c, int nup, int ndw, const double *gs, int kind, int iorb, int jorb, int ngfiter, int mode,
+                  double *norm2, double *alanc, double *blanc) {
+  int64_t idim = (int64_t)orc_binomial(c->ns, nup) * orc_binomial(c->ns, ndw);
+  double *vv = (double *)xmalloc((size_t)idim * sizeof(double));
+  orc_chi_start_vector(c, nup, ndw, gs, kind, iorb, jorb, vv, norm2);
+  int nlanc = (idim < ngfiter) ? (int)idim : ngfiter;
+  for (int k = 0; k < nlanc; k++) { alanc[k] = 0.0; blanc[k] = 0.0; }
+  orc_sector *s = orc_build_hv_sector(c, nup, ndw, 0, 1, mode == 0);
+  orc_lanc_tridiag_sector(s, mode, vv, alanc, blanc, nlanc, 1.0e-12);
+  orc_delete_hv_sector(s);
+  free(vv);
+  return nlanc;
+}
+
 /* Sigma = G0^-1 - G^-1, G0^-1 = z + xmu - impHloc - sum_k V_k^2/(z - e_k) */
 void orc_sigma_normal(const orc_ctx *c, int iorb, int ispin, const double *zin, int l,
                       const double *g, double *sigma, double *invg0) {

@@ -160,6 +160,17 @@ void orc_sigma_normal(const orc_ctx *c, int iorb, int ispin, const double *z, in
                       const double *g, double *sigma, double *invg0);
 void orc_allocate_grids(double beta, int lmats, double wini, double wfin, int lreal,
                         double *wm, double *wr);
+/* Susceptibility chains, ED_GF_CHISPIN.f90:114-415 / ED_GF_CHIDENS.f90:111-426 (ed_total_ud = T): start vector
+ * O|gs> in the state's own sector.  kind 0 = spin (O = Sz), 1 = density (O = n); iorb == jorb >= 1: one orbital,
+ * iorb == 0: total over the impurity orbitals, iorb != jorb: the mixed combination O_i + O_j. */
+int64_t orc_chi_start_vector(const orc_ctx *c, int nup, int ndw, const double *gs, int kind, int iorb, int jorb,
+                             double *vvinit, double *norm2);
+int orc_chi_chain(const orc_ctx *c, int nup, int ndw, const double *gs, int kind, int iorb, int jorb, int ngfiter, int mode,
+                  double *norm2, double *alanc, double *blanc);
+/* add_to_lanczos_spinChi / _densChi (identical), T = 0.  vm[0..lmats], tau[0..ltau], vr[lreal]; chi_w interleaved. */
+void orc_add_to_lanczos_chi(double norm2, double zeta, double ei, double beta, const double *alanc, const double *blanc, int nlanc,
+                            const double *vm, int lmats, double *chi_iv, const double *tau, int ltau, double *chi_tau,
+                            const double *vr, int lreal, double eps, double *chi_w);
 
 #ifdef __cplusplus
 }

@@ -109,6 +109,11 @@ def lib():
         L.orc_observables_normal.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dp, C.c_double, C.POINTER(Observables)]
         L.orc_sigma_normal.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dp, C.c_int, c_dp, c_dp, c_dp]
         L.orc_allocate_grids.argtypes = [C.c_double, C.c_int, C.c_double, C.c_double, C.c_int, c_dp, c_dp]
+        L.orc_chi_start_vector.restype = C.c_int64
+        L.orc_chi_start_vector.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dp, C.c_int, C.c_int, C.c_int, c_dp, c_dp]
+        L.orc_chi_chain.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_dp]
+        L.orc_add_to_lanczos_chi.argtypes = [C.c_double, C.c_double, C.c_double, C.c_double, c_dp, c_dp, C.c_int,
+                                             c_dp, C.c_int, c_dp, c_dp, C.c_int, c_dp, c_dp, C.c_int, C.c_double, c_dp]
         _LIB = L
     return _LIB
 
@@ -336,6 +341,23 @@ class Oracle:
                                   "blanc": chain[p, 1 + ngfiter:1 + ngfiter + n].copy(), "nlanc": n})
         return out
 
+    def chi_start_vector(self, nup, ndw, gs, kind, iorb, jorb):
+        """O|gs> normalised, and its norm2 (ED_GF_CHISPIN.f90 / ED_GF_CHIDENS.f90 start vectors)."""
+        gs = _f64(gs)
+        vv = np.zeros_like(gs)
+        n2 = C.c_double(0.0)
+        lib().orc_chi_start_vector(self.h, nup, ndw, _dp(gs), kind, iorb, jorb, _dp(vv), C.byref(n2))
+        return vv, n2.value
+
+    def chi_chain(self, nup, ndw, gs, kind, iorb, jorb, ngfiter=200, mode=0):
+        """One susceptibility chain: dict(norm2, alanc, blanc, nlanc)."""
+        gs = _f64(gs)
+        a = np.zeros(ngfiter)
+        b = np.zeros(ngfiter)
+        n2 = C.c_double(0.0)
+        n = lib().orc_chi_chain(self.h, nup, ndw, _dp(gs), kind, iorb, jorb, ngfiter, mode, C.byref(n2), _dp(a), _dp(b))
+        return {"norm2": n2.value, "alanc": a[:n].copy(), "blanc": b[:n].copy(), "nlanc": n}
+
     def observables(self, nup, ndw, gs, zeta=1.0):
         """lanc_observables + lanc_local_energy of one state at T = 0 (ED_OBSERVABLES.f90:95-363, 372-600)."""
         gs = _f64(gs)
@@ -368,6 +390,19 @@ def add_to_lanczos_gf(norm2, ei, alanc, blanc, isign, wm, wr, eps, zeta=1.0):
     lib().orc_add_to_lanczos_gf(norm2, zeta, ei, _dp(a), _dp(b), a.size, isign, _dp(wm), wm.size,
                                 gm.ctypes.data_as(c_dp), _dp(wr), wr.size, eps, gr.ctypes.data_as(c_dp))
     return gm, gr
+
+
+def add_to_lanczos_chi(norm2, ei, beta, alanc, blanc, vm, tau, vr, eps, zeta=1.0):
+    """add_to_lanczos_spinChi / _densChi at T = 0: (chi_iv[0..Lmats], chi_tau[0..Ltau], chi_w[Lreal])."""
+    a, b = _f64(alanc), _f64(blanc)
+    vm, tau, vr = _f64(vm), _f64(tau), _f64(vr)
+    civ = np.zeros(len(vm))
+    ctau = np.zeros(len(tau))
+    cw = np.zeros(len(vr), dtype=np.complex128)
+    lib().orc_add_to_lanczos_chi(C.c_double(norm2), C.c_double(zeta), C.c_double(ei), C.c_double(beta), _dp(a), _dp(b), a.size,
+                                 _dp(vm), len(vm) - 1, _dp(civ), _dp(tau), len(tau) - 1, _dp(ctau),
+                                 _dp(vr), len(vr), C.c_double(eps), cw.ctypes.data_as(c_dp))
+    return civ, ctau, cw
 
 
 def tql2(d, e):

@@ -102,6 +102,14 @@ def main():
                             check("gf norm2 spin %d" % sp, abs(r["norm2"] - rc["norm2"]) < 1e-12)
                             check("gf a spin %d" % sp, np.abs(r["alanc"][:m] - rc["alanc"][:m]).max() < 1e-8)
                             check("gf b spin %d" % sp, np.abs(r["blanc"][:m] - rc["blanc"][:m]).max() < 1e-8)
+            # susceptibility chains on shards: a diagonal operator on every rank's own columns (ED_GF_CHISPIN.f90:114-207)
+            if cfg["norb"] == 1:
+                rs = s.chi_chains(0, [(1, 1), (0, 0)], nlanc_max=40)
+                rc_ = o.chi_chain(sec[0], sec[1], vec_ref, 0, 1, 1, ngfiter=40)
+                for r in rs:
+                    m = min(15, rc_["nlanc"])
+                    check("chi norm2", abs(r["norm2"] - rc_["norm2"]) < 1e-12)
+                    check("chi a", r["nlanc"] == rc_["nlanc"] and np.abs(r["alanc"][:m] - rc_["alanc"][:m]).max() < 1e-8)
         s.close()
     t = torch.tensor([len(fails)], device="cuda")
     dist.all_reduce(t)

@@ -300,3 +300,48 @@ def test_sparse_column_block_and_sharded_cpu_paths():
     assert np.abs(hv - ref).max() < 1e-12 * np.abs(ref).max()
     for s in secs:
         s.close()
+
+
+def test_chi_chains_known_answers():
+    """Susceptibility chains restated from ED_GF_CHISPIN.f90:114-488 / ED_GF_CHIDENS.f90:111-489, pinned on physics
+    and on a dense spectral sum: chi(tau = 0) = norm2 = <gs|O^2|gs>, i.e. <Sz^2> = (<n> - 2<n_up n_dw>)/4 for the spin
+    chain of one orbital and <n^2> = <n> + 2<n_up n_dw> for the density chain (numbers from the observables
+    restatement); the mixed chain of two orbitals is norm2(i) + norm2(j) + 2<O_i O_j>; and the Lanczos chi(tau) equals
+    sum_n |<n|O|gs>|^2 exp(-tau (E_n - E_0)) from a full diagonalisation of the sector."""
+    cfg, o = make_oracle("NS6")
+    nup = ndw = 3
+    with o.sector(nup, ndw) as s:
+        h = s.hmat()
+        w, v = np.linalg.eigh(h)
+        gs, e0 = v[:, 0], w[0]
+        mu, md, du = s.map_up(), s.map_dw(), s.dimup
+    ob = o.observables(nup, ndw, gs)
+    tau = np.linspace(0.0, 3.0, 7)
+    vm = np.pi / 50.0 * 2 * np.arange(5)
+    vr = np.linspace(-2, 2, 5)
+    for kind, expect in [(0, (ob["dens"][0] - 2 * ob["docc"][0]) / 4), (1, ob["dens"][0] + 2 * ob["docc"][0])]:
+        vv, n2 = o.chi_start_vector(nup, ndw, gs, kind, 1, 1)
+        assert abs(n2 - expect) < 1e-10 and abs(np.linalg.norm(vv) - 1) < 1e-12
+        ch = o.chi_chain(nup, ndw, gs, kind, 1, 1, ngfiter=150)
+        assert abs(ch["norm2"] - n2) < 1e-13
+        civ, ctau, cw = O.add_to_lanczos_chi(ch["norm2"], e0, 50.0, ch["alanc"], ch["blanc"], vm, tau, vr, 0.01)
+        assert abs(ctau[0] - n2) < 1e-10
+        # dense spectral sum with the operator built from the bit maps
+        nu = (mu[np.arange(h.shape[0]) % du] & 1).astype(float)
+        nd = (md[np.arange(h.shape[0]) // du] & 1).astype(float)
+        op = 0.5 * (nu - nd) if kind == 0 else nu + nd
+        amp2 = (v.T @ (op * gs)) ** 2
+        ref = np.array([(amp2 * np.exp(-t * (w - e0))).sum() for t in tau])
+        assert np.abs(ctau - ref).max() < 1e-8
+    # total == the single orbital for Norb = 1; two-orbital model: mixed chain norm
+    vv1, n1 = o.chi_start_vector(nup, ndw, gs, 0, 1, 1)
+    vv0, n0 = o.chi_start_vector(nup, ndw, gs, 0, 0, 0)
+    assert np.array_equal(vv0, vv1) and n0 == n1
+    cfg4, o4 = make_oracle("C4")
+    with o4.sector(5, 5) as s:
+        e4, g4, _, _ = s.lanc_eigh(v0=np.ones(s.dim) / np.sqrt(s.dim))
+    _, na = o4.chi_start_vector(5, 5, g4, 1, 1, 1)
+    _, nb = o4.chi_start_vector(5, 5, g4, 1, 2, 2)
+    _, nm = o4.chi_start_vector(5, 5, g4, 1, 1, 2)
+    _, nt = o4.chi_start_vector(5, 5, g4, 1, 0, 0)
+    assert abs(nm - nt) < 1e-12 and nm > na and nm > nb            # n_1 + n_2 is the total for two orbitals
