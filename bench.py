@@ -438,6 +438,18 @@ def measure(H, workload, steps, full):
         H.barrier()
         res["chain_s"] = H.maxr(time.perf_counter() - t0)
         res["chain_steps"] = nl
+        # e2e of the ground-state solve ED_DIAG.f90:174-186 makes: one sp_lanc_eigh call on host arrays (start vector
+        # in, eigenvector out, both sweeps of the recurrence on the device), the reference's defaults except that the
+        # step count is capped so that the line stays short
+        H.barrier()
+        nit = 120
+        v_h.numpy()[:] = 1.0 / np.sqrt(float(res["dim"]))
+        H.barrier()
+        t0 = time.perf_counter()
+        e0, nle = s.sp_lanc_eigh_ptr(v_h.data_ptr(), nitermax=nit, threshold=1e-12)
+        H.barrier()
+        res["eigh"] = {"seconds": H.maxr(time.perf_counter() - t0), "nlanc": int(nle), "hxv": 2 * int(nle), "e0": float(e0),
+                       "call": "edgpu_sp_lanc_eigh(Nitermax=%d, threshold=1e-12), pinned host vector in/out" % nit}
         del hv_h, v_h
     s.dev_free(d_v)
     s.dev_free(d_hv)
@@ -515,7 +527,8 @@ def run_b200(args):
                 "host_gbs_per_gpu_each_way": 8 * nloc / max((res["e2e_s"] - ms_step * 1e-3) / 2, 1e-9) / 1e9,
                 "numa_node": H.numa,
                 "chain_hxv_per_s": res["chain_steps"] / res["chain_s"],
-                "chain_call": "edgpu_sp_lanc_tridiag, %d steps, start vector from host" % res["chain_steps"]},
+                "chain_call": "edgpu_sp_lanc_tridiag, %d steps, start vector from host" % res["chain_steps"],
+                "eigh": res.get("eigh")},
         "parity_check": res["parity_check"],
         "gpu_launches": res["launches"],
         "clocks": clk,

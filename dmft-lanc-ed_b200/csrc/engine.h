@@ -24,6 +24,7 @@ struct LancState {              // device-resident Lanczos scalars (no host sync
   double sx;                    // v_k     = sx * X
   double cprev;                 // beta_{k-1} * (scale of Xp)
   double norm2;
+  double sw_a, sw_zk;           // second sweep of sp_lanc_eigh (k_fcol's epilogue when a vect pointer is passed): a_k, Z(k,1)
 };
 
 #define EDGPU_MAXP 8            // ranks of one NVLink domain (peer-mapped symmetric slab)
@@ -88,6 +89,7 @@ struct edgpu_ctx {
   int gs_nup = -1, gs_ndw = -1;
   int64_t gs_nloc = 0;
   double gs_e0 = 0.0;
+  double *sweep_vect = nullptr;               // non-null only while the second sweep of sp_lanc_eigh runs: vect += zk * v_k in k_fcol's epilogue
   bool lv_valid = false;                      // d_lv holds the normalised eigenvector of the last sp_lanc_eigh (live sector)
   // options
   int algo = EDGPU_ALGO_AUTO;

@@ -174,8 +174,10 @@ struct FColArgs {
   int norb;
   double uloc[EDGPU_MAX_ORB];
   double ust;
-  // MODE == 2 (Lanczos epilogue): w = sx*(y + F x) - cprev*xp, written over xp; partials of (sx*x).w
+  // MODE == 2 (Lanczos epilogue): w = sx*(y + F x) - cprev*xp, written over xp; partials of (sx*x).w.  vect != nullptr
+  // (second sweep of sp_lanc_eigh): also w -= sw_a*(sx*x) and vect += sw_zk*(sx*x), scalars in the LancState
   double *xp;
+  double *vect;
   const LancState *st;
   double *partials;
   // LISTS (sharded vector): the dw hops the row pass left out, entries lptr[j] .. lptr[j+1] of local column j: amplitude
@@ -367,7 +369,13 @@ __global__ void __launch_bounds__(FCOL_THREADS, 1) k_fcol(FColArgs a) {
         }
         if (MODE == 2) {
           double *wp = a.xp + j * (int64_t)n + r;
-          const double w = lsx * acc0 - lcp * __ldcs(wp);
+          double w = lsx * acc0 - lcp * __ldcs(wp);
+          if (a.vect) {                                            // second sweep of sp_lanc_eigh: all scalars known
+            const double xv = lsx * xs[r], lsa = __ldg(&a.st->sw_a), lzk = __ldg(&a.st->sw_zk);   // uniform, L1 resident
+            w -= lsa * xv;
+            double *vp = a.vect + j * (int64_t)n + r;
+            __stcs(vp, fma(lzk, xv, __ldcs(vp)));
+          }
           __stcs(wp, w);
           lsum = fma(lsx * xs[r], w, lsum);
         } else {
@@ -482,7 +490,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FCOL_THREADS, 1) k_f
       }
       if (MODE == 2) {
         double *wp = a.xp + j * (int64_t)n + r0 + r;
-        const double w = lsx * acc0 - lcp * __ldcs(wp);
+        double w = lsx * acc0 - lcp * __ldcs(wp);
+        if (a.vect) {
+          const double xv = lsx * buf[r], lsa = __ldg(&a.st->sw_a), lzk = __ldg(&a.st->sw_zk);
+          w -= lsa * xv;
+          double *vp = a.vect + j * (int64_t)n + r0 + r;
+          __stcs(vp, fma(lzk, xv, __ldcs(vp)));
+        }
         __stcs(wp, w);
         lsum = fma(lsx * buf[r], w, lsum);
       } else {
@@ -1390,6 +1404,7 @@ int fast_apply_col(edgpu_ctx *c, int k, bool with_diag, bool acc, const double *
   // *npartials on entry = partial sums already in c->d_partials (earlier column windows of the same H*v)
   const int pbase = (npartials && d_xp) ? *npartials : 0;
   a.xp = d_xp; a.st = c->d_st; a.partials = c->d_partials + pbase;
+  a.vect = (d_xp && c->sweep_vect) ? c->sweep_vect + list_col0 * c->dimup : nullptr;
   if (npartials) *npartials = pbase + grid;
   if (use2) {
     if (diag != 0) return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "cluster column kernel has no fused diagonal");

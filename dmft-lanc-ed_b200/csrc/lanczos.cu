@@ -116,6 +116,10 @@ __global__ void __launch_bounds__(RED_THREADS) k_lanc_sweep(const double *__rest
     vect[i] += zk * xv;
   }
 }
+// scalars of one step of the second sweep into the device state (read by k_fcol's Lanczos epilogue)
+__global__ void k_set_sweep(LancState *st, double sx, double cprev, double a, double zk) {
+  st->sx = sx; st->cprev = cprev; st->sw_a = a; st->sw_zk = zk;
+}
 __global__ void k_scale(double *__restrict__ x, int64_t n, double s) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] *= s;
 }
@@ -390,15 +394,32 @@ static int lanc_eigh_core(edgpu_ctx *c, int nitermax, int iverbose, double thres
   CK(cudaMemsetAsync(c->d_lp, 0, (size_t)nloc * sizeof(double), c->stream));
   CK(cudaMemsetAsync(c->d_lv, 0, (size_t)nloc * sizeof(double), c->stream));
   double sx = 1.0 / norm0, cprev = 0.0;
+  const bool fused_sweep = hxv_fast_path(c, c->d_lx);
   for (int k = 0; k < nlanc; k++) {
-    TRY(hxv_apply(c, c->d_lx, c->d_lt));
-    k_lanc_sweep<<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(c->d_lt, c->d_lx, c->d_lp, c->d_lv, c->nloc, sx, cprev,
-                                                             alanc[k], z[(size_t)k]);
-    CKL(c);
+    if (fused_sweep) {
+      // the whole vector update of the step rides in the column kernel's epilogue: w = sx*Hx - cprev*xp - a*v over xp,
+      // vect += Z(k,1)*v (ED_DIAG.f90:174-186 -> sp_lanc_eigh's second recurrence)
+      k_set_sweep<<<1, 1, 0, c->stream>>>(c->d_st, sx, cprev, alanc[k], z[(size_t)k]);
+      CKL(c);
+      c->sweep_vect = c->d_lv;
+      int nb = 0;
+      const int rc2 = fast_apply_local(c, c->d_lx, c->d_lt, c->d_lp, &nb);
+      c->sweep_vect = nullptr;
+      if (rc2) return rc2;
+    } else {
+      TRY(hxv_apply(c, c->d_lx, c->d_lt));
+      k_lanc_sweep<<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(c->d_lt, c->d_lx, c->d_lp, c->d_lv, c->nloc, sx, cprev,
+                                                               alanc[k], z[(size_t)k]);
+      CKL(c);
+    }
     std::swap(c->d_lx, c->d_lp);
     const double b = blanc[k + 1];
     cprev = b * sx;
     sx = (b != 0.0) ? 1.0 / b : 0.0;
+  }
+  if (fused_sweep) {                                               // leave no sweep scalars behind for the next recurrence
+    k_set_sweep<<<1, 1, 0, c->stream>>>(c->d_st, 0.0, 0.0, 0.0, 0.0);
+    CKL(c);
   }
   k_norm2<<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(c->d_lv, c->nloc, c->d_partials);
   CKL(c);

@@ -295,6 +295,16 @@ class Solver:
                                      C.byref(nl), _dp(a), _dp(b)))
         return egs.value, v, a[:nl.value].copy(), b[:nl.value].copy()
 
+    def sp_lanc_eigh_ptr(self, vect_ptr, nitermax=512, threshold=1e-18, ncheck=10):
+        """The same call on a caller-owned host buffer given by address (start vector in, eigenvector out; e.g. pinned
+        memory): no copies on the Python side.  Returns (egs, nlanc)."""
+        nit = int(min(self.dimup * self.dimdw, nitermax))
+        egs = C.c_double(0.0)
+        nl = C.c_int(0)
+        _ck(lib().edgpu_sp_lanc_eigh(self.h, C.byref(egs), C.cast(C.c_void_p(int(vect_ptr)), c_dp), self.nloc, nit, 0, threshold, ncheck,
+                                     C.byref(nl), None, None))
+        return egs.value, nl.value
+
     def sp_lanc_tridiag(self, vin, nlanc, threshold=1e-12):
         v = np.ascontiguousarray(vin, dtype=np.float64)
         a = np.zeros(nlanc)
