@@ -40,7 +40,8 @@ static int load_params(edgpu_ctx *c, const edgpu_params *p) {
   if (p->norb < 1 || p->norb > EDGPU_MAX_ORB) return edgpu_set_err(EDGPU_ERR_INVALID, "NORB out of range");
   if (p->nspin < 1 || p->nspin > 2) return edgpu_set_err(EDGPU_ERR_INVALID, "NSPIN out of range");
   if (p->nph != 0) return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "DimPh > 1 (NPH /= 0) is outside the hot path");
-  if (!p->ed_total_ud) return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "ed_total_ud = F (_orbs variants) is outside the hot path");
+  if (!p->ed_total_ud && p->norb > 1 && (p->jx != 0.0 || p->jp != 0.0))     // ED_SETUP.f90:69-71
+    return edgpu_set_err(EDGPU_ERR_INVALID, "ed_total_ud = F can not be used with Jx != 0 or Jp != 0");
   int ns = (p->nbath + 1) * p->norb;                        // ED_SETUP.f90:113-116, bath_type normal
   if (p->nbath < 1 || ns > EDGPU_MAX_SITES - 1) return edgpu_set_err(EDGPU_ERR_INVALID, "Ns = %d out of range", ns);
   if (!p->bath_e || !p->bath_v) return edgpu_set_err(EDGPU_ERR_INVALID, "bath arrays == NULL");
@@ -178,6 +179,14 @@ static int64_t binom64(const edgpu_ctx *c, int n, int k) {
   return c->h_binom[n * EDGPU_BINOM_LD + k];
 }
 extern "C" int edgpu_vecdim_hv_sector(const edgpu_ctx *c, int isector, int64_t *vecdim) {
+  if (c && !c->hp.ed_total_ud) {                              // product of the 2*Norb word dimensions, single rank
+    int nups[EDGPU_MAX_ORB], ndws[EDGPU_MAX_ORB];
+    TRY(edgpu_get_qn_orbs(c, isector, nups, ndws));
+    int64_t d = 1;
+    for (int k = 0; k < c->dp.norb; k++) d *= binom64(c, c->dp.nbath + 1, nups[k]) * binom64(c, c->dp.nbath + 1, ndws[k]);
+    *vecdim = d;
+    return EDGPU_OK;
+  }
   int nup, ndw;
   TRY(edgpu_get_nup_ndw(c, isector, &nup, &ndw));
   int64_t q;
@@ -328,6 +337,14 @@ extern "C" int edgpu_build_hv_sector(edgpu_ctx *c, int isector) {
   if (!c) return edgpu_set_err(EDGPU_ERR_INVALID, "ctx == NULL");
   if (c->hstatus) return edgpu_set_err(EDGPU_ERR_INVALID, "build_Hv_sector: a sector is already live (Hstatus=T)");
   CK(cudaSetDevice(c->device));
+  if (!c->hp.ed_total_ud) {                                   // ed_buildh_orbs: its own builder and operator (orbs.cu)
+    c->isector = isector; c->nup = -1; c->ndw = -1;
+    c->hstatus = true;
+    int rc = orbs_build(c, isector);
+    if (rc) { edgpu_delete_hv_sector(c); return rc; }
+    g_current = c;
+    return EDGPU_OK;
+  }
   int nup, ndw;
   TRY(edgpu_get_nup_ndw(c, isector, &nup, &ndw));
   c->isector = isector; c->nup = nup; c->ndw = ndw;
@@ -396,6 +413,7 @@ extern "C" int edgpu_delete_hv_sector(edgpu_ctx *c) {
   cudaStreamSynchronize(c->stream);
   tiled_plan_free(c);
   fast_plan_free(c);
+  orbs_free(c);
   free_factor(c->up);
   free_factor(c->dw);
   cudaFree(c->d_diag); c->d_diag = nullptr;
@@ -476,6 +494,7 @@ extern "C" int edgpu_get_dims(const edgpu_ctx *c, int64_t *dimup, int64_t *dimdw
 }
 extern "C" int edgpu_get_sector_map(const edgpu_ctx *c, int which, int32_t *out) {
   if (!c || !c->hstatus) return edgpu_set_err(EDGPU_ERR_INVALID, "no live sector");
+  if (c->orbs) return edgpu_set_err(EDGPU_ERR_INVALID, "ed_total_ud = F: use edgpu_get_orbs_factor");
   const Factor &f = which ? c->dw : c->up;
   CK(cudaMemcpy(out, f.d_map, (size_t)f.n * sizeof(int32_t), cudaMemcpyDeviceToHost));
   return EDGPU_OK;
@@ -483,6 +502,7 @@ extern "C" int edgpu_get_sector_map(const edgpu_ctx *c, int which, int32_t *out)
 extern "C" int edgpu_get_csr(const edgpu_ctx *c, int which, int64_t *nrow, int64_t *nnz,
                              int64_t *rowptr, int64_t *cols, double *vals) {
   if (!c || !c->hstatus) return edgpu_set_err(EDGPU_ERR_INVALID, "no live sector");
+  if (c->orbs) return edgpu_set_err(EDGPU_ERR_INVALID, "ed_total_ud = F: use edgpu_get_orbs_factor");
   if (which == 2) {
     if (nrow) *nrow = c->dp.jhflag ? c->nloc : 0;
     if (nnz) *nnz = c->nd_nnz;

@@ -44,6 +44,7 @@ static_assert(sizeof(SRowRec) == 80, "SRowRec is copied in 16-byte units");
 
 struct TiledPlan;               // hxv_tiled.cu
 struct FastPlan;                // hxv_fast.cu
+struct OrbsPlan;                // orbs.cu
 
 struct edgpu_ctx {
   int device = 0;
@@ -96,6 +97,7 @@ struct edgpu_ctx {
   int64_t opt_tile_rows = 0, opt_tile_h = -1, opt_col_h = -1;
   TiledPlan *plan = nullptr;
   FastPlan *fplan = nullptr;
+  OrbsPlan *orbs = nullptr;                   // live sector of an ed_total_ud = F model (orbs.cu); then up / dw are empty
   int64_t opt_srow_lr = 0, opt_srow_t = 0, opt_no_uniform = 0, opt_no_fuse = 0, opt_no_peer = 0, opt_col_cluster = 0;
   int64_t opt_halo_ctas = 0, opt_no_overlap = 0, opt_no_batch = 0, opt_halo_windows = 0;
   int64_t launches = 0;
@@ -151,6 +153,10 @@ int edgpu_set_err(int code, const char *fmt, ...);
 int hxv_apply(edgpu_ctx *c, const double *d_x, double *d_y);
 // true when hxv_apply would take the fast two-kernel path for this vector (then the Lanczos epilogue can be fused)
 bool hxv_fast_path(edgpu_ctx *c, const double *d_x);
+// orbs.cu: ed_total_ud = F (one (Nup, Ndw) pair per orbital)
+int orbs_build(edgpu_ctx *c, int isector);
+int orbs_free(edgpu_ctx *c);
+int orbs_apply(edgpu_ctx *c, const double *d_x, double *d_y);
 // hxv_tiled.cu
 int tiled_plan_build(edgpu_ctx *c);
 int tiled_plan_free(edgpu_ctx *c);

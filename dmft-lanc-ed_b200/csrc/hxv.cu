@@ -162,12 +162,13 @@ static int pick_col(edgpu_ctx *c) {
 }
 
 bool hxv_fast_path(edgpu_ctx *c, const double *d_x) {
-  if (c->dp.jhflag || c->opt_no_fuse) return false;
+  if (c->orbs || c->dp.jhflag || c->opt_no_fuse) return false;
   if (c->nranks == 1) return pick_local(c) == EDGPU_ALGO_FAST && fast_supported_local(c);
   return (c->algo == EDGPU_ALGO_AUTO || c->algo == EDGPU_ALGO_FAST) && fast_peer_ready(c) && fast_supported_local(c);
 }
 
 int hxv_apply(edgpu_ctx *c, const double *d_x, double *d_y) {
+  if (c->orbs) return orbs_apply(c, d_x, d_y);                     // ed_total_ud = F (spMatVec_orbs)
   if (c->nranks == 1) {
     const int algo = pick_local(c);
     if (algo == EDGPU_ALGO_FAST) {

@@ -905,7 +905,7 @@ __global__ void k_halo_wait(const unsigned long long *flags, int nranks, int me,
       unsigned long long v;
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + p) : "memory");
       if (v >= epoch) break;
-      if (clock64() - t0 > 60000000000LL) __trap();                // ~30 s: a peer died -- fail loudly instead of hanging
+      if (clock64() - t0 > 1200000000000LL) __trap();              // ~10 min (ranks may arrive late after host work): a peer died -- fail loudly instead of hanging
       __nanosleep(200);
     }
   }

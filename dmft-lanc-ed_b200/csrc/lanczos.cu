@@ -472,7 +472,7 @@ extern "C" int edgpu_diag_sectors(edgpu_ctx *c, int nsectors, const int *isector
   CK(cudaSetDevice(c->device));
   int ibest = -1;
   std::vector<int> src((size_t)nsectors, -1);                      // twin: index of the sector whose result is copied
-  for (int s = 0; s < nsectors; s++) {
+  for (int s = 0; s < nsectors && c->hp.ed_total_ud; s++) {        // (twin reuse for ed_total_ud = F: not built, every sector is solved)
     int nup, ndw;
     TRY(edgpu_get_nup_ndw(c, isector[s], &nup, &ndw));
     if (twin && nup < ndw)
@@ -497,7 +497,7 @@ extern "C" int edgpu_diag_sectors(edgpu_ctx *c, int nsectors, const int *isector
     if (nlanc) nlanc[s] = nl;
     if (!rc && (ibest < 0 || e0[s] < e0[ibest])) {
       ibest = s;
-      rc = edgpu_gf_set_state_from_eigh(c);
+      if (c->hp.ed_total_ud) rc = edgpu_gf_set_state_from_eigh(c);   // (no chains / observables for ed_total_ud = F)
     }
     edgpu_delete_hv_sector(c);
     if (rc) return rc;
@@ -573,6 +573,7 @@ extern "C" int edgpu_dev_dot(edgpu_ctx *c, int64_t nloc, const double *d_a, cons
 // ---- Green's function chains ------------------------------------------------------------------------
 extern "C" int edgpu_gf_set_state(edgpu_ctx *c, int isector, const double *gs, int64_t nloc, double e0) {
   if (!c) return edgpu_set_err(EDGPU_ERR_INVALID, "ctx == NULL");
+  if (!c->hp.ed_total_ud) return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "ed_total_ud = F: the chains / observables of an orbital-resolved state are not built");
   CK(cudaSetDevice(c->device));
   int nup, ndw;
   TRY(edgpu_get_nup_ndw(c, isector, &nup, &ndw));
@@ -844,6 +845,7 @@ extern "C" int edgpu_gf_chains(edgpu_ctx *c, int nchains, const int *iorb, const
                                const int *addrem, int nlanc_max, double threshold,
                                double *norm2, int *nlanc, double *alanc, double *blanc) {
   if (!c || !c->d_gs) return edgpu_set_err(EDGPU_ERR_INVALID, "gf_chains: no state set (edgpu_gf_set_state)");
+  if (!c->hp.ed_total_ud) return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "ed_total_ud = F: GF chains of an orbital-resolved state are not built");
   if (c->hstatus) return edgpu_set_err(EDGPU_ERR_INVALID, "gf_chains: a sector is live; call delete_Hv_sector first");
   CK(cudaSetDevice(c->device));
   std::vector<int> done((size_t)nchains, 0);
@@ -915,6 +917,7 @@ __global__ void k_chi_start(const int32_t *__restrict__ map_up, const int32_t *_
 extern "C" int edgpu_chi_chains(edgpu_ctx *c, int kind, int nchains, const int *iorb, const int *jorb, int nlanc_max,
                                 double threshold, double *norm2, int *nlanc, double *alanc, double *blanc) {
   if (!c || !c->d_gs) return edgpu_set_err(EDGPU_ERR_INVALID, "chi_chains: no state set (edgpu_gf_set_state)");
+  if (!c->hp.ed_total_ud) return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "ed_total_ud = F: susceptibility chains of an orbital-resolved state are not built");
   if (c->hstatus) return edgpu_set_err(EDGPU_ERR_INVALID, "chi_chains: a sector is live; call delete_Hv_sector first");
   if (kind != 0 && kind != 1) return edgpu_set_err(EDGPU_ERR_INVALID, "chi_chains: kind is 0 (spin) or 1 (density)");
   CK(cudaSetDevice(c->device));

@@ -131,6 +131,7 @@ static void launch_weights(int grid, cudaStream_t st, const double *gs, const in
 
 extern "C" int edgpu_observables_normal(edgpu_ctx *c, double zeta, edgpu_observables *out) {
   if (!c || !out) return edgpu_set_err(EDGPU_ERR_INVALID, "observables: bad arguments");
+  if (!c->hp.ed_total_ud) return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "ed_total_ud = F: observables of an orbital-resolved state are not built");
   if (!c->d_gs) return edgpu_set_err(EDGPU_ERR_INVALID, "observables: no state set (edgpu_gf_set_state / edgpu_gf_set_state_from_eigh)");
   if (!(zeta > 0.0)) return edgpu_set_err(EDGPU_ERR_INVALID, "observables: zeta_function must be positive");
   CK(cudaSetDevice(c->device));

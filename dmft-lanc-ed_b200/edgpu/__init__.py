@@ -33,7 +33,8 @@ ABI_SYMBOLS = [
     "edgpu_get_sector", "edgpu_get_nup_ndw", "edgpu_split", "edgpu_transpose_plan", "edgpu_build_hv_sector",
     "edgpu_delete_hv_sector", "edgpu_vecdim_hv_sector", "edgpu_hxv", "edgpu_sphtimesv",
     "edgpu_hxv_device", "edgpu_sp_lanc_eigh", "edgpu_sp_lanc_tridiag", "edgpu_diag_sectors", "edgpu_gf_set_state", "edgpu_gf_set_state_from_eigh",
-    "edgpu_gf_chains", "edgpu_add_to_lanczos_gf", "edgpu_chi_chains", "edgpu_add_to_lanczos_chi", "edgpu_observables_normal", "edgpu_get_dims", "edgpu_get_sector_map",
+    "edgpu_gf_chains", "edgpu_add_to_lanczos_gf", "edgpu_chi_chains", "edgpu_add_to_lanczos_chi", "edgpu_get_sector_orbs", "edgpu_get_qn_orbs", "edgpu_get_orbs_dims",
+    "edgpu_get_orbs_factor", "edgpu_get_orbs_diag", "edgpu_observables_normal", "edgpu_get_dims", "edgpu_get_sector_map",
     "edgpu_get_csr", "edgpu_get_diag", "edgpu_dev_alloc", "edgpu_dev_free", "edgpu_dev_upload",
     "edgpu_dev_download", "edgpu_dev_fill_bench_vector", "edgpu_sync", "edgpu_dev_dot", "edgpu_time_hxv_device",
     "edgpu_time_lanczos_device", "edgpu_launch_count", "edgpu_time_hxv_passes", "edgpu_halo_info",
@@ -107,6 +108,11 @@ def lib():
         L.edgpu_gf_set_state.argtypes = [C.c_void_p, C.c_int, c_dp, C.c_int64, C.c_double]
         L.edgpu_gf_set_state_from_eigh.argtypes = [C.c_void_p]
         L.edgpu_gf_chains.argtypes = [C.c_void_p, C.c_int, c_ip, c_ip, c_ip, C.c_int, C.c_double, c_dp, c_ip, c_dp, c_dp]
+        L.edgpu_get_sector_orbs.argtypes = [C.c_void_p, c_ip, c_ip, c_ip]
+        L.edgpu_get_qn_orbs.argtypes = [C.c_void_p, C.c_int, c_ip, c_ip]
+        L.edgpu_get_orbs_dims.argtypes = [C.c_void_p, c_i64p, c_i64p]
+        L.edgpu_get_orbs_factor.argtypes = [C.c_void_p, C.c_int, c_i32p, c_i64p, c_i64p, c_i64p, c_dp]
+        L.edgpu_get_orbs_diag.argtypes = [C.c_void_p, c_dp]
         L.edgpu_chi_chains.argtypes = [C.c_void_p, C.c_int, C.c_int, c_ip, c_ip, C.c_int, C.c_double, c_dp, c_ip, c_dp, c_dp]
         L.edgpu_add_to_lanczos_chi.argtypes = [C.c_double, C.c_double, C.c_double, C.c_double, c_dp, c_dp, C.c_int,
                                                c_dp, C.c_int, c_dp, c_dp, C.c_int, c_dp, c_dp, C.c_int, C.c_double, c_dp]
@@ -188,8 +194,9 @@ class Solver:
     """Module-global ED state + the live sector (ED_VARS_GLOBAL / ED_HAMILTONIAN_COMMON)."""
 
     def __init__(self, norb, nbath, nspin=1, uloc=(2.0,), ust=0.0, jh=0.0, jx=0.0, jp=0.0, xmu=0.0, hfmode=True,
-                 imphloc=None, bath_e=None, bath_v=None, ed_sparse_h=True, device=-1):
+                 imphloc=None, bath_e=None, bath_v=None, ed_sparse_h=True, device=-1, ed_total_ud=True):
         self.norb, self.nbath, self.nspin = norb, nbath, nspin
+        self.ed_total_ud = bool(ed_total_ud)
         self.ns = (nbath + 1) * norb
         if bath_e is None or bath_v is None:
             bath_e, bath_v = configs.init_dmft_bath(norb, nbath, nspin)
@@ -202,7 +209,7 @@ class Solver:
     def _pack(self, uloc, ust, jh, jx, jp, xmu, hfmode, imphloc, bath_e, bath_v, ed_sparse_h):
         p = Params()
         p.norb, p.nbath, p.nspin = self.norb, self.nbath, self.nspin
-        p.hfmode, p.ed_sparse_h, p.nph, p.ed_total_ud = int(bool(hfmode)), int(bool(ed_sparse_h)), 0, 1
+        p.hfmode, p.ed_sparse_h, p.nph, p.ed_total_ud = int(bool(hfmode)), int(bool(ed_sparse_h)), 0, int(getattr(self, "ed_total_ud", True))
         for i in range(5):
             p.uloc[i] = float(uloc[i]) if i < len(uloc) else 0.0
         p.ust, p.jh, p.jx, p.jp, p.xmu = ust, jh, jx, jp, xmu
@@ -239,6 +246,43 @@ class Solver:
         s = C.c_int(0)
         _ck(lib().edgpu_get_sector(self.h, nup, ndw, C.byref(s)))
         return s.value
+
+    # ed_total_ud = F: one (Nup, Ndw) pair per orbital
+    def get_sector_orbs(self, nups, ndws):
+        n = self.norb
+        s = C.c_int(0)
+        _ck(lib().edgpu_get_sector_orbs(self.h, (C.c_int * n)(*nups), (C.c_int * n)(*ndws), C.byref(s)))
+        return s.value
+
+    def get_qn_orbs(self, isector):
+        n = self.norb
+        a, b = (C.c_int * n)(), (C.c_int * n)()
+        _ck(lib().edgpu_get_qn_orbs(self.h, isector, a, b))
+        return list(a), list(b)
+
+    def orbs_dims(self):
+        d = (C.c_int64 * (2 * self.norb))()
+        tot = C.c_int64(0)
+        _ck(lib().edgpu_get_orbs_dims(self.h, d, C.byref(tot)))
+        return list(d), tot.value
+
+    def orbs_factor(self, f):
+        """(map, rowptr, cols, vals) of factor f of the live ed_total_ud = F sector."""
+        dims, _ = self.orbs_dims()
+        nnz = C.c_int64(0)
+        m = np.zeros(dims[f], np.int32)
+        rp = np.zeros(dims[f] + 1, np.int64)
+        i64p = C.POINTER(C.c_int64)
+        _ck(lib().edgpu_get_orbs_factor(self.h, f, m.ctypes.data_as(c_i32p), C.byref(nnz), rp.ctypes.data_as(i64p), None, None))
+        cols = np.zeros(max(nnz.value, 1), np.int64)
+        vals = np.zeros(max(nnz.value, 1))
+        _ck(lib().edgpu_get_orbs_factor(self.h, f, None, None, None, cols.ctypes.data_as(i64p), _dp(vals)))
+        return m, rp, cols[:nnz.value], vals[:nnz.value]
+
+    def orbs_diag(self):
+        d = np.zeros(self.nloc)
+        _ck(lib().edgpu_get_orbs_diag(self.h, _dp(d)))
+        return d
 
     def get_nup_ndw(self, isector):
         a, b = C.c_int(0), C.c_int(0)

@@ -51,6 +51,16 @@ def config(name):
         e, v = init_dmft_bath(2, 4)     # e = -2,-0.1,0.1,2 ; V = 0.5
         return dict(norb=2, nbath=4, nspin=1, uloc=(2.0, 2.0), ust=1.0, jh=0.5, jx=0.5, jp=0.5, xmu=0.0,
                     hfmode=True, bath_e=e, bath_v=v, nup=5, ndw=5)
+    if name in ("ORB2", "ORB2B", "ORB3"):  # density-density multi-orbital models for ed_total_ud = F (Jx = Jp = 0)
+        norb, nbath = {"ORB2": (2, 2), "ORB2B": (2, 4), "ORB3": (3, 2)}[name]
+        e, v = init_dmft_bath(norb, nbath)
+        k = np.arange(nbath, dtype=np.float64).reshape(1, 1, nbath)
+        o = np.arange(norb, dtype=np.float64).reshape(1, norb, 1)
+        v = v * (1.0 + 0.2 * o) + 0.05 * k      # orbital- and level-dependent hybridisations
+        e = e + 0.1 * o
+        tot = norb * (nbath + 1) // 2
+        return dict(norb=norb, nbath=nbath, nspin=1, uloc=tuple(2.0 + 0.5 * i for i in range(norb)), ust=1.0, jh=0.4, jx=0.0, jp=0.0,
+                    xmu=0.1, hfmode=True, bath_e=e, bath_v=v, nup=tot, ndw=tot)
     if name.startswith("NS"):           # e.g. NS10 -> single band Ns=10 half filling; NS10V: level-dependent V_k
         vary = name.endswith("V")
         ns = int(name[2:-1] if vary else name[2:])

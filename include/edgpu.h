@@ -139,6 +139,22 @@ int  edgpu_sp_lanc_tridiag(edgpu_ctx *c, const double *vin, int64_t nloc, double
 int  edgpu_diag_sectors(edgpu_ctx *c, int nsectors, const int *isector, int nitermax, double threshold,
                         int ncheck, int twin, double *e0, int *nlanc, int *best);
 
+/* ---- ed_total_ud = F: one (Nup, Ndw) pair per orbital (Ns_Ud = Norb, Ns_Orb = 1 + Nbath) ------------------------
+ * ed_buildh_orbs / spMatVec_orbs / directMatVec_orbs (ED_HAMILTONIAN_SPARSE_HxV.f90:206-370, 487-564) with
+ * stored/Orbs/H_local.f90, H_up.f90, H_dw.f90; needs Jx = Jp = 0 (ED_SETUP.f90:69-71).  With params.ed_total_ud = 0
+ * the sector number is get_Sector([Nups, Ndws], Ns_Orb) (ED_SETUP.f90:446-457); edgpu_build_hv_sector, edgpu_hxv*,
+ * edgpu_sp_lanc_eigh, edgpu_sp_lanc_tridiag and edgpu_diag_sectors work on it unchanged (the vector runs over
+ * [DimUps, DimDws], first index fastest, ED_SETUP.f90:520-545).  Single rank; chains and observables of such a state
+ * return EDGPU_ERR_UNSUPPORTED. */
+int  edgpu_get_sector_orbs(const edgpu_ctx *c, const int *nups, const int *ndws, int *isector);
+int  edgpu_get_qn_orbs(const edgpu_ctx *c, int isector, int *nups, int *ndws);           /* get_Nup / get_Ndw, :477-500 */
+/* introspection of the live sector: dims[2*Norb] (up words of orbital 1..Norb, then the dw words); factor f: map =
+ * Hs(f)%map, CSR of spH0ups(f+1) resp. spH0dws(f+1-Norb) in insertion order (0-based; arrays may be NULL); the stored
+ * diagonal spH0d (ed_sparse_h = 1). */
+int  edgpu_get_orbs_dims(const edgpu_ctx *c, int64_t *dims, int64_t *dim);
+int  edgpu_get_orbs_factor(const edgpu_ctx *c, int f, int32_t *map, int64_t *nnz, int64_t *rowptr, int64_t *cols, double *vals);
+int  edgpu_get_orbs_diag(const edgpu_ctx *c, double *out);
+
 /* ---- Green's function chains (lanc_build_gf_normal_main, ED_GF_NORMAL.f90:124-334) --------------- */
 /* Keeps the ground state of sector (nup,ndw) on device for the chains; gs is the local shard.
  * Replaces es_return_cvector + the master-only c/cdg loops (:184-216, :259-290). */

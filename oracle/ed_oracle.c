@@ -1313,6 +1313,139 @@ void orc_lanc_build_gf_normal_main(const orc_ctx *c, int nup, int ndw, const dou
 }
 
 /* ===================================================================================== */
+/* ed_total_ud = F: one (Nup, Ndw) pair per orbital (Ns_Ud = Norb, Ns_Orb = 1 + Nbath)    */
+/* ===================================================================================== */
+/* get_Sector, ED_SETUP.f90:446-457 with QN = [Nups, Ndws] and N = Ns_Orb */
+int orc_get_sector_orbs(const orc_ctx *c, const int *nups, const int *ndws) {
+  const int nind = 2 * c->norb, factor = c->nbath + 1 + 1;
+  int isector = 1;
+  for (int i = nind; i >= 1; i--) {
+    int qn = (i <= c->norb) ? nups[i - 1] : ndws[i - 1 - c->norb];
+    int pw = 1;
+    for (int k = 0; k < nind - i; k++) pw *= factor;
+    isector = isector + qn * pw;
+  }
+  return isector;
+}
+
+/* ed_buildh_orbs (ED_HAMILTONIAN_SPARSE_HxV.f90:206-370) with stored/Orbs/H_local.f90, H_up.f90, H_dw.f90: per
+ * orbital and spin the star of that orbital's impurity site (bit 0 of the orbital word) and its own bath levels (bits
+ * 1..Nbath); the diagonal from the occupations reordered to the Ns site numbering (breorder, ED_SETUP.f90:963-979:
+ * impurity orbitals first, then the bath levels of orbital 1, 2, ...).  Serial only (rank 0 of 1). */
+orc_sector_orbs *orc_build_hv_sector_orbs(const orc_ctx *c, const int *nups, const int *ndws) {
+  orc_sector_orbs *s = (orc_sector_orbs *)xcalloc(1, sizeof(*s));
+  const int norb = c->norb, nso = c->nbath + 1;
+  s->ctx = c; s->nfac = 2 * norb; s->dim = 1;
+  for (int f = 0; f < 2 * norb; f++) {
+    int n = (f < norb) ? nups[f] : ndws[f - norb];
+    s->nq[f] = n;
+    s->dims[f] = orc_binomial(nso, n);
+    s->map[f] = (int32_t *)xmalloc((size_t)s->dims[f] * 4);
+    orc_build_sector_map(nso, n, s->map[f]);
+    s->dim *= s->dims[f];
+  }
+  /* H_up / H_dw of every orbital, insertion order: outer loop over the source state, kp inner (Orbs/H_up.f90) */
+  for (int f = 0; f < 2 * norb; f++) {
+    const int io = f % norb, is = (f < norb) ? 0 : c->nspin - 1;
+    rl_mat m;
+    rl_init(&m, s->dims[f]);
+    for (int64_t j = 0; j < s->dims[f]; j++) {
+      int32_t mm = s->map[f][j];
+      int occ[64];
+      bdecomp(mm, nso, occ);
+      for (int kp = 1; kp <= c->nbath; kp++) {
+        int ialfa = 1 + kp;
+        double v = BATHV(c, is, io, kp - 1);
+        if (v != 0.0 && occ[0] == 1 && occ[ialfa - 1] == 0) {
+          int32_t k1, k2; double sg1, sg2;
+          orc_c(1, mm, &k1, &sg1); orc_cdg(ialfa, k1, &k2, &sg2);
+          int64_t i = orc_binary_search(s->map[f], s->dims[f], k2) - 1;
+          rl_insert(&m, v * sg1 * sg2, i, j);
+        }
+        if (v != 0.0 && occ[0] == 0 && occ[ialfa - 1] == 1) {
+          int32_t k1, k2; double sg1, sg2;
+          orc_c(ialfa, mm, &k1, &sg1); orc_cdg(1, k1, &k2, &sg2);
+          int64_t i = orc_binary_search(s->map[f], s->dims[f], k2) - 1;
+          rl_insert(&m, v * sg1 * sg2, i, j);
+        }
+      }
+    }
+    rl_to_csr(&m, &s->h[f]);
+  }
+  /* diagonal */
+  s->h0d = (double *)xmalloc((size_t)s->dim * sizeof(double));
+  for (int64_t i = 0; i < s->dim; i++) {
+    int nup[64], ndw[64];
+    int64_t count = i;
+    for (int k = 0; k < c->ns; k++) { nup[k] = 0; ndw[k] = 0; }
+    for (int f = 0; f < 2 * norb; f++) {
+      int64_t idx = count % s->dims[f];
+      count /= s->dims[f];
+      int occ[64];
+      bdecomp(s->map[f][idx], nso, occ);
+      int io = f % norb;
+      int *dst = (f < norb) ? nup : ndw;
+      dst[io] = occ[0];
+      for (int kp = 1; kp <= c->nbath; kp++) dst[orc_bath_stride(c, io + 1, kp) - 1] = occ[kp];
+    }
+    s->h0d[i] = h_local_element(c, nup, ndw);
+  }
+  return s;
+}
+
+void orc_delete_hv_sector_orbs(orc_sector_orbs *s) {
+  if (!s) return;
+  for (int f = 0; f < s->nfac; f++) { free(s->map[f]); csr_free(&s->h[f]); }
+  free(s->h0d);
+  free(s);
+}
+
+/* spMatVec_orbs, ED_HAMILTONIAN_SPARSE_HxV.f90:487-564 (DimPh = 1): diagonal, then per element and per orbital the up
+ * entries followed by the dw entries. */
+void orc_spmatvec_orbs(const orc_sector_orbs *s, int64_t nloc, const double *v, double *hv) {
+  const int norb = s->nfac / 2;
+  for (int64_t i = 0; i < nloc; i++) hv[i] = 0.0;
+  for (int64_t i = 0; i < nloc; i++) hv[i] = hv[i] + s->h0d[i] * v[i];
+  int64_t stride[2 * ORC_MAX_ORB];
+  stride[0] = 1;
+  for (int f = 1; f < s->nfac; f++) stride[f] = stride[f - 1] * s->dims[f - 1];
+  for (int64_t i = 0; i < nloc; i++) {
+    int64_t idx[2 * ORC_MAX_ORB], count = i;
+    for (int f = 0; f < s->nfac; f++) { idx[f] = count % s->dims[f]; count /= s->dims[f]; }
+    for (int iud = 0; iud < norb; iud++) {
+      for (int sp = 0; sp < 2; sp++) {                       /* UP then DW of this orbital */
+        const int f = iud + sp * norb;
+        const orc_csr *h = &s->h[f];
+        for (int64_t p = h->rowptr[idx[f]]; p < h->rowptr[idx[f] + 1]; p++) {
+          int64_t j = i + (h->cols[p] - idx[f]) * stride[f];
+          hv[i] = hv[i] + h->vals[p] * v[j];
+        }
+      }
+    }
+  }
+}
+
+static void orbs_matvec(void *u, int64_t n, const double *v, double *hv) { orc_spmatvec_orbs((const orc_sector_orbs *)u, n, v, hv); }
+int orc_lanc_eigh_sector_orbs(const orc_sector_orbs *s, double *egs, double *vect, int nitermax, double threshold, int ncheck,
+                              int *nlanc_out, double *alanc_out, double *blanc_out) {
+  return orc_sp_lanc_eigh(orbs_matvec, (void *)s, s->dim, egs, vect, nitermax, threshold, ncheck, nlanc_out, alanc_out, blanc_out);
+}
+int orc_lanc_tridiag_sector_orbs(const orc_sector_orbs *s, double *vin, double *alanc, double *blanc, int nitermax, double threshold) {
+  return orc_sp_lanc_tridiag(orbs_matvec, (void *)s, s->dim, vin, alanc, blanc, nitermax, threshold);
+}
+void orc_sector_orbs_info(const orc_sector_orbs *s, int64_t *dim, int64_t *dims) {
+  *dim = s->dim;
+  for (int f = 0; f < s->nfac; f++) dims[f] = s->dims[f];
+}
+void orc_sector_orbs_get(const orc_sector_orbs *s, int f, int32_t *map, int64_t *rowptr, int64_t *cols, double *vals, double *h0d) {
+  if (map) memcpy(map, s->map[f], (size_t)s->dims[f] * 4);
+  if (rowptr) memcpy(rowptr, s->h[f].rowptr, (size_t)(s->dims[f] + 1) * 8);
+  if (cols) memcpy(cols, s->h[f].cols, (size_t)s->h[f].rowptr[s->dims[f]] * 8);
+  if (vals) memcpy(vals, s->h[f].vals, (size_t)s->h[f].rowptr[s->dims[f]] * 8);
+  if (h0d) memcpy(h0d, s->h0d, (size_t)s->dim * 8);
+}
+
+/* ===================================================================================== */
 /* ED_GF_CHISPIN / ED_GF_CHIDENS (ed_total_ud = T: ialfa = 1, iorb1 = iorb)              */
 /* ===================================================================================== */
 /* start vector O|gs> in the state's own sector, then norm2 and normalisation.

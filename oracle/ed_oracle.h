@@ -160,6 +160,27 @@ void orc_sigma_normal(const orc_ctx *c, int iorb, int ispin, const double *z, in
                       const double *g, double *sigma, double *invg0);
 void orc_allocate_grids(double beta, int lmats, double wini, double wfin, int lreal,
                         double *wm, double *wr);
+/* ---- ed_total_ud = F (Ns_Ud = Norb): ed_buildh_orbs / spMatVec_orbs, ED_HAMILTONIAN_SPARSE_HxV.f90:206-370, 487-564,
+ * with ED_HAMILTONIAN/stored/Orbs/H_local.f90, H_up.f90, H_dw.f90.  Factor f < Norb: up word of orbital f+1, else the
+ * dw word of orbital f+1-Norb; the vector index runs over [DimUps, DimDws] with the first factor fastest
+ * (state2indices, ED_SETUP.f90:520-545).  Serial. */
+typedef struct orc_sector_orbs {
+  const orc_ctx *ctx;
+  int nfac, nq[2 * ORC_MAX_ORB];
+  int64_t dims[2 * ORC_MAX_ORB], dim;
+  int32_t *map[2 * ORC_MAX_ORB];
+  orc_csr h[2 * ORC_MAX_ORB];   /* spH0ups(iud), spH0dws(iud) */
+  double *h0d;                  /* spH0d, one value per state */
+} orc_sector_orbs;
+int orc_get_sector_orbs(const orc_ctx *c, const int *nups, const int *ndws);
+orc_sector_orbs *orc_build_hv_sector_orbs(const orc_ctx *c, const int *nups, const int *ndws);
+void orc_delete_hv_sector_orbs(orc_sector_orbs *s);
+void orc_spmatvec_orbs(const orc_sector_orbs *s, int64_t nloc, const double *v, double *hv);
+int orc_lanc_eigh_sector_orbs(const orc_sector_orbs *s, double *egs, double *vect, int nitermax, double threshold, int ncheck,
+                              int *nlanc_out, double *alanc_out, double *blanc_out);
+int orc_lanc_tridiag_sector_orbs(const orc_sector_orbs *s, double *vin, double *alanc, double *blanc, int nitermax, double threshold);
+void orc_sector_orbs_info(const orc_sector_orbs *s, int64_t *dim, int64_t *dims);
+void orc_sector_orbs_get(const orc_sector_orbs *s, int f, int32_t *map, int64_t *rowptr, int64_t *cols, double *vals, double *h0d);
 /* Susceptibility chains, ED_GF_CHISPIN.f90:114-415 / ED_GF_CHIDENS.f90:111-426 (ed_total_ud = T): start vector
  * O|gs> in the state's own sector.  kind 0 = spin (O = Sz), 1 = density (O = n); iorb == jorb >= 1: one orbital,
  * iorb == 0: total over the impurity orbitals, iorb != jorb: the mixed combination O_i + O_j. */

@@ -109,6 +109,15 @@ def lib():
         L.orc_observables_normal.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dp, C.c_double, C.POINTER(Observables)]
         L.orc_sigma_normal.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dp, C.c_int, c_dp, c_dp, c_dp]
         L.orc_allocate_grids.argtypes = [C.c_double, C.c_int, C.c_double, C.c_double, C.c_int, c_dp, c_dp]
+        L.orc_get_sector_orbs.argtypes = [C.c_void_p, c_ip, c_ip]
+        L.orc_build_hv_sector_orbs.restype = C.c_void_p
+        L.orc_build_hv_sector_orbs.argtypes = [C.c_void_p, c_ip, c_ip]
+        L.orc_delete_hv_sector_orbs.argtypes = [C.c_void_p]
+        L.orc_spmatvec_orbs.argtypes = [C.c_void_p, C.c_int64, c_dp, c_dp]
+        L.orc_lanc_eigh_sector_orbs.argtypes = [C.c_void_p, c_dp, c_dp, C.c_int, C.c_double, C.c_int, c_ip, c_dp, c_dp]
+        L.orc_lanc_tridiag_sector_orbs.argtypes = [C.c_void_p, c_dp, c_dp, c_dp, C.c_int, C.c_double]
+        L.orc_sector_orbs_info.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.orc_sector_orbs_get.argtypes = [C.c_void_p, C.c_int, c_i32p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), c_dp, c_dp]
         L.orc_chi_start_vector.restype = C.c_int64
         L.orc_chi_start_vector.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dp, C.c_int, C.c_int, C.c_int, c_dp, c_dp]
         L.orc_chi_chain.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_dp]
@@ -259,6 +268,81 @@ class Sector:
         return a, b
 
 
+class OrbsSector:
+    """build_Hv_sector for ed_total_ud = F (one (Nup, Ndw) per orbital): ed_buildh_orbs + spMatVec_orbs."""
+
+    def __init__(self, ora, nups, ndws):
+        self.ora = ora
+        self.norb = len(nups)
+        nu = (C.c_int * self.norb)(*nups)
+        nd = (C.c_int * self.norb)(*ndws)
+        self.isector = lib().orc_get_sector_orbs(ora.h, nu, nd)
+        self.s = lib().orc_build_hv_sector_orbs(ora.h, nu, nd)
+        dim = C.c_int64(0)
+        dims = (C.c_int64 * (2 * self.norb))()
+        lib().orc_sector_orbs_info(self.s, C.byref(dim), dims)
+        self.dim, self.dims = dim.value, list(dims)
+
+    def close(self):
+        if self.s:
+            lib().orc_delete_hv_sector_orbs(self.s)
+            self.s = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def factor(self, f):
+        """(map, rowptr, cols, vals) of factor f: up word of orbital f+1 for f < Norb, dw word of orbital f+1-Norb else."""
+        n = self.dims[f]
+        m = np.zeros(n, np.int32)
+        rp = np.zeros(n + 1, np.int64)
+        lib().orc_sector_orbs_get(self.s, f, m.ctypes.data_as(c_i32p), rp.ctypes.data_as(C.POINTER(C.c_int64)), None, None, None)
+        cols = np.zeros(max(int(rp[-1]), 1), np.int64)
+        vals = np.zeros(max(int(rp[-1]), 1))
+        lib().orc_sector_orbs_get(self.s, f, None, None, cols.ctypes.data_as(C.POINTER(C.c_int64)), _dp(vals), None)
+        return m, rp, cols[:rp[-1]], vals[:rp[-1]]
+
+    def h0d(self):
+        d = np.zeros(self.dim)
+        lib().orc_sector_orbs_get(self.s, 0, None, None, None, None, _dp(d))
+        return d
+
+    def spmatvec(self, v):
+        v = _f64(v)
+        hv = np.zeros(self.dim)
+        lib().orc_spmatvec_orbs(self.s, self.dim, _dp(v), _dp(hv))
+        return hv
+
+    def hmat(self):
+        h = np.zeros((self.dim, self.dim))
+        e = np.zeros(self.dim)
+        for j in range(self.dim):
+            e[:] = 0.0
+            e[j] = 1.0
+            h[:, j] = self.spmatvec(e)
+        return h
+
+    def lanc_eigh(self, v0=None, nitermax=512, threshold=1e-18, ncheck=10):
+        vect = np.zeros(self.dim) if v0 is None else _f64(v0).copy()
+        nit = min(self.dim, nitermax)
+        egs = C.c_double(0.0)
+        nl = C.c_int(0)
+        a = np.zeros(nit + 1)
+        b = np.zeros(nit + 1)
+        lib().orc_lanc_eigh_sector_orbs(self.s, C.byref(egs), _dp(vect), nit, threshold, ncheck, C.byref(nl), _dp(a), _dp(b))
+        return egs.value, vect, a[:nl.value].copy(), b[:nl.value].copy()
+
+    def lanc_tridiag(self, vin, nlanc, threshold=1e-12):
+        v = _f64(vin).copy()
+        a = np.zeros(nlanc)
+        b = np.zeros(nlanc)
+        lib().orc_lanc_tridiag_sector_orbs(self.s, _dp(v), _dp(a), _dp(b), nlanc, threshold)
+        return a, b
+
+
 class Oracle:
     """Holds the module-global inputs of the reference (orc_ctx)."""
 
@@ -292,6 +376,9 @@ class Oracle:
 
     def sector(self, nup, ndw, rank=0, nranks=1, sparse_h=True):
         return Sector(self, nup, ndw, rank, nranks, sparse_h)
+
+    def sector_orbs(self, nups, ndws):
+        return OrbsSector(self, nups, ndws)
 
     def vecdim(self, nup, ndw, rank, nranks):
         return lib().orc_vecdim_hv_sector(self.h, nup, ndw, rank, nranks)

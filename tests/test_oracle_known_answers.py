@@ -345,3 +345,43 @@ def test_chi_chains_known_answers():
     _, nm = o4.chi_start_vector(5, 5, g4, 1, 1, 2)
     _, nt = o4.chi_start_vector(5, 5, g4, 1, 0, 0)
     assert abs(nm - nt) < 1e-12 and nm > na and nm > nb            # n_1 + n_2 is the total for two orbitals
+
+
+def test_orbs_operator_known_answers():
+    """ed_total_ud = F restated from ed_buildh_orbs / spMatVec_orbs (ED_HAMILTONIAN_SPARSE_HxV.f90:206-370, 487-564,
+    stored/Orbs/*.f90), pinned on the independently checked ed_total_ud = T path: without inter-orbital hopping and with
+    Jx = Jp = 0 the total (Nup, Ndw) sector is block diagonal in the per-orbital occupations, so the union of the spectra
+    of all orbital-resolved sectors with the same totals IS the spectrum of the total sector (400 eigenvalues at
+    Norb = 2, Nbath = 2).  Plus: hermiticity, the sector numbering of get_Sector with QN = [Nups, Ndws], and the U = 0 /
+    Ust = Jh = 0 limit where the ground-state energy is the sum of the orbitals' single-band energies."""
+    cfg, o = make_oracle("ORB2")
+    nt, nso = cfg["nup"], cfg["nbath"] + 1
+    with o.sector(nt, nt) as s:
+        w = np.linalg.eigvalsh(s.hmat())
+    allw, secs = [], set()
+    for nu1 in range(nso + 1):
+        for nd1 in range(nso + 1):
+            nu2, nd2 = nt - nu1, nt - nd1
+            if not (0 <= nu2 <= nso and 0 <= nd2 <= nso):
+                continue
+            with o.sector_orbs([nu1, nu2], [nd1, nd2]) as so:
+                hm = so.hmat()
+                assert np.abs(hm - hm.T).max() < 1e-14
+                allw += list(np.linalg.eigvalsh(hm))
+                assert so.isector == 1 + nd2 + (nso + 1) * (nd1 + (nso + 1) * (nu2 + (nso + 1) * nu1))
+                secs.add(so.isector)
+                assert so.dim == int(np.prod(so.dims)) and so.dims[0] == O.lib().orc_binomial(nso, nu1)
+    assert len(allw) == len(w) and np.abs(np.sort(allw) - w).max() < 1e-12
+    # decoupled orbitals: E0(orbs sector) = E0(orbital 1 alone) + E0(orbital 2 alone)
+    kw = configs.solver_kwargs(cfg)
+    kw.update(ust=0.0, jh=0.0)
+    o2 = O.Oracle(**kw)
+    with o2.sector_orbs([1, 2], [2, 1]) as so:
+        e_pair = np.linalg.eigvalsh(so.hmat())[0]
+    e_sum = 0.0
+    for io, (nu, nd) in enumerate([(1, 2), (2, 1)]):
+        k1 = dict(norb=1, nbath=cfg["nbath"], nspin=1, uloc=(cfg["uloc"][io],), ust=0.0, jh=0.0, jx=0.0, jp=0.0, xmu=cfg["xmu"],
+                  hfmode=True, bath_e=np.asarray(cfg["bath_e"])[:, io:io + 1, :], bath_v=np.asarray(cfg["bath_v"])[:, io:io + 1, :])
+        with O.Oracle(**k1).sector(nu, nd) as s1:
+            e_sum += np.linalg.eigvalsh(s1.hmat())[0]
+    assert abs(e_pair - e_sum) < 1e-12
