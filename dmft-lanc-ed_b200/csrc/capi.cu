@@ -39,7 +39,8 @@ static int load_params(edgpu_ctx *c, const edgpu_params *p) {
   if (!p) return edgpu_set_err(EDGPU_ERR_INVALID, "params == NULL");
   if (p->norb < 1 || p->norb > EDGPU_MAX_ORB) return edgpu_set_err(EDGPU_ERR_INVALID, "NORB out of range");
   if (p->nspin < 1 || p->nspin > 2) return edgpu_set_err(EDGPU_ERR_INVALID, "NSPIN out of range");
-  if (p->nph != 0) return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "DimPh > 1 (NPH /= 0) is outside the hot path");
+  if (p->nph < 0 || p->nph > 1000) return edgpu_set_err(EDGPU_ERR_INVALID, "NPH out of range");
+  if (p->nph > 0 && !p->ed_total_ud) return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "phonons with ed_total_ud = F are not built");
   if (!p->ed_total_ud && p->norb > 1 && (p->jx != 0.0 || p->jp != 0.0))     // ED_SETUP.f90:69-71
     return edgpu_set_err(EDGPU_ERR_INVALID, "ed_total_ud = F can not be used with Jx != 0 or Jp != 0");
   int ns = (p->nbath + 1) * p->norb;                        // ED_SETUP.f90:113-116, bath_type normal
@@ -47,6 +48,7 @@ static int load_params(edgpu_ctx *c, const edgpu_params *p) {
   if (!p->bath_e || !p->bath_v) return edgpu_set_err(EDGPU_ERR_INVALID, "bath arrays == NULL");
   c->hp = *p;
   c->ns = ns;
+  c->dimph = p->nph + 1;
   size_t nh = (size_t)p->nspin * p->nspin * p->norb * p->norb, nb = (size_t)p->nspin * p->norb * p->nbath;
   c->h_hloc.assign(nh, 0.0);
   if (p->imphloc) memcpy(c->h_hloc.data(), p->imphloc, nh * sizeof(double));
@@ -191,7 +193,7 @@ extern "C" int edgpu_vecdim_hv_sector(const edgpu_ctx *c, int isector, int64_t *
   TRY(edgpu_get_nup_ndw(c, isector, &nup, &ndw));
   int64_t q;
   edgpu_split(binom64(c, c->ns, ndw), c->nranks, c->rank, &q, nullptr);
-  *vecdim = binom64(c, c->ns, nup) * q;                     // DimUp*mpiQdw*DimPh
+  *vecdim = binom64(c, c->ns, nup) * q * c->dimph;          // DimUp*mpiQdw*DimPh
   return EDGPU_OK;
 }
 
@@ -355,39 +357,40 @@ extern "C" int edgpu_build_hv_sector(edgpu_ctx *c, int isector) {
                          (long long)c->dimdw, c->nranks);
   edgpu_split(c->dimdw, c->nranks, c->rank, &c->qdw, &c->coloff);
   edgpu_split(c->dimup, c->nranks, c->rank, &c->qup, &c->rowoff);
-  c->nloc = c->dimup * c->qdw;
+  c->nel = c->dimup * c->qdw;
+  c->nloc = c->nel * c->dimph;
   const bool stored = c->hp.ed_sparse_h != 0;
   c->hstatus = true;
   int rc = build_factor(c, c->up, 0, nup, stored);
   if (!rc) rc = build_factor(c, c->dw, 1, ndw, stored);
   if (rc) { edgpu_delete_hv_sector(c); return rc; }
   if (stored) {
-    CK(cudaMalloc(&c->d_diag, (size_t)c->nloc * sizeof(double)));
+    CK(cudaMalloc(&c->d_diag, (size_t)c->nel * sizeof(double)));
     dim3 grid((unsigned)((c->dimup + 255) / 256), (unsigned)(c->qdw < 32768 ? c->qdw : 32768));
     k_diag_stored<<<grid, 256, 0, c->stream>>>(c->dp, c->up.d_map, c->dw.d_map, c->dimup, c->coloff, c->qdw, c->d_diag);
     CKL(c);
   }
   if (c->dp.jhflag) {
     int64_t *d_counts = nullptr;
-    CK(cudaMalloc(&d_counts, (size_t)(c->nloc + 1) * sizeof(int64_t)));
-    CK(cudaMemsetAsync(d_counts, 0, (size_t)(c->nloc + 1) * sizeof(int64_t), c->stream));
-    if (c->nloc + 1 > (int64_t)0x7fffffff * 128)
-      return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "spH0nd: local dimension %lld exceeds the builder's grid", (long long)c->nloc);
-    const unsigned blocks = (unsigned)((c->nloc + 127) / 128);
-    k_nd_count<<<blocks, 128, 0, c->stream>>>(c->dp, c->up.d_map, c->dw.d_map, c->dimup, c->coloff, c->nloc, d_counts);
+    CK(cudaMalloc(&d_counts, (size_t)(c->nel + 1) * sizeof(int64_t)));
+    CK(cudaMemsetAsync(d_counts, 0, (size_t)(c->nel + 1) * sizeof(int64_t), c->stream));
+    if (c->nel + 1 > (int64_t)0x7fffffff * 128)
+      return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "spH0nd: local dimension %lld exceeds the builder's grid", (long long)c->nel);
+    const unsigned blocks = (unsigned)((c->nel + 127) / 128);
+    k_nd_count<<<blocks, 128, 0, c->stream>>>(c->dp, c->up.d_map, c->dw.d_map, c->dimup, c->coloff, c->nel, d_counts);
     CKL(c);
-    CK(cudaMalloc(&c->d_nd_rowptr, (size_t)(c->nloc + 1) * sizeof(int64_t)));
+    CK(cudaMalloc(&c->d_nd_rowptr, (size_t)(c->nel + 1) * sizeof(int64_t)));
     size_t tmp_bytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_counts, c->d_nd_rowptr, (int64_t)(c->nloc + 1), c->stream);
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_counts, c->d_nd_rowptr, (int64_t)(c->nel + 1), c->stream);
     void *d_tmp = nullptr;
     CK(cudaMalloc(&d_tmp, tmp_bytes));
-    cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_counts, c->d_nd_rowptr, (int64_t)(c->nloc + 1), c->stream);
+    cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_counts, c->d_nd_rowptr, (int64_t)(c->nel + 1), c->stream);
     c->launches++;
-    CK(cudaMemcpyAsync(&c->nd_nnz, c->d_nd_rowptr + c->nloc, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(&c->nd_nnz, c->d_nd_rowptr + c->nel, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaMalloc(&c->d_nd_cols, (size_t)(c->nd_nnz > 0 ? c->nd_nnz : 1) * sizeof(int64_t)));
     CK(cudaMalloc(&c->d_nd_vals, (size_t)(c->nd_nnz > 0 ? c->nd_nnz : 1) * sizeof(double)));
-    k_nd_fill<<<blocks, 128, 0, c->stream>>>(c->dp, c->up.d_map, c->dw.d_map, c->dimup, c->dimdw, c->coloff, c->nloc,
+    k_nd_fill<<<blocks, 128, 0, c->stream>>>(c->dp, c->up.d_map, c->dw.d_map, c->dimup, c->dimdw, c->coloff, c->nel,
                                              c->d_nd_rowptr, c->d_nd_cols, c->d_nd_vals);
     CKL(c);
     CK(cudaStreamSynchronize(c->stream));
@@ -504,10 +507,10 @@ extern "C" int edgpu_get_csr(const edgpu_ctx *c, int which, int64_t *nrow, int64
   if (!c || !c->hstatus) return edgpu_set_err(EDGPU_ERR_INVALID, "no live sector");
   if (c->orbs) return edgpu_set_err(EDGPU_ERR_INVALID, "ed_total_ud = F: use edgpu_get_orbs_factor");
   if (which == 2) {
-    if (nrow) *nrow = c->dp.jhflag ? c->nloc : 0;
+    if (nrow) *nrow = c->dp.jhflag ? c->nel : 0;
     if (nnz) *nnz = c->nd_nnz;
     if (!rowptr || !c->dp.jhflag) return EDGPU_OK;
-    CK(cudaMemcpy(rowptr, c->d_nd_rowptr, (size_t)(c->nloc + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(rowptr, c->d_nd_rowptr, (size_t)(c->nel + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(cols, c->d_nd_cols, (size_t)c->nd_nnz * sizeof(int64_t), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(vals, c->d_nd_vals, (size_t)c->nd_nnz * sizeof(double), cudaMemcpyDeviceToHost));
     return EDGPU_OK;
@@ -538,7 +541,7 @@ __global__ void k_diag_direct(DevParams P, const int32_t *__restrict__ map_up, c
 extern "C" int edgpu_get_diag(const edgpu_ctx *cc, double *out, int64_t nloc) {
   edgpu_ctx *c = const_cast<edgpu_ctx *>(cc);
   if (!c || !c->hstatus) return edgpu_set_err(EDGPU_ERR_INVALID, "no live sector");
-  if (nloc != c->nloc) return edgpu_set_err(EDGPU_ERR_INVALID, "nloc mismatch");
+  if (nloc != c->nel) return edgpu_set_err(EDGPU_ERR_INVALID, "get_diag: nloc is the electron part DimUp*mpiQdw");
   if (c->d_diag) {
     CK(cudaMemcpy(out, c->d_diag, (size_t)nloc * sizeof(double), cudaMemcpyDeviceToHost));
     return EDGPU_OK;

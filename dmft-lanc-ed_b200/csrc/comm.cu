@@ -284,8 +284,8 @@ extern "C" void edgpu_transpose_plan(int64_t dimup, int64_t dimdw, int nranks, i
 // V(DimUp, qdw) -> Vt(DimDw, qup): block (me -> d) = V[rows(d), :] transposed
 int comm_transpose_fwd(edgpu_ctx *c, const double *d_x, double *d_vt) {
   const int P = c->nranks;
-  TRY(ensure(&c->d_send, c->nloc > c->dimdw * c->qup ? c->nloc : c->dimdw * c->qup));
-  TRY(ensure(&c->d_recv, c->nloc > c->dimdw * c->qup ? c->nloc : c->dimdw * c->qup));
+  TRY(ensure(&c->d_send, c->nel > c->dimdw * c->qup ? c->nel : c->dimdw * c->qup));
+  TRY(ensure(&c->d_recv, c->nel > c->dimdw * c->qup ? c->nel : c->dimdw * c->qup));
   int64_t soff[64] = {0}, scnt[64] = {0}, roff[64] = {0}, rcnt[64] = {0};
   edgpu_transpose_plan(c->dimup, c->dimdw, P, c->rank, 0, soff, scnt, roff, rcnt);
   for (int p = 0; p < P; p++) {
@@ -345,10 +345,10 @@ int comm_allgather(edgpu_ctx *c, const double *d_x, double *d_full) {
     int64_t qc, co;
     edgpu_split(c->dimdw, P, p, &qc, &co);
     if (p == me) continue;
-    NK(g_nccl.Send(d_x, (size_t)c->nloc, ncclDouble, p, (ncclComm_t)c->comm, c->stream));
+    NK(g_nccl.Send(d_x, (size_t)c->nel, ncclDouble, p, (ncclComm_t)c->comm, c->stream));
     NK(g_nccl.Recv(d_full + co * c->dimup, (size_t)(qc * c->dimup), ncclDouble, p, (ncclComm_t)c->comm, c->stream));
   }
   NK(g_nccl.GroupEnd());
-  CK(cudaMemcpyAsync(d_full + c->coloff * c->dimup, d_x, (size_t)c->nloc * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  CK(cudaMemcpyAsync(d_full + c->coloff * c->dimup, d_x, (size_t)c->nel * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
   return EDGPU_OK;
 }

@@ -67,7 +67,9 @@ struct edgpu_ctx {
   bool hstatus = false;
   int isector = 0, nup = 0, ndw = 0;
   int64_t dimup = 0, dimdw = 0;
-  int64_t qdw = 0, coloff = 0, nloc = 0;      // dw split (columns owned)
+  int64_t qdw = 0, coloff = 0, nloc = 0;      // dw split (columns owned); nloc = vecDim_Hv_sector = nel * dimph
+  int64_t nel = 0;                            // electron part of the local vector: DimUp * mpiQdw
+  int dimph = 1;                              // DimPh = Nph + 1 phonon slabs (phonon index slowest, ED_SETUP.f90:133)
   int64_t qup = 0, rowoff = 0;                // up split used by the transposed layout
   Factor up, dw;
   double *d_diag = nullptr;                   // spH0d (stored mode), nloc values

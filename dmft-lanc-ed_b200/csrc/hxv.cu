@@ -162,13 +162,46 @@ static int pick_col(edgpu_ctx *c) {
 }
 
 bool hxv_fast_path(edgpu_ctx *c, const double *d_x) {
-  if (c->orbs || c->dp.jhflag || c->opt_no_fuse) return false;
+  if (c->orbs || c->dimph > 1 || c->dp.jhflag || c->opt_no_fuse) return false;
   if (c->nranks == 1) return pick_local(c) == EDGPU_ALGO_FAST && fast_supported_local(c);
   return (c->algo == EDGPU_ALGO_AUTO || c->algo == EDGPU_ALGO_FAST) && fast_peer_ready(c) && fast_supported_local(c);
 }
 
+// Phonon slabs (DimPh > 1): y(:, iph) += w0 iph x(:, iph) + E(i_el) [sqrt(iph+1) x(:, iph+1) + sqrt(iph) x(:, iph-1)] with
+// E = sum_orb g_orb (n_up + n_dw - 1): spH0_ph, spH0e_eph x spH0ph_eph (stored/H_ph.f90, H_e_ph.f90;
+// ED_HAMILTONIAN_SPARSE_HxV.f90:445-468), elementwise on top of the electronic H*v of every slab.
+struct PhArgs { double g[EDGPU_MAX_ORB]; double w0; int norb, dimph; };
+__global__ void k_phonon(PhArgs P, const int32_t *__restrict__ map_up, const int32_t *__restrict__ map_dw, int64_t dimup,
+                         int64_t coloff, int64_t nel, const double *__restrict__ x, double *__restrict__ y) {
+  for (int64_t ie = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; ie < nel; ie += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t mu = (uint32_t)map_up[ie % dimup], md = (uint32_t)map_dw[coloff + ie / dimup];
+    double e = 0.0;
+    for (int o = 0; o < P.norb; o++) e = e + P.g[o] * ((double)(((mu >> o) & 1u) + ((md >> o) & 1u)) - 1.0);
+    for (int iph = 0; iph < P.dimph; iph++) {
+      const int64_t i = ie + (int64_t)iph * nel;
+      double acc = y[i] + (P.w0 * (double)iph) * x[i];
+      if (iph + 1 < P.dimph) acc = acc + (e * sqrt((double)(iph + 1))) * x[i + nel];
+      if (iph > 0) acc = acc + (e * sqrt((double)iph)) * x[i - nel];
+      y[i] = acc;
+    }
+  }
+}
+static int hxv_apply_el(edgpu_ctx *c, const double *d_x, double *d_y);
 int hxv_apply(edgpu_ctx *c, const double *d_x, double *d_y) {
   if (c->orbs) return orbs_apply(c, d_x, d_y);                     // ed_total_ud = F (spMatVec_orbs)
+  if (c->dimph == 1) return hxv_apply_el(c, d_x, d_y);
+  for (int iph = 0; iph < c->dimph; iph++) TRY(hxv_apply_el(c, d_x + (int64_t)iph * c->nel, d_y + (int64_t)iph * c->nel));
+  PhArgs P{};
+  for (int o = 0; o < EDGPU_MAX_ORB; o++) P.g[o] = c->hp.g_ph[o];
+  P.w0 = c->hp.w0_ph; P.norb = c->dp.norb; P.dimph = c->dimph;
+  prof_mark(c, "k_phonon");
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((c->nel + 255) / 256, (int64_t)c->sm_count * 8));
+  k_phonon<<<grid, 256, 0, c->stream>>>(P, c->up.d_map, c->dw.d_map, c->dimup, c->coloff, c->nel, d_x, d_y);
+  CKL(c);
+  return EDGPU_OK;
+}
+// the electronic operator on ONE phonon slab (the whole vector when DimPh = 1)
+static int hxv_apply_el(edgpu_ctx *c, const double *d_x, double *d_y) {
   if (c->nranks == 1) {
     const int algo = pick_local(c);
     if (algo == EDGPU_ALGO_FAST) {

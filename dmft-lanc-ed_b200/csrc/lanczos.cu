@@ -497,7 +497,7 @@ extern "C" int edgpu_diag_sectors(edgpu_ctx *c, int nsectors, const int *isector
     if (nlanc) nlanc[s] = nl;
     if (!rc && (ibest < 0 || e0[s] < e0[ibest])) {
       ibest = s;
-      if (c->hp.ed_total_ud) rc = edgpu_gf_set_state_from_eigh(c);   // (no chains / observables for ed_total_ud = F)
+      if (c->hp.ed_total_ud && c->dimph == 1) rc = edgpu_gf_set_state_from_eigh(c);   // (no chains / observables for ed_total_ud = F or DimPh > 1)
     }
     edgpu_delete_hv_sector(c);
     if (rc) return rc;
@@ -574,6 +574,7 @@ extern "C" int edgpu_dev_dot(edgpu_ctx *c, int64_t nloc, const double *d_a, cons
 extern "C" int edgpu_gf_set_state(edgpu_ctx *c, int isector, const double *gs, int64_t nloc, double e0) {
   if (!c) return edgpu_set_err(EDGPU_ERR_INVALID, "ctx == NULL");
   if (!c->hp.ed_total_ud) return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "ed_total_ud = F: the chains / observables of an orbital-resolved state are not built");
+  if (c->dimph > 1) return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "DimPh > 1: the chains / observables of an electron-phonon state are not built");
   CK(cudaSetDevice(c->device));
   int nup, ndw;
   TRY(edgpu_get_nup_ndw(c, isector, &nup, &ndw));
@@ -593,6 +594,7 @@ extern "C" int edgpu_gf_set_state(edgpu_ctx *c, int isector, const double *gs, i
 // (ED_EIGENSPACE.f90:502-572): every rank keeps its own shard.
 extern "C" int edgpu_gf_set_state_from_eigh(edgpu_ctx *c) {
   if (!c || !c->hstatus) return edgpu_set_err(EDGPU_ERR_INVALID, "gf_set_state_from_eigh: Hsector NOT set");
+  if (c->orbs || c->dimph > 1) return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "chains / observables of an orbital-resolved or electron-phonon state are not built");
   if (!c->lv_valid || !c->d_lv) return edgpu_set_err(EDGPU_ERR_INVALID, "gf_set_state_from_eigh: no eigenvector of this sector on the device (call edgpu_sp_lanc_eigh first)");
   CK(cudaSetDevice(c->device));
   cudaFree(c->d_gs); c->d_gs = nullptr;

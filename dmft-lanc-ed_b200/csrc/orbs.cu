@@ -191,7 +191,7 @@ int orbs_build(edgpu_ctx *c, int isector) {
   c->dimup = 1; c->dimdw = 1;
   for (int f = 0; f < norb; f++) { c->dimup *= p->dims[f]; c->dimdw *= p->dims[f + norb]; }
   c->qdw = c->dimdw; c->coloff = 0; c->qup = c->dimup; c->rowoff = 0;
-  c->nloc = dim;
+  c->nloc = dim; c->nel = dim;
   if (c->hp.ed_sparse_h) {
     CK(cudaMalloc(&p->d_diag, (size_t)std::max<int64_t>(dim, 1) * sizeof(double)));
     OrbsArgs a{};

@@ -68,7 +68,7 @@ class Params(C.Structure):
                 ("ed_sparse_h", C.c_int32), ("nph", C.c_int32), ("ed_total_ud", C.c_int32),
                 ("reserved", C.c_int32), ("uloc", C.c_double * 5), ("ust", C.c_double), ("jh", C.c_double),
                 ("jx", C.c_double), ("jp", C.c_double), ("xmu", C.c_double),
-                ("imphloc", c_dp), ("bath_e", c_dp), ("bath_v", c_dp)]
+                ("imphloc", c_dp), ("bath_e", c_dp), ("bath_v", c_dp), ("g_ph", C.c_double * 5), ("w0_ph", C.c_double)]
 
 
 def lib():
@@ -194,9 +194,10 @@ class Solver:
     """Module-global ED state + the live sector (ED_VARS_GLOBAL / ED_HAMILTONIAN_COMMON)."""
 
     def __init__(self, norb, nbath, nspin=1, uloc=(2.0,), ust=0.0, jh=0.0, jx=0.0, jp=0.0, xmu=0.0, hfmode=True,
-                 imphloc=None, bath_e=None, bath_v=None, ed_sparse_h=True, device=-1, ed_total_ud=True):
+                 imphloc=None, bath_e=None, bath_v=None, ed_sparse_h=True, device=-1, ed_total_ud=True, nph=0, g_ph=(), w0_ph=0.0):
         self.norb, self.nbath, self.nspin = norb, nbath, nspin
         self.ed_total_ud = bool(ed_total_ud)
+        self.nph, self.g_ph, self.w0_ph = int(nph), tuple(g_ph), float(w0_ph)
         self.ns = (nbath + 1) * norb
         if bath_e is None or bath_v is None:
             bath_e, bath_v = configs.init_dmft_bath(norb, nbath, nspin)
@@ -209,7 +210,10 @@ class Solver:
     def _pack(self, uloc, ust, jh, jx, jp, xmu, hfmode, imphloc, bath_e, bath_v, ed_sparse_h):
         p = Params()
         p.norb, p.nbath, p.nspin = self.norb, self.nbath, self.nspin
-        p.hfmode, p.ed_sparse_h, p.nph, p.ed_total_ud = int(bool(hfmode)), int(bool(ed_sparse_h)), 0, int(getattr(self, "ed_total_ud", True))
+        p.hfmode, p.ed_sparse_h, p.nph, p.ed_total_ud = int(bool(hfmode)), int(bool(ed_sparse_h)), int(getattr(self, "nph", 0)), int(getattr(self, "ed_total_ud", True))
+        for i, g in enumerate(getattr(self, "g_ph", ())):
+            p.g_ph[i] = float(g)
+        p.w0_ph = float(getattr(self, "w0_ph", 0.0))
         for i in range(5):
             p.uloc[i] = float(uloc[i]) if i < len(uloc) else 0.0
         p.ust, p.jh, p.jx, p.jp, p.xmu = ust, jh, jx, jp, xmu

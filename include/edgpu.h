@@ -50,14 +50,16 @@ typedef struct edgpu_params {
   int32_t norb, nbath, nspin;          /* NORB, NBATH, NSPIN; Ns = (Nbath+1)*Norb */
   int32_t hfmode;                      /* HFMODE */
   int32_t ed_sparse_h;                 /* ED_SPARSE_H: 1 = stored (spMatVec_*), 0 = direct */
-  int32_t nph;                         /* NPH, must be 0 (DimPh = 1) */
-  int32_t ed_total_ud;                 /* must be 1 */
+  int32_t nph;                         /* NPH: DimPh = NPH + 1 phonon states (0: no phonons) */
+  int32_t ed_total_ud;                 /* ED_TOTAL_UD: 1 = total (Nup, Ndw) sectors, 0 = one pair per orbital */
   int32_t reserved;
   double  uloc[EDGPU_MAX_ORB];         /* ULOC */
   double  ust, jh, jx, jp, xmu;        /* UST, JH, JX, JP, XMU */
   const double *imphloc;               /* impHloc(Nspin,Nspin,Norb,Norb), may be NULL (=0) */
   const double *bath_e;                /* dmft_bath%e(Nspin,Norb,Nbath) */
   const double *bath_v;                /* dmft_bath%v(Nspin,Norb,Nbath) */
+  double  g_ph[EDGPU_MAX_ORB];         /* G_PH: electron-phonon couplings (NPH > 0) */
+  double  w0_ph;                       /* W0_PH: phonon frequency */
 } edgpu_params;
 
 typedef struct edgpu_ctx edgpu_ctx;    /* opaque: one per process, mirrors the module state */

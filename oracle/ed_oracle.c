@@ -1313,6 +1313,69 @@ void orc_lanc_build_gf_normal_main(const orc_ctx *c, int nup, int ndw, const dou
 }
 
 /* ===================================================================================== */
+/* DimPh > 1: one local phonon mode (stored/H_ph.f90, H_e_ph.f90; spMatVec_main :391-485)  */
+/* ===================================================================================== */
+/* v(i_el, iph), i = i_el + (iph-1)*DimUp*DimDw, iph = 1..DimPh = Nph+1.  Term order of spMatVec_main: diagonal for every
+ * element; then per phonon slab: dw hops, up hops, phonon energy w0*(iph-1), electron-phonon coupling
+ * [sum_orb g_orb (n_up + n_dw - 1)] * (b + b^+) with the entries of spH0ph_eph in insertion order (destruction first:
+ * column iph+1 with sqrt(iph), then construction: column iph-1 with sqrt(iph-1)); non-local terms last.  Serial. */
+void orc_spmatvec_main_ph(const orc_sector *s, int nph, const double *g_ph, double w0_ph, int64_t nloc, const double *v, double *hv) {
+  const int64_t du = s->dimup, dd = s->dimdw, nel = du * dd;
+  const int dimph = nph + 1;
+  const orc_ctx *c = s->ctx;
+  if (nloc != nel * dimph) { fprintf(stderr, "spMatVec_main: Nloc != dim*DimPh\n"); abort(); }
+  /* spH0e_eph, stored/H_e_ph.f90:1-26 */
+  double *eeph = (double *)xmalloc((size_t)nel * sizeof(double));
+  for (int64_t i = 0; i < nel; i++) {
+    int nu[64], nd[64];
+    bdecomp(s->map_up[i % du], c->ns, nu);
+    bdecomp(s->map_dw[i / du], c->ns, nd);
+    double htmp = 0.0;
+    for (int io = 0; io < c->norb; io++) htmp = htmp + g_ph[io] * ((double)(nu[io] + nd[io]) - 1.0);
+    eeph[i] = htmp;
+  }
+  for (int64_t i = 0; i < nloc; i++) hv[i] = 0.0;
+  for (int64_t i = 0; i < nloc; i++) hv[i] = hv[i] + s->h0d[i % nel] * v[i];
+  for (int iph = 0; iph < dimph; iph++) {
+    const int64_t off = (int64_t)iph * nel;
+    for (int64_t iup = 0; iup < du; iup++)
+      for (int64_t idw = 0; idw < dd; idw++) {
+        int64_t i = iup + idw * du + off;
+        for (int64_t jj = s->hdw.rowptr[idw]; jj < s->hdw.rowptr[idw + 1]; jj++)
+          hv[i] = hv[i] + s->hdw.vals[jj] * v[iup + s->hdw.cols[jj] * du + off];
+      }
+    for (int64_t idw = 0; idw < dd; idw++)
+      for (int64_t iup = 0; iup < du; iup++) {
+        int64_t i = iup + idw * du + off;
+        for (int64_t jj = s->hup.rowptr[iup]; jj < s->hup.rowptr[iup + 1]; jj++)
+          hv[i] = hv[i] + s->hup.vals[jj] * v[s->hup.cols[jj] + idw * du + off];
+      }
+    if (dimph > 1)
+      for (int64_t ie = 0; ie < nel; ie++) {
+        int64_t i = ie + off;
+        hv[i] = hv[i] + (w0_ph * (double)iph) * v[i];                                   /* spH0_ph, H_ph.f90 */
+        if (iph + 1 < dimph) hv[i] = hv[i] + (eeph[ie] * sqrt((double)(iph + 1))) * v[ie + off + nel];   /* b   */
+        if (iph > 0) hv[i] = hv[i] + (eeph[ie] * sqrt((double)iph)) * v[ie + off - nel];                 /* b^+ */
+      }
+  }
+  if (c->jhflag)
+    for (int64_t i = 0; i < nloc; i++)
+      for (int64_t jj = s->hnd.rowptr[i % nel]; jj < s->hnd.rowptr[i % nel + 1]; jj++)
+        hv[i] = hv[i] + s->hnd.vals[jj] * v[s->hnd.cols[jj] + (i / nel) * nel];
+  free(eeph);
+}
+typedef struct { const orc_sector *s; int nph; const double *g; double w0; } ph_mv;
+static void ph_matvec(void *u, int64_t n, const double *v, double *hv) {
+  ph_mv *m = (ph_mv *)u;
+  orc_spmatvec_main_ph(m->s, m->nph, m->g, m->w0, n, v, hv);
+}
+int orc_lanc_eigh_sector_ph(const orc_sector *s, int nph, const double *g_ph, double w0_ph, double *egs, double *vect,
+                            int nitermax, double threshold, int ncheck, int *nlanc_out, double *alanc_out, double *blanc_out) {
+  ph_mv m = { s, nph, g_ph, w0_ph };
+  return orc_sp_lanc_eigh(ph_matvec, &m, s->dim * (nph + 1), egs, vect, nitermax, threshold, ncheck, nlanc_out, alanc_out, blanc_out);
+}
+
+/* ===================================================================================== */
 /* ed_total_ud = F: one (Nup, Ndw) pair per orbital (Ns_Ud = Norb, Ns_Orb = 1 + Nbath)    */
 /* ===================================================================================== */
 /* get_Sector, ED_SETUP.f90:446-457 with QN = [Nups, Ndws] and N = Ns_Orb */

@@ -160,6 +160,11 @@ void orc_sigma_normal(const orc_ctx *c, int iorb, int ispin, const double *z, in
                       const double *g, double *sigma, double *invg0);
 void orc_allocate_grids(double beta, int lmats, double wini, double wfin, int lreal,
                         double *wm, double *wr);
+/* ---- DimPh = Nph + 1 > 1: one local phonon mode (stored/H_ph.f90, H_e_ph.f90; spMatVec_main :391-485).  v(i_el, iph),
+ * phonon index slowest.  s: the electron sector (serial, stored diagonal). */
+void orc_spmatvec_main_ph(const orc_sector *s, int nph, const double *g_ph, double w0_ph, int64_t nloc, const double *v, double *hv);
+int orc_lanc_eigh_sector_ph(const orc_sector *s, int nph, const double *g_ph, double w0_ph, double *egs, double *vect,
+                            int nitermax, double threshold, int ncheck, int *nlanc_out, double *alanc_out, double *blanc_out);
 /* ---- ed_total_ud = F (Ns_Ud = Norb): ed_buildh_orbs / spMatVec_orbs, ED_HAMILTONIAN_SPARSE_HxV.f90:206-370, 487-564,
  * with ED_HAMILTONIAN/stored/Orbs/H_local.f90, H_up.f90, H_dw.f90.  Factor f < Norb: up word of orbital f+1, else the
  * dw word of orbital f+1-Norb; the vector index runs over [DimUps, DimDws] with the first factor fastest

@@ -109,6 +109,9 @@ def lib():
         L.orc_observables_normal.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dp, C.c_double, C.POINTER(Observables)]
         L.orc_sigma_normal.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dp, C.c_int, c_dp, c_dp, c_dp]
         L.orc_allocate_grids.argtypes = [C.c_double, C.c_int, C.c_double, C.c_double, C.c_int, c_dp, c_dp]
+        L.orc_spmatvec_main_ph.argtypes = [C.POINTER(_Sector), C.c_int, c_dp, C.c_double, C.c_int64, c_dp, c_dp]
+        L.orc_lanc_eigh_sector_ph.argtypes = [C.POINTER(_Sector), C.c_int, c_dp, C.c_double, c_dp, c_dp, C.c_int, C.c_double, C.c_int,
+                                              c_ip, c_dp, c_dp]
         L.orc_get_sector_orbs.argtypes = [C.c_void_p, c_ip, c_ip]
         L.orc_build_hv_sector_orbs.restype = C.c_void_p
         L.orc_build_hv_sector_orbs.argtypes = [C.c_void_p, c_ip, c_ip]
@@ -240,6 +243,26 @@ class Sector:
         rc = lib().orc_spmatvec_block_cols(self.p, colidx.ctypes.data_as(C.POINTER(C.c_int64)), colidx.size, _dp(x), _dp(hv))
         assert rc == 0
         return hv
+
+    def spmatvec_ph(self, v, nph, g_ph, w0_ph):
+        """spMatVec_main with DimPh = nph + 1 phonon slabs (v of length dim*(nph+1), phonon index slowest)."""
+        v = _f64(v)
+        g = _f64(list(g_ph) + [0.0] * (5 - len(g_ph)))
+        hv = np.zeros(self.dim * (nph + 1))
+        lib().orc_spmatvec_main_ph(self.p, nph, _dp(g), C.c_double(w0_ph), v.size, _dp(v), _dp(hv))
+        return hv
+
+    def lanc_eigh_ph(self, nph, g_ph, w0_ph, v0, nitermax=512, threshold=1e-18, ncheck=10):
+        vect = _f64(v0).copy()
+        g = _f64(list(g_ph) + [0.0] * (5 - len(g_ph)))
+        nit = min(vect.size, nitermax)
+        egs = C.c_double(0.0)
+        nl = C.c_int(0)
+        a = np.zeros(nit + 1)
+        b = np.zeros(nit + 1)
+        lib().orc_lanc_eigh_sector_ph(self.p, nph, _dp(g), C.c_double(w0_ph), C.byref(egs), _dp(vect), nit, threshold, ncheck,
+                                      C.byref(nl), _dp(a), _dp(b))
+        return egs.value, vect, a[:nl.value].copy(), b[:nl.value].copy()
 
     def directmatvec(self, v):
         v = _f64(v)

@@ -111,6 +111,32 @@ def main():
                     check("chi norm2", abs(r["norm2"] - rc_["norm2"]) < 1e-12)
                     check("chi a", r["nlanc"] == rc_["nlanc"] and np.abs(r["alanc"][:m] - rc_["alanc"][:m]).max() < 1e-8)
         s.close()
+    # one phonon mode on shards: every rank holds DimPh slabs of its own i_dw columns (v(i + (iph-1)*DimUp*mpiQdw))
+    for name, sec, nph in [("NS10", (5, 5), 2)]:
+        cfg = configs.config(name)
+        kw = configs.solver_kwargs(cfg)
+        o = O.Oracle(**kw)
+        s = edgpu.Solver(nph=nph, g_ph=(0.4,), w0_ph=0.6, device=local, **kw)
+        s.set_comm(rank, world, fresh_uid())
+        with o.sector(*sec) as full, o.sector(sec[0], sec[1], rank, world) as mine:
+            n = full.dim * (nph + 1)
+            v = configs.bench_vector(n)
+            v /= np.linalg.norm(v)
+            ref = full.spmatvec_ph(v, nph, (0.4,), 0.6)
+            s.build_Hv_sector(s.get_sector(*sec))
+            check("ph nloc", s.nloc == mine.nloc * (nph + 1))
+            loc = np.concatenate([v[k * full.dim + mine.ishift:k * full.dim + mine.ishift + mine.nloc] for k in range(nph + 1)])
+            rloc = np.concatenate([ref[k * full.dim + mine.ishift:k * full.dim + mine.ishift + mine.nloc] for k in range(nph + 1)])
+            hv = s.spHtimesV(loc)
+            err = np.abs(hv - rloc).max() / np.abs(ref).max()
+            check("ph hxv", err < 1e-13, "err %.3e" % err)
+            v0 = np.ones(n) / np.sqrt(n)
+            e_ref = full.lanc_eigh_ph(nph, (0.4,), 0.6, v0)[0]
+            l0 = np.concatenate([v0[k * full.dim + mine.ishift:k * full.dim + mine.ishift + mine.nloc] for k in range(nph + 1)])
+            e0 = s.sp_lanc_eigh(l0)[0]
+            check("ph E0", abs(e0 - e_ref) < 1e-12 * abs(e_ref), "%.15g vs %.15g" % (e0, e_ref))
+            s.delete_Hv_sector()
+        s.close()
     t = torch.tensor([len(fails)], device="cuda")
     dist.all_reduce(t)
     for f in fails:

@@ -740,3 +740,40 @@ def test_orbs_sector_scan_finds_the_total_ground_state():
             s.gf_chains([(1, 1, 1)])                             # chains of an orbital-resolved state: refused, not faked
     finally:
         s.close()
+
+
+@pytest.mark.parametrize("name,sec,nph,sparse", [("NS6", (3, 3), 3, True), ("C1", (4, 4), 2, False), ("NS10V", (5, 4), 4, True),
+                                                 ("C4", (5, 5), 1, True)])
+def test_phonon_operator_matches_oracle(name, sec, nph, sparse):
+    """DimPh = Nph + 1 > 1 (one local phonon mode, stored/H_ph.f90 + H_e_ph.f90): the sector vector is v(i_el, iph) with
+    the phonon index slowest; the electronic H*v runs on every slab (the fast two-pass path where it applies), the
+    phonon energy and the electron-phonon coupling ride on top.  H*v to 1e-13, E0 to 1e-12 and the Lanczos coefficients
+    to 1e-8 against the oracle's spMatVec_main with phonons (ED_HAMILTONIAN_SPARSE_HxV.f90:391-485)."""
+    cfg, o = make_oracle(name)
+    g = tuple(0.3 + 0.2 * k for k in range(cfg["norb"]))
+    w0 = 0.5
+    s = edgpu.Solver(ed_sparse_h=sparse, nph=nph, g_ph=g, w0_ph=w0, **configs.solver_kwargs(cfg))
+    try:
+        with o.sector(*sec) as so:
+            isec = s.get_sector(*sec)
+            n = so.dim * (nph + 1)
+            assert s.vecDim_Hv_sector(isec) == n
+            s.build_Hv_sector(isec)
+            assert s.nloc == n
+            v = configs.bench_vector(n)
+            v /= np.linalg.norm(v)
+            ref = so.spmatvec_ph(v, nph, g, w0)
+            hv = s.spHtimesV(v)
+            assert np.abs(hv - ref).max() <= 1e-13 * np.abs(ref).max()
+            v0 = np.ones(n) / np.sqrt(n)
+            e_ref, vec_ref, a_ref, b_ref = so.lanc_eigh_ph(nph, g, w0, v0)
+            e0, vec, a, b = s.sp_lanc_eigh(v0)
+            assert abs(e0 - e_ref) <= 1e-12 * abs(e_ref)
+            m = min(20, len(a), len(a_ref))
+            assert np.abs(a[:m] - a_ref[:m]).max() < 1e-8 and np.abs(b[:m] - b_ref[:m]).max() < 1e-8
+            assert abs(abs(vec @ vec_ref) - 1) < 1e-9
+            s.delete_Hv_sector()
+            with pytest.raises(edgpu.EdgpuError):
+                s.gf_set_state(isec, vec_ref, e_ref)                 # chains of an electron-phonon state: refused
+    finally:
+        s.close()

@@ -385,3 +385,28 @@ def test_orbs_operator_known_answers():
         with O.Oracle(**k1).sector(nu, nd) as s1:
             e_sum += np.linalg.eigvalsh(s1.hmat())[0]
     assert abs(e_pair - e_sum) < 1e-12
+
+
+def test_phonon_operator_known_answers():
+    """spMatVec_main with DimPh > 1 (ED_HAMILTONIAN_SPARSE_HxV.f90:391-485, stored/H_ph.f90, H_e_ph.f90) against the
+    Kronecker construction H = 1_ph x H_el + diag(w0 n) x 1_el + (b + b^+) x diag(sum_orb g (n_up + n_dw - 1)) built with
+    numpy from the electron sector's dense matrix and the basis maps; g = 0 decouples (spectrum = E_el + w0 n)."""
+    cfg, o = make_oracle("NS6")
+    nph, g, w0 = 3, (0.7,), 0.4
+    with o.sector(3, 3) as s:
+        hel = s.hmat()
+        mu, md, du, dim = s.map_up(), s.map_dw(), s.dimup, s.dim
+        nimp = (mu[np.arange(dim) % du] & 1) + (md[np.arange(dim) // du] & 1)
+        e = g[0] * (nimp - 1.0)
+        b = np.diag(np.sqrt(np.arange(1, nph + 1)), 1)                      # destruction operator
+        hfull = np.kron(np.eye(nph + 1), hel) + np.kron(np.diag(w0 * np.arange(nph + 1)), np.eye(dim)) + np.kron(b + b.T, np.diag(e))
+        rng = np.random.default_rng(3)
+        v = rng.standard_normal(dim * (nph + 1))
+        assert np.abs(s.spmatvec_ph(v, nph, g, w0) - hfull @ v).max() < 1e-12
+        w_el = np.linalg.eigvalsh(hel)
+        v0 = np.ones(dim * (nph + 1)) / np.sqrt(dim * (nph + 1))
+        e0, vec, _, _ = s.lanc_eigh_ph(nph, g, w0, v0)
+        assert abs(e0 - np.linalg.eigvalsh(hfull)[0]) < 1e-10
+        e00, _, _, _ = s.lanc_eigh_ph(nph, (0.0,), w0, v0)
+        assert abs(e00 - w_el[0]) < 1e-10                                   # g = 0: the phonon vacuum on top of the electron ground state
+        assert e0 < e00                                                     # the coupling lowers the energy (second order)
