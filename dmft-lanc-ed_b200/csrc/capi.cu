@@ -43,38 +43,64 @@ static int load_params(edgpu_ctx *c, const edgpu_params *p) {
   if (p->nph > 0 && !p->ed_total_ud) return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "phonons with ed_total_ud = F are not built");
   if (!p->ed_total_ud && p->norb > 1 && (p->jx != 0.0 || p->jp != 0.0))     // ED_SETUP.f90:69-71
     return edgpu_set_err(EDGPU_ERR_INVALID, "ed_total_ud = F can not be used with Jx != 0 or Jp != 0");
-  int ns = (p->nbath + 1) * p->norb;                        // ED_SETUP.f90:113-116, bath_type normal
+  const int bt = p->bath_type;
+  if (bt < 0 || bt > 2) return edgpu_set_err(EDGPU_ERR_INVALID, "BATH_TYPE must be 0 (normal), 1 (hybrid) or 2 (replica)");
+  if (!p->ed_total_ud && bt != 0) return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "ed_total_ud = F is built for the normal bath only (hybrid: ED_SETUP.f90:70)");
+  int ns = (bt == 1) ? p->norb + p->nbath : (p->nbath + 1) * p->norb;   // ED_SETUP.f90:113-121
   if (p->nbath < 1 || ns > EDGPU_MAX_SITES - 1) return edgpu_set_err(EDGPU_ERR_INVALID, "Ns = %d out of range", ns);
-  if (!p->bath_e || !p->bath_v) return edgpu_set_err(EDGPU_ERR_INVALID, "bath arrays == NULL");
+  if (!p->bath_v || (bt != 2 && !p->bath_e) || (bt == 2 && !p->bath_h)) return edgpu_set_err(EDGPU_ERR_INVALID, "bath arrays == NULL");
+  if (bt == 2 && (p->norb > 3 || p->nbath > EDGPU_MAX_REPL_BATH))
+    return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "replica bath: Norb <= 3 and Nbath <= %d", EDGPU_MAX_REPL_BATH);
   c->hp = *p;
   c->ns = ns;
   c->dimph = p->nph + 1;
-  size_t nh = (size_t)p->nspin * p->nspin * p->norb * p->norb, nb = (size_t)p->nspin * p->norb * p->nbath;
+  const int nsn = p->nspin, sl = p->nspin - 1;
+  size_t nh = (size_t)nsn * nsn * p->norb * p->norb;
+  const size_t ne = (bt == 0) ? (size_t)nsn * p->norb * p->nbath : (bt == 1 ? (size_t)nsn * p->nbath : 0);
+  const size_t nv = (bt == 2) ? (size_t)nsn * p->nbath : (size_t)nsn * p->norb * p->nbath;
+  const size_t nbh = (bt == 2) ? nh * p->nbath : 0;
   c->h_hloc.assign(nh, 0.0);
   if (p->imphloc) memcpy(c->h_hloc.data(), p->imphloc, nh * sizeof(double));
-  c->h_be.assign(p->bath_e, p->bath_e + nb);
-  c->h_bv.assign(p->bath_v, p->bath_v + nb);
+  c->h_be.assign(std::max<size_t>(ne, 1), 0.0);
+  if (ne) memcpy(c->h_be.data(), p->bath_e, ne * sizeof(double));
+  c->h_bv.assign(p->bath_v, p->bath_v + nv);
+  c->h_bh.assign(std::max<size_t>(nbh, 1), 0.0);
+  if (nbh) memcpy(c->h_bh.data(), p->bath_h, nbh * sizeof(double));
   c->hp.imphloc = c->h_hloc.data();
   c->hp.bath_e = c->h_be.data();
   c->hp.bath_v = c->h_bv.data();
+  c->hp.bath_h = nbh ? c->h_bh.data() : nullptr;
   DevParams &d = c->dp;
   memset(&d, 0, sizeof(d));
   d.norb = p->norb; d.nbath = p->nbath; d.ns = ns; d.hfmode = p->hfmode; d.nspin = p->nspin;
+  d.bath_type = bt; d.nfoo = (bt == 1) ? 1 : p->norb;
   d.jhflag = (p->norb > 1 && (p->jx != 0.0 || p->jp != 0.0));   // ED_SETUP.f90:147-148
   for (int i = 0; i < EDGPU_MAX_ORB; i++) d.uloc[i] = (i < p->norb) ? p->uloc[i] : 0.0;
   d.ust = p->ust; d.jh = p->jh; d.jx = p->jx; d.jp = p->jp; d.xmu = p->xmu;
-  const int nsn = p->nspin, sl = p->nspin - 1;
   for (int io = 0; io < p->norb; io++)
     for (int jo = 0; jo < p->norb; jo++) {
       d.hloc_up[io * EDGPU_MAX_ORB + jo] = c->h_hloc[0 + nsn * (0 + nsn * (io + p->norb * jo))];
       d.hloc_dw[io * EDGPU_MAX_ORB + jo] = c->h_hloc[sl + nsn * (sl + nsn * (io + p->norb * jo))];
     }
+  // diag_hybr / bath_diag as ed_buildh_main assembles them per bath type (ED_HAMILTONIAN_SPARSE_HxV.f90:46-76)
+  auto hb = [&](int is, int io, int jo, int kp) { return c->h_bh[(size_t)is + nsn * ((size_t)is + nsn * ((size_t)io + p->norb * ((size_t)jo + p->norb * (size_t)kp)))]; };
   for (int io = 0; io < p->norb; io++)
     for (int kp = 0; kp < p->nbath; kp++) {
-      d.be_up[io * p->nbath + kp] = c->h_be[0 + nsn * (io + p->norb * kp)];
-      d.be_dw[io * p->nbath + kp] = c->h_be[sl + nsn * (io + p->norb * kp)];
-      d.bv_up[io * p->nbath + kp] = c->h_bv[0 + nsn * (io + p->norb * kp)];
-      d.bv_dw[io * p->nbath + kp] = c->h_bv[sl + nsn * (io + p->norb * kp)];
+      const int at = io * p->nbath + kp;
+      if (bt == 0) {
+        d.be_up[at] = c->h_be[0 + nsn * (io + p->norb * kp)];
+        d.be_dw[at] = c->h_be[sl + nsn * (io + p->norb * kp)];
+        d.bv_up[at] = c->h_bv[0 + nsn * (io + p->norb * kp)];
+        d.bv_dw[at] = c->h_bv[sl + nsn * (io + p->norb * kp)];
+      } else if (bt == 1) {
+        if (io == 0) { d.be_up[at] = c->h_be[0 + nsn * kp]; d.be_dw[at] = c->h_be[sl + nsn * kp]; }
+        d.bv_up[at] = c->h_bv[0 + nsn * (io + p->norb * kp)];
+        d.bv_dw[at] = c->h_bv[sl + nsn * (io + p->norb * kp)];
+      } else {
+        d.be_up[at] = hb(0, io, io, kp); d.be_dw[at] = hb(sl, io, io, kp);
+        d.bv_up[at] = c->h_bv[0 + nsn * kp]; d.bv_dw[at] = c->h_bv[sl + nsn * kp];
+        for (int jo = 0; jo < p->norb; jo++) { d.hb_up[kp * 9 + io * 3 + jo] = hb(0, io, jo, kp); d.hb_dw[kp * 9 + io * 3 + jo] = hb(sl, io, jo, kp); }
+      }
     }
   return EDGPU_OK;
 }

@@ -55,7 +55,7 @@ struct edgpu_ctx {
   int sm_count = 148;
   // inputs
   edgpu_params hp{};
-  std::vector<double> h_hloc, h_be, h_bv;
+  std::vector<double> h_hloc, h_be, h_bv, h_bh;
   DevParams dp{};
   int ns = 0;
   uint32_t h_binom[EDGPU_BINOM_LD * EDGPU_BINOM_LD];

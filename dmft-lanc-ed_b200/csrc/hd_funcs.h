@@ -13,19 +13,25 @@
 
 #define EDGPU_MAX_ORB 5
 #define EDGPU_MAX_SITES 32          // Ns <= 31 so that a spin word fits int32 like the reference
-#define EDGPU_MAX_ROW_NNZ 96        // >= Norb^2 + 2*Norb*Nbath for every supported model
+#define EDGPU_MAX_ROW_NNZ 96        // >= Norb^2 + 2*Norb*Nbath (+ Norb^2*Nbath, replica) for every supported model
+#define EDGPU_MAX_REPL_BATH 10      // replica baths: Nbath <= 10 and Norb <= 3 (the Hbath matrices travel as kernel parameters)
 #define EDGPU_BINOM_LD 33
 
 // Parameters the kernels need, by value (fits the 4 KB kernel-argument space).
 struct DevParams {
-  int norb, nbath, ns, hfmode, nspin, jhflag, pad0, pad1;
+  int norb, nbath, ns, hfmode, nspin, jhflag;
+  int bath_type, nfoo;                             // 0 normal, 1 hybrid, 2 replica; nfoo = size(bath_diag,2): 1 for hybrid
   double uloc[EDGPU_MAX_ORB];
   double ust, jh, jx, jp, xmu;
   double hloc_up[EDGPU_MAX_ORB * EDGPU_MAX_ORB];   // impHloc(1,1,io,jo)       [io*5+jo]
   double hloc_dw[EDGPU_MAX_ORB * EDGPU_MAX_ORB];   // impHloc(Nspin,Nspin,io,jo)
   double be_up[EDGPU_MAX_SITES], be_dw[EDGPU_MAX_SITES];   // bath_diag(1|Nspin, io, kp) [io*nbath+kp]
   double bv_up[EDGPU_MAX_SITES], bv_dw[EDGPU_MAX_SITES];   // diag_hybr(1|Nspin, io, kp)
+  // replica: Hbath(1,1,io,jo,kp) / Hbath(Nspin,Nspin,io,jo,kp), [kp*9 + io*3 + jo] (Norb <= 3, Nbath <= 10)
+  double hb_up[EDGPU_MAX_REPL_BATH * 9], hb_dw[EDGPU_MAX_REPL_BATH * 9];
 };
+// 1-based site of bath level kp (0-based) of orbital io (0-based): getBathStride, ED_SETUP.f90:358-375
+#define HD_BATH_SITE(P, io, kp) ((P).bath_type == 1 ? (P).norb + (kp) + 1 : ((P).bath_type == 2 ? (io) + 1 + ((kp) + 1) * (P).norb : (P).norb + (io) * (P).nbath + (kp) + 1))
 
 HD int hd_popc(uint32_t x) {
 #if defined(__CUDA_ARCH__)
@@ -137,9 +143,9 @@ HD double hd_diag_element(const DevParams &P, uint32_t mup, uint32_t mdw) {
         }
     }
   }
-  for (int io = 0; io < P.norb; io++)
+  for (int io = 0; io < P.nfoo; io++)                      // size(bath_diag,2)
     for (int kp = 0; kp < P.nbath; kp++) {
-      int site = P.norb + io * P.nbath + kp + 1;            // getBathStride, ED_SETUP.f90:360-364
+      int site = HD_BATH_SITE(P, io, kp);
       h = hd_add(h, hd_mul(P.be_up[io * P.nbath + kp], (double)HD_BIT(mup, site)));
       h = hd_add(h, hd_mul(P.be_dw[io * P.nbath + kp], (double)HD_BIT(mdw, site)));
     }
@@ -175,11 +181,27 @@ HD int hd_factor_row_sources(const DevParams &P, int spin, uint32_t t, uint32_t 
         src[n] = m; val[n] = v; n++;
       }
     }
+  if (P.bath_type == 2) {                                    // replica inter-orbital bath hopping, stored/H_up.f90:26-50
+    const double *hb = spin ? P.hb_dw : P.hb_up;
+    for (int kp = 0; kp < P.nbath; kp++)
+      for (int io = 0; io < P.norb; io++)
+        for (int jo = 0; jo < P.norb; jo++) {
+          double a = hb[kp * 9 + io * 3 + jo];
+          int ialfa = HD_BATH_SITE(P, io, kp), ibeta = HD_BATH_SITE(P, jo, kp);
+          // source n[ibeta]=1, n[ialfa]=0  ->  target n[ibeta]=0, n[ialfa]=1
+          if (io != jo && a != 0.0 && HD_BIT(t, ialfa) == 1 && HD_BIT(t, ibeta) == 0) {
+            uint32_t m = (t & ~(1u << (ialfa - 1))) | (1u << (ibeta - 1));
+            double v;
+            hd_hop(m, ibeta, ialfa, a, &v);
+            src[n] = m; val[n] = v; n++;
+          }
+        }
+  }
   for (int io = 0; io < P.norb; io++)
     for (int kp = 0; kp < P.nbath; kp++) {
       double a = bv[io * P.nbath + kp];
       if (a == 0.0) continue;
-      int ialfa = P.norb + io * P.nbath + kp + 1;
+      int ialfa = HD_BATH_SITE(P, io, kp);
       // source n[io]=1,n[ialfa]=0 (c(io), cdg(ialfa))  ->  target n[io]=0,n[ialfa]=1
       if (HD_BIT(t, io + 1) == 0 && HD_BIT(t, ialfa) == 1) {
         uint32_t m = (t | (1u << io)) & ~(1u << (ialfa - 1));
@@ -283,9 +305,9 @@ HD double hd_diag_factor(const DevParams &P, int spin, uint32_t m) {
       }
     }
   }
-  for (int io = 0; io < P.norb; io++)
+  for (int io = 0; io < P.nfoo; io++)
     for (int kp = 0; kp < P.nbath; kp++)
-      h += be[io * P.nbath + kp] * HD_BIT(m, P.norb + io * P.nbath + kp + 1);
+      h += be[io * P.nbath + kp] * HD_BIT(m, HD_BATH_SITE(P, io, kp));
   return h;
 }
 HD double hd_diag_cross(const DevParams &P, uint32_t mup, uint32_t mdw) {

@@ -22,6 +22,7 @@ static DevParams make_dp(const edgpu_params *p) {
   DevParams d;
   memset(&d, 0, sizeof(d));
   d.norb = p->norb; d.nbath = p->nbath; d.ns = (p->nbath + 1) * p->norb; d.hfmode = p->hfmode; d.nspin = p->nspin;
+  d.bath_type = 0; d.nfoo = p->norb;                               // the host self-tests cover the normal bath
   d.jhflag = (p->norb > 1 && (p->jx != 0.0 || p->jp != 0.0));
   for (int i = 0; i < EDGPU_MAX_ORB; i++) d.uloc[i] = (i < p->norb) ? p->uloc[i] : 0.0;
   d.ust = p->ust; d.jh = p->jh; d.jx = p->jx; d.jp = p->jp; d.xmu = p->xmu;

@@ -66,9 +66,10 @@ class Observables(C.Structure):
 class Params(C.Structure):
     _fields_ = [("norb", C.c_int32), ("nbath", C.c_int32), ("nspin", C.c_int32), ("hfmode", C.c_int32),
                 ("ed_sparse_h", C.c_int32), ("nph", C.c_int32), ("ed_total_ud", C.c_int32),
-                ("reserved", C.c_int32), ("uloc", C.c_double * 5), ("ust", C.c_double), ("jh", C.c_double),
+                ("bath_type", C.c_int32), ("uloc", C.c_double * 5), ("ust", C.c_double), ("jh", C.c_double),
                 ("jx", C.c_double), ("jp", C.c_double), ("xmu", C.c_double),
-                ("imphloc", c_dp), ("bath_e", c_dp), ("bath_v", c_dp), ("g_ph", C.c_double * 5), ("w0_ph", C.c_double)]
+                ("imphloc", c_dp), ("bath_e", c_dp), ("bath_v", c_dp), ("g_ph", C.c_double * 5), ("w0_ph", C.c_double),
+                ("bath_h", c_dp)]
 
 
 def lib():
@@ -194,12 +195,16 @@ class Solver:
     """Module-global ED state + the live sector (ED_VARS_GLOBAL / ED_HAMILTONIAN_COMMON)."""
 
     def __init__(self, norb, nbath, nspin=1, uloc=(2.0,), ust=0.0, jh=0.0, jx=0.0, jp=0.0, xmu=0.0, hfmode=True,
-                 imphloc=None, bath_e=None, bath_v=None, ed_sparse_h=True, device=-1, ed_total_ud=True, nph=0, g_ph=(), w0_ph=0.0):
+                 imphloc=None, bath_e=None, bath_v=None, ed_sparse_h=True, device=-1, ed_total_ud=True, nph=0, g_ph=(), w0_ph=0.0,
+                 bath_type=0, bath_h=None):
+        """bath_type 0 normal: bath_e, bath_v (nspin,norb,nbath); 1 hybrid: bath_e (nspin,1,nbath), bath_v (nspin,norb,nbath);
+        2 replica: bath_v (nspin,nbath), bath_h (nspin,nspin,norb,norb,nbath) = the replicas' Hbath matrices."""
         self.norb, self.nbath, self.nspin = norb, nbath, nspin
+        self.bath_type, self._bath_h = int(bath_type), bath_h
         self.ed_total_ud = bool(ed_total_ud)
         self.nph, self.g_ph, self.w0_ph = int(nph), tuple(g_ph), float(w0_ph)
-        self.ns = (nbath + 1) * norb
-        if bath_e is None or bath_v is None:
+        self.ns = norb + nbath if self.bath_type == 1 else (nbath + 1) * norb
+        if self.bath_type == 0 and (bath_e is None or bath_v is None):
             bath_e, bath_v = configs.init_dmft_bath(norb, nbath, nspin)
         self._keep = self._pack(uloc, ust, jh, jx, jp, xmu, hfmode, imphloc, bath_e, bath_v, ed_sparse_h)
         self.h = C.c_void_p(None)
@@ -217,14 +222,24 @@ class Solver:
         for i in range(5):
             p.uloc[i] = float(uloc[i]) if i < len(uloc) else 0.0
         p.ust, p.jh, p.jx, p.jp, p.xmu = ust, jh, jx, jp, xmu
+        bt = int(getattr(self, "bath_type", 0))
+        p.bath_type = bt
         shp = (self.nspin, self.norb, self.nbath)
-        fe = np.ravel(np.asarray(bath_e, dtype=np.float64).reshape(shp, order="F"), order="F").copy()
-        fv = np.ravel(np.asarray(bath_v, dtype=np.float64).reshape(shp, order="F"), order="F").copy()
+        if bt == 0:
+            fe = np.ravel(np.asarray(bath_e, dtype=np.float64).reshape(shp, order="F"), order="F").copy()
+            fv = np.ravel(np.asarray(bath_v, dtype=np.float64).reshape(shp, order="F"), order="F").copy()
+        else:
+            fe = np.ravel(np.asarray(bath_e, dtype=np.float64), order="F").copy() if bath_e is not None else np.zeros(1)
+            fv = np.ravel(np.asarray(bath_v, dtype=np.float64), order="F").copy()
+        fb = None
+        if bt == 2:
+            fb = np.ravel(np.asarray(getattr(self, "_bath_h"), dtype=np.float64), order="F").copy()
+            p.bath_h = _dp(fb)
         if imphloc is None:
             imphloc = np.zeros((self.nspin, self.nspin, self.norb, self.norb))
         fh = np.ravel(np.asarray(imphloc, dtype=np.float64), order="F").copy()
         p.imphloc, p.bath_e, p.bath_v = _dp(fh), _dp(fe), _dp(fv)
-        return (p, fe, fv, fh)
+        return (p, fe, fv, fh, fb)
 
     def close(self):
         if self.h:

@@ -52,14 +52,16 @@ typedef struct edgpu_params {
   int32_t ed_sparse_h;                 /* ED_SPARSE_H: 1 = stored (spMatVec_*), 0 = direct */
   int32_t nph;                         /* NPH: DimPh = NPH + 1 phonon states (0: no phonons) */
   int32_t ed_total_ud;                 /* ED_TOTAL_UD: 1 = total (Nup, Ndw) sectors, 0 = one pair per orbital */
-  int32_t reserved;
+  int32_t bath_type;                   /* BATH_TYPE: 0 normal, 1 hybrid (Ns = Norb + Nbath), 2 replica (ED_SETUP.f90:113-121, 358-375) */
   double  uloc[EDGPU_MAX_ORB];         /* ULOC */
   double  ust, jh, jx, jp, xmu;        /* UST, JH, JX, JP, XMU */
   const double *imphloc;               /* impHloc(Nspin,Nspin,Norb,Norb), may be NULL (=0) */
-  const double *bath_e;                /* dmft_bath%e(Nspin,Norb,Nbath) */
-  const double *bath_v;                /* dmft_bath%v(Nspin,Norb,Nbath) */
+  const double *bath_e;                /* dmft_bath%e(Nspin,Norb,Nbath); hybrid: (Nspin,1,Nbath); replica: unused */
+  const double *bath_v;                /* dmft_bath%v(Nspin,Norb,Nbath); replica: dmft_bath%item(k)%v(ispin) as (Nspin,Nbath) */
   double  g_ph[EDGPU_MAX_ORB];         /* G_PH: electron-phonon couplings (NPH > 0) */
   double  w0_ph;                       /* W0_PH: phonon frequency */
+  const double *bath_h;                /* replica only: Hbath(Nspin,Nspin,Norb,Norb,Nbath) = bath_from_sym(lambda) of every
+                                        * replica, as ed_buildh_main assembles it (ED_HAMILTONIAN_SPARSE_HxV.f90:61-75) */
 } edgpu_params;
 
 typedef struct edgpu_ctx edgpu_ctx;    /* opaque: one per process, mirrors the module state */

@@ -80,11 +80,41 @@ orc_ctx *orc_ctx_create(int norb, int nbath, int nspin, int hfmode, const double
   if (imphloc) memcpy(c->imphloc, imphloc, nh * sizeof(double));
   memcpy(c->bath_e, bath_e, nb * sizeof(double));
   memcpy(c->bath_v, bath_v, nb * sizeof(double));
+  c->bath_type = 0; c->nfoo = norb; c->bath_h = NULL;
+  return c;
+}
+orc_ctx *orc_ctx_create_bt(int norb, int nbath, int nspin, int hfmode, const double *uloc,
+                           double ust, double jh, double jx, double jp, double xmu, const double *imphloc,
+                           int bath_type, const double *bath_e, const double *bath_v, const double *bath_h) {
+  if (bath_type == 0) return orc_ctx_create(norb, nbath, nspin, hfmode, uloc, ust, jh, jx, jp, xmu, imphloc, bath_e, bath_v);
+  size_t nb = (size_t)nspin * norb * nbath;
+  double *e = (double *)xcalloc(nb, sizeof(double)), *v = (double *)xcalloc(nb, sizeof(double));
+  for (int is = 0; is < nspin; is++)
+    for (int io = 0; io < norb; io++)
+      for (int kp = 0; kp < nbath; kp++) {
+        size_t at = (size_t)is + nspin * ((size_t)io + norb * (size_t)kp);
+        if (bath_type == 1) {                              /* hybrid */
+          v[at] = bath_v[at];
+          if (io == 0) e[at] = bath_e[is + nspin * kp];
+        } else {                                           /* replica, ED_HAMILTONIAN_SPARSE_HxV.f90:61-75 */
+          v[at] = bath_v[is + nspin * kp];
+          e[at] = bath_h[is + nspin * (is + nspin * (io + norb * (io + norb * (size_t)kp)))];
+        }
+      }
+  orc_ctx *c = orc_ctx_create(norb, nbath, nspin, hfmode, uloc, ust, jh, jx, jp, xmu, imphloc, e, v);
+  free(e); free(v);
+  c->bath_type = bath_type;
+  if (bath_type == 1) { c->ns = norb + nbath; c->nfoo = 1; }
+  if (bath_type == 2) {
+    size_t nh = (size_t)nspin * nspin * norb * norb * nbath;
+    c->bath_h = (double *)xcalloc(nh, sizeof(double));
+    memcpy(c->bath_h, bath_h, nh * sizeof(double));
+  }
   return c;
 }
 void orc_ctx_destroy(orc_ctx *c) {
   if (!c) return;
-  free(c->imphloc); free(c->bath_e); free(c->bath_v); free(c);
+  free(c->imphloc); free(c->bath_e); free(c->bath_v); free(c->bath_h); free(c);
 }
 
 /* init_dmft_bath, bath_type normal: ED_BATH/dmft_aux.f90:102-133.  Arrays (nspin,norb,nbath). */
@@ -189,9 +219,11 @@ void orc_get_nup_ndw(int isector, int ns, int *nup, int *ndw) {
   *ndw = count % (ns + 1);
   *nup = count / (ns + 1);
 }
-/* getBathStride, normal bath: ED_SETUP.f90:360-364.  iorb,kp 1-based; returns 1-based site */
+/* getBathStride, ED_SETUP.f90:358-375.  iorb,kp 1-based; returns 1-based site */
 int orc_bath_stride(const orc_ctx *c, int iorb, int kp) {
-  return c->norb + (iorb - 1) * c->nbath + kp;
+  if (c->bath_type == 1) return c->norb + kp;                /* hybrid */
+  if (c->bath_type == 2) return iorb + kp * c->norb;         /* replica */
+  return c->norb + (iorb - 1) * c->nbath + kp;               /* normal */
 }
 
 static void bdecomp(int32_t m, int ns, int *ivec) {        /* ED_SETUP.f90:937-947 */
@@ -276,7 +308,7 @@ static double h_local_element(const orc_ctx *c, const int *nup, const int *ndw) 
         }
     }
   }
-  for (int io = 0; io < norb; io++)                        /* size(bath_diag,2) = Norb, normal */
+  for (int io = 0; io < c->nfoo; io++)                     /* size(bath_diag,2): Norb (normal, replica), 1 (hybrid) */
     for (int kp = 0; kp < nbath; kp++) {
       int ialfa = orc_bath_stride(c, io + 1, kp + 1) - 1;
       htmp = htmp + BATHE(c, 0, io, kp) * (double)nup[ialfa];
@@ -301,6 +333,18 @@ static void one_spin_hops(const orc_ctx *c, int is, int32_t m, hop_emit_fn emit,
         emit(u, k2, HLOC(c, is, is, io, jo) * sg1 * sg2);
       }
     }
+  if (c->bath_type == 2)                                   /* replica inter-orbital bath hopping, H_up.f90:26-50 */
+    for (int kp = 0; kp < c->nbath; kp++)
+      for (int io = 0; io < c->norb; io++)
+        for (int jo = 0; jo < c->norb; jo++) {
+          int ialfa = orc_bath_stride(c, io + 1, kp + 1), ibeta = orc_bath_stride(c, jo + 1, kp + 1);
+          double hb = c->bath_h[is + c->nspin * (is + c->nspin * (io + c->norb * (jo + c->norb * (size_t)kp)))];
+          if (hb != 0.0 && n[ibeta - 1] == 1 && n[ialfa - 1] == 0) {
+            orc_c(ibeta, m, &k1, &sg1);
+            orc_cdg(ialfa, k1, &k2, &sg2);
+            emit(u, k2, hb * sg1 * sg2);
+          }
+        }
   for (int io = 0; io < c->norb; io++)
     for (int kp = 0; kp < c->nbath; kp++) {
       int ialfa = orc_bath_stride(c, io + 1, kp + 1);      /* 1-based */

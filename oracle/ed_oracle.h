@@ -35,6 +35,12 @@ typedef struct orc_ctx {
   double *imphloc;              /* (nspin,nspin,norb,norb) Fortran order */
   double *bath_e;               /* dmft_bath%e(nspin,norb,nbath) Fortran order */
   double *bath_v;               /* dmft_bath%v(nspin,norb,nbath) Fortran order */
+  /* bath_type (ED_SETUP.f90:113-121, 358-375): 0 normal, 1 hybrid (Ns = Norb + Nbath, every level shared by all
+   * orbitals: bath_e only uses orbital column 1, nfoo = 1), 2 replica (Ns = Norb*(Nbath+1), level kp = one replica of
+   * the impurity with its own Norb x Norb matrix bath_h(:,:,:,:,kp) and ONE hybridisation v(ispin,kp) for all orbitals;
+   * bath_e then holds its diagonal and bath_v the replicated v) */
+  int bath_type, nfoo;
+  double *bath_h;               /* replica: Hbath(nspin,nspin,norb,norb,nbath) Fortran order, else NULL */
 } orc_ctx;
 
 /* Row-list sparse matrix flattened to CSR in insertion order (ED_SPARSE_MATRIX.f90:13-30). */
@@ -63,6 +69,12 @@ typedef struct orc_sector {
 orc_ctx *orc_ctx_create(int norb, int nbath, int nspin, int hfmode, const double *uloc,
                         double ust, double jh, double jx, double jp, double xmu,
                         const double *imphloc, const double *bath_e, const double *bath_v);
+/* the same for bath_type 1 (hybrid: bath_e(nspin,1,nbath), bath_v(nspin,norb,nbath)) and 2 (replica: bath_e unused,
+ * bath_v(nspin,nbath), bath_h(nspin,nspin,norb,norb,nbath) = bath_from_sym(lambda) as ed_buildh_main assembles it,
+ * ED_HAMILTONIAN_SPARSE_HxV.f90:61-75) */
+orc_ctx *orc_ctx_create_bt(int norb, int nbath, int nspin, int hfmode, const double *uloc,
+                           double ust, double jh, double jx, double jp, double xmu, const double *imphloc,
+                           int bath_type, const double *bath_e, const double *bath_v, const double *bath_h);
 void orc_ctx_destroy(orc_ctx *c);
 void orc_init_dmft_bath(int norb, int nbath, int nspin, double hwband, double *e, double *v);
 

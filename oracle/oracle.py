@@ -69,6 +69,9 @@ def lib():
         L.orc_ctx_create.restype = C.c_void_p
         L.orc_ctx_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, c_dp, C.c_double, C.c_double,
                                      C.c_double, C.c_double, C.c_double, c_dp, c_dp, c_dp]
+        L.orc_ctx_create_bt.restype = C.c_void_p
+        L.orc_ctx_create_bt.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, c_dp, C.c_double, C.c_double,
+                                        C.c_double, C.c_double, C.c_double, c_dp, C.c_int, c_dp, c_dp, c_dp]
         L.orc_ctx_destroy.argtypes = [C.c_void_p]
         L.orc_init_dmft_bath.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, c_dp, c_dp]
         L.orc_binomial.restype = C.c_int
@@ -370,11 +373,26 @@ class Oracle:
     """Holds the module-global inputs of the reference (orc_ctx)."""
 
     def __init__(self, norb, nbath, nspin=1, uloc=(2.0,), ust=0.0, jh=0.0, jx=0.0, jp=0.0, xmu=0.0,
-                 hfmode=True, imphloc=None, bath_e=None, bath_v=None, hwband=2.0):
+                 hfmode=True, imphloc=None, bath_e=None, bath_v=None, hwband=2.0, bath_type=0, bath_h=None):
+        """bath_type 0 normal: bath_e, bath_v (nspin,norb,nbath); 1 hybrid: bath_e (nspin,1,nbath), bath_v (nspin,norb,nbath);
+        2 replica: bath_v (nspin,nbath), bath_h (nspin,nspin,norb,norb,nbath)."""
         self.norb, self.nbath, self.nspin = norb, nbath, nspin
-        self.ns = (nbath + 1) * norb
+        self.bath_type = int(bath_type)
+        self.ns = {0: (nbath + 1) * norb, 1: norb + nbath, 2: (nbath + 1) * norb}[self.bath_type]
         ul = np.zeros(5)
         ul[:len(uloc)] = uloc
+        if self.bath_type != 0:
+            if imphloc is None:
+                imphloc = np.zeros((nspin, nspin, norb, norb))
+            self.imphloc = np.asfortranarray(imphloc, dtype=np.float64)
+            fh = np.ravel(self.imphloc, order="F").copy()
+            fv = np.ravel(np.asarray(bath_v, dtype=np.float64), order="F").copy()
+            fe = np.ravel(np.asarray(bath_e, dtype=np.float64), order="F").copy() if bath_e is not None else np.zeros(1)
+            fb = np.ravel(np.asarray(bath_h, dtype=np.float64), order="F").copy() if bath_h is not None else np.zeros(1)
+            self.uloc, self.ust, self.jh, self.jx, self.jp, self.xmu, self.hfmode = ul, ust, jh, jx, jp, xmu, hfmode
+            self.h = lib().orc_ctx_create_bt(norb, nbath, nspin, int(hfmode), _dp(ul), ust, jh, jx, jp, xmu, _dp(fh),
+                                             self.bath_type, _dp(fe), _dp(fv), _dp(fb))
+            return
         if bath_e is None or bath_v is None:
             bath_e, bath_v = init_dmft_bath(norb, nbath, nspin, hwband)
         self.bath_e = np.asfortranarray(bath_e, dtype=np.float64).reshape((nspin, norb, nbath), order="F")

@@ -410,3 +410,59 @@ def test_phonon_operator_known_answers():
         e00, _, _, _ = s.lanc_eigh_ph(nph, (0.0,), w0, v0)
         assert abs(e00 - w_el[0]) < 1e-10                                   # g = 0: the phonon vacuum on top of the electron ground state
         assert e0 < e00                                                     # the coupling lowers the energy (second order)
+
+
+def test_hybrid_and_replica_baths_known_answers():
+    """bath_type hybrid and replica (getBathStride ED_SETUP.f90:358-375, the replica inter-orbital bath hopping of
+    stored/H_up.f90:26-50, bath_diag / diag_hybr of ed_buildh_main :46-76) pinned on (1) a replica bath with DIAGONAL
+    Hbath matrices is the normal bath with e(a,k) = Hbath(a,a,k), V(a,k) = v(k) up to a relabelling of the sites: identical
+    spectra, interaction, spin-exchange and pair-hopping included; (2) at U = 0 the ground-state energy of any sector is
+    the sum of the lowest one-body levels of the Ns x Ns hopping matrix, for a replica bath with off-diagonal Hbath and
+    for a hybrid bath."""
+    norb, nbath = 2, 2
+    rng = np.random.default_rng(1)
+    hb = np.zeros((1, 1, norb, norb, nbath))
+    for kp in range(nbath):
+        for io in range(norb):
+            hb[0, 0, io, io, kp] = rng.standard_normal()
+    v = np.array([[0.4, 0.7]])
+    kw = dict(norb=norb, nbath=nbath, nspin=1, uloc=(2.0, 1.5), ust=0.8, jh=0.3, jx=0.3, jp=0.3, xmu=0.2, hfmode=True)
+    orep = O.Oracle(bath_type=2, bath_v=v, bath_h=hb, **kw)
+    e = np.zeros((1, norb, nbath))
+    vv = np.zeros((1, norb, nbath))
+    for io in range(norb):
+        for kp in range(nbath):
+            e[0, io, kp], vv[0, io, kp] = hb[0, 0, io, io, kp], v[0, kp]
+    onor = O.Oracle(bath_e=e, bath_v=vv, **kw)
+    for sec in [(3, 3), (2, 4)]:
+        with orep.sector(*sec) as a, onor.sector(*sec) as b:
+            assert np.abs(np.linalg.eigvalsh(a.hmat()) - np.linalg.eigvalsh(b.hmat())).max() < 1e-12
+    hb2 = hb.copy()
+    hb2[0, 0, 0, 1, :] = hb2[0, 0, 1, 0, :] = [0.3, -0.2]
+    kw0 = dict(norb=norb, nbath=nbath, nspin=1, uloc=(0.0, 0.0), ust=0.0, jh=0.0, jx=0.0, jp=0.0, xmu=0.0, hfmode=False)
+    o0 = O.Oracle(bath_type=2, bath_v=v, bath_h=hb2, **kw0)
+    ns = norb * (nbath + 1)
+    h1 = np.zeros((ns, ns))
+    for kp in range(nbath):
+        for io in range(norb):
+            sb = io + (kp + 1) * norb
+            h1[io, sb] = h1[sb, io] = v[0, kp]
+            for jo in range(norb):
+                h1[sb, jo + (kp + 1) * norb] = hb2[0, 0, io, jo, kp]
+    w1 = np.linalg.eigvalsh(h1)
+    for sec in [(3, 3), (2, 1)]:
+        with o0.sector(*sec) as a:
+            assert abs(np.linalg.eigvalsh(a.hmat())[0] - (w1[:sec[0]].sum() + w1[:sec[1]].sum())) < 1e-12
+    vh = np.array([[[0.5, 0.3, 0.2], [0.1, 0.4, 0.6]]])
+    eh = np.array([[[-1.0, 0.2, 0.9]]])
+    oh = O.Oracle(norb=2, nbath=3, nspin=1, uloc=(0.0, 0.0), ust=0.0, jh=0.0, jx=0.0, jp=0.0, xmu=0.0, hfmode=False,
+                  bath_type=1, bath_e=eh, bath_v=vh)
+    h1 = np.zeros((5, 5))
+    for kp in range(3):
+        h1[2 + kp, 2 + kp] = eh[0, 0, kp]
+        for io in range(2):
+            h1[io, 2 + kp] = h1[2 + kp, io] = vh[0, io, kp]
+    w1 = np.linalg.eigvalsh(h1)
+    for sec in [(2, 3), (1, 1)]:
+        with oh.sector(*sec) as a:
+            assert abs(np.linalg.eigvalsh(a.hmat())[0] - (w1[:sec[0]].sum() + w1[:sec[1]].sum())) < 1e-12
