@@ -69,14 +69,37 @@ __global__ void __launch_bounds__(RED_THREADS) k_lanc_a(const double *__restrict
   s = block_sum(s);
   if (threadIdx.x == 0) partials[blockIdx.x] = s;
 }
-// w -= a*(sx*x), partial of b^2 = w.w
+// w -= a*(sx*x), partial of b^2 = w.w.  Pure streaming (24 B/element): 16-byte accesses, four independent pairs per
+// thread and trip in flight, streaming cache hints (nothing is reused before the next pass evicts it).
 __global__ void __launch_bounds__(RED_THREADS) k_lanc_b(double *__restrict__ w, const double *__restrict__ x, int64_t n,
                                                         const LancState *st, double *__restrict__ partials) {
-  const double sx = st->sx, a = st->alpha;
+  const double al = st->alpha, sx = st->sx;                        // same expression order as before: w - a*(sx*x)
   double s = 0.0;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    double v = w[i] - a * (sx * x[i]);
-    w[i] = v;
+  const int64_t n2 = n >> 1, stride = (int64_t)gridDim.x * blockDim.x;
+  double2 *w2 = reinterpret_cast<double2 *>(w);
+  const double2 *x2 = reinterpret_cast<const double2 *>(x);
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n2; i += 4 * stride) {
+    double2 a[4], b[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) { a[q] = __ldcs(w2 + i + q * stride); b[q] = __ldcs(x2 + i + q * stride); }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      a[q].x = a[q].x - al * (sx * b[q].x); a[q].y = a[q].y - al * (sx * b[q].y);
+      __stcs(w2 + i + q * stride, a[q]);
+      s += a[q].x * a[q].x; s += a[q].y * a[q].y;
+    }
+  }
+  for (; i < n2; i += stride) {
+    double2 a = __ldcs(w2 + i);
+    const double2 b = __ldcs(x2 + i);
+    a.x = a.x - al * (sx * b.x); a.y = a.y - al * (sx * b.y);
+    __stcs(w2 + i, a);
+    s += a.x * a.x; s += a.y * a.y;
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {             // odd length: the last element
+    const double v = w[n - 1] - al * (sx * x[n - 1]);
+    w[n - 1] = v;
     s += v * v;
   }
   s = block_sum(s);
