@@ -1569,9 +1569,10 @@ int fast_apply_local(edgpu_ctx *c, const double *d_x, double *d_y, double *d_xp,
     prof_mark(c, "k_fcol");
     return fast_apply_col(c, 0, false, true, d_x, d_y, c->qdw, c->coloff, d_xp, npartials, true, 0, 0);
   }
-  // CTAs (= SMs) of the push next to the row pass: from 4 ranks on the push is the critical path and the row pass short
-  // (measured at 8 ranks, C3: 64 CTAs 0.88 ms per H*v, 32 CTAs 0.96 ms), below that the two are balanced at 32
-  const int hctas = (int)std::max<int64_t>(1, std::min<int64_t>(c->opt_halo_ctas > 0 ? c->opt_halo_ctas : (c->nranks >= 4 ? 64 : 32), c->sm_count / 2));
+  // CTAs (= SMs) of the push next to the row pass, measured on C3: at 8 ranks the push is the critical path and the row
+  // pass short (64 CTAs 0.88 ms per H*v, 32 CTAs 0.96 ms); at 4 ranks the row pass still needs its SMs (64 CTAs 1.30 ms,
+  // 32 CTAs 1.14 ms); at 2 the two are balanced at 32
+  const int hctas = (int)std::max<int64_t>(1, std::min<int64_t>(c->opt_halo_ctas > 0 ? c->opt_halo_ctas : (c->nranks >= 8 ? 64 : 32), c->sm_count / 2));
   CK(cudaEventRecord(c->ev_fork, c->stream));
   CK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
   for (int w = 0; w < K; w++) TRY(fast_halo_push(c, d_x, c->stream2, hctas, w));
