@@ -116,7 +116,6 @@ static int create_device_state(edgpu_ctx *c) {
   CK(cudaEventCreate(&c->ev1));
   CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
-  for (int w = 0; w < EDGPU_MAX_WINDOWS; w++) CK(cudaEventCreateWithFlags(&c->ev_win[w], cudaEventDisableTiming));
   // exact binomials by Pascal's rule (== binomial(), ED_SETUP.f90:1017-1035, for these sizes)
   memset(c->h_binom, 0, sizeof(c->h_binom));
   for (int n = 0; n < EDGPU_BINOM_LD; n++) {
@@ -471,7 +470,6 @@ extern "C" int edgpu_destroy(edgpu_ctx *c) {
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
-  for (int w = 0; w < EDGPU_MAX_WINDOWS; w++) if (c->ev_win[w]) cudaEventDestroy(c->ev_win[w]);
   if (c->stream2) cudaStreamDestroy(c->stream2);
   for (int i = 0; i < 8; i++) if (c->pev[i]) cudaEventDestroy(c->pev[i]);
   if (c->stream) cudaStreamDestroy(c->stream);

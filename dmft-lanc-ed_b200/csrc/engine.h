@@ -28,7 +28,7 @@ struct LancState {              // device-resident Lanczos scalars (no host sync
 };
 
 #define EDGPU_MAXP 8            // ranks of one NVLink domain (peer-mapped symmetric slab)
-#define EDGPU_MAX_WINDOWS 8
+#define EDGPU_MAX_WINDOWS 8     // column windows of the sharded H*v pipeline (push of window w+1 under the column pass of w)
 #define EDGPU_HALO_HDR 1024     // bytes of arrival flags in front of the halo buffers: [window][source rank] 64-bit epochs
 
 // One low group of the structured row kernel (hxv_fast.cu), precomputed per sector: 80 bytes, bulk-copied next
@@ -50,7 +50,7 @@ struct edgpu_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;             // halo copy next to the row kernel (sharded fast path)
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr, ev_win[EDGPU_MAX_WINDOWS] = {nullptr};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;   // fork / join of stream2 around an H*v
   bool fast_attrs_set = false, tiled_attrs_set = false;   // per-device function attributes (this context's device)
   int sm_count = 148;
   // inputs

@@ -10,6 +10,6 @@ FLAGS="-O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompil
 while [ $# -ge 2 ]; do
   name=$1; defs=$2; shift 2
   $NVCC $FLAGS $defs -c hxv_fast.cu -o build_var/hxv_fast_$name.o
-  $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o ../variants/libedgpu_$name.so build/capi.o build/hxv.o build/hxv_tiled.o build_var/hxv_fast_$name.o build/lanczos.o build/comm.o -ldl
+  $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o ../variants/libedgpu_$name.so $(ls build/*.o | grep -v -e hxv_fast.o -e selftest.o) build_var/hxv_fast_$name.o -ldl
   echo built $name
 done
