@@ -303,3 +303,38 @@ extern "C" int edgpu_selftest_halo_tables(const edgpu_params *p, int ndw, int nr
   info[0] = ok ? 1 : 0; info[1] = (int32_t)entries; info[2] = (int32_t)remote; info[3] = (int32_t)triples; info[4] = maxslot; info[5] = K;
   return 0;
 }
+
+// HOST ONLY: the halo tables of ONE rank as build_Hv_sector computes them (the world_size-2 gloo test drives a real
+// inter-process exchange with them).  info[4] = {slots of this rank, largest slot count of any rank, triples, list
+// entries}; lcol2[cap_e]; pdst / pslot / psrc[cap_p]; pwin[K + 1].  Returns 0, 1 when a capacity was too small, -1 when
+// the structured row kernel does not apply.
+extern "C" int edgpu_selftest_halo_rank(const edgpu_params *p, int ndw, int nranks, int rank, int64_t lr, int64_t tbits_opt, int K,
+                                        int32_t *info, int32_t *lcol2, int cap_e, int32_t *pdst, int32_t *pslot, int32_t *psrc,
+                                        int cap_p, int32_t *pwin) {
+  DevParams d = make_dp(p);
+  const int64_t n = edgpu_selftest_map(d.ns, ndw, nullptr);
+  std::vector<int32_t> map((size_t)n), rp((size_t)n + 1), cc;
+  std::vector<double> vv;
+  edgpu_selftest_map(d.ns, ndw, map.data());
+  int32_t cb[EDGPU_MAX_ROW_NNZ]; double vb[EDGPU_MAX_ROW_NNZ];
+  for (int64_t i = 0; i < n; i++) {
+    rp[(size_t)i] = (int32_t)cc.size();
+    const int m = hd_factor_row(d, 1, map.data(), n, (uint32_t)map[(size_t)i], cb, vb);
+    for (int k = 0; k < m; k++) { cc.push_back(cb[k]); vv.push_back(vb[k]); }
+  }
+  rp[(size_t)n] = (int32_t)cc.size();
+  SRowHostPlan hp;
+  if (srow_plan_host(d.ns, ndw, n, nranks, rank, (int)lr, (int)tbits_opt, hp) != 1) return -1;
+  srow_lists_host(hp, rank, n, map.data(), rp.data(), cc.data(), vv.data());
+  std::vector<int> l2, pd, ps, pr;
+  int pw[EDGPU_MAX_WINDOWS + 1], nslot = 0, maxslot = 0;
+  if (K < 1 || K > EDGPU_MAX_WINDOWS) return -1;
+  if (halo_tables_host(d.ns, ndw, n, nranks, rank, (int)lr, (int)tbits_opt, hp, map.data(), rp.data(), cc.data(), vv.data(), K, l2, pd, ps, pr,
+                       pw, &nslot, &maxslot)) return -1;
+  info[0] = nslot; info[1] = maxslot; info[2] = (int32_t)pd.size(); info[3] = (int32_t)l2.size();
+  if ((int)l2.size() > cap_e || (int)pd.size() > cap_p) return 1;
+  for (size_t k = 0; k < l2.size(); k++) lcol2[k] = l2[k];
+  for (size_t k = 0; k < pd.size(); k++) { pdst[k] = pd[k]; pslot[k] = ps[k]; psrc[k] = pr[k]; }
+  for (int w = 0; w <= K; w++) pwin[w] = pw[w];
+  return 0;
+}

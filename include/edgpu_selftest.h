@@ -39,6 +39,12 @@ int edgpu_selftest_srow_plan(const edgpu_params *p, int ndw, int nranks, int ran
  * its target; no stray triples; same slab layout on every rank.  info[6] = {ok, list entries, remote entries, triples,
  * largest slot count, windows}. */
 int edgpu_selftest_halo_tables(const edgpu_params *p, int ndw, int nranks, int64_t lr, int64_t tbits_opt, int K, int32_t *info);
+/* HOST ONLY: the halo tables of ONE rank (lcol2 per list entry; the (peer, slot, own column) triples it stores, sorted by
+ * (window, source column); pwin[K+1]).  info[4] = {slots, largest slot count of any rank, triples, list entries}.
+ * Returns 0, 1 = capacity too small, -1 = the structured row kernel does not apply. */
+int edgpu_selftest_halo_rank(const edgpu_params *p, int ndw, int nranks, int rank, int64_t lr, int64_t tbits_opt, int K,
+                             int32_t *info, int32_t *lcol2, int cap_e, int32_t *pdst, int32_t *pslot, int32_t *psrc,
+                             int cap_p, int32_t *pwin);
 /* GPU: the sharded fast H*v path with `nranks` ranks emulated by `nranks` contexts on ONE device (every rank's halo
  * slab is a plain allocation, the pushes of all ranks run first, no arrival flags); x, y are full host vectors.  Test
  * instrumentation only. */
