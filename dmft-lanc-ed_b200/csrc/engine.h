@@ -193,7 +193,7 @@ int halo_tables_host(int ns, int ndw, int64_t dimdw, int P, int me, int lr, int 
 // hxv_fast.cu: TMA-staged whole-column kernel + structured single-band row kernel
 int fast_plan_build(edgpu_ctx *c);
 int fast_plan_free(edgpu_ctx *c);
-bool fast_supported_local(edgpu_ctx *c);          // full operator on the local shard (peer reads when nranks > 1)
+bool fast_supported_local(edgpu_ctx *c);          // full operator on the local shard (pushed halo when nranks > 1)
 bool fast_supported_col(edgpu_ctx *c, int k);     // whole-column kernel for factor k
 int fast_apply_local(edgpu_ctx *c, const double *d_x, double *d_y, double *d_xp = nullptr, int *npartials = nullptr);
 int fast_apply_col(edgpu_ctx *c, int k, bool with_diag, bool acc, const double *d_x, double *d_y, int64_t ncols, int64_t coloff,

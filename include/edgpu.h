@@ -112,7 +112,9 @@ int  edgpu_vecdim_hv_sector(const edgpu_ctx *c, int isector, int64_t *vecdim);
 /* dd_sparse_HxV(Nloc,v,Hv) (ED_VARS_GLOBAL.f90:75-81) as held by spHtimesV_p: host in, host out.
  * Replaces spMatVec_main / spMatVec_MPI_main (ED_HAMILTONIAN_SPARSE_HxV.f90:391-485, 568-694)
  * and directMatVec_main / directMatVec_MPI_main (ED_HAMILTONIAN_DIRECT_HxV.f90:21-95, 180-284),
- * selected by ed_sparse_h like build_Hv_sector does (ED_HAMILTONIAN.f90:139-166). */
+ * selected by ed_sparse_h like build_Hv_sector does (ED_HAMILTONIAN.f90:139-166).  With NPH > 0 the phonon
+ * terms (:445-468) are included and nloc = DimUp*mpiQdw*DimPh; with ed_total_ud = 0 the operator is spMatVec_orbs
+ * (:487-564).  On a sharded sector the call is collective (every rank applies the operator). */
 int  edgpu_hxv(edgpu_ctx *c, int64_t nloc, const double *v, double *hv);
 /* Fortran procedure-pointer compatible form: uses the context made current by the last
  * edgpu_build_hv_sector in this process; aborts (like the reference's stop) on error. */

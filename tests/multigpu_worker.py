@@ -35,8 +35,8 @@ def main():
         if not ok:
             fails.append("%s rank %d %s" % (name, rank, detail))
 
-    # (config, sector, stored?, engine options).  Single-band cases run the sharded fast path (halo pulled from the
-    # peers over NVLink next to k_srow, remote / boundary hops applied by the column pass); "no_peer" forces the
+    # (config, sector, stored?, engine options).  Single-band cases run the sharded fast path (halo columns pushed by
+    # their owners over NVLink next to k_srow, remote / boundary hops applied by the column pass); "no_peer" forces the
     # all-to-all transposes; C4 (spin-exchange / pair-hopping) uses the all-gather path.
     cases = [("C1", (4, 4), True, {}), ("C1", (4, 4), False, {}), ("C1", (5, 3), True, {"srow_t": 1}),
              ("NS10", (5, 5), False, {"srow_lr": 4, "srow_t": 3}), ("NS10", (6, 4), True, {}),
