@@ -448,7 +448,8 @@ class Solver:
         return rp, cols[:nnz.value], vals[:nnz.value]
 
     def diag(self):
-        d = np.zeros(self.nloc)
+        """spH0d of the local electron part (DimUp * mpiQdw values; the phonon slabs share it)."""
+        d = np.zeros(self.dimup * self.qdw)
         _ck(lib().edgpu_get_diag(self.h, _dp(d), d.size))
         return d
 

@@ -227,7 +227,8 @@ int  edgpu_get_sector_map(const edgpu_ctx *c, int which, int32_t *out);
  * CSR in the reference's insertion order, 0-based, int64. */
 int  edgpu_get_csr(const edgpu_ctx *c, int which, int64_t *nrow, int64_t *nnz,
                    int64_t *rowptr, int64_t *cols, double *vals);
-/* spH0d, one value per local row (stored mode) or the recomputed diagonal (direct mode) */
+/* spH0d, one value per local ELECTRON row (nloc = DimUp*mpiQdw; the phonon slabs share it): stored mode, or the
+ * recomputed diagonal (direct mode) */
 int  edgpu_get_diag(const edgpu_ctx *c, double *out, int64_t nloc);
 
 /* ---- device-resident vector helpers (used by bench.py and by hosts that keep vectors in HBM) ------ */
