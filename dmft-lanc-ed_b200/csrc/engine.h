@@ -159,6 +159,8 @@ bool hxv_fast_path(edgpu_ctx *c, const double *d_x);
 int orbs_build(edgpu_ctx *c, int isector);
 int orbs_free(edgpu_ctx *c);
 int orbs_apply(edgpu_ctx *c, const double *d_x, double *d_y);
+void orbs_factor_host(const DevParams &dp, int f, int n, std::vector<int32_t> &map, std::vector<int32_t> &rowptr,
+                      std::vector<int32_t> &cols, std::vector<double> &vals);   // host arithmetic of one factor
 // hxv_tiled.cu
 int tiled_plan_build(edgpu_ctx *c);
 int tiled_plan_free(edgpu_ctx *c);

@@ -135,6 +135,44 @@ static void fill_args(const edgpu_ctx *c, OrbsArgs &a) {
   a.diag = p->d_diag;
 }
 
+// One factor on the host (pure arithmetic, also reachable without a GPU through edgpu_selftest_orbs_factor): Hs(f)%map
+// = the ascending words of Ns_Orb bits with n set (build_sector, ED_SETUP.f90:764-777) and spH0ups(iorb) / spH0dws(iorb)
+// in the reference's insertion order -- outer loop over the source state, bath level inner (stored/Orbs/H_up.f90).
+void orbs_factor_host(const DevParams &dp, int f, int n, std::vector<int32_t> &map, std::vector<int32_t> &rowptr,
+                      std::vector<int32_t> &cols, std::vector<double> &vals) {
+  const int norb = dp.norb, nbath = dp.nbath, nso = nbath + 1;
+  map.clear(); rowptr.clear(); cols.clear(); vals.clear();
+  for (uint32_t w = 0; w < (1u << nso); w++) if (__builtin_popcount(w) == n) map.push_back((int32_t)w);
+  const int64_t dim = (int64_t)map.size();
+  const int io = f % norb;
+  const double *v = (f < norb) ? dp.bv_up : dp.bv_dw;
+  std::vector<std::vector<int32_t>> rc((size_t)dim);
+  std::vector<std::vector<double>> rv((size_t)dim);
+  for (int64_t j = 0; j < dim; j++) {
+    const uint32_t m = (uint32_t)map[(size_t)j];
+    for (int kp = 1; kp <= nbath; kp++) {
+      const double vk = v[io * nbath + kp - 1];
+      if (vk == 0.0) continue;
+      const bool imp = (m & 1u) != 0, bath = ((m >> kp) & 1u) != 0;
+      if (imp == bath) continue;
+      const uint32_t k2 = m ^ 1u ^ (1u << kp);
+      // imp -> bath: c(1) has no sites below it, cdg(1+kp) counts the occupied sites below it on the state without
+      // the impurity electron; bath -> imp: c(1+kp) counts them on m (impurity empty), cdg(1) none
+      const uint32_t below = (imp ? (m & ~1u) : m) & ((1u << kp) - 1u);
+      const double sg = (__builtin_popcount(below) & 1) ? -1.0 : 1.0;
+      const int64_t i = std::lower_bound(map.begin(), map.end(), (int32_t)k2) - map.begin();   // binary_search
+      rc[(size_t)i].push_back((int32_t)j);
+      rv[(size_t)i].push_back(vk * sg);
+    }
+  }
+  rowptr.assign(1, 0);
+  for (int64_t i = 0; i < dim; i++) {
+    cols.insert(cols.end(), rc[(size_t)i].begin(), rc[(size_t)i].end());
+    vals.insert(vals.end(), rv[(size_t)i].begin(), rv[(size_t)i].end());
+    rowptr.push_back((int32_t)cols.size());
+  }
+}
+
 // build_Hv_sector for ed_total_ud = F.  The factors are tiny (C(Ns_Orb, n) rows): built on the host in the reference's
 // insertion order (outer loop over the source state, bath level inner; stored/Orbs/H_up.f90), then uploaded.
 int orbs_build(edgpu_ctx *c, int isector) {
@@ -153,36 +191,7 @@ int orbs_build(edgpu_ctx *c, int isector) {
     p->stride[f] = dim;
     dim *= p->dims[f];
     if (dim > ((int64_t)1 << 40)) return edgpu_set_err(EDGPU_ERR_UNSUPPORTED, "sector too large");
-    // Hs(f)%map: ascending words of Ns_Orb bits with n set (build_sector, ED_SETUP.f90:764-777)
-    std::vector<int32_t> &map = p->h_map[f];
-    for (uint32_t w = 0; w < (1u << nso); w++) if (__builtin_popcount(w) == n) map.push_back((int32_t)w);
-    const int io = f % norb;
-    const double *v = (f < norb) ? c->dp.bv_up : c->dp.bv_dw;
-    std::vector<std::vector<int32_t>> rc((size_t)p->dims[f]);
-    std::vector<std::vector<double>> rv((size_t)p->dims[f]);
-    for (int64_t j = 0; j < p->dims[f]; j++) {
-      const uint32_t m = (uint32_t)map[(size_t)j];
-      for (int kp = 1; kp <= nbath; kp++) {
-        const double vk = v[io * nbath + kp - 1];
-        if (vk == 0.0) continue;
-        const bool imp = (m & 1u) != 0, bath = ((m >> kp) & 1u) != 0;
-        if (imp == bath) continue;
-        const uint32_t k2 = m ^ 1u ^ (1u << kp);
-        // imp -> bath: c(1) has no sites below it, cdg(1+kp) counts the occupied sites below it on the state without
-        // the impurity electron; bath -> imp: c(1+kp) counts them on m (impurity empty), cdg(1) none
-        const uint32_t below = (imp ? (m & ~1u) : m) & ((1u << kp) - 1u);
-        const double sg = (__builtin_popcount(below) & 1) ? -1.0 : 1.0;
-        const int64_t i = std::lower_bound(map.begin(), map.end(), (int32_t)k2) - map.begin();   // binary_search
-        rc[(size_t)i].push_back((int32_t)j);
-        rv[(size_t)i].push_back(vk * sg);
-      }
-    }
-    p->h_rowptr[f].assign(1, 0);
-    for (int64_t i = 0; i < p->dims[f]; i++) {
-      p->h_cols[f].insert(p->h_cols[f].end(), rc[(size_t)i].begin(), rc[(size_t)i].end());
-      p->h_vals[f].insert(p->h_vals[f].end(), rv[(size_t)i].begin(), rv[(size_t)i].end());
-      p->h_rowptr[f].push_back((int32_t)p->h_cols[f].size());
-    }
+    orbs_factor_host(c->dp, f, n, p->h_map[f], p->h_rowptr[f], p->h_cols[f], p->h_vals[f]);
     TRY(up(&p->d_map[f], p->h_map[f]));
     TRY(up(&p->d_rowptr[f], p->h_rowptr[f]));
     TRY(up(&p->d_cols[f], p->h_cols[f]));

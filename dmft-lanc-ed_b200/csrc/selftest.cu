@@ -338,3 +338,20 @@ extern "C" int edgpu_selftest_halo_rank(const edgpu_params *p, int ndw, int nran
   for (int w = 0; w <= K; w++) pwin[w] = pw[w];
   return 0;
 }
+
+// HOST ONLY: factor f of an ed_total_ud = F sector exactly as build_Hv_sector computes it (f < Norb: up word of orbital
+// f+1 with n electrons, else the dw word of orbital f+1-Norb).  Returns the dimension; arrays may be NULL (count only);
+// *nnz = number of entries.
+extern "C" int64_t edgpu_selftest_orbs_factor(const edgpu_params *p, int f, int n, int32_t *map, int64_t *nnz, int64_t *rowptr,
+                                              int64_t *cols, double *vals) {
+  DevParams d = make_dp(p);
+  std::vector<int32_t> m, rp, cc;
+  std::vector<double> vv;
+  orbs_factor_host(d, f, n, m, rp, cc, vv);
+  if (nnz) *nnz = (int64_t)cc.size();
+  if (map) for (size_t k = 0; k < m.size(); k++) map[k] = m[k];
+  if (rowptr) for (size_t k = 0; k < rp.size(); k++) rowptr[k] = rp[k];
+  if (cols) for (size_t k = 0; k < cc.size(); k++) cols[k] = cc[k];
+  if (vals) for (size_t k = 0; k < vv.size(); k++) vals[k] = vv[k];
+  return (int64_t)m.size();
+}

@@ -39,6 +39,11 @@ int edgpu_selftest_srow_plan(const edgpu_params *p, int ndw, int nranks, int ran
  * its target; no stray triples; same slab layout on every rank.  info[6] = {ok, list entries, remote entries, triples,
  * largest slot count, windows}. */
 int edgpu_selftest_halo_tables(const edgpu_params *p, int ndw, int nranks, int64_t lr, int64_t tbits_opt, int K, int32_t *info);
+/* HOST ONLY: factor f of an ed_total_ud = F sector (f < Norb: up word of orbital f+1, else dw word of orbital f+1-Norb) with
+ * n electrons, as build_Hv_sector computes it on the host: Hs(f)%map and the CSR of spH0ups / spH0dws(iorb) in insertion
+ * order.  Returns the dimension; arrays may be NULL. */
+int64_t edgpu_selftest_orbs_factor(const edgpu_params *p, int f, int n, int32_t *map, int64_t *nnz, int64_t *rowptr,
+                                   int64_t *cols, double *vals);
 /* HOST ONLY: the halo tables of ONE rank (lcol2 per list entry; the (peer, slot, own column) triples it stores, sorted by
  * (window, source column); pwin[K+1]).  info[4] = {slots, largest slot count of any rank, triples, list entries}.
  * Returns 0, 1 = capacity too small, -1 = the structured row kernel does not apply. */

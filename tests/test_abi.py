@@ -271,3 +271,28 @@ def test_halo_push_tables_match_the_source_lists(name, ndw, nranks, lr, st, nwin
     assert ok == 1, info
     assert remote == triples and entries >= remote and k == nwin
     assert remote > 0 and maxslot > 0                               # every split of these sectors crosses a rank boundary
+
+
+@pytest.mark.parametrize("name,nups,ndws", [("ORB2", [1, 2], [2, 1]), ("ORB2B", [3, 2], [2, 3]), ("ORB3", [2, 1, 2], [1, 2, 1])])
+def test_orbs_factors_on_host_match_oracle(name, nups, ndws):
+    """Host arithmetic of the orbital-resolved sectors (csrc/orbs.cu: orbs_factor_host), without a GPU: every word map
+    and every spH0ups(iorb) / spH0dws(iorb) -- structure in insertion order AND values -- bit-exact against the oracle's
+    ed_buildh_orbs restatement (ED_HAMILTONIAN_SPARSE_HxV.f90:206-370, stored/Orbs/H_up.f90, H_dw.f90)."""
+    cfg, o = make_oracle(name)
+    keep = _params(cfg)
+    L = edgpu.selftest_lib()
+    L.edgpu_selftest_orbs_factor.restype = C.c_int64
+    i64p = C.POINTER(C.c_int64)
+    with o.sector_orbs(nups, ndws) as so:
+        for f in range(2 * cfg["norb"]):
+            n = (nups + ndws)[f]
+            nnz = C.c_int64(0)
+            dim = L.edgpu_selftest_orbs_factor(C.byref(keep[0]), f, n, None, C.byref(nnz), None, None, None)
+            assert dim == so.dims[f]
+            m = np.zeros(dim, np.int32); rp = np.zeros(dim + 1, np.int64)
+            cols = np.zeros(max(nnz.value, 1), np.int64); vals = np.zeros(max(nnz.value, 1))
+            L.edgpu_selftest_orbs_factor(C.byref(keep[0]), f, n, m.ctypes.data_as(C.POINTER(C.c_int32)), None, rp.ctypes.data_as(i64p),
+                                         cols.ctypes.data_as(i64p), vals.ctypes.data_as(C.POINTER(C.c_double)))
+            om, orp, ocols, ovals = so.factor(f)
+            assert np.array_equal(m, om) and np.array_equal(rp, orp)
+            assert np.array_equal(cols[:nnz.value], ocols) and np.array_equal(vals[:nnz.value], ovals)
