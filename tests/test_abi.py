@@ -296,3 +296,23 @@ def test_orbs_factors_on_host_match_oracle(name, nups, ndws):
             om, orp, ocols, ovals = so.factor(f)
             assert np.array_equal(m, om) and np.array_equal(rp, orp)
             assert np.array_equal(cols[:nnz.value], ocols) and np.array_equal(vals[:nnz.value], ovals)
+
+
+def test_header_is_plain_c_and_the_c_host_example_links(tmp_path):
+    """include/edgpu.h is a C header (the Fortran shim binds it through ISO_C_BINDING): integration/example_host.c, a
+    plain-C99 host that drives the reference's call sequence (build_Hv_sector, spHtimesV_p, sp_lanc_eigh, the GF chains,
+    the observables), compiles with -Wall -Wextra and links against libedgpu.so.  (Running it needs a B200.)"""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = os.path.join(ROOT, "integration", "example_host.c")
+    inc = os.path.join(ROOT, "include")
+    libdir = os.path.join(ROOT, "dmft-lanc-ed_b200")
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", inc, "-fsyntax-only", src], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = str(tmp_path / "example_host")
+    r = subprocess.run([gcc, "-std=c99", "-I", inc, src, "-L", libdir, "-ledgpu", "-Wl,--allow-shlib-undefined", "-lm", "-o", out],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
