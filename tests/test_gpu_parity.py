@@ -825,3 +825,47 @@ def test_hybrid_and_replica_baths_match_oracle(kind, sparse):
             s.delete_Hv_sector()
     finally:
         s.close()
+
+
+def test_noninteracting_gf_is_the_hybridisation_formula_on_gpu():
+    """No oracle in the loop: at U = 0 the engine's own chain -- sector scan on the device (edgpu_diag_sectors), the
+    eigenvector handed to the chains without leaving HBM, c / c^+ on the device, batched GF Lanczos, add_to_lanczos_gf --
+    must reproduce G(iw) = 1 / (iw + mu - sum_k V_k^2 / (iw - e_k)) to 1e-6, i.e. Sigma = 0 (the closed form behind
+    build_sigma_normal, ED_GF_NORMAL.f90:935-1002, ED_BATH_FUNCTIONS.f90:163-195)."""
+    cfg = configs.config("NS8V")
+    cfg["uloc"] = (0.0,)
+    cfg["hfmode"] = False
+    kw = configs.solver_kwargs(cfg)
+    s = edgpu.Solver(**kw)
+    try:
+        ns = cfg["nbath"] + 1
+        secs = [s.get_sector(nu, nd) for nu in range(ns + 1) for nd in range(ns + 1)]
+        e0s, nl, best = s.diag_sectors(secs, threshold=1e-16, twin=False)
+        e0 = e0s[best]
+        # the same number from the one-body spectrum: fill the negative levels of each spin (the chemical potential acts
+        # on the impurity only, stored/H_local.f90:13-18; the bath levels are bare)
+        h1 = np.zeros((ns, ns))
+        e = np.asarray(cfg["bath_e"]).reshape(-1)
+        v = np.asarray(cfg["bath_v"]).reshape(-1)
+        h1[0, 0] = -cfg["xmu"]
+        for k in range(ns - 1):
+            h1[k + 1, k + 1] = e[k]
+            h1[0, k + 1] = h1[k + 1, 0] = v[k]
+        w1 = np.linalg.eigvalsh(h1)
+        assert abs(e0 - 2 * w1[w1 < 0].sum()) < 1e-10
+        res = s.gf_chains([(1, 1, +1), (1, 1, -1)], nlanc_max=200)
+        beta, lmats = 50.0, 64
+        z = 1j * np.pi / beta * (2 * np.arange(1, lmats + 1) - 1)
+        g = np.zeros(lmats, dtype=complex)
+        for r, isign in zip(res, (1, -1)):
+            g += edgpu.add_to_lanczos_gf(r["norm2"], e0, r["alanc"], r["blanc"], isign, z)
+        delta = (v[None, :] ** 2 / (z[:, None] - e[None, :])).sum(axis=1)
+        # the state is the Lanczos eigenvector of the scan (energy converged to 1e-16, vector to its square root), and
+        # G is first order in the vector error
+        err = np.abs(g - 1.0 / (z + cfg["xmu"] - delta)).max()
+        assert err < 1e-6, err
+        sig, _ = edgpu.sigma_normal(z, g, cfg["xmu"], 0.0, e, v)
+        assert np.abs(sig).max() < 1e-5, np.abs(sig).max()
+        assert abs(res[0]["norm2"] + res[1]["norm2"] - 1.0) < 1e-12
+    finally:
+        s.close()

@@ -466,3 +466,35 @@ def test_hybrid_and_replica_baths_known_answers():
     for sec in [(2, 3), (1, 1)]:
         with oh.sector(*sec) as a:
             assert abs(np.linalg.eigvalsh(a.hmat())[0] - (w1[:sec[0]].sum() + w1[:sec[1]].sum())) < 1e-12
+
+
+def test_noninteracting_gf_is_the_hybridisation_formula():
+    """U = 0: the impurity Green's function of the whole chain (ground state by Lanczos, c / c^+ start vectors, GF
+    Lanczos chains, add_to_lanczos_gf_normal) must equal 1 / (iw + mu - e_imp - sum_k V_k^2 / (iw - e_k)) -- the
+    closed form behind build_sigma_normal (ED_GF_NORMAL.f90:935-1002, ED_BATH_FUNCTIONS.f90:163-195) -- so Sigma
+    vanishes identically.  Ties the sign / site conventions of the operators, the chains' weights and poles, and the
+    bath formula together without any reference output."""
+    cfg = configs.config("NS6V")                                   # level-dependent V_k, asymmetric levels, xmu != 0
+    cfg["uloc"] = (0.0,)
+    cfg["hfmode"] = False
+    o = O.Oracle(**configs.solver_kwargs(cfg))
+    # ground state over all sectors at U = 0: fill the lowest one-body levels of each spin
+    ns = cfg["nbath"] + 1
+    best = None
+    for nup in range(ns + 1):
+        for ndw in range(ns + 1):
+            with o.sector(nup, ndw) as s:
+                w, v = np.linalg.eigh(s.hmat())
+            if best is None or w[0] < best[0] - 1e-12:
+                best = (w[0], v[:, 0], nup, ndw)
+    e0, gs, nup, ndw = best
+    r = o.build_gf_normal(nup, ndw, gs, e0, 1, lmats=64, lreal=8, ngfiter=200)
+    wm = r["wm"]
+    e = np.asarray(cfg["bath_e"]).reshape(-1)
+    v = np.asarray(cfg["bath_v"]).reshape(-1)
+    z = 1j * wm
+    delta = (v[None, :] ** 2 / (z[:, None] - e[None, :])).sum(axis=1)
+    g_exact = 1.0 / (z + cfg["xmu"] - delta)
+    assert np.abs(r["gmats"] - g_exact).max() < 1e-9
+    sig, _ = o.sigma_normal(1, 1, z, r["gmats"])
+    assert np.abs(sig).max() < 1e-8
