@@ -32,6 +32,7 @@ os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 METRIC = "lanczos_hxv_per_s"
 UNIT = "H*v/s"
+OPERATOR = "spHtimesV_p: Hv = Hd*v + (Hdw x 1)v + (1 x Hup)v on the whole sector"   # config.operator of BOTH arms
 WORKLOADS = {
     "C1": "single-band Hubbard Norb=1 Nbath=7 (Ns=8), sector 4:4, dim 4900",
     "C2": "single-band Hubbard Norb=1 Nbath=13 (Ns=14), sector 7:7, dim 11778624",
@@ -193,8 +194,8 @@ def run_reference(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": max(1, args.warmup),
             "ms_per_step": 1000.0 * dt / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": WORKLOADS[args.workload], "operator": "stored sparse (ED_SPARSE_H=T), CPU",
-                       "vector": "v_i = sin(0.37 i) + 0.1"},
+            "config": {"workload": WORKLOADS[args.workload], "operator": OPERATOR, "vector": "v_i = sin(0.37 i) + 0.1"},
+            "operator_form": "stored sparse (ED_SPARSE_H=T), CPU",
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": ref.threads, "kind": "port",
                              "sample": "every step = one full H*v of %s through the restated spMatVec_MPI_main (gcc -O3): %d ranks on %d host "
                                        "threads, both vector_transpose_MPI exchanges included" % (args.workload, ref.P, ref.threads)},
@@ -517,9 +518,11 @@ def run_b200(args):
         "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload], "operator": "stored (ED_SPARSE_H=T)" if args.stored else "direct (ED_SPARSE_H=F, diagonal recomputed)",
+        "config": {"workload": WORKLOADS[args.workload], "operator": OPERATOR,
                    "algo": args.algo, "l2": "input vector %.0f MB per GPU, larger than the 126 MB L2; no flush" % (8 * nloc / 1e6),
                    "sharding": "i_dw columns, %d rank(s)" % world, "vector": "v_i = sin(0.37 i) + 0.1"},
+        # the same operator in both arms (stored == direct to 1e-12, tests/test_gpu_parity.py); how each arm evaluates it:
+        "operator_form": "stored (ED_SPARSE_H=T)" if args.stored else "direct (ED_SPARSE_H=F, diagonal recomputed)",
         "lanczos_iter_per_s": 1000.0 / res["lanczos_ms_per_iter"],
         "roofline": roof,
         "e2e": {"value": 1.0 / res["e2e_s"], "unit": UNIT, "h2d_bytes_per_step": 8 * res["dim"], "d2h_bytes_per_step": 8 * res["dim"],
