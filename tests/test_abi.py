@@ -316,3 +316,31 @@ def test_header_is_plain_c_and_the_c_host_example_links(tmp_path):
     r = subprocess.run([gcc, "-std=c99", "-I", inc, src, "-L", libdir, "-ledgpu", "-Wl,--allow-shlib-undefined", "-lm", "-o", out],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_add_to_lanczos_chi_host_formula_on_cpu():
+    """edgpu_add_to_lanczos_chi is host arithmetic on a chain's coefficients (add_to_lanczos_spinChi / _densChi,
+    ED_GF_CHISPIN.f90:434-488): checked on the CPU against the oracle's restatement on real chain coefficients, and on a
+    one-pole chain against the closed form chi(tau) = norm2 exp(-tau dE), chi(i nu) = norm2 (1 - e^{-beta dE}) 2 dE / (nu^2 + dE^2)."""
+    import oracle as O
+    cfg, o = make_oracle("NS6")
+    with o.sector(3, 3) as s:
+        e0, gs, _, _ = s.lanc_eigh(v0=np.ones(s.dim) / np.sqrt(s.dim))
+    beta = 40.0
+    vm = np.pi / beta * 2 * np.arange(7)
+    tau = np.linspace(0.0, beta, 9)
+    vr = np.linspace(-2.5, 2.5, 11)
+    for kind in (0, 1):
+        ch = o.chi_chain(3, 3, gs, kind, 1, 1, ngfiter=40)
+        got = edgpu.add_to_lanczos_chi(ch["norm2"], e0, beta, ch["alanc"], ch["blanc"], vm, tau, vr, 0.02)
+        want = O.add_to_lanczos_chi(ch["norm2"], e0, beta, ch["alanc"], ch["blanc"], vm, tau, vr, 0.02)
+        for g_, w_ in zip(got, want):
+            assert np.abs(g_ - w_).max() < 1e-11
+    de, n2 = 0.7, 0.3
+    civ, ctau, cw = edgpu.add_to_lanczos_chi(n2, -1.0, beta, np.array([-1.0 + de]), np.array([0.0]), vm, tau, vr, 0.02)
+    bose = 1.0 - np.exp(-beta * de)
+    assert np.abs(ctau - n2 * np.exp(-tau * de)).max() < 1e-14
+    assert abs(civ[0] - n2 * 2 * bose / de) < 1e-14
+    assert np.abs(civ[1:] - n2 * bose * 2 * de / (vm[1:] ** 2 + de ** 2)).max() < 1e-14
+    w = vr + 0.02j
+    assert np.abs(cw + n2 * bose * (1.0 / (w - de) - 1.0 / (w + de))).max() < 1e-13
