@@ -498,3 +498,29 @@ def test_noninteracting_gf_is_the_hybridisation_formula():
     assert np.abs(r["gmats"] - g_exact).max() < 1e-9
     sig, _ = o.sigma_normal(1, 1, z, r["gmats"])
     assert np.abs(sig).max() < 1e-8
+
+
+def test_golden_fixture_round2():
+    """tests/golden/round2_golden.npz (tests/golden/make_golden.py::round2) freezes the oracle's outputs for the round-2
+    additions -- susceptibility chains, orbital-resolved operator, phonon terms, replica and hybrid baths -- so that later
+    edits of the restatement cannot drift silently: integer structure bit-exact, values to rounding."""
+    import os
+    import runpy
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "round2_golden.npz"))
+    mod = runpy.run_path(os.path.join(os.path.dirname(__file__), "golden", "make_golden.py"))
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        mod["round2"].__globals__["HERE"] = td                      # regenerate next to nothing, compare key by key
+        mod["round2"]()
+        new = np.load(os.path.join(td, "round2_golden.npz"))
+        assert set(new.files) == set(gold.files)
+        for k in gold.files:
+            a, b = gold[k], new[k]
+            if np.issubdtype(a.dtype, np.integer):
+                assert np.array_equal(a, b), k
+            elif k.endswith("_vals") or k.endswith("_h0d"):
+                assert np.array_equal(a, b), k                      # matrix elements and diagonals are deterministic sums
+            elif k.endswith("anc"):
+                assert np.abs(a[:10] - b[:10]).max() < 1e-10, k     # Lanczos coefficients: the stable prefix
+            else:
+                assert np.abs(a - b).max() <= 1e-12 * max(1.0, np.abs(a).max()), k
